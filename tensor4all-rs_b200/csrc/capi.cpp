@@ -1,0 +1,183 @@
+// extern "C" boundary of libt4b.so (declared in include/t4b.h).
+#include <cstring>
+#include <string>
+
+#include "../../include/t4b.h"
+#include "dla.h"
+#include "host/tensor.h"
+
+using namespace t4b;
+
+struct t4b_ctx {
+    dla::Ctx* c;
+};
+
+static thread_local std::string g_last_error;
+
+#define T4B_TRY try {
+#define T4B_CATCH                                                      \
+    }                                                                  \
+    catch (const t4b::Error& e) {                                      \
+        g_last_error = e.what();                                       \
+        return (int)e.code;                                            \
+    }                                                                  \
+    catch (const std::exception& e) {                                  \
+        g_last_error = e.what();                                       \
+        return T4B_INTERNAL;                                           \
+    }                                                                  \
+    catch (...) {                                                      \
+        g_last_error = "unknown error";                                \
+        return T4B_INTERNAL;                                           \
+    }                                                                  \
+    return T4B_OK;
+
+static void require_ctx(t4b_ctx* ctx) {
+    if (!ctx || !ctx->c) throw Error(t4b::ST_INVALID_ARGUMENT, "null context");
+}
+static DType to_dtype(int d) {
+    if (d == T4B_F64) return F64;
+    if (d == T4B_C64) return C64;
+    throw Error(t4b::ST_INVALID_ARGUMENT, "dtype must be T4B_F64 or T4B_C64");
+}
+
+extern "C" {
+
+const char* t4b_last_error(void) { return g_last_error.c_str(); }
+const char* t4b_version(void) { return "t4b 0.1.0 (sm_100a)"; }
+
+int t4b_ctx_create(int device, void* cuda_stream, t4b_ctx** out) {
+    T4B_TRY
+    if (!out) throw Error(t4b::ST_INVALID_ARGUMENT, "null out pointer");
+    dla::Ctx* c = dla::ctx_create(device, cuda_stream);
+    *out = new t4b_ctx{c};
+    T4B_CATCH
+}
+int t4b_ctx_destroy(t4b_ctx* ctx) {
+    T4B_TRY
+    if (ctx) {
+        dla::ctx_destroy(ctx->c);
+        delete ctx;
+    }
+    T4B_CATCH
+}
+int t4b_ctx_sync(t4b_ctx* ctx) {
+    T4B_TRY
+    require_ctx(ctx);
+    dla::sync(ctx->c);
+    T4B_CATCH
+}
+int t4b_ctx_launch_count(t4b_ctx* ctx, int64_t* out) {
+    T4B_TRY
+    require_ctx(ctx);
+    *out = dla::ctx_launch_count(ctx->c);
+    T4B_CATCH
+}
+int t4b_malloc(t4b_ctx* ctx, size_t bytes, void** dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    *dev = dla::alloc(ctx->c, bytes);
+    T4B_CATCH
+}
+int t4b_free(t4b_ctx* ctx, void* dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    dla::release(ctx->c, dev);
+    T4B_CATCH
+}
+int t4b_upload(t4b_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    T4B_TRY
+    require_ctx(ctx);
+    dla::h2d(ctx->c, dev, host, bytes);
+    T4B_CATCH
+}
+int t4b_download(t4b_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    T4B_TRY
+    require_ctx(ctx);
+    dla::d2h(ctx->c, host, dev, bytes);
+    dla::sync(ctx->c);
+    T4B_CATCH
+}
+
+int t4b_tensordot(t4b_ctx* ctx, int dtype, const void* a_dev, int rank_a, const int64_t* shape_a,
+                  int conj_a, const void* b_dev, int rank_b, const int64_t* shape_b, int conj_b,
+                  int naxes, const int32_t* axes_a, const int32_t* axes_b, void* out_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    DType dt = to_dtype(dtype);
+    T4B_REQUIRE(rank_a >= 0 && rank_b >= 0 && naxes >= 0 && naxes <= rank_a && naxes <= rank_b,
+                "tensordot: bad ranks/axes");
+    std::vector<Index> ia(rank_a), ib(rank_b);
+    for (int i = 0; i < rank_a; ++i) ia[i] = new_index(shape_a[i]);
+    for (int i = 0; i < rank_b; ++i) ib[i] = new_index(shape_b[i]);
+    std::vector<char> used_a(rank_a, 0), used_b(rank_b, 0);
+    for (int k = 0; k < naxes; ++k) {
+        int xa = axes_a[k], xb = axes_b[k];
+        T4B_REQUIRE(xa >= 0 && xa < rank_a && xb >= 0 && xb < rank_b, "tensordot: axis out of range");
+        T4B_REQUIRE(!used_a[xa] && !used_b[xb], "tensordot: duplicate axis");
+        T4B_REQUIRE(shape_a[xa] == shape_b[xb], "tensordot: contracted dimensions differ");
+        used_a[xa] = used_b[xb] = 1;
+        ib[xb] = ia[xa];
+    }
+    // keep the pairing order of axes_a for the K composite index: contract_pair orders common
+    // indices by appearance in A, B's K group follows the same Index order, so any pairing is valid.
+    Tensor A = wrap_device(ctx->c, dt, ia, const_cast<void*>(a_dev));
+    Tensor B = wrap_device(ctx->c, dt, ib, const_cast<void*>(b_dev));
+    std::vector<Index> out_inds;
+    for (int i = 0; i < rank_a; ++i) if (!used_a[i]) out_inds.push_back(ia[i]);
+    for (int i = 0; i < rank_b; ++i) if (!used_b[i]) out_inds.push_back(ib[i]);
+    // write straight into the caller's buffer
+    Tensor out = wrap_device(ctx->c, dt, out_inds, out_dev);
+    // contract_pair allocates; reproduce its body with the external output instead
+    {
+        std::vector<Index> common = common_indices(A, B);
+        std::vector<Index> a_free = indices_except(A.inds, common);
+        std::vector<Index> b_free = indices_except(B.inds, common);
+        auto strides = [](const std::vector<Index>& v) {
+            std::vector<int64_t> s(v.size());
+            int64_t acc = 1;
+            for (size_t i = 0; i < v.size(); ++i) { s[i] = acc; acc *= v[i].dim; }
+            return s;
+        };
+        auto grp = [&](const std::vector<Index>& axes, const std::vector<Index>& owner) {
+            auto st = strides(owner);
+            Group g;
+            T4B_REQUIRE((int)axes.size() <= kMaxGroupDims, "tensordot: too many axes in one group");
+            for (auto& ix : axes) {
+                for (size_t a = 0; a < owner.size(); ++a)
+                    if (owner[a] == ix) { g.dim[g.nd] = ix.dim; g.str[g.nd] = st[a]; ++g.nd; }
+            }
+            return g;
+        };
+        Group am = grp(a_free, A.inds), ak = grp(common, A.inds);
+        Group bk = grp(common, B.inds), bn = grp(b_free, B.inds);
+        Group cm = grp(a_free, out.inds), cn = grp(b_free, out.inds);
+        dla::gemm(ctx->c, dt, am.size(), bn.size(), ak.size(), 1.0, A.data(), am, ak, conj_a != 0,
+                  B.data(), bk, bn, conj_b != 0, 0.0, out.data(), cm, cn);
+    }
+    T4B_CATCH
+}
+
+int t4b_permute(t4b_ctx* ctx, int dtype, const void* in_dev, int rank, const int64_t* shape,
+                const int32_t* perm, int conj, void* out_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    DType dt = to_dtype(dtype);
+    T4B_REQUIRE(rank >= 0 && rank <= kMaxGroupDims, "permute: rank must be <= 6");
+    std::vector<int64_t> st(rank);
+    int64_t acc = 1;
+    for (int i = 0; i < rank; ++i) { st[i] = acc; acc *= shape[i]; }
+    Group g;
+    std::vector<char> seen(rank, 0);
+    for (int i = 0; i < rank; ++i) {
+        int p = perm[i];
+        T4B_REQUIRE(p >= 0 && p < rank && !seen[p], "permute: perm is not a permutation");
+        seen[p] = 1;
+        g.dim[g.nd] = shape[p];
+        g.str[g.nd] = st[p];
+        ++g.nd;
+    }
+    dla::permute(ctx->c, dt, out_dev, in_dev, g, conj != 0);
+    T4B_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// dla.h — device linear-algebra primitives: the only seam between the host-side
+// sweep drivers (csrc/host/*.cpp) and the hand-written sm_100a kernels
+// (csrc/kernels/*.cu).  No CUDA types appear here so the drivers compile as
+// plain C++.  All matrix/tensor pointers are DEVICE pointers, column-major,
+// Complex64 = interleaved (re,im) f64 pairs (reference docs/CAPI_DESIGN.md:128-134).
+//
+// The product implementation is csrc/kernels/ (CUDA only; there is no CPU
+// fallback: ctx_create throws if no CUDA device is usable).  tests/hostsim/
+// holds a test double of this interface used ONLY by the `-m "not gpu"` tests
+// to exercise the host drivers; it is never linked into libt4b.so.
+#pragma once
+#include "common.h"
+
+namespace t4b {
+namespace dla {
+
+struct Ctx;  // one per (device, stream); not thread-safe, create one per host thread
+
+Ctx* ctx_create(int device, void* cuda_stream /* may be null: library-owned stream */);
+void ctx_destroy(Ctx*);
+void* ctx_stream(Ctx*);
+int ctx_device(Ctx*);
+// Number of kernels launched through this context since creation (bench.py's gpu_launches).
+int64_t ctx_launch_count(Ctx*);
+
+// Stream-ordered memory.
+void* alloc(Ctx*, size_t bytes);
+void release(Ctx*, void* p);
+void h2d(Ctx*, void* dst, const void* src, size_t bytes);
+void d2h(Ctx*, void* dst, const void* src, size_t bytes);  // asynchronous; call sync() before reading dst
+void d2d(Ctx*, void* dst, const void* src, size_t bytes);
+void zero(Ctx*, void* dst, size_t bytes);
+void sync(Ctx*);
+
+// C[cm,cn] = alpha * op(A)[am,ak] * op(B)[bk,bn] + beta * C, op = conj or identity.
+// Every operand is addressed through two composite indices (Group), so any
+// permute/reshape of the underlying tensors is folded into the operand loads
+// and the result store (replaces tenferro dot_general_with_conj,
+// reference crates/tensor4all-core/src/defaults/idx_tensor.rs:3578-3580, and the
+// pairwise steps of einsum, crates/tensor4all-tensorbackend/src/tenferro_bridge.rs:1586).
+void gemm(Ctx*, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const void* A,
+          const Group& am, const Group& ak, bool conjA, const void* B, const Group& bk,
+          const Group& bn, bool conjB, double beta, void* C, const Group& cm, const Group& cn);
+
+// out[i] (contiguous, i over g.dim first-fastest) = op(in[offset_g(i)])
+// (materialised permute; reference idx_tensor.rs:3389,3445).
+void permute(Ctx*, DType dt, void* out, const void* in, const Group& g, bool conj);
+
+// A (m x n, ld = m) -> Q (m x k, ld = m), R (k x n, ld = k, upper trapezoidal), k = min(m,n).
+// Householder; A is destroyed.  Q may be null (R only).
+// Replaces tenferro `.qr()` (reference crates/tensor4all-core/src/defaults/qr.rs:258-260,
+// crates/tensor4all-tensorbackend/src/backend.rs:742-762).
+void qr_thin(Ctx*, DType dt, int64_t m, int64_t n, void* A, void* Q, void* R);
+
+// Thin SVD A = U diag(S) Vh; U m x k, S k (f64, non-increasing), Vh k x n (= V^H), k = min(m,n).
+// A is destroyed.  U or Vh may be null when the caller rebuilds that side with a gemm.
+// QR-preconditioned one-sided block Jacobi.  Replaces tenferro `.svd()`
+// (reference crates/tensor4all-core/src/defaults/svd.rs:265-267, backend.rs:715-734).
+void svd_thin(Ctx*, DType dt, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh);
+
+// Hermitian eigendecomposition G = W diag(lam) W^H of an n x n matrix (ld = n);
+// lam ascending is NOT guaranteed (Jacobi order) - callers sort.  G destroyed.
+// Replaces tenferro eigh (reference crates/tensor4all-tensorbackend/src/matrix.rs:660-900).
+void eigh(Ctx*, DType dt, int64_t n, void* G, double* lam, void* W);
+
+// Full-pivot rank-revealing LU in place on A (m x n, ld = m), bit-compatible with
+// reference crates/tensor4all-core/src/matrixlu.rs:735-819.  row_perm (m) / col_perm (n)
+// are device int64 arrays.  Returns the pivot count; *last_error as lu.error.
+int64_t rrlu(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t max_rank, double rel_tol,
+             double abs_tol, bool left_orthogonal, int64_t* row_perm, int64_t* col_perm,
+             double* last_error);
+
+// Triangular solve with an n x n triangular T (ld = ldt):
+//   left_side : X <- op(T)^-1 X  (X is n x nrhs, ld = ldx)
+//   !left_side: X <- X op(T)^-1  (X is nrhs x n, ld = ldx)
+// (reference crates/tensor4all-tensorbackend/src/backend.rs:924-937).
+void trsm(Ctx*, DType dt, bool left_side, bool lower, bool transpose, bool unit_diag, int64_t n,
+          int64_t nrhs, const void* T, int64_t ldt, void* X, int64_t ldx);
+
+// A[i,j] *= s[j] (cols) or s[i] (rows); s real, device.  invert => divide.
+void scale_cols(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t lda, const double* s,
+                bool invert);
+void scale_rows(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t lda, const double* s,
+                bool invert);
+// out[i] = sqrt(sum_{j>=i} |R[i,j]|^2), i < min(k,n): the row norms used by the QR rank rule
+// (reference crates/tensor4all-core/src/defaults/qr.rs:108-149).
+void upper_row_norms(Ctx*, DType dt, int64_t k, int64_t n, const void* R, int64_t ldr, double* out);
+// *out (device scalar, f64) = sum |x_i|^2
+void sumsq(Ctx*, DType dt, int64_t n, const void* x, double* out);
+// x *= alpha
+void scal(Ctx*, DType dt, int64_t n, void* x, double alpha);
+// y += alpha * x
+void axpy(Ctx*, DType dt, int64_t n, double alpha, const void* x, void* y);
+
+}  // namespace dla
+}  // namespace t4b

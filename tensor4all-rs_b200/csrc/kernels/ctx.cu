@@ -1,0 +1,274 @@
+// Context, stream-ordered memory and the small HBM-bound elementwise kernels
+// (permute / scale / norms).  sm_100a only; no CPU fallback.
+#include "ctx.cuh"
+
+namespace t4b {
+namespace dla {
+
+void* Ctx::get_scratch(size_t bytes) {
+    if (bytes > scratch_bytes) {
+        // the old block may still be in use by queued kernels: free it stream-ordered
+        if (scratch) T4B_CUDA_CHECK(cudaFreeAsync(scratch, stream));
+        size_t nb = bytes + bytes / 2 + (1 << 16);
+        T4B_CUDA_CHECK(cudaMallocAsync(&scratch, nb, stream));
+        scratch_bytes = nb;
+    }
+    return scratch;
+}
+
+void* Ctx::get_pinned(size_t bytes) {
+    if (bytes > pinned_bytes) {
+        if (pinned) {
+            T4B_CUDA_CHECK(cudaStreamSynchronize(stream));
+            T4B_CUDA_CHECK(cudaFreeHost(pinned));
+        }
+        size_t nb = bytes < 4096 ? 4096 : bytes * 2;
+        T4B_CUDA_CHECK(cudaMallocHost(&pinned, nb));
+        pinned_bytes = nb;
+    }
+    return pinned;
+}
+
+Ctx* ctx_create(int device, void* cuda_stream) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(ST_CUDA_ERROR,
+                    std::string("t4b requires a CUDA device (sm_100a); none usable: ") +
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) throw Error(ST_INVALID_ARGUMENT, "bad device ordinal");
+    T4B_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    T4B_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        throw Error(ST_CUDA_ERROR, "t4b kernels are built for sm_100a only; device is sm_" +
+                                        std::to_string(prop.major * 10 + prop.minor));
+    Ctx* c = new Ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        T4B_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+    }
+    // keep freed blocks cached in the default pool: sweeps re-allocate the same shapes
+    cudaMemPool_t pool;
+    T4B_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    T4B_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    return c;
+}
+
+void ctx_destroy(Ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->scratch) cudaFreeAsync(c->scratch, c->stream);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* ctx_stream(Ctx* c) { return (void*)c->stream; }
+int ctx_device(Ctx* c) { return c->device; }
+int64_t ctx_launch_count(Ctx* c) { return c->launches; }
+
+void* alloc(Ctx* c, size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    T4B_CUDA_CHECK(cudaMallocAsync(&p, bytes, c->stream));
+    return p;
+}
+void release(Ctx* c, void* p) {
+    if (p) T4B_CUDA_CHECK(cudaFreeAsync(p, c->stream));
+}
+void h2d(Ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes) T4B_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+}
+void d2h(Ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes) T4B_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+}
+void d2d(Ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes)
+        T4B_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+}
+void zero(Ctx* c, void* dst, size_t bytes) {
+    if (bytes) T4B_CUDA_CHECK(cudaMemsetAsync(dst, 0, bytes, c->stream));
+}
+void sync(Ctx* c) { T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+
+// ---------------------------------------------------------------------------------------
+// permute: out contiguous, in gathered.  HBM-bound; grid-stride, one element per thread per
+// step, output writes fully coalesced.
+template <bool CPLX>
+__global__ void permute_kernel(double* __restrict__ out, const double* __restrict__ in, Group g,
+                               int64_t total, bool conj) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t off = group_offset(g, i);
+        if (CPLX) {
+            double2 v = reinterpret_cast<const double2*>(in)[off];
+            if (conj) v.y = -v.y;
+            reinterpret_cast<double2*>(out)[i] = v;
+        } else {
+            out[i] = in[off];
+        }
+    }
+}
+
+static int grid_for(Ctx* c, int64_t total, int threads, int per_sm = 8) {
+    int64_t blocks = (total + threads - 1) / threads;
+    int64_t cap = (int64_t)c->num_sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+void permute(Ctx* c, DType dt, void* out, const void* in, const Group& g, bool conj) {
+    int64_t total = g.size();
+    if (total == 0) return;
+    int grid = grid_for(c, total, 256);
+    if (dt == C64)
+        permute_kernel<true><<<grid, 256, 0, c->stream>>>((double*)out, (const double*)in, g, total, conj);
+    else
+        permute_kernel<false><<<grid, 256, 0, c->stream>>>((double*)out, (const double*)in, g, total, false);
+    c->launched("permute");
+}
+
+// ---------------------------------------------------------------------------------------
+template <bool CPLX, bool ROWS>
+__global__ void scale_kernel(double* __restrict__ A, int64_t m, int64_t n, int64_t lda,
+                             const double* __restrict__ s, bool invert) {
+    int64_t total = m * n;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        int64_t j = e / m, i = e - j * m;
+        double f = s[ROWS ? i : j];
+        int64_t idx = i + j * lda;
+        if (CPLX) {
+            double2 v = reinterpret_cast<double2*>(A)[idx];
+            if (invert) { v.x = v.x / f; v.y = v.y / f; } else { v.x *= f; v.y *= f; }
+            reinterpret_cast<double2*>(A)[idx] = v;
+        } else {
+            A[idx] = invert ? A[idx] / f : A[idx] * f;
+        }
+    }
+}
+
+void scale_cols(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t lda, const double* s,
+                bool invert) {
+    if (m * n == 0) return;
+    int grid = grid_for(c, m * n, 256);
+    if (dt == C64) scale_kernel<true, false><<<grid, 256, 0, c->stream>>>((double*)A, m, n, lda, s, invert);
+    else scale_kernel<false, false><<<grid, 256, 0, c->stream>>>((double*)A, m, n, lda, s, invert);
+    c->launched("scale_cols");
+}
+void scale_rows(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t lda, const double* s,
+                bool invert) {
+    if (m * n == 0) return;
+    int grid = grid_for(c, m * n, 256);
+    if (dt == C64) scale_kernel<true, true><<<grid, 256, 0, c->stream>>>((double*)A, m, n, lda, s, invert);
+    else scale_kernel<false, true><<<grid, 256, 0, c->stream>>>((double*)A, m, n, lda, s, invert);
+    c->launched("scale_rows");
+}
+
+// row norms of an upper-trapezoidal R: one warp per row i, summing j = i..n-1 in the
+// reference's order is not required (the rule compares against rtol * max).
+template <bool CPLX>
+__global__ void upper_row_norms_kernel(const double* __restrict__ R, int64_t k, int64_t n,
+                                       int64_t ldr, double* __restrict__ out) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x & 31;
+    int64_t kk = k < n ? k : n;
+    if (row >= kk) return;
+    double acc = 0.0;
+    for (int64_t j = row + lane; j < n; j += 32) {
+        if (CPLX) {
+            double2 v = reinterpret_cast<const double2*>(R)[row + j * ldr];
+            acc += v.x * v.x + v.y * v.y;
+        } else {
+            double v = R[row + j * ldr];
+            acc += v * v;
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = sqrt(acc);
+}
+
+void upper_row_norms(Ctx* c, DType dt, int64_t k, int64_t n, const void* R, int64_t ldr,
+                     double* out) {
+    int64_t kk = k < n ? k : n;
+    if (kk == 0) return;
+    int grid = (int)((kk + 7) / 8);
+    if (dt == C64) upper_row_norms_kernel<true><<<grid, 256, 0, c->stream>>>((const double*)R, k, n, ldr, out);
+    else upper_row_norms_kernel<false><<<grid, 256, 0, c->stream>>>((const double*)R, k, n, ldr, out);
+    c->launched("upper_row_norms");
+}
+
+// deterministic two-pass sum of squares (no atomics: bit-stable results run to run)
+__global__ void sumsq_partial_kernel(const double* __restrict__ x, int64_t n_doubles,
+                                     double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_doubles; i += stride) {
+        double v = x[i];
+        acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+__global__ void sum_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) *out = v;
+    }
+}
+
+void sumsq(Ctx* c, DType dt, int64_t n, const void* x, double* out) {
+    int64_t nd = n * (dt == C64 ? 2 : 1);
+    int grid = grid_for(c, nd, 256, 4);
+    double* partial = (double*)c->get_scratch(sizeof(double) * grid);
+    sumsq_partial_kernel<<<grid, 256, 0, c->stream>>>((const double*)x, nd, partial);
+    c->launched("sumsq_partial");
+    sum_final_kernel<<<1, 256, 0, c->stream>>>(partial, grid, out);
+    c->launched("sum_final");
+}
+
+__global__ void scal_kernel(double* __restrict__ x, int64_t n, double a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] *= a;
+}
+void scal(Ctx* c, DType dt, int64_t n, void* x, double alpha) {
+    int64_t nd = n * (dt == C64 ? 2 : 1);
+    if (nd == 0) return;
+    scal_kernel<<<grid_for(c, nd, 256), 256, 0, c->stream>>>((double*)x, nd, alpha);
+    c->launched("scal");
+}
+__global__ void axpy_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n, double a) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += a * x[i];
+}
+void axpy(Ctx* c, DType dt, int64_t n, double alpha, const void* x, void* y) {
+    int64_t nd = n * (dt == C64 ? 2 : 1);
+    if (nd == 0) return;
+    axpy_kernel<<<grid_for(c, nd, 256), 256, 0, c->stream>>>((double*)y, (const double*)x, nd, alpha);
+    c->launched("axpy");
+}
+
+}  // namespace dla
+}  // namespace t4b

@@ -1,0 +1,68 @@
+// Internal CUDA-side context shared by the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../dla.h"
+
+namespace t4b {
+namespace dla {
+
+#define T4B_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            throw ::t4b::Error(::t4b::ST_CUDA_ERROR, std::string(#expr) + ": " +             \
+                                                          cudaGetErrorString(_e));             \
+    } while (0)
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // grow-only scratch (offset tables, small reductions); stream-ordered reuse is safe
+    // because every user runs on `stream`.
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned host mailbox for small device->host results (ranks, flags, errors)
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    void* get_scratch(size_t bytes);
+    void* get_pinned(size_t bytes);
+    void launched(const char* what) {
+        ++launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            throw ::t4b::Error(::t4b::ST_CUDA_ERROR,
+                               std::string("kernel launch failed (") + what + "): " +
+                                   cudaGetErrorString(e));
+    }
+};
+
+// ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ int64_t group_offset(const Group& g, int64_t i) {
+    int64_t off = 0;
+#pragma unroll
+    for (int d = 0; d < kMaxGroupDims; ++d) {
+        if (d < g.nd) {
+            int64_t q = i / g.dim[d];
+            off += (i - q * g.dim[d]) * g.str[d];
+            i = q;
+        }
+    }
+    return off;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dla
+}  // namespace t4b

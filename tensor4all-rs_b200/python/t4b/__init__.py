@@ -1,0 +1,149 @@
+"""ctypes harness over libt4b.so (the C ABI in include/t4b.h).
+
+This is test/bench plumbing only: the product is the shared library.  The Rust shim described
+in INTEGRATION.md binds exactly the same symbols.  Importing this module never touches the
+oracle; creating a Context without a usable sm_100 GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(os.path.dirname(_HERE))
+LIB_PATH = os.environ.get("T4B_LIB", os.path.join(_PKG, "lib", "libt4b.so"))
+
+F64, C64 = 0, 1
+
+
+class T4BError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"t4b error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise T4BError(-1, f"{LIB_PATH} not built; run python tensor4all-rs_b200/build.py")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.t4b_last_error.restype = C.c_char_p
+        _lib.t4b_version.restype = C.c_char_p
+    return _lib
+
+
+def _check(code):
+    if code != 0:
+        raise T4BError(code, lib().t4b_last_error().decode())
+
+
+def dtype_of(arr) -> int:
+    if arr.dtype == np.float64:
+        return F64
+    if arr.dtype == np.complex128:
+        return C64
+    raise TypeError(f"unsupported dtype {arr.dtype}")
+
+
+def np_dtype(dt: int):
+    return np.float64 if dt == F64 else np.complex128
+
+
+def _i64(seq):
+    return (C.c_int64 * len(seq))(*[int(x) for x in seq])
+
+
+def _i32(seq):
+    return (C.c_int32 * len(seq))(*[int(x) for x in seq])
+
+
+class DeviceArray:
+    """A dense column-major device buffer with a shape (first index fastest)."""
+
+    def __init__(self, ctx, shape, dt, ptr=None):
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in shape)
+        self.dt = dt
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * (8 if dt == F64 else 16)
+        self.owned = ptr is None
+        if ptr is None:
+            p = C.c_void_p()
+            _check(lib().t4b_malloc(ctx.h, C.c_size_t(max(self.nbytes, 16)), C.byref(p)))
+            ptr = p.value
+        self.ptr = ptr
+
+    def free(self):
+        if self.owned and self.ptr:
+            _check(lib().t4b_free(self.ctx.h, C.c_void_p(self.ptr)))
+            self.ptr = None
+
+    def get(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=np_dtype(self.dt), order="F")
+        if self.nbytes:
+            _check(lib().t4b_download(self.ctx.h, out.ctypes.data_as(C.c_void_p),
+                                      C.c_void_p(self.ptr), C.c_size_t(self.nbytes)))
+        return out
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.h = C.c_void_p()
+        _check(lib().t4b_ctx_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().t4b_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        _check(lib().t4b_ctx_sync(self.h))
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        _check(lib().t4b_ctx_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    # ---- memory ----
+    def empty(self, shape, dt=F64) -> DeviceArray:
+        return DeviceArray(self, shape, dt)
+
+    def upload(self, arr: np.ndarray) -> DeviceArray:
+        a = np.asfortranarray(arr)
+        d = DeviceArray(self, a.shape, dtype_of(a))
+        if d.nbytes:
+            _check(lib().t4b_upload(self.h, C.c_void_p(d.ptr), a.ctypes.data_as(C.c_void_p),
+                                    C.c_size_t(d.nbytes)))
+            self.sync()  # `a` may be a temporary
+        return d
+
+    # ---- ops ----
+    def tensordot(self, a: DeviceArray, b: DeviceArray, axes_a, axes_b, conj_a=False, conj_b=False,
+                  out: DeviceArray | None = None) -> DeviceArray:
+        fa = [s for i, s in enumerate(a.shape) if i not in axes_a]
+        fb = [s for i, s in enumerate(b.shape) if i not in axes_b]
+        if out is None:
+            out = self.empty(fa + fb, a.dt)
+        _check(lib().t4b_tensordot(self.h, a.dt, C.c_void_p(a.ptr), len(a.shape), _i64(a.shape),
+                                   int(conj_a), C.c_void_p(b.ptr), len(b.shape), _i64(b.shape),
+                                   int(conj_b), len(axes_a), _i32(axes_a), _i32(axes_b),
+                                   C.c_void_p(out.ptr)))
+        return out
+
+    def permute(self, a: DeviceArray, perm, conj=False) -> DeviceArray:
+        out = self.empty([a.shape[p] for p in perm], a.dt)
+        _check(lib().t4b_permute(self.h, a.dt, C.c_void_p(a.ptr), len(a.shape), _i64(a.shape),
+                                 _i32(perm), int(conj), C.c_void_p(out.ptr)))
+        return out

@@ -1,0 +1,90 @@
+"""Parity of the DMMA tensordot kernel (C ABI t4b_tensordot) against numpy f64 tensordot.
+
+Tolerance: relative Frobenius error <= 1e-13 (f64 accumulation order differs from BLAS; the
+north_star's 1e-10 TT-level budget leaves three orders of magnitude for the sweep)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-13
+
+
+def _rand(rng, shape, cplx):
+    a = rng.standard_normal(shape)
+    if cplx:
+        a = a + 1j * rng.standard_normal(shape)
+    return np.asfortranarray(a)
+
+
+def _relerr(x, y):
+    return np.linalg.norm((x - y).ravel()) / max(np.linalg.norm(y.ravel()), 1e-300)
+
+
+CASES = [
+    # (shape_a, shape_b, axes_a, axes_b)
+    ((37, 53), (53, 29), [1], [0]),               # plain NN, ragged
+    ((53, 37), (53, 29), [0], [0]),               # TN
+    ((37, 53), (29, 53), [1], [1]),               # NT
+    ((53, 37), (29, 53), [0], [1]),               # TT
+    ((128, 256), (256, 128), [1], [0]),
+    ((200, 300), (300, 150), [1], [0]),
+    ((1, 64), (64, 1), [1], [0]),                 # inner product
+    ((64, 1), (1, 64), [1], [0]),                 # outer product, K = 1
+    ((16, 8, 12), (8, 4, 4, 10), [1], [0]),       # zip-up style R.A: contract the middle axis
+    ((16, 12, 4, 9), (12, 4, 5, 7), [1, 2], [0, 1]),   # (RA).B over (b,s)
+    ((6, 5, 4, 3), (3, 5, 7, 4), [1, 3, 2], [1, 0, 3]),  # scrambled pairing
+    ((33, 2, 65), (65, 2, 31), [2], [0]),         # two-site A.B
+    ((5, 7), (3, 2), [], []),                     # pure outer product
+    ((130, 70), (70, 260), [1], [0]),
+]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("case", CASES)
+def test_tensordot_matches_numpy(ctx, case, cplx):
+    sa, sb, xa, xb = case
+    rng = np.random.default_rng(1234 + len(sa) * 7 + len(sb))
+    a, b = _rand(rng, sa, cplx), _rand(rng, sb, cplx)
+    ref = np.tensordot(a, b, axes=(xa, xb))
+    da, db = ctx.upload(a), ctx.upload(b)
+    out = ctx.tensordot(da, db, xa, xb).get()
+    assert out.shape == ref.shape
+    assert _relerr(out, ref) <= TOL
+
+
+@pytest.mark.parametrize("conj_a,conj_b", [(True, False), (False, True), (True, True)])
+def test_tensordot_conj_flags(ctx, conj_a, conj_b):
+    rng = np.random.default_rng(7)
+    a, b = _rand(rng, (40, 9, 33), True), _rand(rng, (33, 9, 21), True)
+    ref = np.tensordot(a.conj() if conj_a else a, b.conj() if conj_b else b, axes=([2, 1], [0, 1]))
+    out = ctx.tensordot(ctx.upload(a), ctx.upload(b), [2, 1], [0, 1], conj_a, conj_b).get()
+    assert _relerr(out, ref) <= TOL
+
+
+def test_tensordot_c3_bulk_shapes(ctx):
+    """BASELINE C3 shapes at reduced chi (chi=64, d=4, w=8): R.A then (RA).B, then two-site."""
+    rng = np.random.default_rng(3)
+    n = chi = 64
+    d, w = 4, 8
+    R = _rand(rng, (n, chi, w), False)
+    A = _rand(rng, (chi, d, chi), False)
+    B = _rand(rng, (w, d, d, w), False)
+    dR, dA, dB = ctx.upload(R), ctx.upload(A), ctx.upload(B)
+    RA = ctx.tensordot(dR, dA, [1], [0])                 # [n, w, d, chi']
+    M = ctx.tensordot(RA, dB, [1, 2], [0, 1])            # [n, chi', d_out, w']
+    ref = np.einsum("nab,asc,bstd->nctd", R, A, B, optimize=True)
+    assert _relerr(M.get(), ref) <= TOL
+
+
+def test_permute(ctx):
+    rng = np.random.default_rng(5)
+    for cplx in (False, True):
+        a = _rand(rng, (7, 5, 3, 4), cplx)
+        d = ctx.upload(a)
+        for perm in ([0, 1, 2, 3], [3, 1, 0, 2], [1, 0, 3, 2]):
+            out = ctx.permute(d, perm).get()
+            assert np.array_equal(out, np.transpose(a, perm))
+        if cplx:
+            out = ctx.permute(d, [2, 0, 1, 3], conj=True).get()
+            assert np.array_equal(out, np.transpose(a, [2, 0, 1, 3]).conj())
