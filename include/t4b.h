@@ -67,6 +67,12 @@ int t4b_tensordot(t4b_ctx* ctx, int dtype, const void* a_dev, int rank_a, const 
 int t4b_permute(t4b_ctx* ctx, int dtype, const void* in_dev, int rank, const int64_t* shape,
                 const int32_t* perm, int conj, void* out_dev);
 
+/* ---- factorisations ----------------------------------------------------------------------
+ * Thin Householder QR: a (m x n, ld = m, DESTROYED) -> q (m x k), r (k x n), k = min(m,n).
+ * q_dev may be NULL (R only).  Replaces qr_backend (tensorbackend/src/backend.rs:742-762) and
+ * EagerTensor::qr (core/src/defaults/qr.rs:258-260). */
+int t4b_qr_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* q_dev, void* r_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,4 +180,12 @@ int t4b_permute(t4b_ctx* ctx, int dtype, const void* in_dev, int rank, const int
     T4B_CATCH
 }
 
+int t4b_qr_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* q_dev, void* r_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(m >= 0 && n >= 0, "qr_thin: negative dimension");
+    dla::qr_thin(ctx->c, to_dtype(dtype), m, n, a_dev, q_dev, r_dev);
+    T4B_CATCH
+}
+
 }  // extern "C"

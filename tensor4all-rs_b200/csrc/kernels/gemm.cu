@@ -34,6 +34,10 @@ struct GemmParams {
     double alpha, beta;
     int conjA, conjB;
     int tiles_m;
+    // split-K: blockIdx.y = split; raw partial sums go to `partial` (dense M x N per split)
+    int ksplit;
+    int64_t kt_per_split;
+    double* partial;
 };
 
 __device__ __forceinline__ int64_t off_of(const int64_t* tbl, int64_t stride, int64_t i) {
@@ -98,12 +102,15 @@ gemm_kernel(GemmParams p) {
 #pragma unroll
             for (int e = 0; e < 2 * ES; ++e) acc[i][j][e] = 0.0;
 
-    const int64_t KT = (p.K + BK - 1) / BK;
+    const int64_t KT_all = (p.K + BK - 1) / BK;
+    const int64_t kt_begin = (int64_t)blockIdx.y * p.kt_per_split;
+    const int64_t kt_stop = (kt_begin + p.kt_per_split < KT_all) ? kt_begin + p.kt_per_split : KT_all;
+    const int64_t KT = kt_stop > kt_begin ? kt_stop - kt_begin : 0;  // k-tiles of this split
 
     auto load_tile = [&](int64_t kt, int stage) {
         double* sA = smem + (size_t)stage * STAGE_DOUBLES;
         double* sB = sA + A_ELEMS * ES;
-        const int64_t k0 = kt * BK;
+        const int64_t k0 = (kt_begin + kt) * BK;
 #pragma unroll
         for (int i = 0; i < A_ITERS; ++i) {
             int e = tid + i * NT;
@@ -194,6 +201,32 @@ gemm_kernel(GemmParams p) {
     cp_async_wait<0>();
 
     // epilogue: thread holds rows (grp) and columns (2*tig, 2*tig+1) of each 8x8 fragment
+    if (p.ksplit > 1) {
+        double* part = p.partial + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N * ES;
+#pragma unroll
+        for (int i = 0; i < MF; ++i) {
+            int64_t gm = m0 + wm0 + i * 8 + grp;
+            if (gm >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    int64_t gn = n0 + wn0 + j * 8 + 2 * tig + c;
+                    if (gn >= p.N) continue;
+                    size_t o = (size_t)gm + (size_t)gn * (size_t)p.M;
+                    if constexpr (CPLX) {
+                        double2 r;
+                        r.x = acc[i][j][c];
+                        r.y = acc[i][j][2 * ES - 2 + c];
+                        reinterpret_cast<double2*>(part)[o] = r;
+                    } else {
+                        part[o] = acc[i][j][c];
+                    }
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < MF; ++i) {
         int64_t gm = m0 + wm0 + i * 8 + grp;
@@ -222,6 +255,36 @@ gemm_kernel(GemmParams p) {
                     p.C[o] = r;
                 }
             }
+        }
+    }
+}
+
+// deterministic split-K reduction: C = alpha * sum_s partial[s] + beta * C
+template <bool CPLX>
+__global__ void splitk_reduce_kernel(const double* __restrict__ partial, int ksplit, int64_t M,
+                                     int64_t N, double alpha, double beta, double* __restrict__ C,
+                                     Group cm, Group cn) {
+    constexpr int ES = CPLX ? 2 : 1;
+    int64_t total = M * N;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        int64_t j = e / M, i = e - j * M;
+        double sr = 0.0, si = 0.0;
+        for (int s = 0; s < ksplit; ++s) {
+            const double* ps = partial + ((size_t)s * (size_t)total + (size_t)e) * ES;
+            sr += ps[0];
+            if (CPLX) si += ps[ES - 1];
+        }
+        int64_t o = group_offset(cm, i) + group_offset(cn, j);
+        if (CPLX) {
+            double2* dst = reinterpret_cast<double2*>(C) + o;
+            double2 r; r.x = alpha * sr; r.y = alpha * si;
+            if (beta != 0.0) { double2 old = *dst; r.x += beta * old.x; r.y += beta * old.y; }
+            *dst = r;
+        } else {
+            double r = alpha * sr;
+            if (beta != 0.0) r += beta * C[o];
+            C[o] = r;
         }
     }
 }
@@ -266,7 +329,7 @@ int64_t min_stride(const Group& g) {
 }
 
 template <bool CPLX, int BM, int BN, int WM, int WN>
-void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay) {
+void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, const Group& cn) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int ES = CPLX ? 2 : 1;
     constexpr int PADMN = CPLX ? 2 : 4;
@@ -279,6 +342,8 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay) {
     int64_t tiles_n = (p.N + BN - 1) / BN;
     int64_t grid = (int64_t)p.tiles_m * tiles_n;
     size_t sm = smem_bytes(alay, blay);
+    const int ksplit = p.ksplit;  // planned by gemm() (scratch already sized)
+    dim3 g3((unsigned)grid, (unsigned)ksplit, 1);
 #define T4B_LAUNCH(AL, BL)                                                                       \
     {                                                                                            \
         auto kern = gemm_kernel<CPLX, BM, BN, WM, WN, AL, BL>;                                   \
@@ -288,7 +353,7 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay) {
                                                 (int)smem_bytes(AL, BL)));                       \
             attr_set = true;                                                                     \
         }                                                                                        \
-        kern<<<(unsigned)grid, NT, sm, c->stream>>>(p);                                          \
+        kern<<<g3, NT, sm, c->stream>>>(p);                                          \
     }
     if (alay == 0 && blay == 0) T4B_LAUNCH(0, 0)
     else if (alay == 0 && blay == 1) T4B_LAUNCH(0, 1)
@@ -296,6 +361,14 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay) {
     else T4B_LAUNCH(1, 1)
 #undef T4B_LAUNCH
     c->launched("gemm");
+    if (ksplit > 1) {
+        int64_t total = p.M * p.N;
+        int rg = (int)((total + 255) / 256);
+        if (rg > c->num_sms * 8) rg = c->num_sms * 8;
+        splitk_reduce_kernel<CPLX><<<rg, 256, 0, c->stream>>>(p.partial, ksplit, p.M, p.N, p.alpha,
+                                                              p.beta, p.C, cm, cn);
+        c->launched("gemm_splitk_reduce");
+    }
 }
 
 }  // namespace
@@ -316,13 +389,36 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
     p.alpha = alpha; p.beta = beta;
     p.conjA = conjA && dt == C64; p.conjB = conjB && dt == C64;
 
+    // tile configuration and split-K plan (split when the output has too few tiles to fill
+    // the chip and K is long, e.g. V^H * A in the QR trailing update)
+    const bool small_tile = (dt == C64) || M <= 64 || N <= 64;
+    const int64_t bm = small_tile ? 64 : 128, bn = small_tile ? 64 : 128;
+    const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
+    const int64_t KT = (K + BK - 1) / BK;
+    int ksplit = 1;
+    if (tiles * 2 <= c->num_sms && KT >= 16) {
+        int64_t s = c->num_sms / tiles;
+        if (s > KT / 8) s = KT / 8;
+        if (s > 64) s = 64;
+        if (s > 1) ksplit = (int)s;
+    }
+    p.kt_per_split = (KT + ksplit - 1) / ksplit;
+    if (p.kt_per_split < 1) p.kt_per_split = 1;
+    if (ksplit > 1) ksplit = (int)((KT + p.kt_per_split - 1) / p.kt_per_split);  // drop empty splits
+    p.ksplit = ksplit;
+    const size_t es = dt == C64 ? 16 : 8;
+    const size_t pbytes = ksplit > 1 ? (size_t)ksplit * (size_t)M * (size_t)N * es : 0;
+
     // offset tables only for genuinely composite groups
     size_t need = 0;
     for (int i = 0; i < 6; ++i)
         if (g[i].nd > 1) need += (size_t)n[i] * sizeof(int64_t);
+    need = ((need + 255) / 256) * 256;
     int64_t* tbl[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    char* scratch_base = (need + pbytes) ? (char*)c->get_scratch(need + pbytes) : nullptr;
+    p.partial = (double*)(scratch_base + need);
     if (need) {
-        char* base = (char*)c->get_scratch(need);
+        char* base = scratch_base;
         int64_t maxn = 1;
         for (int i = 0; i < 6; ++i)
             if (g[i].nd > 1) {
@@ -351,10 +447,10 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
     if (N == 1) blay = 0;
 
     if (dt == C64) {
-        launch_cfg<true, 64, 64, 32, 32>(c, p, alay, blay);
+        launch_cfg<true, 64, 64, 32, 32>(c, p, alay, blay, g[4], g[5]);
     } else {
-        if (M <= 64 || N <= 64) launch_cfg<false, 64, 64, 32, 32>(c, p, alay, blay);
-        else launch_cfg<false, 128, 128, 64, 32>(c, p, alay, blay);
+        if (small_tile) launch_cfg<false, 64, 64, 32, 32>(c, p, alay, blay, g[4], g[5]);
+        else launch_cfg<false, 128, 128, 64, 32>(c, p, alay, blay, g[4], g[5]);
     }
 }
 

@@ -147,3 +147,13 @@ class Context:
         _check(lib().t4b_permute(self.h, a.dt, C.c_void_p(a.ptr), len(a.shape), _i64(a.shape),
                                  _i32(perm), int(conj), C.c_void_p(out.ptr)))
         return out
+
+    def qr_thin(self, a: DeviceArray, want_q=True):
+        """a (m x n) is destroyed.  Returns (Q m x k or None, R k x n)."""
+        m, n = a.shape
+        k = min(m, n)
+        q = self.empty((m, k), a.dt) if want_q else None
+        r = self.empty((k, n), a.dt)
+        _check(lib().t4b_qr_thin(self.h, a.dt, C.c_int64(m), C.c_int64(n), C.c_void_p(a.ptr),
+                                 C.c_void_p(q.ptr if q else 0), C.c_void_p(r.ptr)))
+        return q, r

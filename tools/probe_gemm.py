@@ -13,7 +13,7 @@ import t4b  # noqa: E402
 
 def main():
     torch.cuda.init()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
     ctx = t4b.Context(0, stream.cuda_stream)
     rng = np.random.default_rng(0)
     res = {}
