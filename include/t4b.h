@@ -73,6 +73,98 @@ int t4b_permute(t4b_ctx* ctx, int dtype, const void* in_dev, int rank, const int
  * EagerTensor::qr (core/src/defaults/qr.rs:258-260). */
 int t4b_qr_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* q_dev, void* r_dev);
 
+/* Thin SVD a = u diag(s) vh: a (m x n, DESTROYED), u (m x k), s (k f64, non-increasing, device),
+ * vh (k x n) = V^H, k = min(m,n).  u_dev or vh_dev may be NULL when the caller rebuilds that
+ * side by a contraction (saves the vector accumulation).  QR-preconditioned one-sided block
+ * Jacobi.  Replaces svd_backend (tensorbackend/src/backend.rs:715-734) and EagerTensor::svd
+ * (core/src/defaults/svd.rs:265-267). */
+int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* u_dev,
+                 double* s_dev, void* vh_dev);
+
+/* ---- truncation rules (host only, no GPU needed) ----------------------------------------
+ * Exact restatements of the reference's rank decisions so that the Rust side and the device
+ * sweeps agree: compute_retained_rank (core/src/defaults/svd.rs:151-210), the QR row-norm rule
+ * (core/src/defaults/qr.rs:108-149) and simplett's rule (simplett/src/compression.rs:286-306,
+ * simplett/src/mpo/factorize.rs:206-250). */
+typedef struct {
+    double threshold;
+    int scale;   /* 0 Relative, 1 Absolute            (truncation.rs ThresholdScale) */
+    int measure; /* 0 Value, 1 SquaredValue           (SingularValueMeasure) */
+    int rule;    /* 0 PerValue, 1 DiscardedTailSum    (TruncationRule) */
+} t4b_svd_policy;
+int t4b_retained_rank(const double* s_host, int64_t k, const t4b_svd_policy* policy, int64_t* out);
+int t4b_retained_rank_qr(const double* row_norms_host, int64_t k, double rtol, int64_t* out);
+int t4b_simplett_rank(const double* s_host, int64_t k, double tolerance, int normalize_error,
+                      int64_t max_bond_dim /* 0 = none */, int64_t* out);
+/* Two-site Euler-tour sweep plan (treetn/src/treetn/localupdate.rs:126-152): writes 2*(*nsteps)
+ * ints (u,v pairs); steps_out may be NULL to query the count. */
+int t4b_sweep_plan(int length, int center, int32_t* steps_out, int* nsteps);
+/* Zip-up sweep order (treetn/src/treetn/contraction.rs:384-434). */
+int t4b_zipup_order(int length, int center, int32_t* order_out);
+
+/* ---- rank-revealing LU / matrix cross interpolation ------------------------------------------
+ * Full-pivot prrLU of a (m x n device, preserved), bit-compatible with
+ * core/src/matrixlu.rs:735-819 (rrlu).  Handle accessors mirror RrLU / MatrixLuciFactors. */
+typedef struct t4b_lu t4b_lu;
+int t4b_rrlu(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, const void* a_dev, int64_t max_bond_dim,
+             double rel_tol, double abs_tol, int left_orthogonal, t4b_lu** out);
+int t4b_lu_rank(const t4b_lu* lu, int64_t* out);
+int t4b_lu_last_error(const t4b_lu* lu, double* out);
+int t4b_lu_permutations(const t4b_lu* lu, int64_t* row_perm_host, int64_t* col_perm_host);
+int t4b_lu_pivot_errors(t4b_ctx* ctx, const t4b_lu* lu, double* out_host /* rank + 1 */);
+/* which: 0 L (m x r, unpermuted), 1 U (r x n, unpermuted), 2 left(true), 3 right(true),
+ *        4 MatrixLUCI left (core/src/matrix_luci.rs:206-231), 5 MatrixLUCI right (:191-204) */
+int t4b_lu_factor(t4b_ctx* ctx, const t4b_lu* lu, int which, void* out_dev);
+int t4b_lu_release(t4b_lu* lu);
+
+/* ---- chain tensor networks (tensor4all-treetn, chain topology) ------------------------------
+ * A site is a dense tensor whose axes carry caller-chosen non-negative index ids; equal ids on
+ * neighbouring sites are bonds, equal ids on the same site of two networks are contracted by
+ * t4b_tn_contract (the MPS site leg and the MPO input leg).  Bonds created by the library get
+ * negative ids. */
+typedef struct t4b_tn t4b_tn;
+int t4b_tn_create(t4b_ctx* ctx, int dtype, int length, const int32_t* ranks, const int64_t* shapes,
+                  const int64_t* index_ids, const void* const* site_data, int data_on_device,
+                  t4b_tn** out);
+int t4b_tn_clone(t4b_ctx* ctx, const t4b_tn* tn, t4b_tn** out);
+int t4b_tn_release(t4b_tn* tn);
+int t4b_tn_length(const t4b_tn* tn, int* out);
+int t4b_tn_site_rank(const t4b_tn* tn, int site, int* out);
+int t4b_tn_site_shape(const t4b_tn* tn, int site, int64_t* shape_out, int64_t* index_ids_out);
+int t4b_tn_site_data(const t4b_tn* tn, int site, void** dev_out);
+int t4b_tn_download_site(t4b_ctx* ctx, const t4b_tn* tn, int site, void* host_out);
+int t4b_tn_bond_dims(const t4b_tn* tn, int64_t* out /* length-1 */);
+/* TreeTN::canonicalize (treetn/canonicalize.rs:70-165), TreeTN::truncate (treetn/truncate.rs:82-198);
+ * policy may be NULL (global default, relative per-value 1e-12); max_bond_dim 0 = none. */
+int t4b_tn_canonicalize(t4b_ctx* ctx, t4b_tn* tn, int center);
+int t4b_tn_truncate(t4b_ctx* ctx, t4b_tn* tn, int center, const t4b_svd_policy* policy,
+                    int64_t max_bond_dim);
+/* contract dispatcher (treetn/contraction.rs:1576-1645): method 0 Zipup, 1 Fit, 2 Naive. */
+int t4b_tn_contract(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, int center, int method,
+                    const t4b_svd_policy* policy, int64_t max_bond_dim, int nfullsweeps,
+                    t4b_tn** out);
+int t4b_tn_norm_sqr(t4b_ctx* ctx, const t4b_tn* tn, double* out);
+int t4b_tn_inner(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, double* re, double* im);
+
+/* ---- positional tensor trains / MPOs (tensor4all-simplett) ----------------------------------
+ * rank 3: sites [left, site, right]; rank 4: MPO sites [left, s1, s2, right]. */
+typedef struct t4b_train t4b_train;
+int t4b_train_create(t4b_ctx* ctx, int dtype, int site_rank, int length, const int64_t* dims,
+                     const void* const* site_data_host, t4b_train** out);
+int t4b_train_release(t4b_train* tt);
+int t4b_train_length(const t4b_train* tt, int* out);
+int t4b_train_site_dims(const t4b_train* tt, int site, int64_t* dims_out);
+int t4b_train_download_site(t4b_ctx* ctx, const t4b_train* tt, int site, void* host_out);
+/* SimpleTensorTrain::compress (simplett/src/compression.rs:375-501); method 0 LU, 1 CI, 2 SVD */
+int t4b_train_compress(t4b_ctx* ctx, t4b_train* tt, int method, double tolerance,
+                       int64_t max_bond_dim, int normalize_error);
+/* mpo::contract (simplett/src/mpo/dispatch.rs:67): algorithm 0 ZipUp, 1 Naive (+compress), 2 Naive
+ * without compression */
+int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int algorithm,
+                     double tolerance, int64_t max_bond_dim, t4b_train** out);
+int t4b_train_inner_product(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, double* re,
+                            double* im);
+
 #ifdef __cplusplus
 }
 #endif

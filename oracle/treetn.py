@@ -1,0 +1,295 @@
+"""ORACLE (test infrastructure).  NumPy/LAPACK restatement of the reference's chain TreeTN path:
+
+  factorize / factorize_auto   crates/tensor4all-core/src/defaults/factorize.rs:86-151,507-558
+  svd_truncated_inner          crates/tensor4all-core/src/defaults/svd.rs:255-320
+  qr_with                      crates/tensor4all-core/src/defaults/qr.rs:248-325
+  sweep_edge_full_rank         crates/tensor4all-treetn/src/treetn/mod.rs:616-751
+  canonicalize_impl            crates/tensor4all-treetn/src/treetn/canonicalize.rs:134-165
+  truncate_impl                crates/tensor4all-treetn/src/treetn/truncate.rs:129-198
+  LocalUpdateSweepPlan (nsite=2), TruncateUpdater   .../treetn/localupdate.rs:103-160,526-645
+  contract_zipup_chain         crates/tensor4all-treetn/src/treetn/contraction.rs:438-766
+  contract_fit                 crates/tensor4all-treetn/src/treetn/fit.rs:648-1054,1664-1739
+
+Tensors carry labelled axes (any hashable label) exactly like IdxTensor carries DynIndex ids.
+Dense SVD/QR are LAPACK gesdd/geqrf (the reference forwards them to tenferro/faer): factor values
+are gauge dependent, so results are compared through reconstructed tensors / overlaps / spectra.
+This oracle takes the reference's straightforward route (full two-site SVDs, no shortcuts)."""
+from __future__ import annotations
+
+import itertools
+import string
+
+import numpy as np
+import scipy.linalg as sla
+
+from .truncation import SvdTruncationPolicy, compute_retained_rank_qr, svd_rank
+
+_counter = itertools.count(1)
+
+
+def new_label(prefix="b"):
+    return (prefix, next(_counter))
+
+
+class LT:
+    """Labelled dense tensor."""
+
+    def __init__(self, arr, labels):
+        self.arr = np.asarray(arr)
+        self.labels = list(labels)
+        assert self.arr.ndim == len(self.labels)
+
+    def dim(self, label):
+        return self.arr.shape[self.labels.index(label)]
+
+    def permute(self, labels):
+        return LT(np.transpose(self.arr, [self.labels.index(l) for l in labels]), labels)
+
+    def conj(self):
+        return LT(self.arr.conj(), self.labels)
+
+    def replace(self, old, new):
+        return LT(self.arr, [new if l == old else l for l in self.labels])
+
+
+def contract(tensors):
+    """N-ary contraction over repeated labels; result axes = first-appearance order of the
+    surviving labels (core/src/defaults/contract.rs:901-913)."""
+    letters = {}
+    count = {}
+    for t in tensors:
+        for l in t.labels:
+            count[l] = count.get(l, 0) + 1
+            if l not in letters:
+                letters[l] = string.ascii_letters[len(letters)]
+    out = [l for l in letters if count[l] == 1]
+    expr = ",".join("".join(letters[l] for l in t.labels) for t in tensors) + "->" + "".join(letters[l] for l in out)
+    return LT(np.einsum(expr, *[t.arr for t in tensors], optimize=True), out)
+
+
+def _unfold(t, left):
+    right = [l for l in t.labels if l not in left]
+    p = t.permute(list(left) + right)
+    m = int(np.prod([t.dim(l) for l in left])) if left else 1
+    n = int(np.prod([t.dim(l) for l in right])) if right else 1
+    return p.arr.reshape(m, n, order="F"), list(left), right, p.arr.shape
+
+
+def factorize_svd(t, left, canonical="left", policy=None, max_bond_dim=None, truncate=True):
+    mat, left, right, shape = _unfold(t, left)
+    u, s, vh = sla.svd(mat, full_matrices=False, lapack_driver="gesdd")
+    r = svd_rank(s, policy, max_bond_dim, truncate)
+    u, s_r, vh = u[:, :r], s[:r], vh[:r, :]
+    bond = new_label()
+    ldims = shape[: len(left)]
+    rdims = shape[len(left):]
+    if canonical == "left":
+        lt = LT(u.reshape(*ldims, r, order="F"), left + [bond])
+        rt = LT((s_r[:, None] * vh).reshape(r, *rdims, order="F"), [bond] + right)
+    else:
+        lt = LT((u * s_r[None, :]).reshape(*ldims, r, order="F"), left + [bond])
+        rt = LT(vh.reshape(r, *rdims, order="F"), [bond] + right)
+    return lt, rt, bond, s_r, s
+
+
+def factorize_qr(t, left, rtol=1e-15, truncate=True):
+    mat, left, right, shape = _unfold(t, left)
+    q, r_ = sla.qr(mat, mode="economic")
+    k = min(mat.shape)
+    r = k
+    if truncate:
+        norms = [np.sqrt(np.sum(np.abs(r_[i, i:]) ** 2)) for i in range(k)]
+        r = min(compute_retained_rank_qr(norms, rtol), k)
+    q, r_ = q[:, :r], r_[:r, :]
+    bond = new_label()
+    lt = LT(q.reshape(*shape[: len(left)], r, order="F"), left + [bond])
+    rt = LT(r_.reshape(r, *shape[len(left):], order="F"), [bond] + right)
+    return lt, rt, bond
+
+
+class Chain:
+    """sites: list of LT; bonds[i] = label shared by sites i, i+1."""
+
+    def __init__(self, sites):
+        self.sites = list(sites)
+        self.bonds = []
+        for i in range(len(sites) - 1):
+            common = [l for l in sites[i].labels if l in sites[i + 1].labels]
+            assert len(common) == 1, "neighbouring sites must share exactly one label"
+            self.bonds.append(common[0])
+
+    def copy(self):
+        c = Chain.__new__(Chain)
+        c.sites = [LT(s.arr.copy(), s.labels) for s in self.sites]
+        c.bonds = list(self.bonds)
+        return c
+
+    def __len__(self):
+        return len(self.sites)
+
+    def site_labels(self, i):
+        drop = []
+        if i > 0:
+            drop.append(self.bonds[i - 1])
+        if i + 1 < len(self.sites):
+            drop.append(self.bonds[i])
+        return [l for l in self.sites[i].labels if l not in drop]
+
+    def dense(self):
+        return contract(self.sites)
+
+    def bond_dims(self):
+        return [self.sites[i].dim(b) for i, b in enumerate(self.bonds)]
+
+    def sim_bonds(self):
+        c = self.copy()
+        for i, b in enumerate(list(c.bonds)):
+            nb = new_label()
+            c.sites[i] = c.sites[i].replace(b, nb)
+            c.sites[i + 1] = c.sites[i + 1].replace(b, nb)
+            c.bonds[i] = nb
+        return c
+
+
+def sweep_edge(tn, src, dst):
+    e = min(src, dst)
+    bond = tn.bonds[e]
+    ts = tn.sites[src]
+    left = [l for l in ts.labels if l != bond]
+    if not left:
+        nrm = np.linalg.norm(ts.arr)
+        if nrm > 0:
+            tn.sites[src] = LT(ts.arr / nrm, ts.labels)
+            tn.sites[dst] = LT(tn.sites[dst].arr * nrm, tn.sites[dst].labels)
+        return
+    q, r, nb = factorize_qr(ts, left, truncate=False)
+    tn.sites[src] = q
+    tn.sites[dst] = contract([tn.sites[dst], r])
+    tn.bonds[e] = nb
+
+
+def canonicalize(tn, center):
+    L = len(tn)
+    for i in range(0, center):
+        sweep_edge(tn, i, i + 1)
+    for i in range(L - 1, center, -1):
+        sweep_edge(tn, i, i - 1)
+
+
+def two_site_sweep_plan(L, center):
+    """Euler tour edges of the chain rooted at `center` (named_graph.rs:307-345); petgraph lists
+    the most recently added edge first, i.e. the higher-index neighbour."""
+    steps = []
+    if L <= 1:
+        return steps
+    steps += [(i, i + 1) for i in range(center, L - 1)]
+    steps += [(i, i - 1) for i in range(L - 1, center, -1)]
+    steps += [(i, i - 1) for i in range(center, 0, -1)]
+    steps += [(i, i + 1) for i in range(0, center)]
+    return steps
+
+
+def truncate(tn, center, policy=None, max_bond_dim=None, spectra=None):
+    canonicalize(tn, center)
+    for (u, v) in two_site_sweep_plan(len(tn), center):
+        e = min(u, v)
+        bond = tn.bonds[e]
+        ab = contract([tn.sites[u], tn.sites[v]])
+        left = [l for l in tn.sites[u].labels if l != bond]
+        lt, rt, nb, s_r, s_all = factorize_svd(ab, left, "left", policy, max_bond_dim)
+        if spectra is not None:
+            spectra.append(np.array(s_r))
+        tn.sites[u], tn.sites[v], tn.bonds[e] = lt, rt, nb
+
+
+def zipup_chain_order(L, center):
+    return list(range(L - 1, -1, -1)) if center == 0 else list(range(L))
+
+
+def contract_zipup(a, b, center, policy=None, max_bond_dim=None, final_truncate=True, spectra=None):
+    L = len(a)
+    assert L == len(b)
+    chain = zipup_chain_order(L, center)
+    a, b = a.sim_bonds(), b.sim_bonds()
+    canonicalize(a, chain[0])
+    canonicalize(b, chain[0])
+    if L == 1:
+        return Chain([contract([a.sites[0], b.sites[0]])])
+    res_sites = [None] * L
+    rem = None
+    for k in range(L - 2):
+        s, nx = chain[k], chain[k + 1]
+        ra, rb = a.bonds[min(s, nx)], b.bonds[min(s, nx)]
+        ts = [a.sites[s], b.sites[s]] if rem is None else [rem, a.sites[s], b.sites[s]]
+        contracted = contract(ts)
+        left = [l for l in contracted.labels if l not in (ra, rb)]
+        lt, rt, nb, s_r, _ = factorize_svd(contracted, left, "left", policy, max_bond_dim)
+        if spectra is not None:
+            spectra.append(np.array(s_r))
+        res_sites[s] = lt
+        rem = rt
+    pen, last = chain[L - 2], chain[L - 1]
+    ts = [a.sites[pen], b.sites[pen], a.sites[last], b.sites[last]]
+    if rem is not None:
+        ts = [rem] + ts
+    block = contract(ts)
+    last_sites = a.site_labels(last) + b.site_labels(last)
+    left = [l for l in block.labels if l not in last_sites]
+    lt, rt, nb, s_r, _ = factorize_svd(block, left, "right", policy, max_bond_dim)
+    if spectra is not None:
+        spectra.append(np.array(s_r))
+    res_sites[pen], res_sites[last] = lt, rt
+    res = Chain(res_sites)
+    if final_truncate:
+        truncate(res, center, policy, max_bond_dim, spectra)
+    else:
+        canonicalize(res, center)
+    return res
+
+
+def contract_fit(a, b, center, policy=None, max_bond_dim=None, nfullsweeps=1):
+    L = len(a)
+    a, b = a.sim_bonds(), b.sim_bonds()
+    c = contract_zipup(a, b, center, policy, max_bond_dim, final_truncate=False)
+    if nfullsweeps == 0 or L == 1:
+        return c
+
+    def env_left(i):
+        e = None
+        for j in range(i + 1):
+            ts = [a.sites[j], b.sites[j], c.sites[j].conj()]
+            e = contract(ts if e is None else [e] + ts)
+        return e
+
+    def env_right(i):
+        e = None
+        for j in range(L - 1, i - 1, -1):
+            ts = [a.sites[j], b.sites[j], c.sites[j].conj()]
+            e = contract(ts if e is None else [e] + ts)
+        return e
+
+    for _ in range(nfullsweeps):
+        for (u, v) in two_site_sweep_plan(L, center):
+            lo, hi = min(u, v), max(u, v)
+            ts = [a.sites[u], b.sites[u], a.sites[v], b.sites[v]]
+            if lo > 0:
+                ts.append(env_left(lo - 1))
+            if hi + 1 < L:
+                ts.append(env_right(hi + 1))
+            local = contract(ts)
+            left = list(c.site_labels(u))
+            if u < v and u > 0:
+                left.append(c.bonds[u - 1])
+            if u > v and u + 1 < L:
+                left.append(c.bonds[u])
+            cap = max_bond_dim
+            if cap is None and policy is None:
+                cap = c.sites[lo].dim(c.bonds[lo])
+            lt, rt, nb, _, _ = factorize_svd(local, left, "left", policy, cap)
+            c.sites[u], c.sites[v], c.bonds[lo] = lt, rt, nb
+    return c
+
+
+def inner(a, b):
+    a2 = a.sim_bonds()
+    return complex(contract([s.conj() for s in a2.sites] + list(b.sites)).arr)

@@ -3,42 +3,14 @@
 #include <string>
 
 #include "../../include/t4b.h"
+#include "capi_common.h"
 #include "dla.h"
 #include "host/tensor.h"
 
 using namespace t4b;
 
-struct t4b_ctx {
-    dla::Ctx* c;
-};
-
 static thread_local std::string g_last_error;
-
-#define T4B_TRY try {
-#define T4B_CATCH                                                      \
-    }                                                                  \
-    catch (const t4b::Error& e) {                                      \
-        g_last_error = e.what();                                       \
-        return (int)e.code;                                            \
-    }                                                                  \
-    catch (const std::exception& e) {                                  \
-        g_last_error = e.what();                                       \
-        return T4B_INTERNAL;                                           \
-    }                                                                  \
-    catch (...) {                                                      \
-        g_last_error = "unknown error";                                \
-        return T4B_INTERNAL;                                           \
-    }                                                                  \
-    return T4B_OK;
-
-static void require_ctx(t4b_ctx* ctx) {
-    if (!ctx || !ctx->c) throw Error(t4b::ST_INVALID_ARGUMENT, "null context");
-}
-static DType to_dtype(int d) {
-    if (d == T4B_F64) return F64;
-    if (d == T4B_C64) return C64;
-    throw Error(t4b::ST_INVALID_ARGUMENT, "dtype must be T4B_F64 or T4B_C64");
-}
+std::string& t4b_last_error_ref() { return g_last_error; }
 
 extern "C" {
 
@@ -185,6 +157,16 @@ int t4b_qr_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void
     require_ctx(ctx);
     T4B_REQUIRE(m >= 0 && n >= 0, "qr_thin: negative dimension");
     dla::qr_thin(ctx->c, to_dtype(dtype), m, n, a_dev, q_dev, r_dev);
+    T4B_CATCH
+}
+
+int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* u_dev,
+                 double* s_dev, void* vh_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(m >= 0 && n >= 0, "svd_thin: negative dimension");
+    T4B_REQUIRE(s_dev != nullptr, "svd_thin: s_dev is required");
+    dla::svd_thin(ctx->c, to_dtype(dtype), m, n, a_dev, u_dev, s_dev, vh_dev);
     T4B_CATCH
 }
 

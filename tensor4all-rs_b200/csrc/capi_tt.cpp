@@ -1,0 +1,384 @@
+// extern "C" boundary, part 2: truncation rules, rrLU handles, chain tensor networks and
+// positional tensor trains (declared in include/t4b.h).
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "../../include/t4b.h"
+#include "capi_common.h"
+#include "host/factorize.h"
+#include "host/luci.h"
+#include "host/simplett.h"
+#include "host/treetn.h"
+
+using namespace t4b;
+
+struct t4b_lu {
+    RrLU lu;
+};
+struct t4b_tn {
+    ChainTN tn;
+};
+struct t4b_train {
+    stt::Train tt;
+};
+
+static SvdTruncationPolicy to_policy(const t4b_svd_policy* p) {
+    SvdTruncationPolicy r;
+    r.threshold = p->threshold;
+    T4B_REQUIRE(p->scale == 0 || p->scale == 1, "policy.scale must be 0 or 1");
+    T4B_REQUIRE(p->measure == 0 || p->measure == 1, "policy.measure must be 0 or 1");
+    T4B_REQUIRE(p->rule == 0 || p->rule == 1, "policy.rule must be 0 or 1");
+    r.scale = p->scale ? ThresholdScale::Absolute : ThresholdScale::Relative;
+    r.measure = p->measure ? SingularValueMeasure::SquaredValue : SingularValueMeasure::Value;
+    r.rule = p->rule ? TruncationRule::DiscardedTailSum : TruncationRule::PerValue;
+    return r;
+}
+static std::optional<SvdTruncationPolicy> opt_policy(const t4b_svd_policy* p) {
+    if (!p) return std::nullopt;
+    return to_policy(p);
+}
+static std::optional<int64_t> opt_bond(int64_t v) {
+    T4B_REQUIRE(v >= 0, "max_bond_dim must be >= 0 (0 = none)");
+    if (v == 0) return std::nullopt;
+    return v;
+}
+// caller ids (>= 0) map to internal ids <= -1 so that they never collide with new_index()
+static int64_t ext_to_int(int64_t id) { return -(id + 1); }
+static int64_t int_to_ext(int64_t id) { return id < 0 ? -(id + 1) : -(id + 1); }
+
+extern "C" {
+
+int t4b_retained_rank(const double* s, int64_t k, const t4b_svd_policy* policy, int64_t* out) {
+    T4B_TRY
+    T4B_REQUIRE(out && (s || k == 0) && k >= 0, "retained_rank: bad arguments");
+    SvdTruncationPolicy p = policy ? to_policy(policy) : default_svd_truncation_policy();
+    validate_svd_truncation_options(std::nullopt, p);
+    *out = compute_retained_rank(std::vector<double>(s, s + k), p);
+    T4B_CATCH
+}
+int t4b_retained_rank_qr(const double* norms, int64_t k, double rtol, int64_t* out) {
+    T4B_TRY
+    T4B_REQUIRE(out && (norms || k == 0) && k >= 0, "retained_rank_qr: bad arguments");
+    *out = compute_retained_rank_qr(std::vector<double>(norms, norms + k), rtol);
+    T4B_CATCH
+}
+int t4b_simplett_rank(const double* s, int64_t k, double tolerance, int normalize_error,
+                      int64_t max_bond_dim, int64_t* out) {
+    T4B_TRY
+    T4B_REQUIRE(out && (s || k == 0) && k >= 0, "simplett_rank: bad arguments");
+    *out = stt::simplett_rank(std::vector<double>(s, s + k), tolerance, normalize_error != 0,
+                              opt_bond(max_bond_dim));
+    T4B_CATCH
+}
+int t4b_sweep_plan(int length, int center, int32_t* steps_out, int* nsteps) {
+    T4B_TRY
+    T4B_REQUIRE(length >= 1 && center >= 0 && center < length && nsteps, "sweep_plan: bad arguments");
+    auto plan = two_site_sweep_plan(length, center);
+    *nsteps = (int)plan.size();
+    if (steps_out)
+        for (size_t i = 0; i < plan.size(); ++i) {
+            steps_out[2 * i] = plan[i].first;
+            steps_out[2 * i + 1] = plan[i].second;
+        }
+    T4B_CATCH
+}
+int t4b_zipup_order(int length, int center, int32_t* order_out) {
+    T4B_TRY
+    T4B_REQUIRE(length >= 1 && center >= 0 && center < length && order_out, "zipup_order: bad arguments");
+    auto o = zipup_chain_order(length, center);
+    for (int i = 0; i < length; ++i) order_out[i] = o[i];
+    T4B_CATCH
+}
+
+// ---- rrLU ------------------------------------------------------------------------------------
+int t4b_rrlu(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, const void* a_dev, int64_t max_bond_dim,
+             double rel_tol, double abs_tol, int left_orthogonal, t4b_lu** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(out, "rrlu: null out");
+    RrLUOptions o;
+    o.max_bond_dim = max_bond_dim <= 0 ? INT64_MAX : max_bond_dim;
+    o.rel_tol = rel_tol; o.abs_tol = abs_tol; o.left_orthogonal = left_orthogonal != 0;
+    auto* h = new t4b_lu{rrlu(ctx->c, to_dtype(dtype), m, n, a_dev, o)};
+    *out = h;
+    T4B_CATCH
+}
+int t4b_lu_rank(const t4b_lu* lu, int64_t* out) {
+    T4B_TRY
+    T4B_REQUIRE(lu && out, "null argument");
+    *out = lu->lu.n_pivot;
+    T4B_CATCH
+}
+int t4b_lu_last_error(const t4b_lu* lu, double* out) {
+    T4B_TRY
+    T4B_REQUIRE(lu && out, "null argument");
+    *out = lu->lu.error;
+    T4B_CATCH
+}
+int t4b_lu_permutations(const t4b_lu* lu, int64_t* rp, int64_t* cp) {
+    T4B_TRY
+    T4B_REQUIRE(lu, "null argument");
+    if (rp) std::memcpy(rp, lu->lu.row_permutation.data(), sizeof(int64_t) * lu->lu.m);
+    if (cp) std::memcpy(cp, lu->lu.col_permutation.data(), sizeof(int64_t) * lu->lu.n);
+    T4B_CATCH
+}
+int t4b_lu_pivot_errors(t4b_ctx* ctx, const t4b_lu* lu, double* out_host) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(lu && out_host, "null argument");
+    auto e = pivot_errors(ctx->c, lu->lu);
+    std::memcpy(out_host, e.data(), sizeof(double) * e.size());
+    T4B_CATCH
+}
+int t4b_lu_factor(t4b_ctx* ctx, const t4b_lu* h, int which, void* out_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(h && out_dev, "null argument");
+    const RrLU& lu = h->lu;
+    const size_t es = dtype_size(lu.dt);
+    const int64_t r = lu.n_pivot;
+    if (r == 0) return T4B_OK;
+    switch (which) {
+        case 0: dla::d2d(ctx->c, out_dev, lu.l->p, (size_t)lu.m * r * es); break;
+        case 1: dla::d2d(ctx->c, out_dev, lu.u->p, (size_t)r * lu.n * es); break;
+        case 2: { auto b = lu_left_permuted(ctx->c, lu); dla::d2d(ctx->c, out_dev, b->p, (size_t)lu.m * r * es); dla::sync(ctx->c); break; }
+        case 3: { auto b = lu_right_permuted(ctx->c, lu); dla::d2d(ctx->c, out_dev, b->p, (size_t)r * lu.n * es); dla::sync(ctx->c); break; }
+        case 4:
+        case 5: {
+            LuFactors f = luci_from_rrlu(ctx->c, lu);
+            if (which == 4) dla::d2d(ctx->c, out_dev, f.left->p, (size_t)lu.m * r * es);
+            else dla::d2d(ctx->c, out_dev, f.right->p, (size_t)r * lu.n * es);
+            dla::sync(ctx->c);
+            break;
+        }
+        default: throw Error(ST_INVALID_ARGUMENT, "lu_factor: which must be 0..5");
+    }
+    T4B_CATCH
+}
+int t4b_lu_release(t4b_lu* lu) {
+    T4B_TRY
+    delete lu;
+    T4B_CATCH
+}
+
+// ---- chain tensor networks ---------------------------------------------------------------------
+int t4b_tn_create(t4b_ctx* ctx, int dtype, int length, const int32_t* ranks, const int64_t* shapes,
+                  const int64_t* index_ids, const void* const* site_data, int data_on_device,
+                  t4b_tn** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(length >= 1 && ranks && shapes && index_ids && site_data && out, "tn_create: bad arguments");
+    DType dt = to_dtype(dtype);
+    std::vector<Tensor> sites;
+    size_t off = 0;
+    for (int i = 0; i < length; ++i) {
+        std::vector<Index> inds;
+        for (int a = 0; a < ranks[i]; ++a) {
+            T4B_REQUIRE(index_ids[off + a] >= 0 && shapes[off + a] >= 1, "tn_create: ids must be >= 0, dims >= 1");
+            Index ix;
+            ix.id = ext_to_int(index_ids[off + a]);
+            ix.dim = shapes[off + a];
+            inds.push_back(ix);
+        }
+        off += ranks[i];
+        if (data_on_device) sites.push_back(clone(ctx->c, wrap_device(ctx->c, dt, inds, const_cast<void*>(site_data[i]))));
+        else sites.push_back(from_host(ctx->c, dt, inds, site_data[i]));
+    }
+    dla::sync(ctx->c);   // host buffers may be released by the caller
+    *out = new t4b_tn{make_chain(sites)};
+    T4B_CATCH
+}
+int t4b_tn_clone(t4b_ctx* ctx, const t4b_tn* tn, t4b_tn** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tn && out, "null argument");
+    *out = new t4b_tn{clone_chain(ctx->c, tn->tn)};
+    T4B_CATCH
+}
+int t4b_tn_release(t4b_tn* tn) {
+    T4B_TRY
+    delete tn;
+    T4B_CATCH
+}
+int t4b_tn_length(const t4b_tn* tn, int* out) {
+    T4B_TRY
+    T4B_REQUIRE(tn && out, "null argument");
+    *out = (int)tn->tn.length();
+    T4B_CATCH
+}
+static const Tensor& site_of(const t4b_tn* tn, int site) {
+    T4B_REQUIRE(tn, "null tn");
+    T4B_REQUIRE(site >= 0 && site < (int)tn->tn.length(), "site out of range");
+    return tn->tn.sites[site];
+}
+int t4b_tn_site_rank(const t4b_tn* tn, int site, int* out) {
+    T4B_TRY
+    *out = (int)site_of(tn, site).rank();
+    T4B_CATCH
+}
+int t4b_tn_site_shape(const t4b_tn* tn, int site, int64_t* shape_out, int64_t* ids_out) {
+    T4B_TRY
+    const Tensor& t = site_of(tn, site);
+    for (size_t a = 0; a < t.rank(); ++a) {
+        if (shape_out) shape_out[a] = t.inds[a].dim;
+        // caller ids come back unchanged (>= 0); library-made bonds are reported as negative ids
+        if (ids_out) ids_out[a] = t.inds[a].id < 0 ? int_to_ext(t.inds[a].id) : -t.inds[a].id;
+    }
+    T4B_CATCH
+}
+int t4b_tn_site_data(const t4b_tn* tn, int site, void** dev_out) {
+    T4B_TRY
+    *dev_out = site_of(tn, site).data();
+    T4B_CATCH
+}
+int t4b_tn_download_site(t4b_ctx* ctx, const t4b_tn* tn, int site, void* host_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    to_host(ctx->c, site_of(tn, site), host_out);
+    T4B_CATCH
+}
+int t4b_tn_bond_dims(const t4b_tn* tn, int64_t* out) {
+    T4B_TRY
+    T4B_REQUIRE(tn && out, "null argument");
+    for (size_t i = 0; i < tn->tn.bonds.size(); ++i) out[i] = tn->tn.bonds[i].dim;
+    T4B_CATCH
+}
+int t4b_tn_canonicalize(t4b_ctx* ctx, t4b_tn* tn, int center) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tn, "null tn");
+    canonicalize(ctx->c, tn->tn, center);
+    T4B_CATCH
+}
+int t4b_tn_truncate(t4b_ctx* ctx, t4b_tn* tn, int center, const t4b_svd_policy* policy,
+                    int64_t max_bond_dim) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tn, "null tn");
+    truncate(ctx->c, tn->tn, center, opt_policy(policy), opt_bond(max_bond_dim));
+    T4B_CATCH
+}
+int t4b_tn_contract(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, int center, int method,
+                    const t4b_svd_policy* policy, int64_t max_bond_dim, int nfullsweeps,
+                    t4b_tn** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(a && b && out, "null argument");
+    T4B_REQUIRE(method >= 0 && method <= 2, "method must be 0 (zipup), 1 (fit) or 2 (naive)");
+    ContractionOptions o;
+    o.method = method == 0 ? ContractMethod::Zipup : method == 1 ? ContractMethod::Fit : ContractMethod::Naive;
+    o.svd_policy = opt_policy(policy);
+    o.max_bond_dim = opt_bond(max_bond_dim);
+    o.nfullsweeps = nfullsweeps;
+    *out = new t4b_tn{contract(ctx->c, a->tn, b->tn, center, o)};
+    T4B_CATCH
+}
+int t4b_tn_norm_sqr(t4b_ctx* ctx, const t4b_tn* tn, double* out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tn && out, "null argument");
+    *out = norm_sqr(ctx->c, tn->tn);
+    T4B_CATCH
+}
+int t4b_tn_inner(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, double* re, double* im) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(a && b && re && im, "null argument");
+    inner(ctx->c, a->tn, b->tn, re, im);
+    T4B_CATCH
+}
+
+// ---- positional trains -------------------------------------------------------------------------
+int t4b_train_create(t4b_ctx* ctx, int dtype, int site_rank, int length, const int64_t* dims,
+                     const void* const* site_data_host, t4b_train** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE((site_rank == 3 || site_rank == 4) && length >= 0 && out, "train_create: bad arguments");
+    auto* h = new t4b_train{};
+    h->tt.dt = to_dtype(dtype);
+    h->tt.rank = site_rank;
+    const size_t es = dtype_size(h->tt.dt);
+    for (int i = 0; i < length; ++i) {
+        stt::Site s;
+        int64_t n = 1;
+        for (int a = 0; a < site_rank; ++a) {
+            s.d[a] = dims[(size_t)i * site_rank + a];
+            T4B_REQUIRE(s.d[a] >= 1, "train_create: dims must be >= 1");
+            n *= s.d[a];
+        }
+        s.buf = std::make_shared<Buffer>(ctx->c, (size_t)n * es);
+        dla::h2d(ctx->c, s.buf->p, site_data_host[i], (size_t)n * es);
+        h->tt.sites.push_back(s);
+    }
+    dla::sync(ctx->c);
+    for (int i = 0; i + 1 < length; ++i)
+        T4B_REQUIRE(h->tt.sites[i].d[site_rank - 1] == h->tt.sites[i + 1].d[0], "train_create: bond dimension mismatch");
+    *out = h;
+    T4B_CATCH
+}
+int t4b_train_release(t4b_train* tt) {
+    T4B_TRY
+    delete tt;
+    T4B_CATCH
+}
+int t4b_train_length(const t4b_train* tt, int* out) {
+    T4B_TRY
+    T4B_REQUIRE(tt && out, "null argument");
+    *out = (int)tt->tt.sites.size();
+    T4B_CATCH
+}
+int t4b_train_site_dims(const t4b_train* tt, int site, int64_t* dims_out) {
+    T4B_TRY
+    T4B_REQUIRE(tt && dims_out && site >= 0 && site < (int)tt->tt.sites.size(), "bad arguments");
+    for (int a = 0; a < tt->tt.rank; ++a) dims_out[a] = tt->tt.sites[site].d[a];
+    T4B_CATCH
+}
+int t4b_train_download_site(t4b_ctx* ctx, const t4b_train* tt, int site, void* host_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tt && host_out && site >= 0 && site < (int)tt->tt.sites.size(), "bad arguments");
+    const stt::Site& s = tt->tt.sites[site];
+    int64_t n = 1;
+    for (int a = 0; a < tt->tt.rank; ++a) n *= s.d[a];
+    dla::d2h(ctx->c, host_out, s.buf->p, (size_t)n * dtype_size(tt->tt.dt));
+    dla::sync(ctx->c);
+    T4B_CATCH
+}
+int t4b_train_compress(t4b_ctx* ctx, t4b_train* tt, int method, double tolerance,
+                       int64_t max_bond_dim, int normalize_error) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tt && method >= 0 && method <= 2, "bad arguments");
+    stt::CompressionOptions o;
+    o.method = method == 0 ? stt::CompressionMethod::LU : method == 1 ? stt::CompressionMethod::CI : stt::CompressionMethod::SVD;
+    o.tolerance = tolerance;
+    o.max_bond_dim = opt_bond(max_bond_dim);
+    o.normalize_error = normalize_error != 0;
+    stt::compress(ctx->c, tt->tt, o);
+    T4B_CATCH
+}
+int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int algorithm,
+                     double tolerance, int64_t max_bond_dim, t4b_train** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(a && b && out && algorithm >= 0 && algorithm <= 2, "bad arguments");
+    stt::MpoContractionOptions o;
+    o.tolerance = tolerance;
+    o.max_bond_dim = opt_bond(max_bond_dim);
+    auto* h = new t4b_train{};
+    if (algorithm == 0) h->tt = stt::contract_zipup(ctx->c, a->tt, b->tt, o);
+    else if (algorithm == 1) h->tt = stt::contract_naive(ctx->c, a->tt, b->tt, o);
+    else h->tt = stt::contract_naive(ctx->c, a->tt, b->tt, std::nullopt);
+    *out = h;
+    T4B_CATCH
+}
+int t4b_train_inner_product(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, double* re, double* im) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(a && b && re && im, "null argument");
+    stt::inner_product(ctx->c, a->tt, b->tt, re, im);
+    T4B_CATCH
+}
+
+}  // extern "C"

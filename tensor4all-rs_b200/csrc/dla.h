@@ -70,12 +70,29 @@ int64_t rrlu(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t max_rank, do
              double abs_tol, bool left_orthogonal, int64_t* row_perm, int64_t* col_perm,
              double* last_error);
 
+// Unpermuted factors of the factorisation computed by the immediately preceding rrlu() call on
+// this context (A must be the same, now factorised, buffer): L (m x r), U (r x n) as the
+// reference's extract_lu_from_factorized (matrixlu.rs:614-668).  Must be called exactly once
+// after each rrlu() (it also releases the factorisation workspace); L/U may be null.
+void rrlu_extract(Ctx*, DType dt, int64_t m, int64_t n, const void* A, int64_t r,
+                  bool left_orthogonal, void* L, void* U);
+
+// Row / column permutation by a device int64 index array.
+//   scatter: out[perm[i], :] = in[i, :]     gather: out[i, :] = in[perm[i], :]
+void permute_rows(Ctx*, DType dt, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
+                  int64_t ld_out, const int64_t* perm, bool scatter);
+void permute_cols(Ctx*, DType dt, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
+                  int64_t ld_out, const int64_t* perm, bool scatter);
+
 // Triangular solve with an n x n triangular T (ld = ldt):
 //   left_side : X <- op(T)^-1 X  (X is n x nrhs, ld = ldx)
 //   !left_side: X <- X op(T)^-1  (X is nrhs x n, ld = ldx)
 // (reference crates/tensor4all-tensorbackend/src/backend.rs:924-937).
 void trsm(Ctx*, DType dt, bool left_side, bool lower, bool transpose, bool unit_diag, int64_t n,
           int64_t nrhs, const void* T, int64_t ldt, void* X, int64_t ldx);
+
+// A[0:m, 0:n] (ld = lda) = identity (ones on the main diagonal, zeros elsewhere)
+void set_identity(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t lda);
 
 // A[i,j] *= s[j] (cols) or s[i] (rows); s real, device.  invert => divide.
 void scale_cols(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t lda, const double* s,

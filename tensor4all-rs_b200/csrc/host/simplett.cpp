@@ -1,0 +1,306 @@
+#include "simplett.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace t4b {
+namespace stt {
+
+static Group g1(int64_t dim, int64_t str) {
+    Group g;
+    g.nd = 1; g.dim[0] = dim; g.str[0] = str;
+    return g;
+}
+static Group g2(int64_t d0, int64_t s0, int64_t d1, int64_t s1) {
+    Group g;
+    g.nd = 2; g.dim[0] = d0; g.str[0] = s0; g.dim[1] = d1; g.str[1] = s1;
+    return g;
+}
+static Group g3(int64_t d0, int64_t s0, int64_t d1, int64_t s1, int64_t d2, int64_t s2) {
+    Group g;
+    g.nd = 3; g.dim[0] = d0; g.str[0] = s0; g.dim[1] = d1; g.str[1] = s1; g.dim[2] = d2; g.str[2] = s2;
+    return g;
+}
+
+// reference compression.rs:286-306 / mpo/factorize.rs:206-250: keep while sv >= threshold
+// (non-strict), stop at the cap, floor 1.
+int64_t simplett_rank(const std::vector<double>& s, double tolerance, bool normalize_error,
+                      std::optional<int64_t> max_bond_dim) {
+    double s_max = 0.0;
+    for (double v : s) s_max = std::fmax(s_max, v);
+    const double threshold = normalize_error ? tolerance * s_max : tolerance;
+    int64_t rank = 0;
+    if (!(normalize_error && s_max == 0.0 && tolerance > 0.0)) {
+        for (double sv : s) {
+            if (max_bond_dim && rank >= *max_bond_dim) break;
+            if (sv < threshold) break;
+            ++rank;
+        }
+    }
+    return std::max<int64_t>(rank, 1);
+}
+
+static std::shared_ptr<Buffer> matmul(dla::Ctx* c, DType dt, int64_t m, int64_t n, int64_t k,
+                                      const void* A, const void* B) {
+    auto out = std::make_shared<Buffer>(c, (size_t)m * n * dtype_size(dt));
+    dla::gemm(c, dt, m, n, k, 1.0, A, g1(m, 1), g1(k, m), false, B, g1(k, 1), g1(n, k), false, 0.0,
+              out->p, g1(m, 1), g1(n, m));
+    return out;
+}
+
+// Factorisation of an m x n matrix the way compression.rs:165-341 does it.
+struct Fact {
+    std::shared_ptr<Buffer> left, right;
+    int64_t rank;
+};
+static Fact factorize_matrix(dla::Ctx* c, DType dt, int64_t m, int64_t n, const void* M,
+                             CompressionMethod method, double tolerance, bool normalize_error,
+                             std::optional<int64_t> max_bond_dim, bool left_orthogonal) {
+    Fact f;
+    if (method == CompressionMethod::SVD) {
+        auto rank_fn = [&](const std::vector<double>& s) {
+            return simplett_rank(s, tolerance, normalize_error, max_bond_dim);
+        };
+        MatrixFactors mf = svd_factor_matrix(c, dt, m, n, M, left_orthogonal ? Canonical::Left : Canonical::Right, rank_fn);
+        f.left = mf.left; f.right = mf.right; f.rank = mf.rank;
+        return f;
+    }
+    RrLUOptions o;
+    if (tolerance > 0.0 && !normalize_error) { o.rel_tol = 0.0; o.abs_tol = tolerance; }
+    else if (tolerance > 0.0) { o.rel_tol = tolerance; o.abs_tol = 0.0; }
+    else { o.rel_tol = 1e-14; o.abs_tol = 0.0; }
+    o.max_bond_dim = max_bond_dim.value_or(INT64_MAX);
+    o.left_orthogonal = left_orthogonal;
+    LuFactors lf = method == CompressionMethod::LU ? rrlu_factor_matrix(c, dt, m, n, M, o)
+                                                   : luci_factor_matrix(c, dt, m, n, M, o);
+    T4B_REQUIRE(lf.rank >= 1, "compress: zero matrix encountered in LU/CI factorization");
+    f.left = lf.left; f.right = lf.right; f.rank = lf.rank;
+    return f;
+}
+
+void compress(dla::Ctx* c, Train& tt, const CompressionOptions& o) {
+    T4B_REQUIRE(tt.rank == 3, "compress expects a tensor train of rank-3 sites");
+    const int n = (int)tt.sites.size();
+    if (n <= 1) return;
+    const DType dt = tt.dt;
+    const size_t es = dtype_size(dt);
+    const bool pivoted = o.method != CompressionMethod::SVD;
+    // Left-to-right sweep without truncation (compression.rs:388-443)
+    for (int ell = 0; ell + 1 < n; ++ell) {
+        Site& s = tt.sites[ell];
+        const int64_t l = s.d[0], d = s.d[1], r = s.d[2];
+        std::shared_ptr<Buffer> mat = s.buf;
+        if (pivoted) {
+            // reference row order l*site + s (site fastest): [l,s,r] -> [s,l,r]; pivot ties depend on it
+            mat = std::make_shared<Buffer>(c, (size_t)l * d * r * es);
+            dla::permute(c, dt, mat->p, s.buf->p, g3(d, l, l, 1, r, l * d), false);
+        }
+        Fact f = factorize_matrix(c, dt, l * d, r, mat->p, o.method, 0.0, true, std::nullopt, true);
+        std::shared_ptr<Buffer> left = f.left;
+        if (pivoted) {   // rows back to [l,s] order
+            left = std::make_shared<Buffer>(c, (size_t)l * d * f.rank * es);
+            dla::permute(c, dt, left->p, f.left->p, g3(l, d, d, 1, f.rank, l * d), false);
+        }
+        s.buf = left; s.d[2] = f.rank;
+        Site& nx = tt.sites[ell + 1];
+        // natural reshape [r, s2*r2] (a column permutation of the reference's next_mat: harmless)
+        auto nb = matmul(c, dt, f.rank, nx.d[1] * nx.d[2], r, f.right->p, nx.buf->p);
+        nx.buf = nb; nx.d[0] = f.rank;
+    }
+    // Right-to-left sweep with truncation (compression.rs:446-498)
+    for (int ell = n - 1; ell >= 1; --ell) {
+        Site& s = tt.sites[ell];
+        const int64_t l = s.d[0], d = s.d[1], r = s.d[2];
+        std::shared_ptr<Buffer> mat = s.buf;
+        if (pivoted) {
+            // reference column order s*right + r (r fastest): [l,s,r] -> [l,r,s]
+            mat = std::make_shared<Buffer>(c, (size_t)l * d * r * es);
+            dla::permute(c, dt, mat->p, s.buf->p, g3(l, 1, r, l * d, d, l), false);
+        }
+        Fact f = factorize_matrix(c, dt, l, d * r, mat->p, o.method, o.tolerance, o.normalize_error,
+                                  o.max_bond_dim, false);
+        std::shared_ptr<Buffer> right = f.right;
+        if (pivoted) {   // columns back to [s,r] order: [k,r,s] -> [k,s,r]
+            right = std::make_shared<Buffer>(c, (size_t)f.rank * d * r * es);
+            dla::permute(c, dt, right->p, f.right->p, g3(f.rank, 1, d, f.rank * r, r, f.rank), false);
+        }
+        s.buf = right; s.d[0] = f.rank;
+        Site& pv = tt.sites[ell - 1];
+        auto pb = matmul(c, dt, pv.d[0] * pv.d[1], f.rank, l, pv.buf->p, f.left->p);
+        pv.buf = pb; pv.d[2] = f.rank;
+    }
+}
+
+Train contract_zipup(dla::Ctx* c, const Train& a, const Train& b, const MpoContractionOptions& o) {
+    T4B_REQUIRE(a.rank == 4 && b.rank == 4, "contract_zipup expects MPOs");
+    T4B_REQUIRE(a.sites.size() == b.sites.size(), "MPO length mismatch");
+    T4B_REQUIRE(a.dt == b.dt, "MPO dtype mismatch");
+    const int n = (int)a.sites.size();
+    const DType dt = a.dt;
+    const size_t es = dtype_size(dt);
+    Train res;
+    res.dt = dt; res.rank = 4;
+    if (n == 0) return res;
+    for (int i = 0; i < n; ++i)
+        T4B_REQUIRE(a.sites[i].d[2] == b.sites[i].d[1], "shared site dimension mismatch");
+    // remainder R[new_link, link_a, link_b] = 1
+    auto rem = std::make_shared<Buffer>(c, es);
+    {
+        double one[2] = {1.0, 0.0};
+        dla::h2d(c, rem->p, one, es);
+        dla::sync(c);
+    }
+    int64_t nl = 1;
+    for (int i = 0; i < n; ++i) {
+        const Site& A = a.sites[i];
+        const Site& B = b.sites[i];
+        const int64_t la = A.d[0], s1 = A.d[1], kk = A.d[2], ra = A.d[3];
+        const int64_t lb = B.d[0], s2 = B.d[2], rb = B.d[3];
+        // ra_t[n,b,s,k,c] = sum_a R[n,a,b] A[a,s,k,c]          (contract_zipup.rs:118)
+        auto rat = std::make_shared<Buffer>(c, (size_t)nl * lb * s1 * kk * ra * es);
+        dla::gemm(c, dt, nl * lb, s1 * kk * ra, la, 1.0, rem->p, g2(nl, 1, lb, nl * la), g1(la, nl), false,
+                  A.buf->p, g1(la, 1), g1(s1 * kk * ra, la), false, 0.0, rat->p, g1(nl * lb, 1),
+                  g1(s1 * kk * ra, nl * lb));
+        // C[n,s,t,c,d] = sum_{b,k} ra_t[n,b,s,k,c] B[b,k,t,d]   (contract_zipup.rs:120)
+        auto cbuf = std::make_shared<Buffer>(c, (size_t)nl * s1 * s2 * ra * rb * es);
+        const int64_t st_n = 1, st_b = nl, st_s = nl * lb, st_k = nl * lb * s1, st_c = nl * lb * s1 * kk;
+        dla::gemm(c, dt, nl * s1 * ra, s2 * rb, lb * kk, 1.0, rat->p, g3(nl, st_n, s1, st_s, ra, st_c),
+                  g2(lb, st_b, kk, st_k), false, B.buf->p, g2(lb, 1, kk, lb), g2(s2, lb * kk, rb, lb * kk * s2),
+                  false, 0.0, cbuf->p, g3(nl, 1, s1, nl, ra, nl * s1 * s2),
+                  g2(s2, nl * s1, rb, nl * s1 * s2 * ra));
+        Site out;
+        if (i == n - 1) {
+            out.buf = cbuf;
+            out.d[0] = nl; out.d[1] = s1; out.d[2] = s2; out.d[3] = 1;
+            res.sites.push_back(out);
+            continue;
+        }
+        const int64_t rows = nl * s1 * s2, cols = ra * rb;
+        auto rank_fn = [&](const std::vector<double>& s) {
+            return simplett_rank(s, o.tolerance, true, o.max_bond_dim);
+        };
+        MatrixFactors f = svd_factor_matrix(c, dt, rows, cols, cbuf->p, Canonical::Left, rank_fn);
+        out.buf = f.left;
+        out.d[0] = nl; out.d[1] = s1; out.d[2] = s2; out.d[3] = f.rank;
+        res.sites.push_back(out);
+        rem = f.right;   // [rank, ra, rb]
+        nl = f.rank;
+    }
+    return res;
+}
+
+void right_canonicalize(dla::Ctx* c, Train& mpo) {
+    const int n = (int)mpo.sites.size();
+    const DType dt = mpo.dt;
+    const size_t es = dtype_size(dt);
+    for (int i = n - 1; i >= 1; --i) {
+        Site& s = mpo.sites[i];
+        const int64_t left = s.d[0], rest = s.d[1] * s.d[2] * s.d[3];
+        // M^T = Q R (plain transpose, canonical.rs:44-57)
+        auto mt = std::make_shared<Buffer>(c, (size_t)left * rest * es);
+        dla::permute(c, dt, mt->p, s.buf->p, g2(rest, left, left, 1), false);
+        const int64_t k = std::min(left, rest);
+        auto Q = std::make_shared<Buffer>(c, (size_t)rest * k * es);
+        auto R = std::make_shared<Buffer>(c, (size_t)k * left * es);
+        dla::qr_thin(c, dt, rest, left, mt->p, Q->p, R->p);
+        // new site = Q^T reshaped [k, s1, s2, right]
+        auto ns = std::make_shared<Buffer>(c, (size_t)k * rest * es);
+        dla::permute(c, dt, ns->p, Q->p, g2(k, rest, rest, 1), false);
+        // prev[a,u,s,k] = sum_l prev[a,u,s,l] * R^T[l,k] = sum_l prev[..,l] R[k,l]
+        Site& pv = mpo.sites[i - 1];
+        const int64_t prow = pv.d[0] * pv.d[1] * pv.d[2];
+        auto np = std::make_shared<Buffer>(c, (size_t)prow * k * es);
+        dla::gemm(c, dt, prow, k, left, 1.0, pv.buf->p, g1(prow, 1), g1(left, prow), false, R->p,
+                  g1(left, k), g1(k, 1), false, 0.0, np->p, g1(prow, 1), g1(k, prow));
+        s.buf = ns; s.d[0] = k;
+        pv.buf = np; pv.d[3] = k;
+    }
+}
+
+Train contract_naive(dla::Ctx* c, const Train& a, const Train& b,
+                     const std::optional<MpoContractionOptions>& opts) {
+    T4B_REQUIRE(a.rank == 4 && b.rank == 4, "contract_naive expects MPOs");
+    T4B_REQUIRE(a.sites.size() == b.sites.size(), "MPO length mismatch");
+    const int n = (int)a.sites.size();
+    const DType dt = a.dt;
+    const size_t es = dtype_size(dt);
+    Train res;
+    res.dt = dt; res.rank = 4;
+    for (int i = 0; i < n; ++i) {
+        const Site& A = a.sites[i];
+        const Site& B = b.sites[i];
+        T4B_REQUIRE(A.d[2] == B.d[1], "shared site dimension mismatch");
+        const int64_t la = A.d[0], s1 = A.d[1], kk = A.d[2], ra = A.d[3];
+        const int64_t lb = B.d[0], s2 = B.d[2], rb = B.d[3];
+        // "askr,bktq->bastqr" (environment.rs:74): out [lb, la, s1, s2, rb, ra]
+        auto out = std::make_shared<Buffer>(c, (size_t)la * lb * s1 * s2 * ra * rb * es);
+        const int64_t o_b = 1, o_a = lb, o_s = lb * la, o_t = lb * la * s1, o_q = lb * la * s1 * s2,
+                      o_r = lb * la * s1 * s2 * rb;
+        dla::gemm(c, dt, la * s1 * ra, lb * s2 * rb, kk, 1.0, A.buf->p,
+                  g3(la, 1, s1, la, ra, la * s1 * kk), g1(kk, la * s1), false, B.buf->p, g1(kk, lb),
+                  g3(lb, 1, s2, lb * kk, rb, lb * kk * s2), false, 0.0, out->p,
+                  g3(la, o_a, s1, o_s, ra, o_r), g3(lb, o_b, s2, o_t, rb, o_q));
+        Site s;
+        s.buf = out;
+        s.d[0] = la * lb; s.d[1] = s1; s.d[2] = s2; s.d[3] = ra * rb;
+        res.sites.push_back(s);
+    }
+    if (opts && n > 1) {
+        // compress_mpo (contract_naive.rs:105-169)
+        right_canonicalize(c, res);
+        for (int i = 0; i + 1 < n; ++i) {
+            Site& s = res.sites[i];
+            const int64_t rows = s.d[0] * s.d[1] * s.d[2], right = s.d[3];
+            auto rank_fn = [&](const std::vector<double>& sv) {
+                return simplett_rank(sv, opts->tolerance, true, opts->max_bond_dim);
+            };
+            MatrixFactors f = svd_factor_matrix(c, dt, rows, right, s.buf->p, Canonical::Left, rank_fn);
+            Site& nx = res.sites[i + 1];
+            auto nb = matmul(c, dt, f.rank, nx.d[1] * nx.d[2] * nx.d[3], right, f.right->p, nx.buf->p);
+            s.buf = f.left; s.d[3] = f.rank;
+            nx.buf = nb; nx.d[0] = f.rank;
+        }
+    }
+    return res;
+}
+
+void inner_product(dla::Ctx* c, const Train& a, const Train& b, double* re, double* im) {
+    T4B_REQUIRE(a.rank == 3 && b.rank == 3, "inner_product expects tensor trains");
+    T4B_REQUIRE(a.sites.size() == b.sites.size(), "tensor train length mismatch");
+    const int n = (int)a.sites.size();
+    const DType dt = a.dt;
+    const size_t es = dtype_size(dt);
+    *re = 0.0; *im = 0.0;
+    if (n == 0) return;
+    std::shared_ptr<Buffer> env;   // [ra, rb]
+    int64_t ea = 1, eb = 1;
+    for (int i = 0; i < n; ++i) {
+        const Site& A = a.sites[i];
+        const Site& B = b.sites[i];
+        T4B_REQUIRE(A.d[1] == B.d[1], "site dimension mismatch");
+        const int64_t la = A.d[0], d = A.d[1], ra = A.d[2], lb = B.d[0], rb = B.d[2];
+        std::shared_ptr<Buffer> t;   // t[j, s, k] = sum_i env[i,j] A[i,s,k]
+        if (i == 0) {
+            T4B_REQUIRE(la == 1 && lb == 1, "boundary bonds must be 1");
+            t = A.buf;   // [1, s, ra] viewed as [lb=1, s, ra]
+        } else {
+            T4B_REQUIRE(la == ea && lb == eb, "bond dimension mismatch");
+            t = std::make_shared<Buffer>(c, (size_t)lb * d * ra * es);
+            dla::gemm(c, dt, lb, d * ra, la, 1.0, env->p, g1(lb, la), g1(la, 1), false, A.buf->p, g1(la, 1),
+                      g1(d * ra, la), false, 0.0, t->p, g1(lb, 1), g1(d * ra, lb));
+        }
+        // env'[k,l] = sum_{j,s} t[j,s,k] B[j,s,l]
+        auto ne = std::make_shared<Buffer>(c, (size_t)ra * rb * es);
+        dla::gemm(c, dt, ra, rb, lb * d, 1.0, t->p, g1(ra, lb * d), g1(lb * d, 1), false, B.buf->p,
+                  g1(lb * d, 1), g1(rb, lb * d), false, 0.0, ne->p, g1(ra, 1), g1(rb, ra));
+        env = ne; ea = ra; eb = rb;
+    }
+    double h[2] = {0.0, 0.0};
+    dla::d2h(c, h, env->p, es);
+    dla::sync(c);
+    *re = h[0];
+    *im = dt == C64 ? h[1] : 0.0;
+}
+
+}  // namespace stt
+}  // namespace t4b

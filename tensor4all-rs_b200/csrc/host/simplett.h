@@ -1,0 +1,55 @@
+// Positional tensor-train stack: mirror of tensor4all-simplett's hot functions
+//   compress          reference crates/tensor4all-simplett/src/compression.rs:165-501
+//   mpo::contract_zipup   reference src/mpo/contract_zipup.rs:45-164
+//   mpo::contract_naive / compress_mpo / right_canonicalize
+//                     reference src/mpo/contract_naive.rs:41-169, src/mpo/canonical.rs:35-86
+//   mpo::factorize_svd    reference src/mpo/factorize.rs:182-302
+//   inner_product     reference src/contraction.rs:82-167
+// Site tensors are dense column-major device buffers: Tensor3 [left, site, right],
+// Tensor4 [left, s1, s2, right] (reference src/types.rs:104-127, src/mpo/types.rs:59-68).
+#pragma once
+#include <optional>
+#include <vector>
+
+#include "factorize.h"
+#include "luci.h"
+
+namespace t4b {
+namespace stt {
+
+struct Site {
+    std::shared_ptr<Buffer> buf;
+    int64_t d[4] = {1, 1, 1, 1};   // Tensor3: d[0..2]; Tensor4: d[0..3]
+};
+struct Train {
+    DType dt = F64;
+    int rank = 3;   // 3: tensor train, 4: MPO
+    std::vector<Site> sites;
+};
+
+enum class CompressionMethod { LU, CI, SVD };
+struct CompressionOptions {   // reference compression.rs:88-124
+    CompressionMethod method = CompressionMethod::LU;
+    double tolerance = 1e-12;
+    std::optional<int64_t> max_bond_dim;
+    bool normalize_error = true;
+};
+void compress(dla::Ctx*, Train& tt, const CompressionOptions& opts);
+
+struct MpoContractionOptions {   // reference mpo/types.rs ContractionOptions
+    double tolerance = 1e-12;
+    std::optional<int64_t> max_bond_dim;
+};
+Train contract_zipup(dla::Ctx*, const Train& a, const Train& b, const MpoContractionOptions& opts);
+Train contract_naive(dla::Ctx*, const Train& a, const Train& b,
+                     const std::optional<MpoContractionOptions>& opts);
+void right_canonicalize(dla::Ctx*, Train& mpo);
+// bilinear <a,b> (no conjugation, like the reference); returns (re, im)
+void inner_product(dla::Ctx*, const Train& a, const Train& b, double* re, double* im);
+
+// rank rule shared by compression.rs:286-306 and mpo/factorize.rs:206-250
+int64_t simplett_rank(const std::vector<double>& s, double tolerance, bool normalize_error,
+                      std::optional<int64_t> max_bond_dim);
+
+}  // namespace stt
+}  // namespace t4b

@@ -1,0 +1,396 @@
+#include "treetn.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace t4b {
+
+std::vector<Index> ChainTN::site_inds(int i) const {
+    std::vector<Index> drop;
+    if (i > 0) drop.push_back(bonds[i - 1]);
+    if (i + 1 < (int)sites.size()) drop.push_back(bonds[i]);
+    return indices_except(sites[i].inds, drop);
+}
+
+ChainTN make_chain(const std::vector<Tensor>& sites) {
+    ChainTN tn;
+    tn.sites = sites;
+    const int L = (int)sites.size();
+    T4B_REQUIRE(L >= 1, "chain needs at least one site");
+    for (int i = 0; i + 1 < L; ++i) {
+        std::vector<Index> common = common_indices(sites[i], sites[i + 1]);
+        T4B_REQUIRE(common.size() == 1, "neighbouring chain sites must share exactly one bond index");
+        tn.bonds.push_back(common[0]);
+    }
+    for (int i = 0; i < L; ++i)
+        for (int j = i + 2; j < L; ++j)
+            T4B_REQUIRE(common_indices(sites[i], sites[j]).empty(),
+                        "non-neighbouring chain sites share an index");
+    tn.ortho_dir.assign(std::max(L - 1, 0), 0);
+    tn.center = -1;
+    return tn;
+}
+
+ChainTN clone_chain(dla::Ctx* c, const ChainTN& tn) {
+    ChainTN r = tn;
+    for (auto& s : r.sites) s = clone(c, s);
+    return r;
+}
+
+// reference sweep_edge_full_rank (treetn/mod.rs:616-751): QR at src, absorb R into dst
+static void sweep_edge(dla::Ctx* c, ChainTN& tn, int src, int dst) {
+    const int e = std::min(src, dst);
+    const Index bond = tn.bonds[e];
+    Tensor& ts = tn.sites[src];
+    std::vector<Index> left_inds = indices_except(ts.inds, {bond});
+    if (left_inds.empty()) {
+        // bond-only tensor: move its norm to dst (mod.rs:647-689)
+        double nrm = std::sqrt(norm_sqr(c, ts));
+        if (nrm > 0.0) {
+            Tensor s2 = clone(c, ts);
+            dla::scal(c, s2.dt, s2.numel(), s2.data(), 1.0 / nrm);
+            Tensor d2 = clone(c, tn.sites[dst]);
+            dla::scal(c, d2.dt, d2.numel(), d2.data(), nrm);
+            tn.sites[src] = s2;
+            tn.sites[dst] = d2;
+        }
+    } else {
+        FactorizeOptions o;
+        o.alg = FactorizeAlg::QR;
+        o.canonical = Canonical::Left;
+        o.full_rank = true;
+        FactorizeResult f = factorize(c, ts, left_inds, o);
+        Tensor new_dst = contract_pair(c, tn.sites[dst], replaceind(f.right, f.bond, f.bond));
+        // contract over the OLD bond: f.right carries [new_bond, old_bond]
+        tn.sites[src] = f.left;
+        tn.sites[dst] = new_dst;
+        tn.bonds[e] = f.bond;
+    }
+    tn.ortho_dir[e] = dst > src ? +1 : -1;
+}
+
+void canonicalize(dla::Ctx* c, ChainTN& tn, int center) {
+    const int L = (int)tn.length();
+    T4B_REQUIRE(center >= 0 && center < L, "canonicalize: center out of range");
+    // leaves towards the centre (reference canonicalize_impl).  Sites already known to be
+    // orthogonal towards the centre are skipped while nothing upstream has been modified: the QR
+    // of an isometry returns the same isometry up to a gauge, so the represented TT and its
+    // canonical form are unchanged.
+    bool dirty = false;
+    for (int i = 0; i < center; ++i) {
+        if (!dirty && tn.ortho_dir[i] == +1) continue;
+        sweep_edge(c, tn, i, i + 1);
+        dirty = true;
+    }
+    dirty = false;
+    for (int i = L - 1; i > center; --i) {
+        if (!dirty && tn.ortho_dir[i - 1] == -1) continue;
+        sweep_edge(c, tn, i, i - 1);
+        dirty = true;
+    }
+    tn.center = center;
+}
+
+std::vector<std::pair<int, int>> two_site_sweep_plan(int L, int center) {
+    // DFS Euler tour; petgraph iterates the most recently added edge first, i.e. for a chain
+    // built left-to-right the higher-index neighbour is visited first (named_graph.rs:307-345).
+    std::vector<std::pair<int, int>> steps;
+    if (L <= 1) return steps;
+    for (int i = center; i + 1 < L; ++i) steps.push_back({i, i + 1});
+    for (int i = L - 1; i > center; --i) steps.push_back({i, i - 1});
+    for (int i = center; i > 0; --i) steps.push_back({i, i - 1});
+    for (int i = 0; i < center; ++i) steps.push_back({i, i + 1});
+    return steps;
+}
+
+std::vector<int> zipup_chain_order(int L, int center) {
+    // reference chain_order (contraction.rs:384-434): endpoints sorted by name; sweep ENDS at the
+    // centre when it is endpoint 0, otherwise runs 0 -> L-1.
+    std::vector<int> chain(L);
+    for (int i = 0; i < L; ++i) chain[i] = (center == 0) ? L - 1 - i : i;
+    return chain;
+}
+
+// Two-site update of the truncation sweep (reference TruncateUpdater::update,
+// localupdate.rs:526-645): SVD of A_u A_v with A_u keeping the isometry.
+static void truncate_step(dla::Ctx* c, ChainTN& tn, int u, int v,
+                          std::optional<SvdTruncationPolicy> policy,
+                          std::optional<int64_t> max_bond_dim) {
+    const int e = std::min(u, v);
+    const Index bond = tn.bonds[e];
+    FactorizeOptions o;
+    o.alg = FactorizeAlg::SVD;
+    o.canonical = Canonical::Left;
+    o.max_bond_dim = max_bond_dim;
+    o.svd_policy = policy;
+    const Tensor& au = tn.sites[u];
+    const Tensor& av = tn.sites[v];
+    std::vector<Index> left_inds = indices_except(au.inds, {bond});
+    const bool v_orth_towards_u = tn.ortho_dir[e] == (u < v ? -1 : +1);
+    FactorizeResult f;
+    if (v_orth_towards_u && !left_inds.empty()) {
+        // A_v is an isometry from the bond to its other legs, so the SVD of A_u A_v is the SVD of
+        // A_u alone followed by (S Vh) A_v: identical singular values and subspaces, but the
+        // matrix is (left x bond) instead of (left x right).
+        f = factorize(c, au, left_inds, o);
+        Tensor new_v = contract_pair(c, f.right, av);   // [new_bond, rest of v]
+        f.right = new_v;
+    } else {
+        Tensor ab = contract_pair(c, au, av);
+        f = factorize(c, ab, left_inds, o);
+    }
+    tn.sites[u] = f.left;
+    tn.sites[v] = f.right;
+    tn.bonds[e] = f.bond;
+    tn.ortho_dir[e] = v > u ? +1 : -1;
+    tn.center = v;
+}
+
+void truncate(dla::Ctx* c, ChainTN& tn, int center, std::optional<SvdTruncationPolicy> policy,
+              std::optional<int64_t> max_bond_dim) {
+    validate_svd_truncation_options(max_bond_dim, policy);
+    const int L = (int)tn.length();
+    T4B_REQUIRE(center >= 0 && center < L, "truncate: center out of range");
+    canonicalize(c, tn, center);
+    for (auto& st : two_site_sweep_plan(L, center)) truncate_step(c, tn, st.first, st.second, policy, max_bond_dim);
+    tn.center = center;
+}
+
+ChainTN contract_zipup(dla::Ctx* c, const ChainTN& a_in, const ChainTN& b_in, int center,
+                       std::optional<SvdTruncationPolicy> policy,
+                       std::optional<int64_t> max_bond_dim, bool final_truncate) {
+    validate_svd_truncation_options(max_bond_dim, policy);
+    const int L = (int)a_in.length();
+    T4B_REQUIRE(L == (int)b_in.length(), "contract_zipup: operands must have the same length");
+    T4B_REQUIRE(center >= 0 && center < L, "contract_zipup: center out of range");
+    std::vector<int> chain = zipup_chain_order(L, center);
+    // operands in exact QR form at the first sweep site (contraction.rs:457-471)
+    ChainTN a = a_in, b = b_in;   // shares buffers; canonicalize replaces tensors, never mutates
+    canonicalize(c, a, chain[0]);
+    canonicalize(c, b, chain[0]);
+
+    ChainTN res;
+    res.sites.resize(L);
+    res.bonds.assign(std::max(L - 1, 0), Index{});
+    res.ortho_dir.assign(std::max(L - 1, 0), 0);
+    if (L == 1) {
+        res.sites[0] = contract_pair(c, a.sites[0], b.sites[0]);
+        res.center = 0;
+        return res;
+    }
+    FactorizeOptions fl;
+    fl.alg = FactorizeAlg::SVD; fl.canonical = Canonical::Left;
+    fl.max_bond_dim = max_bond_dim; fl.svd_policy = policy;
+    FactorizeOptions fr = fl;
+    fr.canonical = Canonical::Right;
+
+    auto bond_between = [&](const ChainTN& tn, int s, int t) { return tn.bonds[std::min(s, t)]; };
+    Tensor remainder;
+    bool have_rem = false;
+    for (int k = 0; k + 2 < L; ++k) {
+        const int s = chain[k], nx = chain[k + 1];
+        const Index ra = bond_between(a, s, nx), rb = bond_between(b, s, nx);
+        Tensor contracted;
+        if (have_rem) contracted = contract(c, {&remainder, &a.sites[s], &b.sites[s]});
+        else contracted = contract_pair(c, a.sites[s], b.sites[s]);
+        std::vector<Index> left_inds = indices_except(contracted.inds, {ra, rb});
+        if (left_inds.empty()) {
+            throw Error(ST_UNSUPPORTED, "contract_zipup: sites without external indices are not supported");
+        }
+        FactorizeResult f = factorize_auto(c, contracted, left_inds, fl);
+        res.sites[s] = f.left;
+        res.bonds[std::min(s, nx)] = f.bond;
+        res.ortho_dir[std::min(s, nx)] = nx > s ? +1 : -1;
+        remainder = f.right;
+        have_rem = true;
+    }
+    // final two sites as one block (contraction.rs:570-683)
+    const int pen = chain[L - 2], last = chain[L - 1];
+    Tensor block;
+    if (have_rem) {
+        block = contract(c, {&remainder, &a.sites[pen], &b.sites[pen], &a.sites[last], &b.sites[last]});
+    } else {
+        Tensor ba = contract_pair(c, a.sites[pen], a.sites[last]);
+        Tensor bb = contract_pair(c, b.sites[pen], b.sites[last]);
+        block = contract_pair(c, ba, bb);
+    }
+    std::vector<Index> last_sites = a.site_inds(last);
+    {
+        std::vector<Index> lb = b.site_inds(last);
+        last_sites.insert(last_sites.end(), lb.begin(), lb.end());
+    }
+    std::vector<Index> left_inds = indices_except(block.inds, last_sites);
+    T4B_REQUIRE(!left_inds.empty() && left_inds.size() < block.inds.size(),
+                "contract_zipup: final block needs indices on both sites");
+    FactorizeResult f = factorize_auto(c, block, left_inds, fr);
+    res.sites[pen] = f.left;
+    res.sites[last] = f.right;
+    res.bonds[std::min(pen, last)] = f.bond;
+    res.ortho_dir[std::min(pen, last)] = pen > last ? +1 : -1;   // last is orthogonal towards pen
+    res.center = pen;
+    if (final_truncate) truncate(c, res, center, policy, max_bond_dim);
+    else canonicalize(c, res, center);
+    return res;
+}
+
+namespace {
+
+// Environment tensors of the variational fit for a chain: envL[i] covers sites 0..i (open bonds
+// towards i+1), envR[i] covers sites i..L-1 (reference FitEnvironment, fit.rs:339-402,810-852).
+struct FitEnv {
+    std::vector<Tensor> L, R;
+    std::vector<char> okL, okR;
+};
+
+Tensor env_step(dla::Ctx* c, const Tensor* prev, const Tensor& a, const Tensor& b, const Tensor& cc) {
+    Tensor t = prev ? contract_pair(c, *prev, a) : a;
+    t = contract_pair(c, t, b);
+    return contract_pair(c, t, cc, false, true);   // conj(C)
+}
+
+const Tensor& get_left(dla::Ctx* c, FitEnv& env, const ChainTN& a, const ChainTN& b, const ChainTN& cc, int i) {
+    if (!env.okL[i]) {
+        const Tensor* prev = i > 0 ? &get_left(c, env, a, b, cc, i - 1) : nullptr;
+        env.L[i] = env_step(c, prev, a.sites[i], b.sites[i], cc.sites[i]);
+        env.okL[i] = 1;
+    }
+    return env.L[i];
+}
+const Tensor& get_right(dla::Ctx* c, FitEnv& env, const ChainTN& a, const ChainTN& b, const ChainTN& cc, int i) {
+    const int L = (int)a.length();
+    if (!env.okR[i]) {
+        const Tensor* prev = i + 1 < L ? &get_right(c, env, a, b, cc, i + 1) : nullptr;
+        env.R[i] = env_step(c, prev, a.sites[i], b.sites[i], cc.sites[i]);
+        env.okR[i] = 1;
+    }
+    return env.R[i];
+}
+
+}  // namespace
+
+ChainTN contract_fit(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center,
+                     const ContractionOptions& o) {
+    const int L = (int)a.length();
+    ChainTN cc = contract_zipup(c, a, b, center, o.svd_policy, o.max_bond_dim, /*final_truncate=*/false);
+    if (o.nfullsweeps == 0 || L == 1) return cc;
+    FitEnv env;
+    env.L.resize(L); env.R.resize(L);
+    env.okL.assign(L, 0); env.okR.assign(L, 0);
+    auto plan = two_site_sweep_plan(L, center);
+    for (int sweep = 0; sweep < o.nfullsweeps; ++sweep) {
+        double n_before = 0.0;
+        if (o.convergence_tol > 0.0) n_before = norm_sqr(c, cc);
+        for (auto& st : plan) {
+            const int u = st.first, v = st.second;
+            const int lo = std::min(u, v), hi = std::max(u, v);
+            // local optimum = A_u B_u A_v B_v with the environments of the outer neighbours
+            std::vector<const Tensor*> ts = {&a.sites[u], &b.sites[u], &a.sites[v], &b.sites[v]};
+            if (lo > 0) ts.push_back(&get_left(c, env, a, b, cc, lo - 1));
+            if (hi + 1 < L) ts.push_back(&get_right(c, env, a, b, cc, hi + 1));
+            Tensor local = contract(c, ts);
+            // left indices: site indices of C at u plus C's bond from u to its other neighbour
+            std::vector<Index> left_inds = cc.site_inds(u);
+            if (u < v && u > 0) left_inds.push_back(cc.bonds[u - 1]);
+            if (u > v && u + 1 < L) left_inds.push_back(cc.bonds[u]);
+            FactorizeOptions fo;
+            fo.alg = FactorizeAlg::SVD; fo.canonical = Canonical::Left;
+            fo.svd_policy = o.svd_policy;
+            if (o.max_bond_dim) fo.max_bond_dim = o.max_bond_dim;
+            else if (!o.svd_policy) fo.max_bond_dim = cc.bonds[lo].dim;   // fit.rs:690-700
+            FactorizeResult f = factorize(c, local, left_inds, fo);
+            cc.sites[u] = f.left;
+            cc.sites[v] = f.right;
+            cc.bonds[lo] = f.bond;
+            cc.ortho_dir[lo] = v > u ? +1 : -1;
+            cc.center = v;
+            for (int i = lo; i < L; ++i) env.okL[i] = 0;
+            for (int i = 0; i <= hi; ++i) env.okR[i] = 0;
+        }
+        if (o.convergence_tol > 0.0) {
+            double n_after = norm_sqr(c, cc);
+            double rel = std::fabs(std::sqrt(n_after / n_before) - 1.0);
+            if (rel < o.convergence_tol) break;
+        }
+    }
+    return cc;
+}
+
+ChainTN contract(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center,
+                 const ContractionOptions& o) {
+    validate_svd_truncation_options(o.max_bond_dim, o.svd_policy);
+    switch (o.method) {
+        case ContractMethod::Zipup: return contract_zipup(c, a, b, center, o.svd_policy, o.max_bond_dim);
+        case ContractMethod::Fit: return contract_fit(c, a, b, center, o);
+        case ContractMethod::Naive: {
+            // site-wise product with fused bonds, then truncate (reference contract_naive)
+            const int L = (int)a.length();
+            ChainTN r;
+            r.sites.resize(L);
+            std::vector<Index> fused(std::max(L - 1, 0));
+            for (int i = 0; i + 1 < L; ++i) fused[i] = new_index(a.bonds[i].dim * b.bonds[i].dim);
+            for (int i = 0; i < L; ++i) {
+                Tensor t = contract_pair(c, a.sites[i], b.sites[i]);
+                // order: [la, lb, sites..., ra, rb] so that the bond pairs fuse by reshape
+                std::vector<Index> order;
+                if (i > 0) { order.push_back(a.bonds[i - 1]); order.push_back(b.bonds[i - 1]); }
+                std::vector<Index> drop = order;
+                if (i + 1 < L) { drop.push_back(a.bonds[i]); drop.push_back(b.bonds[i]); }
+                for (auto& ix : indices_except(t.inds, drop)) order.push_back(ix);
+                if (i + 1 < L) { order.push_back(a.bonds[i]); order.push_back(b.bonds[i]); }
+                Tensor p = permute(c, t, order);
+                std::vector<Index> ni;
+                if (i > 0) ni.push_back(fused[i - 1]);
+                for (auto& ix : indices_except(t.inds, drop)) ni.push_back(ix);
+                if (i + 1 < L) ni.push_back(fused[i]);
+                p.inds = ni;
+                r.sites[i] = p;
+            }
+            r.bonds = fused;
+            r.ortho_dir.assign(std::max(L - 1, 0), 0);
+            r.center = -1;
+            truncate(c, r, center, o.svd_policy, o.max_bond_dim);
+            return r;
+        }
+    }
+    throw Error(ST_INTERNAL, "contract: unknown method");
+}
+
+void inner(dla::Ctx* c, const ChainTN& a, const ChainTN& b, double* re, double* im) {
+    const int L = (int)a.length();
+    T4B_REQUIRE(L == (int)b.length(), "inner: length mismatch");
+    // give a's bonds fresh ids so that only the site indices are shared
+    Tensor env;
+    bool have = false;
+    std::vector<Index> abond(std::max(L - 1, 0));
+    for (int i = 0; i + 1 < L; ++i) abond[i] = new_index(a.bonds[i].dim);
+    for (int i = 0; i < L; ++i) {
+        Tensor ai = a.sites[i];
+        if (i > 0) ai = replaceind(ai, a.bonds[i - 1], abond[i - 1]);
+        if (i + 1 < L) ai = replaceind(ai, a.bonds[i], abond[i]);
+        Tensor t = have ? contract_pair(c, env, ai, false, true) : Tensor();
+        if (have) env = contract_pair(c, t, b.sites[i]);
+        else env = contract_pair(c, ai, b.sites[i], true, false);
+        have = true;
+    }
+    T4B_REQUIRE(env.numel() == 1, "inner: site indices of the two chains do not match");
+    double h[2] = {0.0, 0.0};
+    dla::d2h(c, h, env.data(), dtype_size(env.dt));
+    dla::sync(c);
+    *re = h[0];
+    *im = env.dt == C64 ? h[1] : 0.0;
+}
+
+double norm_sqr(dla::Ctx* c, const ChainTN& tn) {
+    if (tn.center >= 0) return norm_sqr(c, tn.sites[tn.center]);   // canonical: centre carries the norm
+    double re, im;
+    inner(c, tn, tn, &re, &im);
+    return re;
+}
+
+Tensor to_dense(dla::Ctx* c, const ChainTN& tn) {
+    Tensor t = tn.sites[0];
+    for (int i = 1; i < (int)tn.length(); ++i) t = contract_pair(c, t, tn.sites[i]);
+    return t;
+}
+
+}  // namespace t4b

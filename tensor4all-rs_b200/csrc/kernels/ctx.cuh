@@ -32,6 +32,12 @@ struct Ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
 
+    // factorisation state handed from rrlu() to rrlu_extract()
+    void* rrlu_ws = nullptr;
+    int* rrlu_rp = nullptr;
+    int* rrlu_cp = nullptr;
+    double* rrlu_pv = nullptr;
+
     void* get_scratch(size_t bytes);
     void* get_pinned(size_t bytes);
     void launched(const char* what) {

@@ -1,0 +1,134 @@
+// misc.cu — small triangular solves and index-array permutations used by the LU/CI factor
+// assembly (reference crates/tensor4all-core/src/matrix_luci.rs:176-279).
+#include "scalar.cuh"
+
+namespace t4b {
+namespace dla {
+
+namespace {
+
+// One thread per right-hand-side vector; the triangular matrix (rank x rank, rank <= a few
+// hundred for TCI bonds) is read through L1.  Solves M x = b with M(i,j) = tr ? T[j,i] : T[i,j].
+template <bool CPLX>
+__global__ void trsm_kernel(int left_side, int lower, int transpose, int unit_diag, int64_t n,
+                            int64_t nrhs, const double* __restrict__ Tp, int64_t ldt, double* Xp,
+                            int64_t ldx) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nrhs) return;
+    const T* Tm = reinterpret_cast<const T*>(Tp);
+    T* X = reinterpret_cast<T*>(Xp);
+    const bool tr = left_side ? (transpose != 0) : (transpose == 0);
+    const bool eff_lower = (lower != 0) != tr;
+    const int64_t xs = left_side ? 1 : ldx;          // stride between vector elements
+    T* x = left_side ? X + v * ldx : X + v;
+    auto M = [&](int64_t i, int64_t j) { return tr ? Tm[j + i * ldt] : Tm[i + j * ldt]; };
+    auto cdiv = [&](T a, T b) {
+        if constexpr (CPLX) {
+            double den = b.x * b.x + b.y * b.y;
+            return make_double2((a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den);
+        } else {
+            return a / b;
+        }
+    };
+    if (eff_lower) {
+        for (int64_t i = 0; i < n; ++i) {
+            T s = x[i * xs];
+            for (int64_t j = 0; j < i; ++j) s = S::sub(s, S::mul(M(i, j), x[j * xs]));
+            x[i * xs] = unit_diag ? s : cdiv(s, M(i, i));
+        }
+    } else {
+        for (int64_t i = n - 1; i >= 0; --i) {
+            T s = x[i * xs];
+            for (int64_t j = i + 1; j < n; ++j) s = S::sub(s, S::mul(M(i, j), x[j * xs]));
+            x[i * xs] = unit_diag ? s : cdiv(s, M(i, i));
+        }
+    }
+}
+
+template <bool CPLX, bool ROWS>
+__global__ void permute_index_kernel(const double* __restrict__ in, int64_t ld_in, double* __restrict__ out,
+                                     int64_t ld_out, int64_t m, int64_t n,
+                                     const int64_t* __restrict__ perm, int scatter) {
+    typedef typename Sc<CPLX>::T T;
+    int64_t total = m * n;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const T* src = reinterpret_cast<const T*>(in);
+    T* dst = reinterpret_cast<T*>(out);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        int64_t j = e / m, i = e - j * m;
+        int64_t si = i, sj = j, di = i, dj = j;
+        if (ROWS) { if (scatter) di = perm[i]; else si = perm[i]; }
+        else { if (scatter) dj = perm[j]; else sj = perm[j]; }
+        dst[di + dj * ld_out] = src[si + sj * ld_in];
+    }
+}
+
+int grid_of(Ctx* c, int64_t total) {
+    int64_t g = (total + 255) / 256;
+    int64_t cap = (int64_t)c->num_sms * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+void trsm(Ctx* c, DType dt, bool left_side, bool lower, bool transpose, bool unit_diag, int64_t n,
+          int64_t nrhs, const void* T, int64_t ldt, void* X, int64_t ldx) {
+    if (n == 0 || nrhs == 0) return;
+    int grid = (int)((nrhs + 63) / 64);
+    if (dt == C64)
+        trsm_kernel<true><<<grid, 64, 0, c->stream>>>(left_side, lower, transpose, unit_diag, n, nrhs, (const double*)T, ldt, (double*)X, ldx);
+    else
+        trsm_kernel<false><<<grid, 64, 0, c->stream>>>(left_side, lower, transpose, unit_diag, n, nrhs, (const double*)T, ldt, (double*)X, ldx);
+    c->launched("trsm");
+}
+
+void permute_rows(Ctx* c, DType dt, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
+                  int64_t ld_out, const int64_t* perm, bool scatter) {
+    if (m * n == 0) return;
+    if (dt == C64)
+        permute_index_kernel<true, true><<<grid_of(c, m * n), 256, 0, c->stream>>>((const double*)in, ld_in, (double*)out, ld_out, m, n, perm, scatter);
+    else
+        permute_index_kernel<false, true><<<grid_of(c, m * n), 256, 0, c->stream>>>((const double*)in, ld_in, (double*)out, ld_out, m, n, perm, scatter);
+    c->launched("permute_rows");
+}
+
+void permute_cols(Ctx* c, DType dt, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
+                  int64_t ld_out, const int64_t* perm, bool scatter) {
+    if (m * n == 0) return;
+    if (dt == C64)
+        permute_index_kernel<true, false><<<grid_of(c, m * n), 256, 0, c->stream>>>((const double*)in, ld_in, (double*)out, ld_out, m, n, perm, scatter);
+    else
+        permute_index_kernel<false, false><<<grid_of(c, m * n), 256, 0, c->stream>>>((const double*)in, ld_in, (double*)out, ld_out, m, n, perm, scatter);
+    c->launched("permute_cols");
+}
+
+namespace {
+template <bool CPLX>
+__global__ void set_identity_block_kernel(double* __restrict__ A, int64_t m, int64_t n, int64_t lda) {
+    typedef typename Sc<CPLX>::T T;
+    int64_t total = m * n;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        int64_t j = e / m, i = e - j * m;
+        reinterpret_cast<T*>(A)[i + j * lda] = i == j ? Sc<CPLX>::one() : Sc<CPLX>::zero();
+    }
+}
+}  // namespace
+
+void set_identity(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t lda) {
+    if (m * n == 0) return;
+    if (dt == C64) set_identity_block_kernel<true><<<grid_of(c, m * n), 256, 0, c->stream>>>((double*)A, m, n, lda);
+    else set_identity_block_kernel<false><<<grid_of(c, m * n), 256, 0, c->stream>>>((double*)A, m, n, lda);
+    c->launched("set_identity");
+}
+
+void eigh(Ctx*, DType, int64_t, void*, double*, void*) {
+    throw Error(ST_UNSUPPORTED, "eigh: not implemented yet (factorize_auto uses the Jacobi SVD)");
+}
+
+}  // namespace dla
+}  // namespace t4b

@@ -12,7 +12,7 @@
 // (crates/tensor4all-tensorbackend/src/backend.rs:742-762).
 #include <cooperative_groups.h>
 
-#include "ctx.cuh"
+#include "scalar.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -37,43 +37,6 @@ struct PanelArgs {
     int64_t rpc;      // rows per CTA
     int use_smem;
 };
-
-template <bool CPLX> struct Sc;
-template <> struct Sc<false> {
-    typedef double T;
-    __device__ static T zero() { return 0.0; }
-    __device__ static T one() { return 1.0; }
-    __device__ static T conj(T a) { return a; }
-    __device__ static T mul(T a, T b) { return a * b; }
-    __device__ static T add(T a, T b) { return a + b; }
-    __device__ static T sub(T a, T b) { return a - b; }
-    __device__ static T neg(T a) { return -a; }
-    __device__ static double abs2(T a) { return a * a; }
-    __device__ static T from_real(double r) { return r; }
-    __device__ static T shfl_xor(T v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
-};
-template <> struct Sc<true> {
-    typedef double2 T;
-    __device__ static T zero() { return make_double2(0.0, 0.0); }
-    __device__ static T one() { return make_double2(1.0, 0.0); }
-    __device__ static T conj(T a) { return make_double2(a.x, -a.y); }
-    __device__ static T mul(T a, T b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-    __device__ static T add(T a, T b) { return make_double2(a.x + b.x, a.y + b.y); }
-    __device__ static T sub(T a, T b) { return make_double2(a.x - b.x, a.y - b.y); }
-    __device__ static T neg(T a) { return make_double2(-a.x, -a.y); }
-    __device__ static double abs2(T a) { return a.x * a.x + a.y * a.y; }
-    __device__ static T from_real(double r) { return make_double2(r, 0.0); }
-    __device__ static T shfl_xor(T v, int o) {
-        return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
-    }
-};
-
-template <bool CPLX>
-__device__ __forceinline__ typename Sc<CPLX>::T warp_sum_t(typename Sc<CPLX>::T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = Sc<CPLX>::add(v, Sc<CPLX>::shfl_xor(v, o));
-    return v;
-}
 
 // LAPACK dlarfg / zlarfg: given alpha and ||x||^2, produce beta (real), tau, scale = 1/(alpha-beta)
 template <bool CPLX>

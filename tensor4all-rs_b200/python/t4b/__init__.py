@@ -157,3 +157,15 @@ class Context:
         _check(lib().t4b_qr_thin(self.h, a.dt, C.c_int64(m), C.c_int64(n), C.c_void_p(a.ptr),
                                  C.c_void_p(q.ptr if q else 0), C.c_void_p(r.ptr)))
         return q, r
+
+    def svd_thin(self, a: DeviceArray, want_u=True, want_vh=True):
+        """a (m x n) is destroyed.  Returns (U or None, S, Vh or None) as DeviceArrays."""
+        m, n = a.shape
+        k = min(m, n)
+        u = self.empty((m, k), a.dt) if want_u else None
+        vh = self.empty((k, n), a.dt) if want_vh else None
+        s = self.empty((k,), F64)
+        _check(lib().t4b_svd_thin(self.h, a.dt, C.c_int64(m), C.c_int64(n), C.c_void_p(a.ptr),
+                                  C.c_void_p(u.ptr if u else 0), C.c_void_p(s.ptr),
+                                  C.c_void_p(vh.ptr if vh else 0)))
+        return u, s, vh

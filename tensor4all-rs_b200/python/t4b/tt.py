@@ -1,0 +1,254 @@
+"""ctypes wrappers for the tensor-train level of the C ABI (include/t4b.h): truncation rules,
+rrLU handles, chain tensor networks (treetn) and positional trains (simplett).
+Test / bench plumbing only."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import C64, F64, Context, DeviceArray, _check, _i32, _i64, dtype_of, lib, np_dtype
+
+
+class SvdPolicy(C.Structure):
+    """t4b_svd_policy: scale 0 rel / 1 abs; measure 0 value / 1 squared; rule 0 per-value / 1 tail."""
+    _fields_ = [("threshold", C.c_double), ("scale", C.c_int), ("measure", C.c_int), ("rule", C.c_int)]
+
+    def __init__(self, threshold=1e-12, scale=0, measure=0, rule=0):
+        super().__init__(threshold, scale, measure, rule)
+
+
+def _pol(policy):
+    return C.byref(policy) if policy is not None else None
+
+
+# ---- host-only rank rules ------------------------------------------------------------------------
+def retained_rank(s, policy: SvdPolicy | None = None) -> int:
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    out = C.c_int64()
+    _check(lib().t4b_retained_rank(s.ctypes.data_as(C.c_void_p), C.c_int64(s.size), _pol(policy), C.byref(out)))
+    return out.value
+
+
+def retained_rank_qr(row_norms, rtol: float) -> int:
+    s = np.ascontiguousarray(row_norms, dtype=np.float64)
+    out = C.c_int64()
+    _check(lib().t4b_retained_rank_qr(s.ctypes.data_as(C.c_void_p), C.c_int64(s.size), C.c_double(rtol), C.byref(out)))
+    return out.value
+
+
+def simplett_rank(s, tolerance, normalize_error=True, max_bond_dim=0) -> int:
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    out = C.c_int64()
+    _check(lib().t4b_simplett_rank(s.ctypes.data_as(C.c_void_p), C.c_int64(s.size), C.c_double(tolerance),
+                                   int(normalize_error), C.c_int64(max_bond_dim), C.byref(out)))
+    return out.value
+
+
+def sweep_plan(length, center):
+    n = C.c_int()
+    _check(lib().t4b_sweep_plan(length, center, None, C.byref(n)))
+    buf = (C.c_int32 * (2 * max(n.value, 1)))()
+    _check(lib().t4b_sweep_plan(length, center, buf, C.byref(n)))
+    return [(buf[2 * i], buf[2 * i + 1]) for i in range(n.value)]
+
+
+def zipup_order(length, center):
+    buf = (C.c_int32 * length)()
+    _check(lib().t4b_zipup_order(length, center, buf))
+    return list(buf)
+
+
+# ---- rrLU ------------------------------------------------------------------------------------------
+class LU:
+    def __init__(self, ctx: Context, a: DeviceArray, max_bond_dim=0, rel_tol=1e-14, abs_tol=0.0, left_orthogonal=True):
+        self.ctx = ctx
+        self.m, self.n = a.shape
+        self.dt = a.dt
+        self.h = C.c_void_p()
+        _check(lib().t4b_rrlu(ctx.h, a.dt, C.c_int64(self.m), C.c_int64(self.n), C.c_void_p(a.ptr),
+                              C.c_int64(max_bond_dim), C.c_double(rel_tol), C.c_double(abs_tol),
+                              int(left_orthogonal), C.byref(self.h)))
+        r = C.c_int64()
+        _check(lib().t4b_lu_rank(self.h, C.byref(r)))
+        self.rank = r.value
+        e = C.c_double()
+        _check(lib().t4b_lu_last_error(self.h, C.byref(e)))
+        self.error = e.value
+        self.row_perm = np.zeros(self.m, np.int64)
+        self.col_perm = np.zeros(self.n, np.int64)
+        _check(lib().t4b_lu_permutations(self.h, self.row_perm.ctypes.data_as(C.c_void_p),
+                                         self.col_perm.ctypes.data_as(C.c_void_p)))
+
+    def pivot_errors(self):
+        out = np.zeros(self.rank + 1)
+        _check(lib().t4b_lu_pivot_errors(self.ctx.h, self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def factor(self, which: int) -> np.ndarray:
+        shape = (self.m, self.rank) if which in (0, 2, 4) else (self.rank, self.n)
+        if self.rank == 0:
+            return np.zeros(shape, dtype=np_dtype(self.dt), order="F")
+        out = self.ctx.empty(shape, self.dt)
+        _check(lib().t4b_lu_factor(self.ctx.h, self.h, which, C.c_void_p(out.ptr)))
+        return out.get()
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().t4b_lu_release(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+# ---- chain tensor networks ---------------------------------------------------------------------------
+class ChainTN:
+    """t4b_tn handle.  sites: list of (ndarray, [index ids])."""
+
+    def __init__(self, ctx: Context, handle, dt=F64):
+        self.ctx = ctx
+        self.h = handle
+        self._dt = dt
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, arrays, ids):
+        L = len(arrays)
+        arrs = [np.asfortranarray(a) for a in arrays]
+        dt = dtype_of(arrs[0])
+        ranks = _i32([a.ndim for a in arrs])
+        shapes = _i64([s for a in arrs for s in a.shape])
+        idl = _i64([i for site in ids for i in site])
+        ptrs = (C.c_void_p * L)(*[a.ctypes.data_as(C.c_void_p).value for a in arrs])
+        h = C.c_void_p()
+        _check(lib().t4b_tn_create(ctx.h, dt, L, ranks, shapes, idl, ptrs, 0, C.byref(h)))
+        return cls(ctx, h, dt)
+
+    def clone(self):
+        h = C.c_void_p()
+        _check(lib().t4b_tn_clone(self.ctx.h, self.h, C.byref(h)))
+        return ChainTN(self.ctx, h, self._dt)
+
+    def length(self):
+        n = C.c_int()
+        _check(lib().t4b_tn_length(self.h, C.byref(n)))
+        return n.value
+
+    def site(self, i):
+        """(ndarray, ids)"""
+        r = C.c_int()
+        _check(lib().t4b_tn_site_rank(self.h, i, C.byref(r)))
+        shape = (C.c_int64 * r.value)()
+        ids = (C.c_int64 * r.value)()
+        _check(lib().t4b_tn_site_shape(self.h, i, shape, ids))
+        dtc = self.dtype()
+        out = np.empty(tuple(shape), dtype=np_dtype(dtc), order="F")
+        _check(lib().t4b_tn_download_site(self.ctx.h, self.h, i, out.ctypes.data_as(C.c_void_p)))
+        return out, list(ids)
+
+    def dtype(self):
+        return self._dt
+
+    def sites(self):
+        return [self.site(i) for i in range(self.length())]
+
+    def bond_dims(self):
+        L = self.length()
+        out = (C.c_int64 * max(L - 1, 1))()
+        _check(lib().t4b_tn_bond_dims(self.h, out))
+        return list(out)[: L - 1]
+
+    def canonicalize(self, center):
+        _check(lib().t4b_tn_canonicalize(self.ctx.h, self.h, center))
+
+    def truncate(self, center, policy: SvdPolicy | None = None, max_bond_dim=0):
+        _check(lib().t4b_tn_truncate(self.ctx.h, self.h, center, _pol(policy), C.c_int64(max_bond_dim)))
+
+    def contract(self, other, center, method=0, policy: SvdPolicy | None = None, max_bond_dim=0, nfullsweeps=1):
+        h = C.c_void_p()
+        _check(lib().t4b_tn_contract(self.ctx.h, self.h, other.h, center, method, _pol(policy),
+                                     C.c_int64(max_bond_dim), nfullsweeps, C.byref(h)))
+        return ChainTN(self.ctx, h, self._dt)
+
+    def norm_sqr(self):
+        v = C.c_double()
+        _check(lib().t4b_tn_norm_sqr(self.ctx.h, self.h, C.byref(v)))
+        return v.value
+
+    def inner(self, other):
+        re, im = C.c_double(), C.c_double()
+        _check(lib().t4b_tn_inner(self.ctx.h, self.h, other.h, C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
+
+    def release(self):
+        if self.h:
+            lib().t4b_tn_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def chain_from_arrays(ctx, arrays, ids):
+    return ChainTN.from_arrays(ctx, arrays, ids)
+
+
+# ---- positional trains -------------------------------------------------------------------------------
+class Train:
+    def __init__(self, ctx: Context, handle, dt, site_rank):
+        self.ctx, self.h, self.dt, self.site_rank = ctx, handle, dt, site_rank
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, arrays):
+        arrs = [np.asfortranarray(a) for a in arrays]
+        dt = dtype_of(arrs[0])
+        r = arrs[0].ndim
+        dims = _i64([s for a in arrs for s in a.shape])
+        ptrs = (C.c_void_p * max(len(arrs), 1))(*[a.ctypes.data_as(C.c_void_p).value for a in arrs])
+        h = C.c_void_p()
+        _check(lib().t4b_train_create(ctx.h, dt, r, len(arrs), dims, ptrs, C.byref(h)))
+        return cls(ctx, h, dt, r)
+
+    def length(self):
+        n = C.c_int()
+        _check(lib().t4b_train_length(self.h, C.byref(n)))
+        return n.value
+
+    def site(self, i):
+        d = (C.c_int64 * self.site_rank)()
+        _check(lib().t4b_train_site_dims(self.h, i, d))
+        out = np.empty(tuple(d), dtype=np_dtype(self.dt), order="F")
+        _check(lib().t4b_train_download_site(self.ctx.h, self.h, i, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def arrays(self):
+        return [self.site(i) for i in range(self.length())]
+
+    def compress(self, method=2, tolerance=1e-12, max_bond_dim=0, normalize_error=True):
+        _check(lib().t4b_train_compress(self.ctx.h, self.h, method, C.c_double(tolerance),
+                                        C.c_int64(max_bond_dim), int(normalize_error)))
+
+    def mpo_contract(self, other, algorithm=0, tolerance=1e-12, max_bond_dim=0):
+        h = C.c_void_p()
+        _check(lib().t4b_mpo_contract(self.ctx.h, self.h, other.h, algorithm, C.c_double(tolerance),
+                                      C.c_int64(max_bond_dim), C.byref(h)))
+        return Train(self.ctx, h, self.dt, 4)
+
+    def inner_product(self, other):
+        re, im = C.c_double(), C.c_double()
+        _check(lib().t4b_train_inner_product(self.ctx.h, self.h, other.h, C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
+
+    def release(self):
+        if self.h:
+            lib().t4b_train_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
