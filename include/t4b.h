@@ -47,6 +47,11 @@ int t4b_ctx_create(int device, void* cuda_stream, t4b_ctx** out);
 int t4b_ctx_destroy(t4b_ctx* ctx);
 int t4b_ctx_sync(t4b_ctx* ctx);
 int t4b_ctx_launch_count(t4b_ctx* ctx, int64_t* out);
+/* Per-kernel-class device timing for the roofline report: begin, run work, then call
+ * t4b_ctx_profile_end(ctx, NULL, 0, &needed) followed by (ctx, buf, needed, NULL); the text has one
+ * line per kernel class: "name launches total_ms algorithmic_work" (flops or bytes). */
+int t4b_ctx_profile_begin(t4b_ctx* ctx);
+int t4b_ctx_profile_end(t4b_ctx* ctx, char* buf, size_t cap, size_t* needed);
 int t4b_malloc(t4b_ctx* ctx, size_t bytes, void** dev);
 int t4b_free(t4b_ctx* ctx, void* dev);
 int t4b_upload(t4b_ctx* ctx, void* dev, const void* host, size_t bytes);   /* async */

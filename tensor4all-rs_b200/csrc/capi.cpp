@@ -171,3 +171,26 @@ int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, voi
 }
 
 }  // extern "C"
+
+// ---- profiling (bench.py roofline) ---------------------------------------------------------------
+extern "C" {
+int t4b_ctx_profile_begin(t4b_ctx* ctx) {
+    T4B_TRY
+    require_ctx(ctx);
+    dla::profile_begin(ctx->c);
+    T4B_CATCH
+}
+int t4b_ctx_profile_end(t4b_ctx* ctx, char* buf, size_t cap, size_t* needed) {
+    T4B_TRY
+    require_ctx(ctx);
+    static thread_local std::string last;
+    if (buf == nullptr || cap == 0) last = dla::profile_end(ctx->c);
+    if (needed) *needed = last.size() + 1;
+    if (buf && cap > 0) {
+        size_t n = last.size() < cap - 1 ? last.size() : cap - 1;
+        memcpy(buf, last.data(), n);
+        buf[n] = 0;
+    }
+    T4B_CATCH
+}
+}

@@ -23,6 +23,16 @@ int ctx_device(Ctx*);
 // Number of kernels launched through this context since creation (bench.py's gpu_launches).
 int64_t ctx_launch_count(Ctx*);
 
+}  // namespace dla
+}  // namespace t4b
+#include <string>
+namespace t4b {
+namespace dla {
+// Per-kernel-class device timing (CUDA events on the launching stream) used by bench.py for
+// the roofline: profile_end returns lines "kernel launches total_ms algorithmic_work".
+void profile_begin(Ctx*);
+std::string profile_end(Ctx*);
+
 // Stream-ordered memory.
 void* alloc(Ctx*, size_t bytes);
 void release(Ctx*, void* p);

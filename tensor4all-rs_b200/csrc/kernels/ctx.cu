@@ -272,3 +272,46 @@ void axpy(Ctx* c, DType dt, int64_t n, double alpha, const void* x, void* y) {
 
 }  // namespace dla
 }  // namespace t4b
+
+// ---- profiling ---------------------------------------------------------------------------------
+namespace t4b {
+namespace dla {
+
+void profile_begin(Ctx* c) {
+    for (auto& r : c->prof) cudaEventDestroy(r.ev);
+    c->prof.clear();
+    if (!c->prof_start) cudaEventCreate(&c->prof_start);
+    T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cudaEventRecord(c->prof_start, c->stream);
+    c->profiling = true;
+}
+
+// Aggregates per kernel class.  Returns text lines "name launches total_ms total_work\n".
+std::string profile_end(Ctx* c) {
+    c->profiling = false;
+    T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    struct Agg { std::string name; int64_t n = 0; double ms = 0.0, work = 0.0; };
+    std::vector<Agg> aggs;
+    cudaEvent_t prev = c->prof_start;
+    for (auto& r : c->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, prev, r.ev);
+        prev = r.ev;
+        Agg* a = nullptr;
+        for (auto& x : aggs) if (x.name == r.name) { a = &x; break; }
+        if (!a) { aggs.push_back(Agg{r.name}); a = &aggs.back(); }
+        a->n += 1; a->ms += ms; a->work += r.work;
+    }
+    std::string out;
+    for (auto& a : aggs) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %lld %.6f %.6e\n", a.name.c_str(), (long long)a.n, a.ms, a.work);
+        out += line;
+    }
+    for (auto& r : c->prof) cudaEventDestroy(r.ev);
+    c->prof.clear();
+    return out;
+}
+
+}  // namespace dla
+}  // namespace t4b

@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../dla.h"
 
@@ -38,15 +39,29 @@ struct Ctx {
     int* rrlu_cp = nullptr;
     double* rrlu_pv = nullptr;
 
+    // optional per-kernel-class profile (bench.py roofline): one CUDA event after every launch
+    // on the launching stream; the gap between consecutive events is that launch's duration.
+    struct ProfRec { const char* name; double work; cudaEvent_t ev; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    cudaEvent_t prof_start = nullptr;
+
     void* get_scratch(size_t bytes);
     void* get_pinned(size_t bytes);
-    void launched(const char* what) {
+    // `work`: algorithmic flops (tensor-bound kernels) or bytes (HBM-bound kernels) of this launch
+    void launched(const char* what, double work = 0.0) {
         ++launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             throw ::t4b::Error(::t4b::ST_CUDA_ERROR,
                                std::string("kernel launch failed (") + what + "): " +
                                    cudaGetErrorString(e));
+        if (profiling) {
+            ProfRec r{what, work, nullptr};
+            cudaEventCreate(&r.ev);
+            cudaEventRecord(r.ev, stream);
+            prof.push_back(r);
+        }
     }
 };
 

@@ -308,7 +308,7 @@ void launch_panel(Ctx* c, PanelArgs& a) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
-    c->launched("qr_panel");
+    c->launched("qr_panel", 2.0 * (double)rows * (double)a.jb * (double)es);  // bytes
 }
 
 }  // namespace

@@ -472,7 +472,7 @@ int jacobi_sweeps(Ctx* c, double* X, int64_t nx, int64_t npad, double* V) {
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
-            c->launched("jacobi_round");
+            c->launched("jacobi_round", 2.0 * (double)(nx + nv) * (double)npad * (double)es);  // bytes: panel read + write
         }
         ++sweeps;
         d2h(c, hflag, flag, 8);

@@ -1,0 +1,95 @@
+"""CPU suite (no GPU): the C-ABI library loads, exports every symbol declared in include/t4b.h,
+fails loudly without a GPU, and its host-only entry points (truncation rules, sweep plans) agree
+with the oracle restatement of the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import t4b
+from t4b import tt as t4tt
+from oracle import treetn as otn
+from oracle.truncation import SvdTruncationPolicy, compute_retained_rank, compute_retained_rank_qr, simplett_rank
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "t4b.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(t4b_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = t4b.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_version_and_last_error():
+    assert b"sm_100a" in t4b.lib().t4b_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(t4b.T4BError) as e:
+        t4b.Context(0)
+    assert "CUDA" in str(e.value)
+
+
+def test_null_arguments_are_rejected_not_crashing():
+    out = C.c_int64()
+    assert t4b.lib().t4b_retained_rank(None, C.c_int64(3), None, C.byref(out)) == 1
+    assert b"bad arguments" in t4b.lib().t4b_last_error()
+    assert t4b.lib().t4b_ctx_sync(None) == 1
+    bad = t4tt.SvdPolicy(float("nan"))
+    s = np.array([1.0, 0.5])
+    assert t4b.lib().t4b_retained_rank(s.ctypes.data_as(C.c_void_p), C.c_int64(2), C.byref(bad), C.byref(out)) == 1
+
+
+def test_retained_rank_matches_oracle_on_random_spectra():
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        k = int(rng.integers(1, 40))
+        s = np.sort(np.abs(rng.standard_normal(k)) * 10.0 ** rng.uniform(-14, 1, k))[::-1].copy()
+        if rng.random() < 0.1:
+            s[rng.integers(0, k):] = 0.0
+        thr = float(10.0 ** rng.uniform(-14, 0)) if rng.random() < 0.9 else 0.0
+        for scale in (0, 1):
+            for measure in (0, 1):
+                for rule in (0, 1):
+                    want = compute_retained_rank(s, SvdTruncationPolicy(thr, scale, measure, rule))
+                    got = t4tt.retained_rank(s, t4tt.SvdPolicy(thr, scale, measure, rule))
+                    assert got == want, (s, thr, scale, measure, rule)
+    assert t4tt.retained_rank([], None) == 1
+    assert t4tt.retained_rank([5.0, 1e-13], None) == 1     # default policy: relative per-value 1e-12
+
+
+def test_qr_and_simplett_rank_match_oracle():
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        k = int(rng.integers(1, 30))
+        v = np.abs(rng.standard_normal(k)) * 10.0 ** rng.uniform(-18, 0, k)
+        rtol = float(10.0 ** rng.uniform(-16, -1))
+        assert t4tt.retained_rank_qr(v, rtol) == compute_retained_rank_qr(v, rtol)
+        s = np.sort(v)[::-1].copy()
+        tol = float(10.0 ** rng.uniform(-14, 0))
+        for norm in (True, False):
+            for cap in (0, 3):
+                assert t4tt.simplett_rank(s, tol, norm, cap) == simplett_rank(s, tol, norm, cap or None)
+
+
+def test_sweep_plan_and_zipup_order():
+    for L in (1, 2, 3, 7):
+        for c in range(L):
+            assert t4tt.sweep_plan(L, c) == otn.two_site_sweep_plan(L, c)
+            assert t4tt.zipup_order(L, c) == otn.zipup_chain_order(L, c)
+    # end-of-chain centre: out and back, 2(L-1) steps (localupdate.rs:126-152)
+    assert t4tt.sweep_plan(4, 0) == [(0, 1), (1, 2), (2, 3), (3, 2), (2, 1), (1, 0)]
+    assert t4tt.zipup_order(4, 0) == [3, 2, 1, 0] and t4tt.zipup_order(4, 2) == [0, 1, 2, 3]
