@@ -122,6 +122,23 @@ int t4b_lu_pivot_errors(t4b_ctx* ctx, const t4b_lu* lu, double* out_host /* rank
 int t4b_lu_factor(t4b_ctx* ctx, const t4b_lu* lu, int which, void* out_dev);
 int t4b_lu_release(t4b_lu* lu);
 
+/* ---- TCI2 two-site pivot update (tensor4all-tensorci) -----------------------------------------
+ * Device part of update_pivots with PivotSearchStrategy::Full (tensorci/src/tensorci2.rs:1821-2007):
+ * pi is the candidate matrix the caller filled through its callbacks, (left_dim*site_dim_b) rows
+ * ordered i*d + s and (site_dim_bp1*right_dim) columns ordered s*#J + j (kronecker_i / kronecker_j,
+ * tensorci2.rs:1224-1246), host or device memory.  The result carries factors.rank, the selected
+ * row / column candidates (non_empty_or_first applied), the bond error and the two site tensors
+ * [left_dim, site_dim_b, r], [r, site_dim_bp1, right_dim] with r = max(rank, 1). */
+typedef struct t4b_tci_update t4b_tci_update;
+int t4b_tci2_update_pivots(t4b_ctx* ctx, int dtype, const void* pi, int pi_on_device, int64_t left_dim,
+                           int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
+                           int64_t max_bond_dim /* 0 = none */, double tolerance, int left_orthogonal,
+                           t4b_tci_update** out);
+int t4b_tci_update_rank(const t4b_tci_update* u, int64_t* rank, int64_t* new_bond_dim, double* bond_error);
+int t4b_tci_update_indices(const t4b_tci_update* u, int64_t* rows_host, int64_t* cols_host, int64_t* n);
+int t4b_tci_update_tensors(t4b_ctx* ctx, const t4b_tci_update* u, void* tensor_b_host, void* tensor_bp1_host);
+int t4b_tci_update_release(t4b_tci_update* u);
+
 /* ---- chain tensor networks (tensor4all-treetn, chain topology) ------------------------------
  * A site is a dense tensor whose axes carry caller-chosen non-negative index ids; equal ids on
  * neighbouring sites are bonds, equal ids on the same site of two networks are contracted by

@@ -382,3 +382,67 @@ int t4b_train_inner_product(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b
 }
 
 }  // extern "C"
+
+// ---- TCI2 two-site pivot update -------------------------------------------------------------------
+#include "host/tci.h"
+struct t4b_tci_update {
+    t4b::TciUpdate u;
+};
+extern "C" {
+int t4b_tci2_update_pivots(t4b_ctx* ctx, int dtype, const void* pi, int pi_on_device, int64_t left_dim,
+                           int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
+                           int64_t max_bond_dim, double tolerance, int left_orthogonal,
+                           t4b_tci_update** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(pi && out, "tci2_update_pivots: null argument");
+    T4B_REQUIRE(left_dim >= 1 && site_dim_b >= 1 && site_dim_bp1 >= 1 && right_dim >= 1, "tci2_update_pivots: dims must be >= 1");
+    DType dt = to_dtype(dtype);
+    const size_t bytes = (size_t)(left_dim * site_dim_b) * (size_t)(site_dim_bp1 * right_dim) * dtype_size(dt);
+    std::shared_ptr<Buffer> staged;
+    const void* pi_dev = pi;
+    if (!pi_on_device) {
+        staged = std::make_shared<Buffer>(ctx->c, bytes);
+        dla::h2d(ctx->c, staged->p, pi, bytes);
+        pi_dev = staged->p;
+    }
+    auto* h = new t4b_tci_update{tci2_update_pivots(ctx->c, dt, pi_dev, left_dim, site_dim_b, site_dim_bp1,
+                                                    right_dim, opt_bond(max_bond_dim), tolerance,
+                                                    left_orthogonal != 0)};
+    *out = h;
+    T4B_CATCH
+}
+int t4b_tci_update_rank(const t4b_tci_update* u, int64_t* rank, int64_t* new_bond_dim, double* bond_error) {
+    T4B_TRY
+    T4B_REQUIRE(u, "null argument");
+    if (rank) *rank = u->u.rank;
+    if (new_bond_dim) *new_bond_dim = u->u.new_bond_dim;
+    if (bond_error) *bond_error = u->u.bond_error;
+    T4B_CATCH
+}
+int t4b_tci_update_indices(const t4b_tci_update* u, int64_t* rows_host, int64_t* cols_host, int64_t* n) {
+    T4B_TRY
+    T4B_REQUIRE(u, "null argument");
+    if (n) *n = (int64_t)u->u.row_indices.size();
+    if (rows_host) std::memcpy(rows_host, u->u.row_indices.data(), sizeof(int64_t) * u->u.row_indices.size());
+    if (cols_host) std::memcpy(cols_host, u->u.col_indices.data(), sizeof(int64_t) * u->u.col_indices.size());
+    T4B_CATCH
+}
+int t4b_tci_update_tensors(t4b_ctx* ctx, const t4b_tci_update* u, void* tensor_b_host, void* tensor_bp1_host) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(u, "null argument");
+    const size_t es = dtype_size(u->u.dt);
+    if (tensor_b_host)
+        dla::d2h(ctx->c, tensor_b_host, u->u.tensor_b->p, (size_t)u->u.left_dim * u->u.site_dim_b * u->u.new_bond_dim * es);
+    if (tensor_bp1_host)
+        dla::d2h(ctx->c, tensor_bp1_host, u->u.tensor_bp1->p, (size_t)u->u.new_bond_dim * u->u.site_dim_bp1 * u->u.right_dim * es);
+    dla::sync(ctx->c);
+    T4B_CATCH
+}
+int t4b_tci_update_release(t4b_tci_update* u) {
+    T4B_TRY
+    delete u;
+    T4B_CATCH
+}
+}

@@ -1,0 +1,55 @@
+#include "tci.h"
+
+#include <algorithm>
+
+namespace t4b {
+
+TciUpdate tci2_update_pivots(dla::Ctx* c, DType dt, const void* pi_dev, int64_t left_dim,
+                             int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
+                             std::optional<int64_t> max_bond_dim, double tolerance,
+                             bool left_orthogonal) {
+    const int64_t nrows = left_dim * site_dim_b, ncols = site_dim_bp1 * right_dim;
+    T4B_REQUIRE(nrows > 0 && ncols > 0, "tci2_update_pivots: empty candidate matrix");
+    const size_t es = dtype_size(dt);
+    RrLUOptions o;   // tensorci2.rs:1895-1903
+    o.max_bond_dim = max_bond_dim.value_or(INT64_MAX);
+    o.rel_tol = tolerance;
+    o.abs_tol = 0.0;
+    o.left_orthogonal = left_orthogonal;
+    LuFactors f = luci_factor_matrix(c, dt, nrows, ncols, pi_dev, o);
+
+    TciUpdate u;
+    u.dt = dt;
+    u.rank = f.rank;
+    u.new_bond_dim = std::max<int64_t>(f.rank, 1);
+    u.row_indices = f.row_indices.empty() ? std::vector<int64_t>{0} : f.row_indices;   // non_empty_or_first
+    u.col_indices = f.col_indices.empty() ? std::vector<int64_t>{0} : f.col_indices;
+    u.pivot_errors = f.pivot_errors;
+    u.bond_error = f.pivot_errors.empty() ? 0.0 : f.pivot_errors.back();
+    u.left_dim = left_dim; u.site_dim_b = site_dim_b; u.site_dim_bp1 = site_dim_bp1; u.right_dim = right_dim;
+    const int64_t r = u.new_bond_dim;
+    u.tensor_b = std::make_shared<Buffer>(c, (size_t)left_dim * site_dim_b * r * es);
+    u.tensor_bp1 = std::make_shared<Buffer>(c, (size_t)r * site_dim_bp1 * right_dim * es);
+    if (f.rank == 0) {
+        dla::zero(c, u.tensor_b->p, (size_t)left_dim * site_dim_b * r * es);
+        dla::zero(c, u.tensor_bp1->p, (size_t)r * site_dim_bp1 * right_dim * es);
+        return u;
+    }
+    // tensor_b[l,s,k] = left[l*d + s, k]           (tensorci2.rs:1951-1971)
+    Group gb;
+    gb.nd = 3;
+    gb.dim[0] = left_dim; gb.str[0] = site_dim_b;
+    gb.dim[1] = site_dim_b; gb.str[1] = 1;
+    gb.dim[2] = r; gb.str[2] = nrows;
+    dla::permute(c, dt, u.tensor_b->p, f.left->p, gb, false);
+    // tensor_bp1[k,s,j] = right[k, s*right_dim + j] (tensorci2.rs:1973-1999)
+    Group gp;
+    gp.nd = 3;
+    gp.dim[0] = r; gp.str[0] = 1;
+    gp.dim[1] = site_dim_bp1; gp.str[1] = r * right_dim;
+    gp.dim[2] = right_dim; gp.str[2] = r;
+    dla::permute(c, dt, u.tensor_bp1->p, f.right->p, gp, false);
+    return u;
+}
+
+}  // namespace t4b

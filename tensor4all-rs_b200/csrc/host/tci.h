@@ -1,0 +1,32 @@
+// TCI2 two-site pivot update, device part (reference crates/tensor4all-tensorci/src/tensorci2.rs:
+// 1821-2007, PivotSearchStrategy::Full): the caller evaluates the candidate matrix Pi through its
+// host callbacks exactly as today; everything after that - the full-pivot prrLU, the MatrixLUCI
+// factor assembly and the reshaping into the two site tensors - runs on the device.
+#pragma once
+#include <optional>
+#include <vector>
+
+#include "luci.h"
+
+namespace t4b {
+
+struct TciUpdate {
+    DType dt = F64;
+    int64_t rank = 0;          // factors.rank (may be 0 for a numerically zero Pi)
+    int64_t new_bond_dim = 1;  // rank.max(1)
+    std::vector<int64_t> row_indices, col_indices;   // non_empty_or_first applied
+    std::vector<double> pivot_errors;
+    double bond_error = 0.0;
+    int64_t left_dim = 1, site_dim_b = 1, site_dim_bp1 = 1, right_dim = 1;
+    std::shared_ptr<Buffer> tensor_b;     // [left_dim, site_dim_b, new_bond_dim]
+    std::shared_ptr<Buffer> tensor_bp1;   // [new_bond_dim, site_dim_bp1, right_dim]
+};
+
+// Pi: (left_dim*site_dim_b) x (site_dim_bp1*right_dim) device matrix, rows i*d + s (local index
+// fastest), columns s*#J + j (reference kronecker_i / kronecker_j, tensorci2.rs:1224-1246).
+TciUpdate tci2_update_pivots(dla::Ctx*, DType dt, const void* pi_dev, int64_t left_dim,
+                             int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
+                             std::optional<int64_t> max_bond_dim, double tolerance,
+                             bool left_orthogonal);
+
+}  // namespace t4b

@@ -6,11 +6,15 @@
 // One kernel launch per round of the round-robin ordering.  Every column-block pair (2 x 16
 // columns) is owned by ONE thread-block cluster: the pair panel is split by rows across the
 // cluster's CTAs and stays resident in shared memory for the whole round:
+//   0. the row chunk of the panel is staged by TMA bulk copies (cp.async.bulk + mbarrier), one
+//      per column, and written back the same way;
 //   1. partial Gram G = P^H P on the FP64 tensor pipe (DMMA), reduced across the cluster through
 //      distributed shared memory in a fixed order (bitwise identical on every CTA);
-//   2. Hermitian Jacobi eigen-solve of the 32 x 32 Gram block in shared memory (parallel
-//      round-robin rotations, accumulated into W) - redundantly on each CTA, no broadcast;
-//   3. P <- P W (and the V rows, when right vectors are accumulated) on DMMA, written back.
+//   2. Hermitian Jacobi on the 32 x 32 Gram block in shared memory: 16 disjoint rotations per
+//      step, every thread owns one 2 x 2 block of G' = Ja^H G Jb, rotations are computed once
+//      per lane and exchanged with warp shuffles, G is ping-ponged (one barrier per step);
+//      redundantly on each CTA of the cluster, no broadcast;
+//   3. P <- P W (and the V rows, when right vectors are accumulated) on DMMA.
 // Convergence is the classical |x_i^H x_j| <= tol ||x_i|| ||x_j|| test, tracked on the device.
 //
 // Replaces tenferro `.svd()` (reference crates/tensor4all-core/src/defaults/svd.rs:265-267,
@@ -35,28 +39,61 @@ constexpr int JT = 256;    // threads per CTA
 constexpr int JW = JT / 32;
 constexpr int WP = 36;     // pitch of the W matrix in shared memory
 constexpr int GP = 33;     // pitch of the G matrix in shared memory
+constexpr int MAXCS = 16;
 
 struct JacobiArgs {
-    double* X; int64_t ldx; int64_t nx;   // X: nx rows
+    double* X; int64_t ldx; int64_t nx;   // X: nx rows (ldx = cs * rpcx, zero padded)
     double* V; int64_t ldv; int64_t nv;   // V: nv rows (0: not accumulated)
     int p;                                // column blocks (even)
     int round;
     int64_t rpcx, rpcv;                   // rows per CTA, multiples of 8
     int64_t ldp;                          // smem panel pitch
-    int inner_max;
     int full_inner;                       // 1: full 32-index round-robin (covers intra-block pairs)
     double tol_rot;
     unsigned long long* flag;             // max off-diagonal cosine seen this sweep (double bits)
 };
 
-struct Rot {
-    int pp, qq, active;
-};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA 1-D bulk copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+template <bool CPLX>
+__device__ __forceinline__ typename Sc<CPLX>::T shfl_t(typename Sc<CPLX>::T v, int src) {
+    if constexpr (CPLX) {
+        return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+    } else {
+        return __shfl_sync(0xffffffffu, v, src);
+    }
+}
 
 template <bool CPLX>
 __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
+    constexpr unsigned ES = CPLX ? 16 : 8;
     cg::cluster_group cluster = cg::this_cluster();
     const int R = (int)cluster.block_rank();
     const int CS = (int)cluster.num_blocks();
@@ -72,38 +109,39 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     if (bi > bj) { int t = bi; bi = bj; bj = t; }
 
     // ---- shared memory carve-up --------------------------------------------------------------
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int64_t ldp = a.ldp;
     const int64_t rt = a.rpcx + a.rpcv;
     T* Ps = reinterpret_cast<T*>(smem_raw);                 // [PW][ldp]
     T* Gp = Ps + (size_t)PW * ldp;                          // [32*32] own partial Gram (col-major)
     T* Gs = Gp + 32 * 32;                                   // [32][GP]
-    T* Ws = Gs + 32 * GP;                                   // [32 cols][WP]
-    T* J11 = Ws + 32 * WP;                                  // 16 each
-    T* J12 = J11 + 16;
-    T* J21 = J12 + 16;
-    T* J22 = J21 + 16;
-    Rot* rot = reinterpret_cast<Rot*>(J22 + 16);            // 16
-    double* redbuf = reinterpret_cast<double*>(rot + 16);   // JW
-    unsigned long long* sweep_max = reinterpret_cast<unsigned long long*>(redbuf + JW);
+    T* Gs2 = Gs + 32 * GP;                                  // ping-pong copy of G
+    T* Ws = Gs2 + 32 * GP;                                  // [32 cols][WP]
+    T* rot_ph = Ws + 32 * WP;                               // 16 rotation phases
+    double* rot_c = reinterpret_cast<double*>(rot_ph + 16);     // 16 cosines
+    double* rot_s = rot_c + 16;                                 // 16 sines
+    double* redbuf = rot_s + 16;                                // JW
+    uint64_t* bar = reinterpret_cast<uint64_t*>(redbuf + JW);
 
-    // ---- load the row chunk of the pair panel ----------------------------------------------
+    // ---- 0. TMA bulk load of the row chunk of the pair panel -------------------------------
     const int64_t x_lo = (int64_t)R * a.rpcx;
     const int64_t v_lo = (int64_t)R * a.rpcv;
-    const T* Xg = reinterpret_cast<const T*>(a.X);
-    const T* Vg = reinterpret_cast<const T*>(a.V);
-    for (int c = warp; c < PW; c += JW) {
-        const int64_t col = c < JB ? (int64_t)bi * JB + c : (int64_t)bj * JB + (c - JB);
-        for (int64_t i = lane; i < a.rpcx; i += 32) {
-            int64_t gi = x_lo + i;
-            Ps[c * ldp + i] = gi < a.nx ? Xg[gi + col * a.ldx] : S::zero();
-        }
-        for (int64_t i = lane; i < a.rpcv; i += 32) {
-            int64_t gi = v_lo + i;
-            Ps[c * ldp + a.rpcx + i] = gi < a.nv ? Vg[gi + col * a.ldv] : S::zero();
-        }
+    T* Xg = reinterpret_cast<T*>(a.X);
+    T* Vg = reinterpret_cast<T*>(a.V);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(bar, (unsigned)(PW * rt * ES));
+        __syncwarp();
+        const int c = lane;
+        const int64_t col = c < JB ? (int64_t)bi * JB + c : (int64_t)bj * JB + (c - JB);
+        bulk_g2s(Ps + c * ldp, Xg + x_lo + col * a.ldx, (unsigned)(a.rpcx * ES), bar);
+        if (a.rpcv) bulk_g2s(Ps + c * ldp + a.rpcx, Vg + v_lo + col * a.ldv, (unsigned)(a.rpcv * ES), bar);
+    }
+    mbar_wait(bar, 0);
 
     // ---- 1. partial Gram on DMMA --------------------------------------------------------------
     {
@@ -128,18 +166,26 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
             }
     }
     cluster.sync();
-    // fixed-order reduction over the cluster: identical bits on every CTA
-    for (int e = tid; e < 32 * 32; e += JT) {
-        T g = S::zero();
-        for (int r = 0; r < CS; ++r) {
-            const T* remote = cluster.map_shared_rank(Gp, r);
-            g = S::add(g, remote[e]);
+    // fixed-order reduction over the cluster (identical bits on every CTA); remote loads are
+    // issued back-to-back before the adds so their DSMEM latency overlaps
+    {
+        const T* rem[MAXCS];
+#pragma unroll
+        for (int r = 0; r < MAXCS; ++r) rem[r] = cluster.map_shared_rank(Gp, r < CS ? r : 0);
+#pragma unroll
+        for (int u = 0; u < 32 * 32 / JT; ++u) {
+            const int e = tid + u * JT;
+            T v[MAXCS];
+#pragma unroll
+            for (int r = 0; r < MAXCS; ++r) v[r] = r < CS ? rem[r][e] : S::zero();
+            T g = v[0];
+#pragma unroll
+            for (int r = 1; r < MAXCS; ++r) if (r < CS) g = S::add(g, v[r]);
+            int row = e & 31, col = e >> 5;
+            Gs[row * GP + col] = g;
+            Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
         }
-        int row = e & 31, col = e >> 5;
-        Gs[row * GP + col] = g;
-        Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
     }
-    if (tid == 0) *sweep_max = 0ull;
     __syncthreads();
 
     // ---- convergence measure: max_{i<j} |G_ij| / sqrt(G_ii G_jj) ------------------------------
@@ -173,86 +219,84 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
         __syncthreads();
     }
     const double panel_off = redbuf[0];
-    __syncthreads();
 
     // ---- 2. Hermitian Jacobi on the 32 x 32 Gram block (skipped when already orthogonal) ---
     const bool need_rot = panel_off > a.tol_rot;
     if (need_rot) {
-        for (int sweep = 0; sweep < a.inner_max; ++sweep) {
-            const int nrr = a.full_inner ? 31 : 16;
-            for (int rr = 0; rr < nrr; ++rr) {
-                if (tid < 16) {
-                    int pp, qq;
-                    if (a.full_inner) {
-                        if (tid == 0) { pp = rr; qq = 31; }
-                        else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
-                        if (pp > qq) { int t = pp; pp = qq; qq = t; }
-                    } else {
-                        // bipartite ordering: only cross pairs (block I x block J); the columns
-                        // inside a block were orthogonalised against each other earlier in the sweep
-                        pp = tid; qq = 16 + ((tid + rr) & 15);
-                    }
-                    double aa = S::real(Gs[pp * GP + pp]), bb = S::real(Gs[qq * GP + qq]);
-                    T g = Gs[pp * GP + qq];
-                    double g2 = S::abs2(g);
-                    int active = 0;
-                    T j11 = S::one(), j12 = S::zero(), j21 = S::zero(), j22 = S::one();
-                    if (g2 > 0.0 && aa > 0.0 && bb > 0.0 &&
-                        g2 > (a.tol_rot * a.tol_rot) * aa * bb) {
-                        double absg = sqrt(g2);
-                        double zeta = (bb - aa) / (2.0 * absg);
-                        double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        double c = 1.0 / sqrt(1.0 + t * t);
-                        double s = c * t;
-                        T ph = S::scale(S::conj(g), 1.0 / absg);   // e^{-i phi}
-                        j11 = S::from_real(c);
-                        j12 = S::from_real(s);
-                        j21 = S::scale(ph, -s);
-                        j22 = S::scale(ph, c);
-                        active = 1;
-                        double ratio = sqrt(g2 / (aa * bb));
-                        atomicMax(sweep_max, (unsigned long long)__double_as_longlong(ratio));
-                    }
-                    rot[tid].pp = pp; rot[tid].qq = qq; rot[tid].active = active;
-                    J11[tid] = j11; J12[tid] = j12; J21[tid] = j21; J22[tid] = j22;
-                }
-                __syncthreads();
-                // column rotations: G <- G J, W <- W J
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int item = tid + u * JT;          // 0..1023
-                    int which = item >> 9;            // 0: G, 1: W
-                    int t = (item >> 5) & 15, i = item & 31;
-                    if (rot[t].active) {
-                        int pp = rot[t].pp, qq = rot[t].qq;
-                        T* xp = which == 0 ? &Gs[i * GP + pp] : &Ws[pp * WP + i];
-                        T* xq = which == 0 ? &Gs[i * GP + qq] : &Ws[qq * WP + i];
-                        T vp = *xp, vq = *xq;
-                        *xp = S::add(S::mul(vp, J11[t]), S::mul(vq, J21[t]));
-                        *xq = S::add(S::mul(vp, J12[t]), S::mul(vq, J22[t]));
-                    }
-                }
-                __syncthreads();
-                // row rotations: G <- J^H G
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    int item = tid + u * JT;          // 0..511
-                    int t = item >> 5, j = item & 31;
-                    if (rot[t].active) {
-                        int pp = rot[t].pp, qq = rot[t].qq;
-                        T vp = Gs[pp * GP + j], vq = Gs[qq * GP + j];
-                        Gs[pp * GP + j] = S::add(S::mul(S::conj(J11[t]), vp), S::mul(S::conj(J21[t]), vq));
-                        Gs[qq * GP + j] = S::add(S::mul(S::conj(J12[t]), vp), S::mul(S::conj(J22[t]), vq));
-                    }
-                }
-                __syncthreads();
+        T* Gcur = Gs;
+        T* Gnxt = Gs2;
+        const int nrr = a.full_inner ? 31 : 16;
+        const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
+        const double tol2 = a.tol_rot * a.tol_rot;
+        for (int rr = 0; rr < nrr; ++rr) {
+            int pa, qa, pb, qb;
+            if (a.full_inner) {
+                if (ta == 0) { pa = rr; qa = 31; } else { pa = (rr + ta) % 31; qa = (rr - ta + 62) % 31; }
+                if (pa > qa) { int t = pa; pa = qa; qa = t; }
+                if (tb == 0) { pb = rr; qb = 31; } else { pb = (rr + tb) % 31; qb = (rr - tb + 62) % 31; }
+                if (pb > qb) { int t = pb; pb = qb; qb = t; }
+            } else {
+                // bipartite ordering: only cross pairs (block I x block J); columns inside a block
+                // were orthogonalised against each other earlier in the sweep
+                pa = ta; qa = 16 + ((ta + rr) & 15);
+                pb = tb; qb = 16 + ((tb + rr) & 15);
             }
-            // stop the inner iteration once this sweep only saw negligible rotations
-            double smax = __longlong_as_double((long long)*sweep_max);
+            // 16 threads compute the 16 rotations of this step (pair t = tid):
+            // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]], J^H [[aa,g],[g*,bb]] J diagonal
+            if (tid < 16) {
+                int pp, qq;
+                if (a.full_inner) {
+                    if (tid == 0) { pp = rr; qq = 31; } else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
+                    if (pp > qq) { int t = pp; pp = qq; qq = t; }
+                } else {
+                    pp = tid; qq = 16 + ((tid + rr) & 15);
+                }
+                double c = 1.0, sn = 0.0;
+                T ph = S::one();
+                const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
+                const T g = Gcur[pp * GP + qq];
+                const double g2 = S::abs2(g);
+                if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
+                    const double inv_absg = rsqrt(g2);
+                    const double absg = g2 * inv_absg;
+                    const double d = 0.5 * (bb - aa);
+                    const double x = d * d + g2;
+                    const double h = x * rsqrt(x);
+                    const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
+                    c = rsqrt(1.0 + t * t);
+                    sn = c * t;
+                    ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
+                }
+                rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
+            }
             __syncthreads();
-            if (tid == 0) *sweep_max = 0ull;
+            const double ca = rot_c[ta], sa = rot_s[ta], cb = rot_c[tb], sb = rot_s[tb];
+            const T pha = rot_ph[ta], phb = rot_ph[tb];
+            // G' = Ja^H G Jb on the 2 x 2 block owned by this thread
+            const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
+            const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
+            const T cpa = S::conj(pha);
+            const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
+            const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
+            const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
+            const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
+            const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
+            const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
+            Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
+            Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
+            Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
+            Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
+            // W <- W Jb for the two rows owned by this thread (exclusive ownership: in place)
+#pragma unroll
+            for (int rrow = 0; rrow < 2; ++rrow) {
+                const int i = ta * 2 + rrow;
+                const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
+                const T fq = S::mul(wq, phb);
+                Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
+                Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
+            }
             __syncthreads();
-            if (smax <= 1e-13) break;
+            T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
         }
 
         // ---- 3. P <- P W on DMMA (all rows: X part and V part) --------------------------------
@@ -277,21 +321,18 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
                 for (int c2 = 0; c2 < 2; ++c2)
                     Ps[(size_t)(nf * 8 + 2 * tig + c2) * ldp + rf * 8 + grp] = acc[nf][c2];
         }
+        // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
 
-        // ---- write back --------------------------------------------------------------------------
-        T* Xw = reinterpret_cast<T*>(a.X);
-        T* Vw = reinterpret_cast<T*>(a.V);
-        for (int c = warp; c < PW; c += JW) {
+        // ---- TMA bulk write-back -------------------------------------------------------------------
+        if (warp == 0) {
+            const int c = lane;
             const int64_t col = c < JB ? (int64_t)bi * JB + c : (int64_t)bj * JB + (c - JB);
-            for (int64_t i = lane; i < a.rpcx; i += 32) {
-                int64_t gi = x_lo + i;
-                if (gi < a.nx) Xw[gi + col * a.ldx] = Ps[c * ldp + i];
-            }
-            for (int64_t i = lane; i < a.rpcv; i += 32) {
-                int64_t gi = v_lo + i;
-                if (gi < a.nv) Vw[gi + col * a.ldv] = Ps[c * ldp + a.rpcx + i];
-            }
+            bulk_s2g(Xg + x_lo + col * a.ldx, Ps + c * ldp, (unsigned)(a.rpcx * ES));
+            if (a.rpcv) bulk_s2g(Vg + v_lo + col * a.ldv, Ps + c * ldp + a.rpcx, (unsigned)(a.rpcv * ES));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
     // no CTA may exit while a peer can still read its Gp through DSMEM
@@ -359,32 +400,33 @@ __global__ void gather_cols_kernel(const double* __restrict__ src, int64_t ld_sr
     }
 }
 
-// X (n x npad, ld = n): first n columns from R (n x n, ld = ldr) or R^H; extra columns zero
+// X (ldx x npad): rows < n of the first n columns from R (n x n, ld = ldr) or R^H; rest zero
 template <bool CPLX>
-__global__ void init_x_kernel(const double* __restrict__ Rm, int64_t ldr, int64_t n, int64_t npad,
-                              int adjoint, double* __restrict__ X) {
+__global__ void init_x_kernel(const double* __restrict__ Rm, int64_t ldr, int64_t n, int64_t ldx,
+                              int64_t npad, int adjoint, double* __restrict__ X) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
-    int64_t total = n * npad;
+    int64_t total = ldx * npad;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const T* r = reinterpret_cast<const T*>(Rm);
     T* x = reinterpret_cast<T*>(X);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        int64_t j = e / n, i = e - j * n;
+        int64_t j = e / ldx, i = e - j * ldx;
         T v = S::zero();
-        if (j < n) v = adjoint ? S::conj(r[j + i * ldr]) : r[i + j * ldr];
+        if (j < n && i < n) v = adjoint ? S::conj(r[j + i * ldr]) : r[i + j * ldr];
         x[e] = v;
     }
 }
 
+// V (ldv x n): identity in the leading n x n block, zero padding rows
 template <bool CPLX>
-__global__ void set_eye_kernel(double* __restrict__ V, int64_t n) {
+__global__ void set_eye_kernel(double* __restrict__ V, int64_t ldv, int64_t n) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
-    int64_t total = n * n;
+    int64_t total = ldv * n;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        int64_t j = e / n, i = e - j * n;
+        int64_t j = e / ldv, i = e - j * ldv;
         reinterpret_cast<T*>(V)[e] = i == j ? S::one() : S::zero();
     }
 }
@@ -403,40 +445,57 @@ Group gg(int64_t dim, int64_t str) {
     return g;
 }
 
-// One-sided block Jacobi on X (nx x npad, ld = nx); V (npad x npad) optional.  Returns sweeps used.
+// Launch geometry of the Jacobi rounds for an nx x npad problem (optionally with V rows).
+struct JacobiPlan {
+    int cs = 1;
+    int64_t rpcx = 0, rpcv = 0, ldp = 0, ldx = 0, ldv = 0;
+    size_t smem = 0;
+};
+
 template <bool CPLX>
-int jacobi_sweeps(Ctx* c, double* X, int64_t nx, int64_t npad, double* V) {
+JacobiPlan plan_jacobi(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
+    const size_t es = CPLX ? 16 : 8;
+    const int pairs = (int)(npad / JB) / 2;
+    const int64_t nv = with_v ? npad : 0;
+    const size_t fixed = (size_t)(32 * 32 + 2 * 32 * GP + 32 * WP + 16) * es + (32 + JW) * 8 + 64 + 128;
+    const size_t budget = 200 * 1024;
+    auto round8 = [](int64_t v) { return (v + 7) / 8 * 8; };
+    JacobiPlan pl;
+    for (int cs = 1;; cs *= 2) {
+        int64_t rpcx = round8((nx + cs - 1) / cs);
+        int64_t rpcv = nv ? round8((nv + cs - 1) / cs) : 0;
+        int64_t rt = rpcx + rpcv;
+        // pitch: == 4 (mod 16) real, == 2 (mod 8) complex => conflict-free fragment loads, and
+        // every column start stays 16-byte aligned for the TMA bulk copies
+        int64_t ldp = rt;
+        if (CPLX) { while (ldp % 8 != 2) ++ldp; }
+        else { while (ldp % 16 != 4) ++ldp; }
+        size_t smem = (size_t)PW * ldp * es + fixed;
+        bool fits = smem <= budget;
+        bool two_per_sm = smem <= 100 * 1024;   // the eig phase is latency-bound: co-residency hides it
+        bool spread = (int64_t)pairs * cs * 2 > c->num_sms || rt <= 64;
+        if ((fits && two_per_sm && spread) || cs == MAXCS) {
+            if (!fits)
+                throw Error(ST_UNSUPPORTED, "svd: matrix too large for the shared-memory Jacobi panel (n > ~10k)");
+            pl.cs = cs; pl.rpcx = rpcx; pl.rpcv = rpcv; pl.ldp = ldp; pl.smem = smem;
+            pl.ldx = (int64_t)cs * rpcx;
+            pl.ldv = (int64_t)cs * rpcv;
+            return pl;
+        }
+    }
+}
+
+// One-sided block Jacobi on X (ldx x npad, nx live rows); V (ldv x npad) optional.  Returns sweeps.
+template <bool CPLX>
+int jacobi_sweeps(Ctx* c, const JacobiPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
     const size_t es = CPLX ? 16 : 8;
     const int p = (int)(npad / JB);
     const int pairs = p / 2;
     const int64_t nv = V ? npad : 0;
-    const size_t fixed = (size_t)(32 * 32 + 32 * GP + 32 * WP + 64) * es + 16 * sizeof(Rot) + JW * 8 + 64;
-    const size_t budget = 200 * 1024;
-    auto round8 = [](int64_t v) { return (v + 7) / 8 * 8; };
-    int cs = 1;
-    int64_t rpcx = 0, rpcv = 0, ldp = 0;
-    size_t smem = 0;
-    for (;; cs *= 2) {
-        rpcx = round8((nx + cs - 1) / cs);
-        rpcv = nv ? round8((nv + cs - 1) / cs) : 0;
-        int64_t rt = rpcx + rpcv;
-        // pitch: == 4 (mod 16) real, == 2 (mod 8) complex => conflict-free fragment loads
-        if (CPLX) { ldp = rt; while (ldp % 8 != 2) ++ldp; }
-        else { ldp = rt; while (ldp % 16 != 4) ++ldp; }
-        smem = (size_t)PW * ldp * es + fixed;
-        bool fits = smem <= budget;
-        bool two_per_sm = smem <= 100 * 1024;   // eig phase is latency-bound: co-residency hides it
-        bool spread = (int64_t)pairs * cs * 2 > c->num_sms || rt <= 64;
-        if (fits && two_per_sm && spread) break;
-        if (cs == 16) {
-            if (fits) break;
-            throw Error(ST_UNSUPPORTED, "svd: matrix too large for the shared-memory Jacobi panel (n > ~10k)");
-        }
-    }
     auto kern = jacobi_round_kernel<CPLX>;
     static bool attr_set = false;
     if (!attr_set) {
-        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_set = true;
     }
@@ -447,10 +506,9 @@ int jacobi_sweeps(Ctx* c, double* X, int64_t nx, int64_t npad, double* V) {
     const int max_sweeps = 40;
     int sweeps = 0;
     JacobiArgs a{};
-    a.X = X; a.ldx = nx; a.nx = nx;
-    a.V = V; a.ldv = npad; a.nv = nv;
-    a.p = p; a.rpcx = rpcx; a.rpcv = rpcv; a.ldp = ldp;
-    a.inner_max = 1;
+    a.X = X; a.ldx = pl.ldx; a.nx = nx;
+    a.V = V; a.ldv = pl.ldv; a.nv = nv;
+    a.p = p; a.rpcx = pl.rpcx; a.rpcv = V ? pl.rpcv : 0; a.ldp = pl.ldp;
     a.tol_rot = tol * 0.25;
     a.flag = flag;
     const int rounds = p - 1;
@@ -460,13 +518,13 @@ int jacobi_sweeps(Ctx* c, double* X, int64_t nx, int64_t npad, double* V) {
             a.round = r;
             a.full_inner = (r == 0) ? 1 : 0;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(pairs * cs), 1, 1);
+            cfg.gridDim = dim3((unsigned)(pairs * pl.cs), 1, 1);
             cfg.blockDim = dim3(JT, 1, 1);
-            cfg.dynamicSmemBytes = smem;
+            cfg.dynamicSmemBytes = pl.smem;
             cfg.stream = c->stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = cs;
+            attr[0].val.clusterDim.x = pl.cs;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
@@ -482,7 +540,7 @@ int jacobi_sweeps(Ctx* c, double* X, int64_t nx, int64_t npad, double* V) {
     release(c, flag);
     if (getenv("T4B_VERBOSE"))
         fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d cs=%d sweeps=%d last_off=%.3e tol=%.3e\n",
-                (long long)nx, (long long)npad, V ? 1 : 0, cs, sweeps, *hflag, tol);
+                (long long)nx, (long long)npad, V ? 1 : 0, pl.cs, sweeps, *hflag, tol);
     return sweeps;
 }
 
@@ -493,26 +551,28 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     const size_t es = CPLX ? 16 : 8;
     const int64_t npad = (n + PW - 1) / PW * PW;
     const bool want_u = U != nullptr, want_v = Vh != nullptr;
+    const bool acc_v = want_u && want_v;
     // QR preconditioner
     void* Q = want_u ? alloc(c, (size_t)m * n * es) : nullptr;
     void* Rm = alloc(c, (size_t)n * n * es);
     qr_thin(c, dt, m, n, A, Q, Rm);
     // X = R (left vectors wanted) or R^H (only right vectors wanted)
     const bool adjoint = !want_u;
-    double* X = (double*)alloc(c, (size_t)n * npad * es);
-    init_x_kernel<CPLX><<<grid1d(c, n * npad), 256, 0, c->stream>>>((const double*)Rm, n, n, npad, adjoint ? 1 : 0, X);
+    const JacobiPlan pl = plan_jacobi<CPLX>(c, n, npad, acc_v);
+    double* X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
+    init_x_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>((const double*)Rm, n, n, pl.ldx, npad, adjoint ? 1 : 0, X);
     c->launched("svd_init_x");
     double* V = nullptr;
-    if (want_u && want_v) {
-        V = (double*)alloc(c, (size_t)npad * npad * es);
-        set_eye_kernel<CPLX><<<grid1d(c, npad * npad), 256, 0, c->stream>>>(V, npad);
+    if (acc_v) {
+        V = (double*)alloc(c, (size_t)pl.ldv * npad * es);
+        set_eye_kernel<CPLX><<<grid1d(c, pl.ldv * npad), 256, 0, c->stream>>>(V, pl.ldv, npad);
         c->launched("svd_set_eye");
     }
-    jacobi_sweeps<CPLX>(c, X, n, npad, V);
+    jacobi_sweeps<CPLX>(c, pl, X, n, npad, V);
 
     double* sig2 = (double*)alloc(c, (size_t)npad * 8);
     int64_t* rank = (int64_t*)alloc(c, (size_t)npad * 8);
-    colnorm2_kernel<CPLX><<<(unsigned)((npad + 7) / 8), 256, 0, c->stream>>>(X, n, n, npad, sig2);
+    colnorm2_kernel<CPLX><<<(unsigned)((npad + 7) / 8), 256, 0, c->stream>>>(X, pl.ldx, n, npad, sig2);
     c->launched("svd_colnorm");
     sort_rank_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, c->stream>>>(sig2, npad, rank, S, n);
     c->launched("svd_sort_rank");
@@ -522,20 +582,20 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         // U_X = sorted, normalised columns of X (n x n); U = Q U_X
         double* UX = (double*)alloc(c, (size_t)n * n * es);
         zero(c, UX, (size_t)n * n * es);
-        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, n, n, npad, rank, sig2, floor_rel, 1, 0, UX, n, n, S);
+        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, 1, 0, UX, n, n, S);
         c->launched("svd_gather_u");
         gemm(c, dt, m, n, n, 1.0, Q, gg(m, 1), gg(n, m), false, UX, gg(n, 1), gg(n, n), false, 0.0, U,
              gg(m, 1), gg(n, m));
         release(c, UX);
         if (want_v) {
             // Vh = (V[0:n, sorted])^H
-            gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(V, npad, n, npad, rank, sig2, 0.0, 0, 1, (double*)Vh, n, n, S);
+            gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(V, pl.ldv, n, npad, rank, sig2, 0.0, 0, 1, (double*)Vh, n, n, S);
             c->launched("svd_gather_vh");
         }
     } else if (want_v) {
         // X = R^H: right vectors of A are the normalised columns of X; Vh = U_X^H
         zero(c, Vh, (size_t)n * n * es);
-        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, n, n, npad, rank, sig2, floor_rel, 1, 1, (double*)Vh, n, n, S);
+        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, 1, 1, (double*)Vh, n, n, S);
         c->launched("svd_gather_vh");
     }
     release(c, sig2); release(c, rank); release(c, X);

@@ -1,0 +1,37 @@
+"""ctypes wrapper of the TCI2 two-site pivot update (t4b_tci2_update_pivots). Test plumbing."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _check, dtype_of, lib, np_dtype
+
+
+class TciUpdate:
+    def __init__(self, ctx, pi: np.ndarray, left_dim, site_dim_b, site_dim_bp1, right_dim,
+                 max_bond_dim=0, tolerance=1e-8, left_orthogonal=True):
+        pi = np.asfortranarray(pi)
+        assert pi.shape == (left_dim * site_dim_b, site_dim_bp1 * right_dim)
+        self.dt = dtype_of(pi)
+        h = C.c_void_p()
+        _check(lib().t4b_tci2_update_pivots(ctx.h, self.dt, pi.ctypes.data_as(C.c_void_p), 0,
+                                            C.c_int64(left_dim), C.c_int64(site_dim_b), C.c_int64(site_dim_bp1),
+                                            C.c_int64(right_dim), C.c_int64(max_bond_dim), C.c_double(tolerance),
+                                            int(left_orthogonal), C.byref(h)))
+        self.h = h
+        r, nb, be = C.c_int64(), C.c_int64(), C.c_double()
+        _check(lib().t4b_tci_update_rank(h, C.byref(r), C.byref(nb), C.byref(be)))
+        self.rank, self.new_bond_dim, self.bond_error = r.value, nb.value, be.value
+        n = C.c_int64()
+        _check(lib().t4b_tci_update_indices(h, None, None, C.byref(n)))
+        self.row_indices = np.zeros(n.value, np.int64)
+        self.col_indices = np.zeros(n.value, np.int64)
+        _check(lib().t4b_tci_update_indices(h, self.row_indices.ctypes.data_as(C.c_void_p),
+                                            self.col_indices.ctypes.data_as(C.c_void_p), None))
+        self.tensor_b = np.empty((left_dim, site_dim_b, nb.value), dtype=np_dtype(self.dt), order="F")
+        self.tensor_bp1 = np.empty((nb.value, site_dim_bp1, right_dim), dtype=np_dtype(self.dt), order="F")
+        _check(lib().t4b_tci_update_tensors(ctx.h, h, self.tensor_b.ctypes.data_as(C.c_void_p),
+                                            self.tensor_bp1.ctypes.data_as(C.c_void_p)))
+        lib().t4b_tci_update_release(h)
+        self.h = None

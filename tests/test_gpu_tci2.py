@@ -1,0 +1,73 @@
+"""TCI2 two-site pivot update parity (C ABI t4b_tci2_update_pivots): whole 2-site sweeps on the
+oscillatory 3-D quantics test function of BASELINE config 4 (reduced R) run twice with identical
+host bookkeeping - once with the oracle's update, once with the device update.  Index / pivot
+sets must be bit-exact after every bond update (north_star); site tensors agree to 1e-10."""
+import numpy as np
+import pytest
+
+from oracle import tci2 as otci
+from t4b.tci import TciUpdate
+
+pytestmark = pytest.mark.gpu
+
+
+def quantics_f(R, cplx=False):
+    """f(x,y,z) = cos(k r) exp(-r^2) on [0,1)^3, interleaved binary quantics (3R sites, d=2)."""
+    def f(idx):
+        x = y = z = 0.0
+        for b in range(R):
+            x += idx[3 * b] * 2.0 ** -(b + 1)
+            y += idx[3 * b + 1] * 2.0 ** -(b + 1)
+            z += idx[3 * b + 2] * 2.0 ** -(b + 1)
+        r = np.sqrt(x * x + y * y + z * z)
+        v = np.cos(25.0 * r) * np.exp(-r * r)
+        return complex(v, np.sin(11.0 * x * y + z)) if cplx else v
+    return f
+
+
+def gpu_backend(ctx):
+    def backend(pi, left_dim, d_b, d_bp1, right_dim, max_bond_dim, tolerance, left_orthogonal):
+        u = TciUpdate(ctx, pi, left_dim, d_b, d_bp1, right_dim, max_bond_dim or 0, tolerance, left_orthogonal)
+        return u.rank, [int(x) for x in u.row_indices], [int(x) for x in u.col_indices], u.tensor_b, u.tensor_bp1, u.bond_error
+    return backend
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_two_site_sweeps_bit_exact_pivots(ctx, cplx):
+    R = 4
+    f = quantics_f(R, cplx)
+    dims = [2] * (3 * R)
+    first = tuple([1, 0, 1] * R)
+    ref = otci.TCI2(f, dims, first)
+    gpu = otci.TCI2(f, dims, first)
+    ref.sweep2site(otci.update_from_pi, 5, max_bond_dim=64, tolerance=1e-9)
+    gpu.sweep2site(gpu_backend(ctx), 5, max_bond_dim=64, tolerance=1e-9)
+    assert len(ref.pivot_log) == len(gpu.pivot_log)
+    for a, b in zip(ref.pivot_log, gpu.pivot_log):
+        assert a == b                       # bond, row candidates, column candidates: bit-exact
+    assert ref.i_set == gpu.i_set and ref.j_set == gpu.j_set
+    assert ref.bond_errors == gpu.bond_errors
+    for ta, tb in zip(ref.site_tensors, gpu.site_tensors):
+        assert ta.shape == tb.shape
+        assert np.abs(ta - tb).max() <= 1e-10 * max(1.0, np.abs(ta).max())
+
+
+def test_zero_pi_keeps_first_candidate(ctx):
+    """non_empty_or_first (tensorci2.rs:1927-1938): a numerically zero Pi must not empty the sets."""
+    u = TciUpdate(ctx, np.zeros((4, 6)), 2, 2, 2, 3, 0, 1e-8, True)
+    assert u.rank == 0 and u.new_bond_dim == 1
+    assert list(u.row_indices) == [0] and list(u.col_indices) == [0]
+    assert not u.tensor_b.any() and not u.tensor_bp1.any()
+
+
+def test_config4_shape_update(ctx):
+    """One update at the BASELINE C4 bond shape (300*2 x 2*300, cap 300) against the oracle."""
+    rng = np.random.default_rng(5)
+    x = np.sort(rng.random(600))
+    y = np.sort(rng.random(600))
+    pi = np.cos(40.0 * np.sqrt(np.add.outer(x * x, y * y))) * np.exp(-np.add.outer(x * x, y * y))
+    got = TciUpdate(ctx, pi, 300, 2, 2, 300, 300, 1e-8, True)
+    rank, rows, cols, tb, tp, err = otci.update_from_pi(np.asfortranarray(pi), 300, 2, 2, 300, 300, 1e-8, True)
+    assert got.rank == rank and list(got.row_indices) == rows and list(got.col_indices) == cols
+    assert got.bond_error == err
+    assert np.abs(got.tensor_b - tb).max() <= 1e-9 and np.abs(got.tensor_bp1 - tp).max() <= 1e-9 * np.abs(tp).max()
