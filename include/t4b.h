@@ -168,6 +168,21 @@ int t4b_tn_contract(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, int center, 
 int t4b_tn_norm_sqr(t4b_ctx* ctx, const t4b_tn* tn, double* out);
 int t4b_tn_inner(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, double* re, double* im);
 
+/* ---- partitioned adaptive truncation (tensor4all-partitionedtreetn; the multi-GPU unit) -----
+ * truncate_adaptive (partitionedtreetn/src/patching.rs:665-718).  A patch is a chain network plus
+ * its volume.  t4b_adaptive_cutoffs is pure host arithmetic in the reference's order of
+ * operations (patch_stats_and_totals :883-897, cutoff formula :697-699): in a sharded run every
+ * rank feeds it the all-gathered (norm^2, volume) list and obtains bit-identical cutoffs.
+ * t4b_tn_truncate_with_cutoff applies the Absolute x SquaredValue x DiscardedTailSum policy
+ * (:970-978) to one patch; t4b_patches_truncate_adaptive is the single-device composition. */
+int t4b_adaptive_cutoffs(int64_t n, const double* norm_sqr, const uint64_t* volume, double cutoff,
+                         double* local_cutoff_sqr_out, int32_t* keep_out, double* total_norm_sqr_out);
+int t4b_tn_truncate_with_cutoff(t4b_ctx* ctx, t4b_tn* tn, int center, double local_cutoff_sqr,
+                                int64_t max_bond_dim);
+int t4b_patches_truncate_adaptive(t4b_ctx* ctx, int64_t n, t4b_tn* const* patches,
+                                  const uint64_t* volume, int center, double cutoff,
+                                  int64_t max_bond_dim, int32_t* keep_out);
+
 /* ---- positional tensor trains / MPOs (tensor4all-simplett) ----------------------------------
  * rank 3: sites [left, site, right]; rank 4: MPO sites [left, s1, s2, right]. */
 typedef struct t4b_train t4b_train;

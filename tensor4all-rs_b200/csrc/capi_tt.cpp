@@ -446,3 +446,42 @@ int t4b_tci_update_release(t4b_tci_update* u) {
     T4B_CATCH
 }
 }
+
+// ---- partitioned adaptive truncation -----------------------------------------------------------------
+#include "host/patching.h"
+extern "C" {
+int t4b_adaptive_cutoffs(int64_t n, const double* norm_sqr, const uint64_t* volume, double cutoff,
+                         double* local_cutoff_sqr_out, int32_t* keep_out, double* total_norm_sqr_out) {
+    T4B_TRY
+    T4B_REQUIRE(n >= 0 && (n == 0 || (norm_sqr && volume)), "adaptive_cutoffs: bad arguments");
+    AdaptivePlan p = adaptive_cutoffs(std::vector<double>(norm_sqr, norm_sqr + n),
+                                      std::vector<uint64_t>(volume, volume + n), cutoff);
+    for (int64_t i = 0; i < n; ++i) {
+        if (local_cutoff_sqr_out) local_cutoff_sqr_out[i] = p.local_cutoff_sqr[i];
+        if (keep_out) keep_out[i] = p.keep[i];
+    }
+    if (total_norm_sqr_out) *total_norm_sqr_out = p.total_norm_sqr;
+    T4B_CATCH
+}
+int t4b_tn_truncate_with_cutoff(t4b_ctx* ctx, t4b_tn* tn, int center, double local_cutoff_sqr, int64_t max_bond_dim) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tn, "null tn");
+    truncate_patch_with_cutoff(ctx->c, tn->tn, center, local_cutoff_sqr, opt_bond(max_bond_dim));
+    T4B_CATCH
+}
+int t4b_patches_truncate_adaptive(t4b_ctx* ctx, int64_t n, t4b_tn* const* patches, const uint64_t* volume,
+                                  int center, double cutoff, int64_t max_bond_dim, int32_t* keep_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && (n == 0 || (patches && volume && keep_out)), "patches_truncate_adaptive: bad arguments");
+    std::vector<ChainTN*> ps;
+    for (int64_t i = 0; i < n; ++i) {
+        T4B_REQUIRE(patches[i], "null patch");
+        ps.push_back(&patches[i]->tn);
+    }
+    auto keep = truncate_adaptive(ctx->c, ps, std::vector<uint64_t>(volume, volume + n), center, cutoff, opt_bond(max_bond_dim));
+    for (int64_t i = 0; i < n; ++i) keep_out[i] = keep[i];
+    T4B_CATCH
+}
+}
