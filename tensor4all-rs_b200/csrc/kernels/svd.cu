@@ -165,140 +165,150 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
                 Gp[col * 32 + row] = acc[jj][c2];
             }
     }
-    cluster.sync();
-    // fixed-order reduction over the cluster (identical bits on every CTA); remote loads are
-    // issued back-to-back before the adds so their DSMEM latency overlaps
-    {
-        const T* rem[MAXCS];
+    cluster.sync();   // #1: every CTA's partial Gram is visible cluster-wide
+    // Rank 0 reduces the partial Grams (fixed order; remote loads issued back-to-back so their
+    // DSMEM latency overlaps), solves the 32 x 32 Hermitian problem ONCE and broadcasts W; the
+    // peers only wait at barrier #2 (their SM time goes to co-resident CTAs of other clusters).
+    if (R == 0) {
+        {
+            const T* rem[MAXCS];
 #pragma unroll
-        for (int r = 0; r < MAXCS; ++r) rem[r] = cluster.map_shared_rank(Gp, r < CS ? r : 0);
+            for (int r = 0; r < MAXCS; ++r) rem[r] = cluster.map_shared_rank(Gp, r < CS ? r : 0);
 #pragma unroll
-        for (int u = 0; u < 32 * 32 / JT; ++u) {
-            const int e = tid + u * JT;
-            T v[MAXCS];
+            for (int u = 0; u < 32 * 32 / JT; ++u) {
+                const int e = tid + u * JT;
+                T v[MAXCS];
 #pragma unroll
-            for (int r = 0; r < MAXCS; ++r) v[r] = r < CS ? rem[r][e] : S::zero();
-            T g = v[0];
+                for (int r = 0; r < MAXCS; ++r) v[r] = r < CS ? rem[r][e] : S::zero();
+                T g = v[0];
 #pragma unroll
-            for (int r = 1; r < MAXCS; ++r) if (r < CS) g = S::add(g, v[r]);
-            int row = e & 31, col = e >> 5;
-            Gs[row * GP + col] = g;
-            Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
-        }
-    }
-    __syncthreads();
-
-    // ---- convergence measure: max_{i<j} |G_ij| / sqrt(G_ii G_jj) ------------------------------
-    {
-        double mx = 0.0;
-        for (int e = tid; e < 32 * 32; e += JT) {
-            int row = e & 31, col = e >> 5;
-            if (row < col) {
-                double gii = S::real(Gs[row * GP + row]), gjj = S::real(Gs[col * GP + col]);
-                double g2 = S::abs2(Gs[row * GP + col]);
-                if (gii > 0.0 && gjj > 0.0) {
-                    double r2 = g2 / (gii * gjj);
-                    if (r2 > mx) mx = r2;
-                }
+                for (int r = 1; r < MAXCS; ++r) if (r < CS) g = S::add(g, v[r]);
+                int row = e & 31, col = e >> 5;
+                Gs[row * GP + col] = g;
+                Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
             }
         }
+        __syncthreads();
+        // convergence measure: max_{i<j} |G_ij| / sqrt(G_ii G_jj)
+        {
+            double mx = 0.0;
+            for (int e = tid; e < 32 * 32; e += JT) {
+                int row = e & 31, col = e >> 5;
+                if (row < col) {
+                    double gii = S::real(Gs[row * GP + row]), gjj = S::real(Gs[col * GP + col]);
+                    double g2 = S::abs2(Gs[row * GP + col]);
+                    if (gii > 0.0 && gjj > 0.0) {
+                        double r2 = g2 / (gii * gjj);
+                        if (r2 > mx) mx = r2;
+                    }
+                }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double other = __shfl_xor_sync(0xffffffffu, mx, o);
-            if (other > mx) mx = other;
+            for (int o = 16; o > 0; o >>= 1) {
+                double other = __shfl_xor_sync(0xffffffffu, mx, o);
+                if (other > mx) mx = other;
+            }
+            if (lane == 0) redbuf[warp] = mx;
+            __syncthreads();
+            if (tid == 0) {
+                double m = 0.0;
+                for (int w = 0; w < JW; ++w) if (redbuf[w] > m) m = redbuf[w];
+                m = sqrt(m);
+                atomicMax(a.flag, (unsigned long long)__double_as_longlong(m));
+                redbuf[0] = m;
+            }
+            __syncthreads();
         }
-        if (lane == 0) redbuf[warp] = mx;
-        __syncthreads();
-        if (tid == 0) {
-            double m = 0.0;
-            for (int w = 0; w < JW; ++w) if (redbuf[w] > m) m = redbuf[w];
-            m = sqrt(m);
-            if (R == 0) atomicMax(a.flag, (unsigned long long)__double_as_longlong(m));
-            redbuf[0] = m;
+        if (redbuf[0] > a.tol_rot) {
+            T* Gcur = Gs;
+            T* Gnxt = Gs2;
+            const int nrr = a.full_inner ? 31 : 16;
+            const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
+            const double tol2 = a.tol_rot * a.tol_rot;
+            for (int rr = 0; rr < nrr; ++rr) {
+                int pa, qa, pb, qb;
+                if (a.full_inner) {
+                    if (ta == 0) { pa = rr; qa = 31; } else { pa = (rr + ta) % 31; qa = (rr - ta + 62) % 31; }
+                    if (pa > qa) { int t = pa; pa = qa; qa = t; }
+                    if (tb == 0) { pb = rr; qb = 31; } else { pb = (rr + tb) % 31; qb = (rr - tb + 62) % 31; }
+                    if (pb > qb) { int t = pb; pb = qb; qb = t; }
+                } else {
+                    // bipartite ordering: only cross pairs (block I x block J); columns inside a block
+                    // were orthogonalised against each other earlier in the sweep
+                    pa = ta; qa = 16 + ((ta + rr) & 15);
+                    pb = tb; qb = 16 + ((tb + rr) & 15);
+                }
+                // 16 threads compute the 16 rotations of this step (pair t = tid):
+                // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]], J^H [[aa,g],[g*,bb]] J diagonal
+                if (tid < 16) {
+                    int pp, qq;
+                    if (a.full_inner) {
+                        if (tid == 0) { pp = rr; qq = 31; } else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
+                        if (pp > qq) { int t = pp; pp = qq; qq = t; }
+                    } else {
+                        pp = tid; qq = 16 + ((tid + rr) & 15);
+                    }
+                    double c = 1.0, sn = 0.0;
+                    T ph = S::one();
+                    const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
+                    const T g = Gcur[pp * GP + qq];
+                    const double g2 = S::abs2(g);
+                    if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
+                        const double inv_absg = rsqrt(g2);
+                        const double absg = g2 * inv_absg;
+                        const double d = 0.5 * (bb - aa);
+                        const double x = d * d + g2;
+                        const double h = x * rsqrt(x);
+                        const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
+                        c = rsqrt(1.0 + t * t);
+                        sn = c * t;
+                        ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
+                    }
+                    rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
+                }
+                __syncthreads();
+                const double ca = rot_c[ta], sa = rot_s[ta], cb = rot_c[tb], sb = rot_s[tb];
+                const T pha = rot_ph[ta], phb = rot_ph[tb];
+                // G' = Ja^H G Jb on the 2 x 2 block owned by this thread
+                const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
+                const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
+                const T cpa = S::conj(pha);
+                const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
+                const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
+                const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
+                const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
+                const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
+                const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
+                Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
+                Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
+                Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
+                Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
+                // W <- W Jb for the two rows owned by this thread (exclusive ownership: in place)
+#pragma unroll
+                for (int rrow = 0; rrow < 2; ++rrow) {
+                    const int i = ta * 2 + rrow;
+                    const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
+                    const T fq = S::mul(wq, phb);
+                    Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
+                    Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
+                }
+                __syncthreads();
+                T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
+            }
         }
-        __syncthreads();
+        // broadcast the flag and W to the peers through distributed shared memory
+        for (int r = 1; r < CS; ++r) {
+            if (redbuf[0] > a.tol_rot) {
+                T* wr = cluster.map_shared_rank(Ws, r);
+                for (int e = tid; e < 32 * WP; e += JT) wr[e] = Ws[e];
+            }
+            if (tid == 0) *cluster.map_shared_rank(redbuf, r) = redbuf[0];
+        }
     }
+    cluster.sync();   // #2: W and the flag are visible on every CTA; no DSMEM access after this point
     const double panel_off = redbuf[0];
-
-    // ---- 2. Hermitian Jacobi on the 32 x 32 Gram block (skipped when already orthogonal) ---
     const bool need_rot = panel_off > a.tol_rot;
     if (need_rot) {
-        T* Gcur = Gs;
-        T* Gnxt = Gs2;
-        const int nrr = a.full_inner ? 31 : 16;
-        const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
-        const double tol2 = a.tol_rot * a.tol_rot;
-        for (int rr = 0; rr < nrr; ++rr) {
-            int pa, qa, pb, qb;
-            if (a.full_inner) {
-                if (ta == 0) { pa = rr; qa = 31; } else { pa = (rr + ta) % 31; qa = (rr - ta + 62) % 31; }
-                if (pa > qa) { int t = pa; pa = qa; qa = t; }
-                if (tb == 0) { pb = rr; qb = 31; } else { pb = (rr + tb) % 31; qb = (rr - tb + 62) % 31; }
-                if (pb > qb) { int t = pb; pb = qb; qb = t; }
-            } else {
-                // bipartite ordering: only cross pairs (block I x block J); columns inside a block
-                // were orthogonalised against each other earlier in the sweep
-                pa = ta; qa = 16 + ((ta + rr) & 15);
-                pb = tb; qb = 16 + ((tb + rr) & 15);
-            }
-            // 16 threads compute the 16 rotations of this step (pair t = tid):
-            // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]], J^H [[aa,g],[g*,bb]] J diagonal
-            if (tid < 16) {
-                int pp, qq;
-                if (a.full_inner) {
-                    if (tid == 0) { pp = rr; qq = 31; } else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
-                    if (pp > qq) { int t = pp; pp = qq; qq = t; }
-                } else {
-                    pp = tid; qq = 16 + ((tid + rr) & 15);
-                }
-                double c = 1.0, sn = 0.0;
-                T ph = S::one();
-                const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
-                const T g = Gcur[pp * GP + qq];
-                const double g2 = S::abs2(g);
-                if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
-                    const double inv_absg = rsqrt(g2);
-                    const double absg = g2 * inv_absg;
-                    const double d = 0.5 * (bb - aa);
-                    const double x = d * d + g2;
-                    const double h = x * rsqrt(x);
-                    const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
-                    c = rsqrt(1.0 + t * t);
-                    sn = c * t;
-                    ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
-                }
-                rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
-            }
-            __syncthreads();
-            const double ca = rot_c[ta], sa = rot_s[ta], cb = rot_c[tb], sb = rot_s[tb];
-            const T pha = rot_ph[ta], phb = rot_ph[tb];
-            // G' = Ja^H G Jb on the 2 x 2 block owned by this thread
-            const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
-            const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
-            const T cpa = S::conj(pha);
-            const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
-            const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
-            const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
-            const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
-            const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
-            const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
-            Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
-            Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
-            Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
-            Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
-            // W <- W Jb for the two rows owned by this thread (exclusive ownership: in place)
-#pragma unroll
-            for (int rrow = 0; rrow < 2; ++rrow) {
-                const int i = ta * 2 + rrow;
-                const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
-                const T fq = S::mul(wq, phb);
-                Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
-                Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
-            }
-            __syncthreads();
-            T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
-        }
-
         // ---- 3. P <- P W on DMMA (all rows: X part and V part) --------------------------------
         for (int64_t rf = warp; rf < rt / 8; rf += JW) {
             T av[8];
@@ -335,8 +345,6 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
-    // no CTA may exit while a peer can still read its Gp through DSMEM
-    cluster.sync();
 }
 
 // sig2[j] = sum_i |X[i,j]|^2, one warp per column
@@ -535,6 +543,7 @@ int jacobi_sweeps(Ctx* c, const JacobiPlan& pl, double* X, int64_t nx, int64_t n
         ++sweeps;
         d2h(c, hflag, flag, 8);
         sync(c);
+        if (getenv("T4B_VERBOSE") && atoi(getenv("T4B_VERBOSE")) > 1) fprintf(stderr, "[t4b]   sweep %d off=%.3e\n", sweeps, *hflag);
         if (*hflag <= tol) break;
     }
     release(c, flag);

@@ -124,3 +124,22 @@ def test_invalid_options_fail_loudly(ctx):
         tn.truncate(0, t4tt.SvdPolicy(float("nan")), 0)
     with pytest.raises(t4b.T4BError):
         tn.truncate(7, None, 0)
+
+
+def test_zipup_c3_reduced_chi64(ctx):
+    """BASELINE C3 at reduced size (L=8, d=4, chi=64, w=8, cap-only truncation): exercises the
+    multi-CTA cluster paths of the QR / Jacobi kernels inside the full sweep."""
+    rng = np.random.default_rng(0x5EED0003)
+    L, d, chi, w = 8, 4, 64, 8
+    ma, mi = random_mps(rng, L, d, chi)
+    oa, oi = random_mpo(rng, L, d, w)
+    policy = SvdTruncationPolicy(0.0)
+    spectra = []
+    ref = otn.contract_zipup(to_oracle_chain(ma, mi), to_oracle_chain(oa, oi), 0, policy, chi, spectra=spectra)
+    out = t4tt.chain_from_arrays(ctx, ma, mi).contract(t4tt.chain_from_arrays(ctx, oa, oi), 0, 0, _pol(policy), chi)
+    assert out.bond_dims() == ref.bond_dims()
+    assert max(out.bond_dims()) == chi
+    # overlap-based comparison (the dense tensor has 4^8 = 65536 entries: still cheap)
+    assert relerr(gpu_chain_dense(out), oracle_chain_dense(ref)) <= TOL
+    n_ref = otn.inner(ref, ref).real
+    assert abs(out.norm_sqr() - n_ref) <= 1e-10 * n_ref
