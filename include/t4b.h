@@ -51,6 +51,8 @@ int t4b_ctx_launch_count(t4b_ctx* ctx, int64_t* out);
  * t4b_ctx_profile_end(ctx, NULL, 0, &needed) followed by (ctx, buf, needed, NULL); the text has one
  * line per kernel class: "name launches total_ms algorithmic_work" (flops or bytes). */
 int t4b_ctx_profile_begin(t4b_ctx* ctx);
+/* Host-side overhead counters of this context (allocator / synchronisation time) as text. */
+int t4b_ctx_host_stats(t4b_ctx* ctx, char* buf, size_t cap);
 int t4b_ctx_profile_end(t4b_ctx* ctx, char* buf, size_t cap, size_t* needed);
 int t4b_malloc(t4b_ctx* ctx, size_t bytes, void** dev);
 int t4b_free(t4b_ctx* ctx, void* dev);

@@ -174,6 +174,16 @@ int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, voi
 
 // ---- profiling (bench.py roofline) ---------------------------------------------------------------
 extern "C" {
+int t4b_ctx_host_stats(t4b_ctx* ctx, char* buf, size_t cap) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(buf && cap > 0, "host_stats: null buffer");
+    std::string s = dla::host_stats(ctx->c);
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+    T4B_CATCH
+}
 int t4b_ctx_profile_begin(t4b_ctx* ctx) {
     T4B_TRY
     require_ctx(ctx);

@@ -32,6 +32,8 @@ namespace dla {
 // the roofline: profile_end returns lines "kernel launches total_ms algorithmic_work".
 void profile_begin(Ctx*);
 std::string profile_end(Ctx*);
+// host-side overhead counters: "alloc_n .. alloc_s .. free_s .. sync_n .. sync_s .. launches .."
+std::string host_stats(Ctx*);
 
 // Stream-ordered memory.
 void* alloc(Ctx*, size_t bytes);

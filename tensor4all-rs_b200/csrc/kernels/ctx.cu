@@ -2,6 +2,8 @@
 // (permute / scale / norms).  sm_100a only; no CPU fallback.
 #include "ctx.cuh"
 
+#include <chrono>
+
 namespace t4b {
 namespace dla {
 
@@ -66,6 +68,9 @@ void ctx_destroy(Ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->scratch) cudaFreeAsync(c->scratch, c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto& kv : c->free_lists)
+        for (void* q : kv.second) cudaFree(q);
+    for (auto& kv : c->live) cudaFree(kv.first);
     if (c->owns_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -74,14 +79,68 @@ void* ctx_stream(Ctx* c) { return (void*)c->stream; }
 int ctx_device(Ctx* c) { return c->device; }
 int64_t ctx_launch_count(Ctx* c) { return c->launches; }
 
+namespace {
+struct HostTimer {
+    double& acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(double& a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}  // namespace
+
+// Exact-size caching allocator.  Every user of a context runs on its single stream, so a block
+// released by the host can be handed out again immediately: stream order guarantees that the
+// kernels still reading it finish before the kernels of the new owner start.  Sweeps re-allocate
+// the same handful of shapes at every site, so after the first site the hit rate is ~100% and no
+// driver allocation (which costs milliseconds for the 64 MB work buffers) is on the hot path.
+static size_t round_size(size_t bytes) {
+    if (bytes < 256) return 256;
+    return (bytes + 255) / 256 * 256;
+}
 void* alloc(Ctx* c, size_t bytes) {
+    HostTimer t(c->host_alloc_s);
+    ++c->host_alloc_n;
+    const size_t sz = round_size(bytes);
+    auto it = c->free_lists.find(sz);
+    if (it != c->free_lists.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        c->cached_bytes -= sz;
+        c->live[p] = sz;
+        return p;
+    }
     void* p = nullptr;
-    if (bytes == 0) bytes = 16;
-    T4B_CUDA_CHECK(cudaMallocAsync(&p, bytes, c->stream));
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {
+        // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (auto& kv : c->free_lists)
+            for (void* q : kv.second) cudaFree(q);
+        c->free_lists.clear();
+        c->cached_bytes = 0;
+        T4B_CUDA_CHECK(cudaMalloc(&p, sz));
+    }
+    c->live[p] = sz;
     return p;
 }
 void release(Ctx* c, void* p) {
-    if (p) T4B_CUDA_CHECK(cudaFreeAsync(p, c->stream));
+    HostTimer t(c->host_free_s);
+    if (!p) return;
+    auto it = c->live.find(p);
+    if (it == c->live.end()) throw Error(ST_INTERNAL, "release of a pointer not owned by this context");
+    const size_t sz = it->second;
+    c->live.erase(it);
+    c->free_lists[sz].push_back(p);
+    c->cached_bytes += sz;
+    // bound the cache: beyond 64 GB of idle blocks return everything to the driver
+    if (c->cached_bytes > ((size_t)64 << 30)) {
+        T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (auto& kv : c->free_lists)
+            for (void* q : kv.second) cudaFree(q);
+        c->free_lists.clear();
+        c->cached_bytes = 0;
+    }
 }
 void h2d(Ctx* c, void* dst, const void* src, size_t bytes) {
     if (bytes) T4B_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -96,7 +155,18 @@ void d2d(Ctx* c, void* dst, const void* src, size_t bytes) {
 void zero(Ctx* c, void* dst, size_t bytes) {
     if (bytes) T4B_CUDA_CHECK(cudaMemsetAsync(dst, 0, bytes, c->stream));
 }
-void sync(Ctx* c) { T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+void sync(Ctx* c) {
+    HostTimer t(c->host_sync_s);
+    ++c->host_sync_n;
+    T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+std::string host_stats(Ctx* c) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "alloc_n %lld alloc_s %.4f free_s %.4f sync_n %lld sync_s %.4f launches %lld",
+             (long long)c->host_alloc_n, c->host_alloc_s, c->host_free_s, (long long)c->host_sync_n, c->host_sync_s,
+             (long long)c->launches);
+    return buf;
+}
 
 // ---------------------------------------------------------------------------------------
 // permute: out contiguous, in gathered.  HBM-bound; grid-stride, one element per thread per

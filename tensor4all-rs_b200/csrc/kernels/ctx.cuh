@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../dla.h"
@@ -42,7 +43,17 @@ struct Ctx {
     // optional per-kernel-class profile (bench.py roofline): one CUDA event after every launch
     // on the launching stream; the gap between consecutive events is that launch's duration.
     struct ProfRec { const char* name; double work; cudaEvent_t ev; };
+    // host-side overhead counters (seconds / counts), see host_stats()
+    double host_alloc_s = 0.0, host_free_s = 0.0, host_sync_s = 0.0;
+    int64_t host_alloc_n = 0, host_sync_n = 0;
+    // exact-size caching allocator (see alloc()/release() in ctx.cu)
+    std::unordered_map<size_t, std::vector<void*>> free_lists;
+    std::unordered_map<void*, size_t> live;
+    size_t cached_bytes = 0;
     bool profiling = false;
+    // "gemm" = tensor contraction called by the sweep drivers; "gemm_factor" = GEMMs issued from
+    // inside the QR / SVD factorisation kernels (panel updates, Q formation)
+    const char* gemm_class = "gemm";
     std::vector<ProfRec> prof;
     cudaEvent_t prof_start = nullptr;
 

@@ -360,7 +360,7 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, cons
     else if (alay == 1 && blay == 0) T4B_LAUNCH(1, 0)
     else T4B_LAUNCH(1, 1)
 #undef T4B_LAUNCH
-    c->launched("gemm", (CPLX ? 8.0 : 2.0) * (double)p.M * (double)p.N * (double)p.K);  // flops
+    c->launched(c->gemm_class, (CPLX ? 8.0 : 2.0) * (double)p.M * (double)p.N * (double)p.K);  // flops
     if (ksplit > 1) {
         int64_t total = p.M * p.N;
         int rg = (int)((total + 255) / 256);

@@ -314,6 +314,7 @@ void launch_panel(Ctx* c, PanelArgs& a) {
 }  // namespace
 
 void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
+    struct ClassGuard { Ctx* c; const char* prev; ClassGuard(Ctx* cc) : c(cc), prev(cc->gemm_class) { cc->gemm_class = "gemm_factor"; } ~ClassGuard() { c->gemm_class = prev; } } class_guard(c);
     const int64_t k = m < n ? m : n;
     if (k == 0) return;
     const size_t es = dtype_size(dt);

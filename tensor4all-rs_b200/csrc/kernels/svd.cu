@@ -616,6 +616,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
 }  // namespace
 
 void svd_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh) {
+    struct ClassGuard { Ctx* c; const char* prev; ClassGuard(Ctx* cc) : c(cc), prev(cc->gemm_class) { cc->gemm_class = "gemm_factor"; } ~ClassGuard() { c->gemm_class = prev; } } class_guard(c);
     if (m == 0 || n == 0) return;
     const size_t es = dtype_size(dt);
     if (m >= n) {
