@@ -12,6 +12,8 @@
 // (crates/tensor4all-tensorbackend/src/backend.rs:742-762).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "scalar.cuh"
 
 namespace cg = cooperative_groups;
@@ -311,6 +313,929 @@ void launch_panel(Ctx* c, PanelArgs& a) {
     c->launched("qr_panel", 2.0 * (double)rows * (double)a.jb * (double)es);  // bytes
 }
 
+
+// =====================================================================================================
+// TSQR panels (communication-avoiding Householder QR).
+//
+// A panel (rows x 32) is cut into row blocks of `h` rows.  Every block is factored by ONE CTA entirely
+// in shared memory (one __syncthreads per column, warp-shuffle dot products, the norm of the next column
+// fused into the update of the current one), producing the block's reflectors V_i (LAPACK storage, in
+// place), its compact-WY factor T_i and its 32 x 32 triangle R_i.  The last CTA to finish stacks the
+// R_i (<= 28 of them) and factors them the same way (level 2: V', T', final R).  The panel's Q is
+// diag(Q_i) * Q'; it is applied to the trailing matrix (and to [I;0] when Q is formed) by a fused
+// compact-WY kernel: W = V^H C on DMMA, W2 = op(T) W, C -= V W2 on DMMA, one CTA per (block, column tile),
+// reading C twice from L2 and writing it once.  No cluster barriers, no split-K, 3-4 launches per panel.
+// =====================================================================================================
+constexpr int FT = 1024;        // factor kernel threads (one warp per panel column)
+constexpr int FW = FT / 32;
+constexpr int AT = 256;         // apply kernel threads
+constexpr int CHR = 64;         // apply chunk rows
+
+int factor_pitch_any(bool cplx, int r);
+
+// TMA 1-D bulk copies (cp.async.bulk + mbarrier), used by the fused apply kernel when every column
+// segment is 16-byte aligned.
+__device__ __forceinline__ unsigned q_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void q_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(q_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void q_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(q_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool q_mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(q_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void q_bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(q_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(q_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void q_bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(q_smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+struct FactorArgs {
+    double* A; int64_t lda;
+    int64_t row0, col0;         // panel origin
+    int64_t rows;               // rows of the panel (m - row0)
+    int jb;
+    int h, nblocks;
+    int pitch;                  // shared-memory pitch of a panel column
+    double* Tw;                 // (nblocks + 1) x NB*NB: T_i of the blocks, then T'
+    double* V2;                 // (nblocks*NB) x NB explicit level-2 reflectors, ld = nblocks*NB
+    unsigned* counter;          // arrival counter of this panel (zero on entry)
+};
+
+// Reflector parameters without divisions on the critical path: with rn = 1/sqrt(|alpha|^2 + xnorm2),
+// beta = -sign(Re alpha) / rn, tau = (beta - alpha) / beta, scale = 1 / (alpha - beta).
+template <bool CPLX>
+__device__ __forceinline__ void larfg_fast(typename Sc<CPLX>::T alpha, double xnorm2, double& beta,
+                                           typename Sc<CPLX>::T& tau, typename Sc<CPLX>::T& scale) {
+    typedef Sc<CPLX> S;
+    if constexpr (CPLX) {
+        if (xnorm2 == 0.0 && alpha.y == 0.0) { tau = S::zero(); scale = S::zero(); beta = alpha.x; return; }
+        const double n2 = alpha.x * alpha.x + alpha.y * alpha.y + xnorm2;
+        const double rn = rsqrt(n2);
+        const double nrm = n2 * rn;
+        beta = alpha.x >= 0.0 ? -nrm : nrm;
+        const double rb = alpha.x >= 0.0 ? -rn : rn;            // 1 / beta
+        tau = make_double2((beta - alpha.x) * rb, -alpha.y * rb);
+        const double dr = alpha.x - beta, di = alpha.y;
+        const double rden = 1.0 / (dr * dr + di * di);
+        scale = make_double2(dr * rden, -di * rden);
+    } else {
+        if (xnorm2 == 0.0) { tau = 0.0; scale = 0.0; beta = alpha; return; }
+        const double n2 = alpha * alpha + xnorm2;
+        const double rn = rsqrt(n2);
+        const double nrm = n2 * rn;
+        beta = alpha >= 0.0 ? -nrm : nrm;
+        tau = 1.0 + fabs(alpha) * rn;                           // (beta - alpha) / beta
+        scale = 1.0 / (alpha - beta);
+    }
+}
+
+// Householder QR of an r x jb block by one CTA of FT = 1024 threads: warp w OWNS column w and keeps it in
+// registers (RPL rows per lane, row = lane + 32 j) for the whole factorisation; only the current pivot
+// column lives in shared memory.  One __syncthreads per column; at step c
+//   warp k > c : trailing update of its register column with reflector c (dot via warp shuffles, axpy);
+//                warp c+1 then also computes the norm of its column, the parameters of reflector c+1 and
+//                publishes the finished column (R above the diagonal, beta, scaled v below) to P[:,c+1];
+//   warp l < c : g[l] = v_l^H v_c from its (finished) register column;
+//   warp c     : column c-1 of the compact-WY factor, T[0:c-1,c-1] = -tau T[0:c-1,0:c-1] g.
+// On exit P holds LAPACK storage and Ts the upper-triangular T (Q = I - V T V^H).
+template <bool CPLX, int RPL>
+__device__ void house_factor_regs(typename Sc<CPLX>::T* P, int pitch, int r, int jb,
+                                  typename Sc<CPLX>::T* tau_s, typename Sc<CPLX>::T (*gv)[NB],
+                                  typename Sc<CPLX>::T (*Ts)[NB + 1]) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < NB * (NB + 1); e += FT) (&Ts[0][0])[e] = S::zero();
+    // own column -> registers (P was filled by the caller; rows >= r read as zero)
+    T x[RPL];
+    T* pw = P + (size_t)warp * pitch;
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+        const int i = lane + 32 * j;
+        x[j] = (warp < jb && i < r) ? pw[i] : S::zero();
+    }
+    // finishes the owner's column as reflector `cc`: norm below the diagonal, parameters, publish
+    auto publish = [&](int cc) {
+        double nacc = 0.0;
+        T alpha = S::zero();
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            const int i = lane + 32 * j;
+            if (i > cc) nacc += S::abs2(x[j]);
+            if (i == cc) alpha = x[j];
+        }
+        nacc = warp_sum(nacc);
+        alpha = shfl_t<CPLX>(alpha, cc & 31);
+        double beta; T tau, scale;
+        larfg_fast<CPLX>(alpha, nacc, beta, tau, scale);
+        const bool triv = S::abs2(tau) == 0.0;
+        if (lane == 0) tau_s[cc] = tau;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            const int i = lane + 32 * j;
+            if (i < r) {
+                T v = x[j];
+                if (!triv) {
+                    if (i > cc) { v = S::mul(v, scale); x[j] = v; }
+                    else if (i == cc) v = S::from_real(beta);
+                }
+                pw[i] = v;
+            }
+        }
+    };
+    if (warp == 0) publish(0);
+    __syncthreads();
+    for (int c = 0; c <= jb; ++c) {
+        if (c < jb && warp > c && warp < jb) {
+            // trailing update of column `warp` with reflector c
+            const T* pc = P + (size_t)c * pitch;
+            const T tau = tau_s[c];
+            if (S::abs2(tau) != 0.0) {
+                T v[RPL];
+                T dot = S::zero();
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) {
+                    const int i = lane + 32 * j;
+                    v[j] = (i > c && i < r) ? pc[i] : ((i == c) ? S::one() : S::zero());
+                    dot = S::add(dot, S::mul(S::conj(v[j]), x[j]));
+                }
+                dot = warp_sum_t<CPLX>(dot);
+                const T f = S::mul(S::conj(tau), dot);
+#pragma unroll
+                for (int j = 0; j < RPL; ++j) x[j] = S::sub(x[j], S::mul(f, v[j]));
+            }
+            if (warp == c + 1) publish(c + 1);
+        } else if (c < jb && warp < c) {
+            // g[l] = v_l^H v_c, l = warp: own column holds v_l below its diagonal (already scaled)
+            const T* pc = P + (size_t)c * pitch;
+            T dot = S::zero();
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                const int i = lane + 32 * j;
+                if (i >= c && i < r) {
+                    const T vc = (i == c) ? S::one() : pc[i];
+                    dot = S::add(dot, S::mul(S::conj(x[j]), vc));
+                }
+            }
+            dot = warp_sum_t<CPLX>(dot);
+            if (lane == 0) gv[c & 1][warp] = dot;
+        } else if (c > 0 && warp == (c < jb ? c : 0)) {
+            // column c-1 of T from g (computed during the previous step)
+            const int cc = c - 1;
+            const T tcc = tau_s[cc];
+            if (lane < cc) {
+                T t = S::zero();
+                for (int l = lane; l < cc; ++l) t = S::add(t, S::mul(Ts[lane][l], gv[cc & 1][l]));
+                Ts[lane][cc] = S::neg(S::mul(tcc, t));
+            } else if (lane == cc) {
+                Ts[cc][cc] = tcc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool CPLX>
+__device__ void house_factor_dispatch(typename Sc<CPLX>::T* P, int pitch, int r, int jb,
+                                      typename Sc<CPLX>::T* tau_s, typename Sc<CPLX>::T (*gv)[NB],
+                                      typename Sc<CPLX>::T (*Ts)[NB + 1]) {
+    if (r <= 256) house_factor_regs<CPLX, 8>(P, pitch, r, jb, tau_s, gv, Ts);
+    else if (r <= 512) house_factor_regs<CPLX, 16>(P, pitch, r, jb, tau_s, gv, Ts);
+    else house_factor_regs<CPLX, CPLX ? 12 : 25>(P, pitch, r, jb, tau_s, gv, Ts);
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(FT, 1) tsqr_factor_kernel(FactorArgs a) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ T tau_s[NB];
+    __shared__ T gv[2][NB];
+    __shared__ int is_last;
+    const int pitch = a.pitch;
+    T* P = reinterpret_cast<T*>(smem_raw);
+    T (*Ts)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>(P + (size_t)NB * pitch);
+    const int jb = a.jb;
+    const int b = blockIdx.x;
+    const int64_t blk0 = (int64_t)b * a.h;
+    const int r = (int)((b == a.nblocks - 1) ? (a.rows - blk0) : a.h);
+    T* Ag = reinterpret_cast<T*>(a.A) + (a.row0 + blk0) + a.col0 * a.lda;
+
+    // ---- level 1: this CTA's row block --------------------------------------------------------------
+    for (int c = warp; c < jb; c += FW)
+        for (int i = lane; i < r; i += 32) P[(size_t)c * pitch + i] = Ag[i + (int64_t)c * a.lda];
+    __syncthreads();
+    house_factor_dispatch<CPLX>(P, pitch, r, jb, tau_s, gv, Ts);
+    for (int c = warp; c < jb; c += FW)
+        for (int i = lane; i < r; i += 32) Ag[i + (int64_t)c * a.lda] = P[(size_t)c * pitch + i];
+    {
+        T* Tg = reinterpret_cast<T*>(a.Tw) + (size_t)b * NB * NB;
+        for (int e = tid; e < NB * NB; e += FT) Tg[e] = Ts[e & 31][e >> 5];
+    }
+    if (a.nblocks == 1) return;
+
+    // ---- level 2: the last block to arrive factors the stacked triangles -----------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned old = atomicAdd(a.counter, 1u);
+        is_last = (old == (unsigned)a.nblocks - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int r2 = a.nblocks * NB;
+    const T* Atop = reinterpret_cast<const T*>(a.A) + a.row0 + a.col0 * a.lda;
+    for (int c = warp; c < jb; c += FW)
+        for (int i = lane; i < r2; i += 32) {
+            const int s = i >> 5, q = i & 31;
+            T v = S::zero();
+            if (q <= c) {
+                const double* src = reinterpret_cast<const double*>(Atop + (int64_t)s * a.h + q + (int64_t)c * a.lda);
+                if constexpr (CPLX) v = make_double2(__ldcg(src), __ldcg(src + 1));
+                else v = __ldcg(src);
+            }
+            P[(size_t)c * pitch + i] = v;
+        }
+    __syncthreads();
+    house_factor_dispatch<CPLX>(P, pitch, r2, jb, tau_s, gv, Ts);
+    T* Aw = reinterpret_cast<T*>(a.A) + a.row0 + a.col0 * a.lda;
+    for (int e = tid; e < NB * NB; e += FT) {
+        const int q = e & 31, c = e >> 5;
+        if (c < jb && q <= c) Aw[q + (int64_t)c * a.lda] = P[(size_t)c * pitch + q];
+    }
+    {
+        // explicit V' (unit diagonal, zeros above it, zero columns beyond jb)
+        T* V2 = reinterpret_cast<T*>(a.V2);
+        for (int c = warp; c < NB; c += FW)
+            for (int i = lane; i < r2; i += 32) {
+                T v = S::zero();
+                if (c < jb) v = i < c ? S::zero() : (i == c ? S::one() : P[(size_t)c * pitch + i]);
+                V2[i + (size_t)c * r2] = v;
+            }
+        T* Tg = reinterpret_cast<T*>(a.Tw) + (size_t)a.nblocks * NB * NB;
+        for (int e = tid; e < NB * NB; e += FT) Tg[e] = Ts[e & 31][e >> 5];
+    }
+}
+
+struct ApplyArgs {
+    const double* V; int64_t ldv;   // contiguous: panel origin inside A (LAPACK storage); gather: explicit V'
+    int v_implicit;                 // 1: unit diagonal / zeros above are implied
+    const double* Tw;               // T of block b at Tw + b * NB*NB
+    int jb;
+    double* C; int64_t ldc;         // target, pointing at (panel row origin, first target column)
+    int64_t ncols;
+    int64_t rows; int h; int nblocks;   // contiguous mode: blocks of h rows (last takes the remainder)
+    int gather;                     // 1: one logical block of cnt*NB rows, logical row q -> (q/NB)*h + q%NB
+    int cnt;
+    int trans;                      // 1: C <- Q^H C, 0: C <- Q C
+};
+
+template <bool CPLX, int NT>
+__global__ void __launch_bounds__(AT) tsqr_apply_kernel(ApplyArgs a) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    constexpr int CP = CPLX ? 66 : 68;      // chunk pitch: == 2 (mod 8) complex, == 4 (mod 16) real
+    constexpr int WPT = CPLX ? 34 : 36;
+    constexpr int NF1 = NT / 16;            // n-fragments per warp in pass 1
+    constexpr int NF2 = NT / 8;             // n-fragments per warp in pass 2
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Vs = reinterpret_cast<T*>(smem_raw);            // [NB][CP]
+    T* Cs = Vs + NB * CP;                              // [NT][CP]
+    T* Wsm = Cs + NT * CP;                             // [NT][WPT]   W  (k fastest)
+    T* W2sm = Wsm + NT * WPT;                          // [NT][WPT]   W2
+    T* Tsm = W2sm + NT * WPT;                          // [NB][NB+1]  T[k][c] at Tsm[c*(NB+1)+k]
+
+    const int b = a.gather ? 0 : blockIdx.x;
+    const int64_t blk0 = a.gather ? 0 : (int64_t)b * a.h;
+    const int r = a.gather ? a.cnt * NB : (int)((b == a.nblocks - 1) ? (a.rows - blk0) : a.h);
+    const int64_t n0 = (int64_t)blockIdx.y * NT;
+    const int jb = a.jb;
+    const T* Vg = reinterpret_cast<const T*>(a.V) + (a.gather ? 0 : blk0);
+    T* Cg = reinterpret_cast<T*>(a.C) + n0 * a.ldc;
+    const T* Tg = reinterpret_cast<const T*>(a.Tw) + (size_t)(a.gather ? 0 : b) * NB * NB;
+    for (int e = tid; e < NB * NB; e += AT) Tsm[(e >> 5) * (NB + 1) + (e & 31)] = Tg[e];
+
+    auto crow = [&](int i) -> int64_t {      // physical row of C for logical block row i
+        return a.gather ? (int64_t)(i >> 5) * a.h + (i & 31) : blk0 + i;
+    };
+    auto load_chunk = [&](int q0) {
+        for (int c = warp; c < NB + NT; c += AT / 32) {
+#pragma unroll
+            for (int u = 0; u < CHR / 32; ++u) {
+                const int q = lane + u * 32, i = q0 + q;
+                T v = S::zero();
+                if (c < NB) {
+                    if (c < jb && i < r) {
+                        if (a.v_implicit && i <= c) v = (i == c) ? S::one() : S::zero();
+                        else v = Vg[i + (int64_t)c * a.ldv];
+                    }
+                    Vs[c * CP + q] = v;
+                } else {
+                    const int cc = c - NB;
+                    if (n0 + cc < a.ncols && i < r) v = Cg[crow(i) + (int64_t)cc * a.ldc];
+                    Cs[cc * CP + q] = v;
+                }
+            }
+        }
+    };
+
+    // ---- pass 1: W = V^H C --------------------------------------------------------------------------
+    const int mf = warp & 3, nh = warp >> 2;
+    T acc1[NF1][2];
+#pragma unroll
+    for (int f = 0; f < NF1; ++f) acc1[f][0] = acc1[f][1] = S::zero();
+    for (int q0 = 0; q0 < r; q0 += CHR) {
+        __syncthreads();
+        load_chunk(q0);
+        __syncthreads();
+        const T* pa = Vs + (mf * 8 + grp) * CP + tig;
+#pragma unroll 4
+        for (int k0 = 0; k0 < CHR; k0 += 4) {
+            const T av = pa[k0];
+#pragma unroll
+            for (int f = 0; f < NF1; ++f) {
+                const T bv = Cs[((nh * NF1 + f) * 8 + grp) * CP + k0 + tig];
+                mma_frag<CPLX, true>(acc1[f], av, bv);
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NF1; ++f)
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2)
+            Wsm[((nh * NF1 + f) * 8 + 2 * tig + c2) * WPT + mf * 8 + grp] = acc1[f][c2];
+    __syncthreads();
+    // ---- W2 = op(T) W ----------------------------------------------------------------------------------
+    for (int e = tid; e < NB * NT; e += AT) {
+        const int mrow = e & 31, n = e >> 5;
+        T t = S::zero();
+        if (a.trans) {
+            for (int l = 0; l <= mrow; ++l) t = S::add(t, S::mul(S::conj(Tsm[mrow * (NB + 1) + l]), Wsm[n * WPT + l]));
+        } else {
+            for (int l = mrow; l < NB; ++l) t = S::add(t, S::mul(Tsm[l * (NB + 1) + mrow], Wsm[n * WPT + l]));
+        }
+        W2sm[n * WPT + mrow] = t;
+    }
+    // ---- pass 2: C -= V W2 -----------------------------------------------------------------------------
+    for (int q0 = 0; q0 < r; q0 += CHR) {
+        __syncthreads();
+        load_chunk(q0);
+        __syncthreads();
+        T av[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) av[ks] = Vs[(ks * 4 + tig) * CP + warp * 8 + grp];
+#pragma unroll
+        for (int f = 0; f < NF2; ++f) {
+            T acc[2];
+            acc[0] = acc[1] = S::zero();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const T bv = W2sm[(f * 8 + grp) * WPT + ks * 4 + tig];
+                mma_frag<CPLX, false>(acc, av[ks], bv);
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                T* pcs = Cs + (f * 8 + 2 * tig + c2) * CP + warp * 8 + grp;
+                *pcs = S::sub(*pcs, acc[c2]);
+            }
+        }
+        __syncthreads();
+        for (int cc = warp; cc < NT; cc += AT / 32) {
+            if (n0 + cc >= a.ncols) continue;
+#pragma unroll
+            for (int u = 0; u < CHR / 32; ++u) {
+                const int q = lane + u * 32, i = q0 + q;
+                if (i < r) Cg[crow(i) + (int64_t)cc * a.ldc] = Cs[cc * CP + q];
+            }
+        }
+    }
+}
+
+template <bool CPLX, int NT>
+void launch_apply(Ctx* c, const ApplyArgs& a) {
+    if (a.ncols <= 0) return;
+    const size_t es = CPLX ? 16 : 8;
+    constexpr int CP = CPLX ? 66 : 68;
+    constexpr int WPT = CPLX ? 34 : 36;
+    const size_t smem = ((size_t)(NB + NT) * CP + 2 * (size_t)NT * WPT + (size_t)NB * (NB + 1)) * es;
+    auto kern = tsqr_apply_kernel<CPLX, NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(a.gather ? 1 : a.nblocks), (unsigned)((a.ncols + NT - 1) / NT), 1);
+    kern<<<grid, AT, smem, c->stream>>>(a);
+    const double rows = a.gather ? (double)a.cnt * NB : (double)a.rows;
+    c->launched("qr_apply", 3.0 * rows * (double)a.ncols * (double)es);   // bytes: C read twice, written once
+}
+
+// ---- fused two-level apply: one cluster per column tile, one CTA per row block ------------------------
+// Every CTA keeps its block of C (r x NT) and of V (r x 32) resident in shared memory: level 1 is local,
+// level 2 (the stacked 32-row tops) is a cluster operation: partial W' = V'_b^H Z_b per CTA, reduce-scatter
+// of W' over distributed shared memory (CTA b owns NT/nblocks columns), W2' = op(T') W' pushed to every
+// CTA, Z_b -= V'_b W2'.  C is read from global once and written once.
+struct FusedApplyArgs {
+    const double* Va; int64_t lda;   // panel origin inside A: level-1 reflectors in LAPACK storage
+    const double* V2;                // explicit V' (nblocks*NB x NB, ld = nblocks*NB)
+    const double* Tw;                // T_b at Tw + b*NB*NB, T' at Tw + nblocks*NB*NB
+    int jb;
+    double* C; int64_t ldc; int64_t ncols;
+    int64_t rows; int h; int nblocks;
+    int rp;                          // shared-memory pitch of a block column
+    int trans;                       // 1: C <- Q^H C, 0: C <- Q C
+    int use_tma;                     // every column segment of V and C is 16-byte aligned
+};
+
+template <bool CPLX, int NT>
+__global__ void __launch_bounds__(AT, 1) tsqr_apply_fused_kernel(FusedApplyArgs a) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    constexpr int WPT = CPLX ? 34 : 36;
+    constexpr int NF1 = NT / 16;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+    const int b = blockIdx.x;            // == cluster rank
+    const int nb = a.nblocks;
+    const int rp = a.rp;
+    const int jb = a.jb;
+    const int64_t blk0 = (int64_t)b * a.h;
+    const int r = (int)((b == nb - 1) ? (a.rows - blk0) : a.h);
+    const int r4 = (r + 3) & ~3, r8 = (r + 7) & ~7;
+    const int64_t n0 = (int64_t)blockIdx.y * NT;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Vs = reinterpret_cast<T*>(smem_raw);          // [NB][rp]
+    T* Cs = Vs + (size_t)NB * rp;                    // [NT][rp]
+    T* Tsm = Cs + (size_t)NT * rp;                   // [NB][NB+1]   T_b
+    T* T2sm = Tsm + NB * (NB + 1);                   // [NB][NB+1]   T'
+    T* V2s = T2sm + NB * (NB + 1);                   // [NB][WPT]    V'_b (32 x 32)
+    T* Wsm = V2s + NB * WPT;                         // [NT][WPT]
+    T* W2sm = Wsm + NT * WPT;                        // [NT][WPT]
+    T* Wp = W2sm + NT * WPT;                         // [NT][WPT]    partial W' of this CTA
+    T* W2p = Wp + NT * WPT;                          // [NT][WPT]    full W2'
+
+    // ---- load ---------------------------------------------------------------------------------------
+    __shared__ uint64_t ld_bar;
+    {
+        constexpr unsigned ES = CPLX ? 16 : 8;
+        const T* Vg = reinterpret_cast<const T*>(a.Va) + blk0;
+        const T* Cg = reinterpret_cast<const T*>(a.C) + blk0 + n0 * a.ldc;
+        if (a.use_tma) {
+            if (tid == 0) {
+                q_mbar_init(&ld_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int ncopies = 0;
+                for (int c = lane; c < NB + NT; c += 32)
+                    if (c < NB ? (c < jb) : (n0 + (c - NB) < a.ncols)) ++ncopies;
+                int total = ncopies;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                if (lane == 0) q_mbar_expect_tx(&ld_bar, (unsigned)total * (unsigned)r * ES);
+                __syncwarp();
+                for (int c = lane; c < NB + NT; c += 32) {
+                    if (c < NB) {
+                        if (c < jb) q_bulk_g2s(Vs + (size_t)c * rp, Vg + (int64_t)c * a.lda, (unsigned)r * ES, &ld_bar);
+                    } else if (n0 + (c - NB) < a.ncols) {
+                        q_bulk_g2s(Cs + (size_t)(c - NB) * rp, Cg + (int64_t)(c - NB) * a.ldc, (unsigned)r * ES, &ld_bar);
+                    }
+                }
+            }
+            // padding rows / absent columns are zeroed with plain stores (disjoint from the bulk copies)
+            for (int c = warp; c < NB + NT; c += AT / 32) {
+                T* dst = c < NB ? Vs + (size_t)c * rp : Cs + (size_t)(c - NB) * rp;
+                const bool present = c < NB ? (c < jb) : (n0 + (c - NB) < a.ncols);
+                for (int i = (present ? r : 0) + lane; i < r8; i += 32) dst[i] = S::zero();
+            }
+            while (!q_mbar_try_wait(&ld_bar, 0)) {}
+            __syncthreads();
+            // implicit unit diagonal / zeros above it
+            for (int e = tid; e < NB * NB; e += AT) {
+                const int i = e & 31, c = e >> 5;
+                if (c < jb && i <= c && i < r) Vs[(size_t)c * rp + i] = (i == c) ? S::one() : S::zero();
+            }
+        } else {
+            for (int c = warp; c < NB; c += AT / 32) {
+                T* dst = Vs + (size_t)c * rp;
+                if (c < jb) {
+                    const T* src = Vg + (int64_t)c * a.lda;
+#pragma unroll 4
+                    for (int i = lane; i < r; i += 32) {
+                        T v = src[i];
+                        if (i <= c) v = (i == c) ? S::one() : S::zero();
+                        dst[i] = v;
+                    }
+                    for (int i = r + lane; i < r8; i += 32) dst[i] = S::zero();
+                } else {
+                    for (int i = lane; i < r8; i += 32) dst[i] = S::zero();
+                }
+            }
+            for (int cc = warp; cc < NT; cc += AT / 32) {
+                T* dst = Cs + (size_t)cc * rp;
+                if (n0 + cc < a.ncols) {
+                    const T* src = Cg + (int64_t)cc * a.ldc;
+#pragma unroll 4
+                    for (int i = lane; i < r; i += 32) dst[i] = src[i];
+                    for (int i = r + lane; i < r8; i += 32) dst[i] = S::zero();
+                } else {
+                    for (int i = lane; i < r8; i += 32) dst[i] = S::zero();
+                }
+            }
+        }
+        const T* Tg = reinterpret_cast<const T*>(a.Tw) + (size_t)b * NB * NB;
+        const T* T2g = reinterpret_cast<const T*>(a.Tw) + (size_t)nb * NB * NB;
+        const T* V2g = reinterpret_cast<const T*>(a.V2) + (size_t)b * NB;
+        for (int e = tid; e < NB * NB; e += AT) {
+            const int q = e & 31, c = e >> 5;
+            Tsm[c * (NB + 1) + q] = Tg[e];
+            if (nb > 1) {
+                T2sm[c * (NB + 1) + q] = T2g[e];
+                V2s[c * WPT + q] = V2g[q + (size_t)c * nb * NB];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int mf = warp & 3, nh = warp >> 2;
+    auto level1 = [&]() {
+        // W = V^H C
+        T acc1[NF1][2];
+#pragma unroll
+        for (int f = 0; f < NF1; ++f) acc1[f][0] = acc1[f][1] = S::zero();
+        const T* pa = Vs + (size_t)(mf * 8 + grp) * rp + tig;
+#pragma unroll 4
+        for (int k0 = 0; k0 < r4; k0 += 4) {
+            const T av = pa[k0];
+#pragma unroll
+            for (int f = 0; f < NF1; ++f) {
+                const T bv = Cs[(size_t)((nh * NF1 + f) * 8 + grp) * rp + k0 + tig];
+                mma_frag<CPLX, true>(acc1[f], av, bv);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NF1; ++f)
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2)
+                Wsm[((nh * NF1 + f) * 8 + 2 * tig + c2) * WPT + mf * 8 + grp] = acc1[f][c2];
+        __syncthreads();
+        // W2 = op(T) W
+        for (int e = tid; e < NB * NT; e += AT) {
+            const int mrow = e & 31, n = e >> 5;
+            T t = S::zero();
+            if (a.trans) {
+                for (int l = 0; l <= mrow; ++l) t = S::add(t, S::mul(S::conj(Tsm[mrow * (NB + 1) + l]), Wsm[n * WPT + l]));
+            } else {
+                for (int l = mrow; l < NB; ++l) t = S::add(t, S::mul(Tsm[l * (NB + 1) + mrow], Wsm[n * WPT + l]));
+            }
+            W2sm[n * WPT + mrow] = t;
+        }
+        __syncthreads();
+        // C -= V W2
+        for (int mfr = warp; mfr < r8 / 8; mfr += AT / 32) {
+            T av[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) av[ks] = Vs[(size_t)(ks * 4 + tig) * rp + mfr * 8 + grp];
+#pragma unroll
+            for (int f = 0; f < NT / 8; ++f) {
+                T acc[2];
+                acc[0] = acc[1] = S::zero();
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const T bv = W2sm[(f * 8 + grp) * WPT + ks * 4 + tig];
+                    mma_frag<CPLX, false>(acc, av[ks], bv);
+                }
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    T* pcs = Cs + (size_t)(f * 8 + 2 * tig + c2) * rp + mfr * 8 + grp;
+                    *pcs = S::sub(*pcs, acc[c2]);
+                }
+            }
+        }
+        __syncthreads();
+    };
+    auto level2 = [&]() {
+        // partial W' = V'_b^H Z_b, Z_b = first 32 rows of this block
+        {
+            T acc1[NF1][2];
+#pragma unroll
+            for (int f = 0; f < NF1; ++f) acc1[f][0] = acc1[f][1] = S::zero();
+#pragma unroll
+            for (int k0 = 0; k0 < NB; k0 += 4) {
+                const T av = V2s[(mf * 8 + grp) * WPT + k0 + tig];
+#pragma unroll
+                for (int f = 0; f < NF1; ++f) {
+                    const T bv = Cs[(size_t)((nh * NF1 + f) * 8 + grp) * rp + k0 + tig];
+                    mma_frag<CPLX, true>(acc1[f], av, bv);
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < NF1; ++f)
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2)
+                    Wp[((nh * NF1 + f) * 8 + 2 * tig + c2) * WPT + mf * 8 + grp] = acc1[f][c2];
+        }
+        cluster.sync();
+        // reduce-scatter: this CTA sums columns [c_lo, c_hi) of W' over all ranks (fixed order)
+        const int c_lo = (b * NT) / nb, c_hi = ((b + 1) * NT) / nb;
+        for (int e = tid; e < NB * (c_hi - c_lo); e += AT) {
+            const int mrow = e & 31, n = c_lo + (e >> 5);
+            T t = S::zero();
+            for (int rr = 0; rr < nb; ++rr) {
+                const T* rem = cluster.map_shared_rank(Wp, rr);
+                t = S::add(t, rem[n * WPT + mrow]);
+            }
+            Wsm[n * WPT + mrow] = t;
+        }
+        __syncthreads();
+        // W2' slice = op(T') W' slice, pushed to every CTA of the cluster
+        for (int e = tid; e < NB * (c_hi - c_lo); e += AT) {
+            const int mrow = e & 31, n = c_lo + (e >> 5);
+            T t = S::zero();
+            if (a.trans) {
+                for (int l = 0; l <= mrow; ++l) t = S::add(t, S::mul(S::conj(T2sm[mrow * (NB + 1) + l]), Wsm[n * WPT + l]));
+            } else {
+                for (int l = mrow; l < NB; ++l) t = S::add(t, S::mul(T2sm[l * (NB + 1) + mrow], Wsm[n * WPT + l]));
+            }
+            for (int rr = 0; rr < nb; ++rr) {
+                T* rem = cluster.map_shared_rank(W2p, rr);
+                rem[n * WPT + mrow] = t;
+            }
+        }
+        cluster.sync();
+        // Z_b -= V'_b W2'
+        {
+#pragma unroll
+            for (int f = 0; f < NF1; ++f) {
+                const int nf = nh * NF1 + f;
+                T acc[2];
+                acc[0] = acc[1] = S::zero();
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const T av = V2s[(ks * 4 + tig) * WPT + mf * 8 + grp];
+                    const T bv = W2p[(nf * 8 + grp) * WPT + ks * 4 + tig];
+                    mma_frag<CPLX, false>(acc, av, bv);
+                }
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    T* pcs = Cs + (size_t)(nf * 8 + 2 * tig + c2) * rp + mf * 8 + grp;
+                    *pcs = S::sub(*pcs, acc[c2]);
+                }
+            }
+        }
+        __syncthreads();
+    };
+
+    if (a.trans) {
+        level1();
+        if (nb > 1) level2();
+    } else {
+        if (nb > 1) level2();
+        level1();
+    }
+    // ---- store ----------------------------------------------------------------------------------------
+    {
+        constexpr unsigned ES = CPLX ? 16 : 8;
+        T* Cg = reinterpret_cast<T*>(a.C) + blk0 + n0 * a.ldc;
+        if (a.use_tma) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (warp == 0) {
+                for (int cc = lane; cc < NT; cc += 32)
+                    if (n0 + cc < a.ncols) q_bulk_s2g(Cg + (int64_t)cc * a.ldc, Cs + (size_t)cc * rp, (unsigned)r * ES);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+        } else {
+            for (int cc = warp; cc < NT; cc += AT / 32) {
+                if (n0 + cc >= a.ncols) continue;
+                const T* srcs = Cs + (size_t)cc * rp;
+                T* dst = Cg + (int64_t)cc * a.ldc;
+#pragma unroll 4
+                for (int i = lane; i < r; i += 32) dst[i] = srcs[i];
+            }
+        }
+    }
+    if (nb > 1) cluster.sync();   // peers may still be reading this CTA's Wp
+}
+
+template <bool CPLX, int NT>
+size_t fused_apply_smem(int rp) {
+    const size_t es = CPLX ? 16 : 8;
+    constexpr int WPT = CPLX ? 34 : 36;
+    return ((size_t)(NB + NT) * rp + 2 * (size_t)NB * (NB + 1) + (size_t)NB * WPT + 4 * (size_t)NT * WPT) * es;
+}
+
+// Returns false when the configuration cannot be made resident (block too tall for shared memory or
+// the cluster cannot be scheduled); the caller then uses the two unfused kernels.
+template <bool CPLX, int NT>
+bool launch_apply_fused(Ctx* c, const FusedApplyArgs& a0) {
+    if (a0.ncols <= 0) return true;
+    if (a0.nblocks > MAXCL) return false;
+    FusedApplyArgs a = a0;
+    const size_t es = CPLX ? 16 : 8;
+    const int rmax = a.nblocks == 1 ? (int)a.rows : a.h;
+    a.rp = factor_pitch_any(CPLX, (rmax + 7) & ~7);
+    const size_t smem = fused_apply_smem<CPLX, NT>(a.rp);
+    if (smem > 220 * 1024) return false;
+    {
+        // bulk copies need 16-byte aligned column segments: complex always; real when every block start,
+        // block height and leading dimension is even
+        bool ok = true;
+        if (!CPLX) {
+            const int64_t last = a.rows - (int64_t)(a.nblocks - 1) * a.h;
+            ok = ((uintptr_t)a.Va % 16 == 0) && ((uintptr_t)a.C % 16 == 0) && (a.lda % 2 == 0) && (a.ldc % 2 == 0) &&
+                 (a.nblocks == 1 ? (a.rows % 2 == 0) : (a.h % 2 == 0 && last % 2 == 0));
+        }
+        a.use_tma = (ok && !getenv("T4B_QR_NOTMA")) ? 1 : 0;
+    }
+    auto kern = tsqr_apply_fused_kernel<CPLX, NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.nblocks, (unsigned)((a.ncols + NT - 1) / NT), 1);
+    cfg.blockDim = dim3(AT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.nblocks;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (a.nblocks > 8) {
+        // non-portable cluster sizes may not be schedulable with this much shared memory
+        static int ok16[MAXCL + 1] = {0};   // 0 unknown, 1 yes, -1 no   (per instantiation)
+        if (ok16[a.nblocks] == 0) {
+            int ncl = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+            if (e != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+            ok16[a.nblocks] = ncl > 0 ? 1 : -1;
+        }
+        if (ok16[a.nblocks] < 0) return false;
+    }
+    T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+    c->launched("qr_apply", 2.0 * (double)a.rows * (double)a.ncols * (double)es);   // bytes: C read + written once
+    return true;
+}
+
+// smem pitch for a factor block of r rows: == 4 (mod 16) real / == 2 (mod 8) complex, >= r rounded to 4
+int factor_pitch_any(bool cplx, int r) {
+    int pch = (r + 3) & ~3;
+    if (cplx) { while (pch % 8 != 2) ++pch; }
+    else { while (pch % 16 != 4) ++pch; }
+    return pch;
+}
+int factor_pitch(bool cplx, int r) {
+    int pch = (r + 3) & ~3;
+    if (cplx) { while (pch % 8 != 2) ++pch; }
+    else { while (pch % 16 != 4) ++pch; }
+    return pch;
+}
+
+// Blocked QR with TSQR panels.  Returns false when the shape does not fit the two-level scheme
+// (level-2 stack larger than shared memory); the caller then uses the cluster panel kernel.
+template <bool CPLX>
+bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
+    const DType dt = CPLX ? C64 : F64;
+    const size_t es = CPLX ? 16 : 8;
+    const int64_t k = m < n ? m : n;
+    const int hmin = CPLX ? 128 : 256;
+    const size_t smem_cap = 220 * 1024;
+    // rows of a factor block that fit in shared memory next to the R/G/T scratch
+    int caprows = (int)((smem_cap / es - NB * (NB + 1)) / NB);
+    while (factor_pitch(CPLX, caprows) > (int)((smem_cap / es - NB * (NB + 1)) / NB)) --caprows;
+    const int cntmax = caprows / NB < MAXCL ? caprows / NB : MAXCL;   // level-2 fan-in (<= max cluster size)
+    if (m > (int64_t)cntmax * caprows) return false;
+    // panel geometry: nblocks row blocks of hb rows (the last takes the remainder, >= NB rows)
+    auto block_geometry = [&](int64_t rows, int& hb, int& nblocks) {
+        int64_t hp = (rows + cntmax - 1) / cntmax;
+        if (hp < hmin) hp = hmin;
+        nblocks = (int)((rows + hp - 1) / hp);
+        if (nblocks < 1) nblocks = 1;
+        hb = (int)((rows + nblocks - 1) / nblocks);
+        if (nblocks > 1 && rows - (int64_t)(nblocks - 1) * hb < NB) { --nblocks; hb = (int)((rows + nblocks - 1) / nblocks); }
+        // even block heights keep every column segment 16-byte aligned (TMA bulk copies)
+        if (nblocks > 1 && (hb & 1) && hb + 1 <= caprows && rows - (int64_t)(nblocks - 1) * (hb + 1) >= NB) ++hb;
+    };
+    int hb0, nb0i;
+    block_geometry(m, hb0, nb0i);
+    const int64_t nb0 = nb0i;
+    auto fk = tsqr_factor_kernel<CPLX>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        attr_set = true;
+    }
+    const int64_t npanels = (k + NB - 1) / NB;
+    const size_t t_stride = (size_t)(nb0 + 1) * NB * NB;          // elements per panel
+    const size_t v2_stride = (size_t)nb0 * NB * NB;
+    char* Tall = (char*)alloc(c, (size_t)npanels * t_stride * es);
+    char* V2all = (char*)alloc(c, (size_t)npanels * v2_stride * es);
+    unsigned* counters = (unsigned*)alloc(c, (size_t)npanels * 4);
+    zero(c, counters, (size_t)npanels * 4);
+
+    auto geometry = [&](int64_t p, int64_t& j0, int& jb, int64_t& rows, int& nblocks, int& h) {
+        j0 = p * NB;
+        jb = (int)((k - j0) < NB ? (k - j0) : NB);
+        rows = m - j0;
+        block_geometry(rows, h, nblocks);
+        if (nblocks > nb0) throw Error(ST_INTERNAL, "qr: panel block count exceeds the workspace");
+    };
+    auto apply_panel = [&](int64_t p, void* Cbase, int64_t ncols, bool trans) {
+        // Cbase points at (row j0, first target column) of a matrix with ld = m
+        int64_t j0, rows; int jb, nblocks, h;
+        geometry(p, j0, jb, rows, nblocks, h);
+        ApplyArgs l1{};
+        l1.V = (const double*)((char*)A + ((size_t)j0 + (size_t)j0 * (size_t)m) * es); l1.ldv = m; l1.v_implicit = 1;
+        l1.Tw = (const double*)(Tall + (size_t)p * t_stride * es);
+        l1.jb = jb; l1.C = (double*)Cbase; l1.ldc = m; l1.ncols = ncols;
+        l1.rows = rows; l1.h = h; l1.nblocks = nblocks; l1.gather = 0; l1.cnt = 0; l1.trans = trans ? 1 : 0;
+        ApplyArgs l2 = l1;
+        l2.V = (const double*)(V2all + (size_t)p * v2_stride * es); l2.ldv = (int64_t)nblocks * NB; l2.v_implicit = 0;
+        l2.Tw = (const double*)(Tall + ((size_t)p * t_stride + (size_t)nblocks * NB * NB) * es);
+        l2.gather = 1; l2.cnt = nblocks;
+        if (!getenv("T4B_QR_UNFUSED")) {
+            FusedApplyArgs fa{};
+            fa.Va = l1.V; fa.lda = m; fa.V2 = l2.V; fa.Tw = l1.Tw; fa.jb = jb;
+            fa.C = (double*)Cbase; fa.ldc = m; fa.ncols = ncols;
+            fa.rows = rows; fa.h = h; fa.nblocks = nblocks; fa.trans = trans ? 1 : 0;
+            if (launch_apply_fused<CPLX, 32>(c, fa)) return;
+        }
+        constexpr int NT1 = CPLX ? 32 : 64;
+        if (trans) {
+            launch_apply<CPLX, NT1>(c, l1);
+            if (nblocks > 1) launch_apply<CPLX, 32>(c, l2);
+        } else {
+            if (nblocks > 1) launch_apply<CPLX, 32>(c, l2);
+            launch_apply<CPLX, NT1>(c, l1);
+        }
+    };
+
+    for (int64_t p = 0; p < npanels; ++p) {
+        int64_t j0, rows; int jb, nblocks, h;
+        geometry(p, j0, jb, rows, nblocks, h);
+        FactorArgs fa{};
+        fa.A = (double*)A; fa.lda = m; fa.row0 = j0; fa.col0 = j0; fa.rows = rows; fa.jb = jb;
+        fa.h = h; fa.nblocks = nblocks;
+        int64_t rmax = nblocks == 1 ? rows : h;
+        if (nblocks > 1 && (int64_t)nblocks * NB > rmax) rmax = (int64_t)nblocks * NB;
+        fa.pitch = factor_pitch(CPLX, (int)rmax);
+        fa.Tw = (double*)(Tall + (size_t)p * t_stride * es);
+        fa.V2 = (double*)(V2all + (size_t)p * v2_stride * es);
+        fa.counter = counters + p;
+        const size_t smem = ((size_t)NB * fa.pitch + NB * (NB + 1)) * es;
+        fk<<<nblocks, FT, smem, c->stream>>>(fa);
+        c->launched("qr_factor", 2.0 * (double)rows * (double)jb * (double)es);   // bytes: panel read + write
+        const int64_t nt = n - (j0 + jb);
+        if (nt > 0) apply_panel(p, (char*)A + ((size_t)j0 + (size_t)(j0 + jb) * (size_t)m) * es, nt, true);
+    }
+    if (Rout) {
+        int64_t total = k * n;
+        int grid = (int)((total + 255) / 256);
+        if (grid > c->num_sms * 8) grid = c->num_sms * 8;
+        extract_r_kernel<CPLX><<<grid, 256, 0, c->stream>>>((const double*)A, m, k, n, (double*)Rout);
+        c->launched("qr_extract_r");
+    }
+    if (Q) {
+        int64_t total = m * k;
+        int grid = (int)((total + 255) / 256);
+        if (grid > c->num_sms * 8) grid = c->num_sms * 8;
+        set_identity_kernel<CPLX><<<grid, 256, 0, c->stream>>>((double*)Q, m, k);
+        c->launched("qr_set_identity");
+        for (int64_t p = npanels - 1; p >= 0; --p) {
+            const int64_t j0 = p * NB;
+            apply_panel(p, (char*)Q + ((size_t)j0 + (size_t)j0 * (size_t)m) * es, k - j0, false);
+        }
+    }
+    release(c, Tall); release(c, V2all); release(c, counters);
+    (void)dt;
+    return true;
+}
+
 }  // namespace
 
 void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
@@ -319,6 +1244,9 @@ void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rou
     if (k == 0) return;
     const size_t es = dtype_size(dt);
     const bool cplx = dt == C64;
+    if (!getenv("T4B_QR_OLD")) {
+        if (cplx ? qr_thin_tsqr<true>(c, m, n, A, Q, Rout) : qr_thin_tsqr<false>(c, m, n, A, Q, Rout)) return;
+    }
 
     // workspaces: Vw (m x NB), T (NB x NB), W (NB x max(n,k)), W2, Gw
     const int64_t wcols = n > k ? n : k;

@@ -46,6 +46,15 @@ __device__ __forceinline__ typename Sc<CPLX>::T warp_sum_t(typename Sc<CPLX>::T 
     return v;
 }
 
+template <bool CPLX>
+__device__ __forceinline__ typename Sc<CPLX>::T shfl_t(typename Sc<CPLX>::T v, int src) {
+    if constexpr (CPLX) {
+        return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+    } else {
+        return __shfl_sync(0xffffffffu, v, src);
+    }
+}
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)

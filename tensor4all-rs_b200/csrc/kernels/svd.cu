@@ -80,12 +80,91 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned 
                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
 
+
+// Hermitian Jacobi on the 32 x 32 Gram block held in shared memory (Gs, ping-pong copy Gs2), rotations
+// accumulated into Ws (initialised to the identity by the caller).  16 disjoint rotations per step;
+// every thread owns one 2 x 2 block of G' = Ja^H G Jb.  full_inner: 31-step round-robin over all 32
+// indices; otherwise the 16-step bipartite ordering (cross pairs block I x block J only).
+// Called by all JT threads; ends with a __syncthreads().
 template <bool CPLX>
-__device__ __forceinline__ typename Sc<CPLX>::T shfl_t(typename Sc<CPLX>::T v, int src) {
-    if constexpr (CPLX) {
-        return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
-    } else {
-        return __shfl_sync(0xffffffffu, v, src);
+__device__ __forceinline__ void jacobi_eig32(typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2,
+                                             typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
+                                             double* rot_c, double* rot_s, int full_inner, double tol_rot,
+                                             int tid) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    T* Gcur = Gs;
+    T* Gnxt = Gs2;
+    const int nrr = full_inner ? 31 : 16;
+    const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
+    const double tol2 = tol_rot * tol_rot;
+    for (int rr = 0; rr < nrr; ++rr) {
+        int pa, qa, pb, qb;
+        if (full_inner) {
+            if (ta == 0) { pa = rr; qa = 31; } else { pa = (rr + ta) % 31; qa = (rr - ta + 62) % 31; }
+            if (pa > qa) { int t = pa; pa = qa; qa = t; }
+            if (tb == 0) { pb = rr; qb = 31; } else { pb = (rr + tb) % 31; qb = (rr - tb + 62) % 31; }
+            if (pb > qb) { int t = pb; pb = qb; qb = t; }
+        } else {
+            pa = ta; qa = 16 + ((ta + rr) & 15);
+            pb = tb; qb = 16 + ((tb + rr) & 15);
+        }
+        // 16 threads compute the 16 rotations of this step (pair t = tid):
+        // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]], J^H [[aa,g],[g*,bb]] J diagonal
+        if (tid < 16) {
+            int pp, qq;
+            if (full_inner) {
+                if (tid == 0) { pp = rr; qq = 31; } else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
+                if (pp > qq) { int t = pp; pp = qq; qq = t; }
+            } else {
+                pp = tid; qq = 16 + ((tid + rr) & 15);
+            }
+            double c = 1.0, sn = 0.0;
+            T ph = S::one();
+            const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
+            const T g = Gcur[pp * GP + qq];
+            const double g2 = S::abs2(g);
+            if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
+                const double inv_absg = rsqrt(g2);
+                const double absg = g2 * inv_absg;
+                const double d = 0.5 * (bb - aa);
+                const double x = d * d + g2;
+                const double h = x * rsqrt(x);
+                const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
+                c = rsqrt(1.0 + t * t);
+                sn = c * t;
+                ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
+            }
+            rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
+        }
+        __syncthreads();
+        const double ca = rot_c[ta], sa = rot_s[ta], cb = rot_c[tb], sb = rot_s[tb];
+        const T pha = rot_ph[ta], phb = rot_ph[tb];
+        // G' = Ja^H G Jb on the 2 x 2 block owned by this thread
+        const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
+        const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
+        const T cpa = S::conj(pha);
+        const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
+        const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
+        const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
+        const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
+        const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
+        const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
+        Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
+        Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
+        Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
+        Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
+        // W <- W Jb for the two rows owned by this thread (exclusive ownership: in place)
+#pragma unroll
+        for (int rrow = 0; rrow < 2; ++rrow) {
+            const int i = ta * 2 + rrow;
+            const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
+            const T fq = S::mul(wq, phb);
+            Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
+            Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
+        }
+        __syncthreads();
+        T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
     }
 }
 
@@ -347,6 +426,349 @@ __global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
     }
 }
 
+
+// =====================================================================================================
+// Persistent data-flow Jacobi: ONE launch runs every round of every sweep.
+//
+// A cluster of `cs` CTAs owns one pair slot q; in global round g = sweep * rounds + r it processes the
+// column-block pair (bi, bj) of the round-robin ordering as soon as both blocks have finished round
+// g - 1 (per-block completion counters in global memory, release/acquire at gpu scope) — there is no
+// grid-wide barrier between rounds, only one per sweep for the convergence decision.  Rows of the pair
+// panel are split across the cluster's CTAs and streamed through two shared-memory chunk buffers with
+// TMA bulk copies (cp.async.bulk + mbarrier); the last two chunks of the Gram pass stay resident for the
+// update pass, so a panel that fits is read from L2 exactly once per round.
+// =====================================================================================================
+struct JPArgs {
+    double* X; int64_t ldx;
+    double* V; int64_t ldv;
+    int p;                 // column blocks (even)
+    int cs;                // CTAs per cluster
+    int nclusters;         // resident clusters (pair slots)
+    int pairs;             // p / 2
+    int rpcx, rpcv;        // rows per CTA (multiples of 8); rpcv = 0: V not accumulated
+    int ch;                // rows per chunk buffer
+    int ldp;               // shared-memory pitch of a chunk column
+    int max_sweeps;
+    double tol, tol_rot;
+    unsigned* ready;       // [p] CTA-completions per column block
+    unsigned* done;        // sweep barrier counter
+    unsigned long long* flag;   // [max_sweeps] max off-diagonal cosine of the sweep (double bits)
+    int* info;             // [0] sweeps executed, [1] converged
+    unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define JP_STAMP(k)                                                     \
+    do {                                                                \
+        if (a.timing && blockIdx.x == 0 && tid == 0) {                   \
+            unsigned long long _t = gtimer();                           \
+            tacc[k] += _t - tprev;                                      \
+            tprev = _t;                                                 \
+        }                                                               \
+    } while (0)
+
+template <bool CPLX>
+__global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long tprev = gtimer();
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    constexpr unsigned ES = CPLX ? 16 : 8;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int R = (int)cluster.block_rank();
+    const int CS = a.cs;
+    const int cl = (int)blockIdx.x / CS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ldp = a.ldp;
+    T* buf0 = reinterpret_cast<T*>(smem_raw);
+    T* buf1 = buf0 + (size_t)PW * ldp;
+    T* Gp0 = buf1 + (size_t)PW * ldp;                       // partial Gram, double buffered across items
+    T* Gs = Gp0 + 2 * 32 * 32;                              // [32][GP]
+    T* Gs2 = Gs + 32 * GP;
+    T* Ws = Gs2 + 32 * GP;                                  // [32 cols][WP]
+    T* rot_ph = Ws + 32 * WP;
+    double* rot_c = reinterpret_cast<double*>(rot_ph + 16);
+    double* rot_s = rot_c + 16;
+    double* redbuf = rot_s + 16;                            // JW + 1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(redbuf + JW + 2);
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned par0 = 0, par1 = 0;
+
+    T* Xg = reinterpret_cast<T*>(a.X);
+    T* Vg = reinterpret_cast<T*>(a.V);
+    const int nchx = (a.rpcx + a.ch - 1) / a.ch;
+    const int nchv = a.rpcv ? (a.rpcv + a.ch - 1) / a.ch : 0;
+    const int npos = nchx + nchv;
+    const int p1 = a.p - 1, rounds = a.p - 1;
+    int item = 0;
+    int sweep = 0;
+    int converged = 0;
+
+    for (; sweep < a.max_sweeps; ++sweep) {
+        for (int r = 0; r < rounds; ++r) {
+            const unsigned g = (unsigned)(sweep * rounds + r);
+            const int full_inner = (r == 0) ? 1 : 0;
+            for (int q = cl; q < a.pairs; q += a.nclusters, ++item) {
+                int bi, bj;
+                if (q == 0) { bi = r % p1; bj = a.p - 1; }
+                else { bi = (r + q) % p1; bj = (r - q + 2 * p1) % p1; }
+                if (bi > bj) { int t = bi; bi = bj; bj = t; }
+
+                // position j of the update pass -> chunk descriptor
+                auto pos_desc = [&](int j, T*& base, int64_t& ld, int64_t& row0, int& nrows) {
+                    if (j < nchx) {
+                        const int i = nchx - 1 - j;
+                        base = Xg; ld = a.ldx; row0 = (int64_t)R * a.rpcx + (int64_t)i * a.ch;
+                        nrows = a.rpcx - i * a.ch; if (nrows > a.ch) nrows = a.ch;
+                    } else {
+                        const int i = j - nchx;
+                        base = Vg; ld = a.ldv; row0 = (int64_t)R * a.rpcv + (int64_t)i * a.ch;
+                        nrows = a.rpcv - i * a.ch; if (nrows > a.ch) nrows = a.ch;
+                    }
+                };
+                auto col_of = [&](int c) -> int64_t {
+                    return c < JB ? (int64_t)bi * JB + c : (int64_t)bj * JB + (c - JB);
+                };
+                // warp 0 only
+                auto issue_load = [&](int j, int b) {
+                    T* base; int64_t ld, row0; int nrows;
+                    pos_desc(j, base, ld, row0, nrows);
+                    uint64_t* bar = &bars[b];
+                    T* dst = b ? buf1 : buf0;
+                    if (lane == 0) mbar_expect_tx(bar, (unsigned)(PW * nrows) * ES);
+                    __syncwarp();
+                    bulk_g2s(dst + (size_t)lane * ldp, base + row0 + col_of(lane) * ld, (unsigned)nrows * ES, bar);
+                };
+                auto wait_load = [&](int b) {
+                    if (b) { while (!mbar_try_wait(&bars[1], par1)) {} par1 ^= 1; }
+                    else { while (!mbar_try_wait(&bars[0], par0)) {} par0 ^= 1; }
+                };
+
+                // ---- 0. wait until both column blocks have finished round g - 1, start the loads ----
+                if (warp == 0) {
+                    if (g > 0 && lane == 0) {
+                        const unsigned need = (unsigned)CS * g;
+                        while (ld_acquire_u32(a.ready + bi) < need) {}
+                        while (ld_acquire_u32(a.ready + bj) < need) {}
+                    }
+                    __syncwarp();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    // Gram-pass chunk i lives in buffer i & 1 and is update-pass position nchx - 1 - i
+                    issue_load(nchx - 1, 0);
+                    if (nchx > 1) issue_load(nchx - 2, 1);
+                    else if (nchv > 0) issue_load(1, 1);       // prefetch the first V chunk
+                }
+                JP_STAMP(0);   // wait for the blocks + issue
+
+                // ---- 1. partial Gram on DMMA ----------------------------------------------------------
+                T* Gp = Gp0 + (item & 1) * 32 * 32;
+                {
+                    const int fi = warp & 3;
+                    const int fj0 = (warp >> 2) * 2;
+                    T acc[2][2];
+                    acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = S::zero();
+                    for (int i = 0; i < nchx; ++i) {
+                        const int b = i & 1;
+                        wait_load(b);
+                        int nrows = a.rpcx - i * a.ch; if (nrows > a.ch) nrows = a.ch;
+                        const T* Ps = b ? buf1 : buf0;
+                        const T* pa = Ps + (size_t)(fi * 8 + grp) * ldp + tig;
+                        const T* pb0 = Ps + (size_t)(fj0 * 8 + grp) * ldp + tig;
+                        const T* pb1 = Ps + (size_t)((fj0 + 1) * 8 + grp) * ldp + tig;
+#pragma unroll 4
+                        for (int k0 = 0; k0 < nrows; k0 += 4) {
+                            T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
+                            mma_frag<CPLX, true>(acc[0], av, b0);
+                            mma_frag<CPLX, true>(acc[1], av, b1);
+                        }
+                        if (i + 2 < nchx) {
+                            __syncthreads();
+                            if (warp == 0) issue_load(nchx - 1 - (i + 2), b);
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            int row = fi * 8 + grp, col = (fj0 + jj) * 8 + 2 * tig + c2;
+                            Gp[col * 32 + row] = acc[jj][c2];
+                        }
+                }
+                JP_STAMP(1);   // load + partial Gram
+                cluster.sync();   // every CTA's partial Gram is visible cluster-wide
+                JP_STAMP(2);   // cluster barrier
+                // every CTA reduces the partial Grams in the same fixed order (bitwise identical G on
+                // every CTA => identical rotations and identical control flow, no broadcast needed)
+                {
+                    const T* rem[MAXCS];
+#pragma unroll
+                    for (int rr = 0; rr < MAXCS; ++rr) rem[rr] = cluster.map_shared_rank(Gp, rr < CS ? rr : 0);
+#pragma unroll
+                    for (int u = 0; u < 32 * 32 / JT; ++u) {
+                        const int e = tid + u * JT;
+                        T v[MAXCS];
+#pragma unroll
+                        for (int rr = 0; rr < MAXCS; ++rr) v[rr] = rr < CS ? rem[rr][e] : S::zero();
+                        T gsum = v[0];
+#pragma unroll
+                        for (int rr = 1; rr < MAXCS; ++rr) if (rr < CS) gsum = S::add(gsum, v[rr]);
+                        int row = e & 31, col = e >> 5;
+                        Gs[row * GP + col] = gsum;
+                        Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
+                    }
+                }
+                __syncthreads();
+                // convergence measure: max_{i<j} |G_ij| / sqrt(G_ii G_jj)
+                {
+                    double mx = 0.0;
+                    for (int e = tid; e < 32 * 32; e += JT) {
+                        int row = e & 31, col = e >> 5;
+                        if (row < col) {
+                            double gii = S::real(Gs[row * GP + row]), gjj = S::real(Gs[col * GP + col]);
+                            double g2 = S::abs2(Gs[row * GP + col]);
+                            if (gii > 0.0 && gjj > 0.0) {
+                                double r2 = g2 / (gii * gjj);
+                                if (r2 > mx) mx = r2;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double other = __shfl_xor_sync(0xffffffffu, mx, o);
+                        if (other > mx) mx = other;
+                    }
+                    if (lane == 0) redbuf[warp] = mx;
+                    __syncthreads();
+                    if (tid == 0) {
+                        double m = 0.0;
+                        for (int w = 0; w < JW; ++w) if (redbuf[w] > m) m = redbuf[w];
+                        m = sqrt(m);
+                        if (R == 0) atomicMax(a.flag + sweep, (unsigned long long)__double_as_longlong(m));
+                        redbuf[JW] = m;
+                    }
+                    __syncthreads();
+                }
+                const bool need_rot = redbuf[JW] > a.tol_rot;
+                JP_STAMP(3);   // reduce + convergence measure
+                if (need_rot) {
+                    jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid);
+                    JP_STAMP(4);   // eig
+                    // ---- 3. update pass: P <- P W chunk by chunk, TMA bulk write-back ------------------
+                    for (int j = 0; j < npos; ++j) {
+                        const int b = (nchx - 1 + j) & 1;
+                        if (j >= 2 || (j == 1 && nchx == 1)) wait_load(b);
+                        T* base; int64_t ld, row0; int nrows;
+                        pos_desc(j, base, ld, row0, nrows);
+                        T* Ps = b ? buf1 : buf0;
+                        for (int rf = warp; rf < nrows / 8; rf += JW) {
+                            T av[8];
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) av[ks] = Ps[(size_t)(ks * 4 + tig) * ldp + rf * 8 + grp];
+                            T acc[4][2];
+#pragma unroll
+                            for (int nf = 0; nf < 4; ++nf) {
+                                acc[nf][0] = acc[nf][1] = S::zero();
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks) {
+                                    T bw = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
+                                    mma_frag<CPLX, false>(acc[nf], av[ks], bw);
+                                }
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                                for (int c2 = 0; c2 < 2; ++c2)
+                                    Ps[(size_t)(nf * 8 + 2 * tig + c2) * ldp + rf * 8 + grp] = acc[nf][c2];
+                        }
+                        // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncthreads();
+                        if (warp == 0) {
+                            bulk_s2g(base + row0 + col_of(lane) * ld, Ps + (size_t)lane * ldp, (unsigned)nrows * ES);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            if (j + 2 < npos) {
+                                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                                __syncwarp();
+                                issue_load(j + 2, b);
+                            }
+                        }
+                    }
+                    JP_STAMP(5);   // update + store issue
+                    if (warp == 0) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    JP_STAMP(6);   // store completion
+                } else if (nchx == 1 && nchv > 0) {
+                    wait_load(1);   // consume the prefetched V chunk
+                }
+                // ---- 4. publish: this CTA's rows of both blocks have finished round g ------------------
+                if (warp == 0) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) {
+                        red_release_add_u32(a.ready + bi, 1u);
+                        red_release_add_u32(a.ready + bj, 1u);
+                    }
+                }
+                __syncthreads();   // Gs / Ws / redbuf are reused by the next item
+            }
+        }
+        // ---- sweep barrier + convergence decision -----------------------------------------------------
+        if (tid == 0) {
+            __threadfence();
+            red_release_add_u32(a.done, 1u);
+            const unsigned need = gridDim.x * (unsigned)(sweep + 1);
+            while (ld_acquire_u32(a.done) < need) {}
+            unsigned long long bits = *((volatile unsigned long long*)(a.flag + sweep));
+            redbuf[JW + 1] = __longlong_as_double((long long)bits);
+        }
+        __syncthreads();
+        const double off = redbuf[JW + 1];
+        __syncthreads();
+        JP_STAMP(7);   // publish + sweep barrier
+        if (off <= a.tol) { converged = 1; ++sweep; break; }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        a.info[0] = sweep; a.info[1] = converged;
+        if (a.timing)
+            for (int k = 0; k < 8; ++k) a.timing[k] = tacc[k];
+    }
+    cluster.sync();   // no CTA may exit while a peer can still read its shared memory
+}
+
 // sig2[j] = sum_i |X[i,j]|^2, one warp per column
 template <bool CPLX>
 __global__ void colnorm2_kernel(const double* __restrict__ X, int64_t ldx, int64_t nx, int64_t ncols,
@@ -553,6 +975,149 @@ int jacobi_sweeps(Ctx* c, const JacobiPlan& pl, double* X, int64_t nx, int64_t n
     return sweeps;
 }
 
+// ---- persistent kernel: launch geometry ------------------------------------------------------------------
+struct JPPlan {
+    int cs = 1, nclusters = 1, pairs = 1, rpcx = 0, rpcv = 0, ch = 0, ldp = 0;
+    int64_t ldx = 0, ldv = 0;
+    size_t smem = 0;
+};
+
+template <bool CPLX>
+size_t jp_smem_bytes(int ldp) {
+    const size_t es = CPLX ? 16 : 8;
+    return (size_t)2 * PW * ldp * es + (size_t)(2 * 32 * 32 + 2 * 32 * GP + 32 * WP + 16) * es +
+           (size_t)(32 + JW + 2) * 8 + 2 * 8 + 128;
+}
+
+template <bool CPLX>
+int jp_max_clusters(int cs, size_t smem) {
+    auto kern = jacobi_persistent_kernel<CPLX>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cs, 1, 1);
+    cfg.blockDim = dim3(JT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    T4B_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    return n;
+}
+
+template <bool CPLX>
+JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
+    static bool attr_set = false;
+    const size_t smem_cap = 227 * 1024;
+    if (!attr_set) {
+        auto kern = jacobi_persistent_kernel<CPLX>;
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    auto roundup = [](int64_t v, int64_t q) { return (v + q - 1) / q * q; };
+    // pitch == 4 (mod 16) real, == 2 (mod 8) complex: conflict-free fragment loads, 16-byte aligned columns
+    const int chq = CPLX ? 8 : 16;
+    const int pad = CPLX ? 2 : 4;
+    int chmax = chq;
+    while (jp_smem_bytes<CPLX>(chmax + chq + pad) <= smem_cap) chmax += chq;
+    const int pairs = (int)(npad / PW);
+    const int cs_force = getenv("T4B_JAC_CS") ? atoi(getenv("T4B_JAC_CS")) : 0;
+    JPPlan best;
+    long best_score = -1;
+    for (int cs = 8; cs >= 1; cs >>= 1) {
+        if (cs_force && cs != cs_force) continue;
+        JPPlan pl;
+        pl.cs = cs; pl.pairs = pairs;
+        pl.rpcx = (int)roundup((nx + cs - 1) / cs, 8);
+        pl.rpcv = with_v ? (int)roundup((npad + cs - 1) / cs, 8) : 0;
+        if (!cs_force && cs > 1 && pl.rpcx < 32) continue;
+        int want = pl.rpcx > pl.rpcv ? pl.rpcx : pl.rpcv;
+        pl.ch = (int)roundup(want, chq);
+        if (pl.ch > chmax) pl.ch = chmax;
+        pl.ldp = pl.ch + pad;
+        pl.smem = jp_smem_bytes<CPLX>(pl.ldp);
+        pl.ldx = (int64_t)cs * pl.rpcx;
+        pl.ldv = (int64_t)cs * pl.rpcv;
+        int maxc = jp_max_clusters<CPLX>(cs, pl.smem);
+        if (maxc < 1) continue;
+        pl.nclusters = maxc < pairs ? maxc : pairs;
+        if (maxc >= pairs) return pl;            // every pair of a round gets its own resident cluster
+        long score = (long)pl.nclusters * cs;
+        if (score > best_score) { best_score = score; best = pl; }
+    }
+    if (best_score < 0) throw Error(ST_INTERNAL, "svd: no resident cluster configuration for the Jacobi kernel");
+    (void)c;
+    return best;
+}
+
+// One-sided block Jacobi on X (ldx x npad, nx live rows); V (ldv x npad) optional.  Asynchronous: the
+// whole iteration (all sweeps, convergence decision included) is one kernel launch.
+template <bool CPLX>
+void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
+    const size_t es = CPLX ? 16 : 8;
+    const int p = (int)(npad / JB);
+    const int max_sweeps = 40;
+    // workspace: flag[max_sweeps] (u64) | timing[8] (u64) | ready[p] | done | info[2]
+    const bool verbose = getenv("T4B_VERBOSE") != nullptr;
+    const size_t ws_bytes = (size_t)(max_sweeps + 8) * 8 + ((size_t)p + 4) * 4;
+    unsigned char* ws = (unsigned char*)alloc(c, ws_bytes);
+    zero(c, ws, ws_bytes);
+    const double eps = 2.220446049250313e-16;
+    const double tol = eps * sqrt((double)(nx > 4 ? nx : 4));
+    JPArgs a{};
+    a.X = X; a.ldx = pl.ldx;
+    a.V = V; a.ldv = pl.ldv;
+    a.p = p; a.cs = pl.cs; a.nclusters = pl.nclusters; a.pairs = pl.pairs;
+    a.rpcx = pl.rpcx; a.rpcv = V ? pl.rpcv : 0; a.ch = pl.ch; a.ldp = pl.ldp;
+    a.max_sweeps = max_sweeps;
+    a.tol = tol; a.tol_rot = tol * 0.25;
+    a.flag = (unsigned long long*)ws;
+    a.timing = verbose ? (unsigned long long*)ws + max_sweeps : nullptr;
+    a.ready = (unsigned*)(ws + (size_t)(max_sweeps + 8) * 8);
+    a.done = a.ready + p;
+    a.info = (int*)(a.done + 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pl.nclusters * pl.cs), 1, 1);
+    cfg.blockDim = dim3(JT, 1, 1);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    auto kern = jacobi_persistent_kernel<CPLX>;
+    T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+    // bytes: per sweep every round reads and writes the live rows of X (and V) once; the sweep count is
+    // only known on the device, the profile uses the typical 10
+    c->launched("jacobi", 10.0 * (double)(p - 1) * 2.0 * (double)(nx + (V ? npad : 0)) * (double)npad * (double)es);
+    if (verbose) {
+        unsigned char* h = (unsigned char*)c->get_pinned(128 + 8 * max_sweeps);
+        d2h(c, h, a.info, 8);
+        d2h(c, h + 64, a.timing, 64);
+        d2h(c, h + 128, a.flag, 8 * max_sweeps);
+        sync(c);
+        if (atoi(getenv("T4B_VERBOSE")) > 1) {
+            fprintf(stderr, "[t4b]   off per sweep:");
+            for (int i = 0; i < ((const int*)h)[0]; ++i) fprintf(stderr, " %.1e", ((const double*)(h + 128))[i]);
+            fprintf(stderr, "\n");
+        }
+        const int* hinfo = (const int*)h;
+        const unsigned long long* t = (const unsigned long long*)(h + 64);
+        fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d cs=%d clusters=%d ch=%d smem=%zu sweeps=%d converged=%d | us: "
+                "wait %.0f gram %.0f csync %.0f reduce %.0f eig %.0f update %.0f store %.0f publish+sweepbar %.0f\n",
+                (long long)nx, (long long)npad, V ? 1 : 0, pl.cs, pl.nclusters, pl.ch, pl.smem, hinfo[0], hinfo[1],
+                t[0] * 1e-3, t[1] * 1e-3, t[2] * 1e-3, t[3] * 1e-3, t[4] * 1e-3, t[5] * 1e-3, t[6] * 1e-3, t[7] * 1e-3);
+    }
+    release(c, ws);
+}
+
 // m >= n.  A destroyed.  U (m x n) / Vh (n x n) optional.
 template <bool CPLX>
 void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh) {
@@ -567,7 +1132,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     qr_thin(c, dt, m, n, A, Q, Rm);
     // X = R (left vectors wanted) or R^H (only right vectors wanted)
     const bool adjoint = !want_u;
-    const JacobiPlan pl = plan_jacobi<CPLX>(c, n, npad, acc_v);
+    const JPPlan pl = plan_jp<CPLX>(c, n, npad, acc_v);
     double* X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
     init_x_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>((const double*)Rm, n, n, pl.ldx, npad, adjoint ? 1 : 0, X);
     c->launched("svd_init_x");
@@ -577,7 +1142,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         set_eye_kernel<CPLX><<<grid1d(c, pl.ldv * npad), 256, 0, c->stream>>>(V, pl.ldv, npad);
         c->launched("svd_set_eye");
     }
-    jacobi_sweeps<CPLX>(c, pl, X, n, npad, V);
+    jacobi_persistent<CPLX>(c, pl, X, n, npad, V);
 
     double* sig2 = (double*)alloc(c, (size_t)npad * 8);
     int64_t* rank = (int64_t*)alloc(c, (size_t)npad * 8);

@@ -7,7 +7,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 1), (5, 3), (3, 5), (32, 32), (33, 31), (64, 40), (100, 100), (128, 64), (257, 70),
-          (600, 130), (2048, 96), (70, 257), (4100, 64), (9000, 40)]
+          (600, 130), (2048, 96), (70, 257), (4100, 64), (9000, 40), (2048, 512), (1000, 1000),
+          (3072, 512), (777, 300)]
 
 
 def _rand(rng, shape, cplx):
