@@ -3,17 +3,18 @@
 //   A (m x n, m >= n) = Q R                      (qr.cu, cluster Householder)
 //   X = R or R^H, X V = U_X diag(sigma)          (this file)
 //
-// One kernel launch per round of the round-robin ordering.  Every column-block pair (2 x 16
-// columns) is owned by ONE thread-block cluster: the pair panel is split by rows across the
-// cluster's CTAs and stays resident in shared memory for the whole round:
-//   0. the row chunk of the panel is staged by TMA bulk copies (cp.async.bulk + mbarrier), one
-//      per column, and written back the same way;
-//   1. partial Gram G = P^H P on the FP64 tensor pipe (DMMA), reduced across the cluster through
-//      distributed shared memory in a fixed order (bitwise identical on every CTA);
+// One persistent kernel launch runs the whole iteration (see jacobi_persistent_kernel).  Every
+// column-block pair (2 x 16 columns) of a round is owned by ONE thread-block cluster; the pair
+// panel is split by rows across the cluster's CTAs:
+//   0. row chunks of the panel are staged by TMA bulk copies (cp.async.bulk + mbarrier), one per
+//      column, and written back the same way;
+//   1. partial Gram on the FP64 tensor pipe (DMMA) - only the 16 x 16 cross block P_i^H P_j: the
+//      diagonal blocks are the diagonal blocks of the rotated Gram of the previous visit and
+//      travel with the column block (refreshed from the data in round 0 of every sweep) - reduced
+//      across the cluster through distributed shared memory in a fixed order (bitwise identical
+//      on every CTA, so every CTA takes the same decisions and no broadcast is needed);
 //   2. Hermitian Jacobi on the 32 x 32 Gram block in shared memory: 16 disjoint rotations per
-//      step, every thread owns one 2 x 2 block of G' = Ja^H G Jb, rotations are computed once
-//      per lane and exchanged with warp shuffles, G is ping-ponged (one barrier per step);
-//      redundantly on each CTA of the cluster, no broadcast;
+//      step, every thread owns one 2 x 2 block of G' = Ja^H G Jb, G is ping-ponged;
 //   3. P <- P W (and the V rows, when right vectors are accumulated) on DMMA.
 // Convergence is the classical |x_i^H x_j| <= tol ||x_i|| ||x_j|| test, tracked on the device.
 //
@@ -40,18 +41,6 @@ constexpr int JW = JT / 32;
 constexpr int WP = 36;     // pitch of the W matrix in shared memory
 constexpr int GP = 33;     // pitch of the G matrix in shared memory
 constexpr int MAXCS = 16;
-
-struct JacobiArgs {
-    double* X; int64_t ldx; int64_t nx;   // X: nx rows (ldx = cs * rpcx, zero padded)
-    double* V; int64_t ldv; int64_t nv;   // V: nv rows (0: not accumulated)
-    int p;                                // column blocks (even)
-    int round;
-    int64_t rpcx, rpcv;                   // rows per CTA, multiples of 8
-    int64_t ldp;                          // smem panel pitch
-    int full_inner;                       // 1: full 32-index round-robin (covers intra-block pairs)
-    double tol_rot;
-    unsigned long long* flag;             // max off-diagonal cosine seen this sweep (double bits)
-};
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -87,15 +76,15 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned 
 // indices; otherwise the 16-step bipartite ordering (cross pairs block I x block J only).
 // Called by all JT threads; ends with a __syncthreads().
 template <bool CPLX>
-__device__ __forceinline__ void jacobi_eig32(typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2,
+__device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32(typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2,
                                              typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
                                              double* rot_c, double* rot_s, int full_inner, double tol_rot,
-                                             int tid) {
+                                             int tid, int inner = 1) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     T* Gcur = Gs;
     T* Gnxt = Gs2;
-    const int nrr = full_inner ? 31 : 16;
+    const int nrr = full_inner ? 31 : 16 * inner;
     const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
     const double tol2 = tol_rot * tol_rot;
     for (int rr = 0; rr < nrr; ++rr) {
@@ -125,15 +114,36 @@ __device__ __forceinline__ void jacobi_eig32(typename Sc<CPLX>::T* Gs, typename 
             const T g = Gcur[pp * GP + qq];
             const double g2 = S::abs2(g);
             if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
-                const double inv_absg = rsqrt(g2);
-                const double absg = g2 * inv_absg;
                 const double d = 0.5 * (bb - aa);
-                const double x = d * d + g2;
-                const double h = x * rsqrt(x);
-                const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
-                c = rsqrt(1.0 + t * t);
-                sn = c * t;
-                ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
+                if constexpr (CPLX) {
+                    const double inv_absg = rsqrt(g2);
+                    const double absg = g2 * inv_absg;
+                    const double x = d * d + g2;
+                    const double h = x * rsqrt(x);
+                    const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
+                    c = rsqrt(1.0 + t * t);
+                    sn = c * t;
+                    ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
+                } else {
+                    // t = sign(d) |g| / (|d| + sqrt(d^2 + g^2)) only steers the convergence, so it is
+                    // evaluated in fp32 on exponent-normalised operands; c = (1 + t^2)^(-1/2) must make
+                    // the rotation orthogonal to fp64 accuracy: fp32 seed + two Newton steps.
+                    const double ag = fabs(g), ad = fabs(d);
+                    const double mx = ag > ad ? ag : ad;
+                    const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+                    const double sc = __hiloint2double((2046 - ex) << 20, 0);     // mx * sc in [1, 2)
+                    const float fd = (float)(ad * sc), fg = (float)(ag * sc);
+                    const float fh = sqrtf(fd * fd + fg * fg);
+                    const float ft = __fdividef(fg, fd + fh);
+                    const double t = d >= 0.0 ? (double)ft : -(double)ft;
+                    const double x = 1.0 + t * t;
+                    double y = (double)rsqrtf((float)x);
+                    y = y * (1.5 - 0.5 * x * y * y);
+                    y = y * (1.5 - 0.5 * x * y * y);
+                    c = y;
+                    sn = c * t;
+                    ph = g >= 0.0 ? 1.0 : -1.0;
+                }
             }
             rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
         }
@@ -166,264 +176,7 @@ __device__ __forceinline__ void jacobi_eig32(typename Sc<CPLX>::T* Gs, typename 
         __syncthreads();
         T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
     }
-}
-
-template <bool CPLX>
-__global__ void __launch_bounds__(JT) jacobi_round_kernel(JacobiArgs a) {
-    typedef Sc<CPLX> S;
-    typedef typename S::T T;
-    constexpr unsigned ES = CPLX ? 16 : 8;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int R = (int)cluster.block_rank();
-    const int CS = (int)cluster.num_blocks();
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int grp = lane >> 2, tig = lane & 3;
-
-    // ---- which pair of column blocks -------------------------------------------------------
-    const int q = blockIdx.x / CS;
-    const int p1 = a.p - 1;
-    int bi, bj;
-    if (q == 0) { bi = a.round % p1; bj = a.p - 1; }
-    else { bi = (a.round + q) % p1; bj = (a.round - q + 2 * p1) % p1; }
-    if (bi > bj) { int t = bi; bi = bj; bj = t; }
-
-    // ---- shared memory carve-up --------------------------------------------------------------
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int64_t ldp = a.ldp;
-    const int64_t rt = a.rpcx + a.rpcv;
-    T* Ps = reinterpret_cast<T*>(smem_raw);                 // [PW][ldp]
-    T* Gp = Ps + (size_t)PW * ldp;                          // [32*32] own partial Gram (col-major)
-    T* Gs = Gp + 32 * 32;                                   // [32][GP]
-    T* Gs2 = Gs + 32 * GP;                                  // ping-pong copy of G
-    T* Ws = Gs2 + 32 * GP;                                  // [32 cols][WP]
-    T* rot_ph = Ws + 32 * WP;                               // 16 rotation phases
-    double* rot_c = reinterpret_cast<double*>(rot_ph + 16);     // 16 cosines
-    double* rot_s = rot_c + 16;                                 // 16 sines
-    double* redbuf = rot_s + 16;                                // JW
-    uint64_t* bar = reinterpret_cast<uint64_t*>(redbuf + JW);
-
-    // ---- 0. TMA bulk load of the row chunk of the pair panel -------------------------------
-    const int64_t x_lo = (int64_t)R * a.rpcx;
-    const int64_t v_lo = (int64_t)R * a.rpcv;
-    T* Xg = reinterpret_cast<T*>(a.X);
-    T* Vg = reinterpret_cast<T*>(a.V);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {
-        if (lane == 0) mbar_expect_tx(bar, (unsigned)(PW * rt * ES));
-        __syncwarp();
-        const int c = lane;
-        const int64_t col = c < JB ? (int64_t)bi * JB + c : (int64_t)bj * JB + (c - JB);
-        bulk_g2s(Ps + c * ldp, Xg + x_lo + col * a.ldx, (unsigned)(a.rpcx * ES), bar);
-        if (a.rpcv) bulk_g2s(Ps + c * ldp + a.rpcx, Vg + v_lo + col * a.ldv, (unsigned)(a.rpcv * ES), bar);
-    }
-    mbar_wait(bar, 0);
-
-    // ---- 1. partial Gram on DMMA --------------------------------------------------------------
-    {
-        const int fi = warp & 3;
-        const int fj0 = (warp >> 2) * 2;
-        T acc[2][2];
-        acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = S::zero();
-        const T* pa = Ps + (size_t)(fi * 8 + grp) * ldp + tig;
-        const T* pb0 = Ps + (size_t)(fj0 * 8 + grp) * ldp + tig;
-        const T* pb1 = Ps + (size_t)((fj0 + 1) * 8 + grp) * ldp + tig;
-        for (int64_t k0 = 0; k0 < a.rpcx; k0 += 4) {
-            T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
-            mma_frag<CPLX, true>(acc[0], av, b0);
-            mma_frag<CPLX, true>(acc[1], av, b1);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-                int row = fi * 8 + grp, col = (fj0 + jj) * 8 + 2 * tig + c2;
-                Gp[col * 32 + row] = acc[jj][c2];
-            }
-    }
-    cluster.sync();   // #1: every CTA's partial Gram is visible cluster-wide
-    // Rank 0 reduces the partial Grams (fixed order; remote loads issued back-to-back so their
-    // DSMEM latency overlaps), solves the 32 x 32 Hermitian problem ONCE and broadcasts W; the
-    // peers only wait at barrier #2 (their SM time goes to co-resident CTAs of other clusters).
-    if (R == 0) {
-        {
-            const T* rem[MAXCS];
-#pragma unroll
-            for (int r = 0; r < MAXCS; ++r) rem[r] = cluster.map_shared_rank(Gp, r < CS ? r : 0);
-#pragma unroll
-            for (int u = 0; u < 32 * 32 / JT; ++u) {
-                const int e = tid + u * JT;
-                T v[MAXCS];
-#pragma unroll
-                for (int r = 0; r < MAXCS; ++r) v[r] = r < CS ? rem[r][e] : S::zero();
-                T g = v[0];
-#pragma unroll
-                for (int r = 1; r < MAXCS; ++r) if (r < CS) g = S::add(g, v[r]);
-                int row = e & 31, col = e >> 5;
-                Gs[row * GP + col] = g;
-                Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
-            }
-        }
-        __syncthreads();
-        // convergence measure: max_{i<j} |G_ij| / sqrt(G_ii G_jj)
-        {
-            double mx = 0.0;
-            for (int e = tid; e < 32 * 32; e += JT) {
-                int row = e & 31, col = e >> 5;
-                if (row < col) {
-                    double gii = S::real(Gs[row * GP + row]), gjj = S::real(Gs[col * GP + col]);
-                    double g2 = S::abs2(Gs[row * GP + col]);
-                    if (gii > 0.0 && gjj > 0.0) {
-                        double r2 = g2 / (gii * gjj);
-                        if (r2 > mx) mx = r2;
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double other = __shfl_xor_sync(0xffffffffu, mx, o);
-                if (other > mx) mx = other;
-            }
-            if (lane == 0) redbuf[warp] = mx;
-            __syncthreads();
-            if (tid == 0) {
-                double m = 0.0;
-                for (int w = 0; w < JW; ++w) if (redbuf[w] > m) m = redbuf[w];
-                m = sqrt(m);
-                atomicMax(a.flag, (unsigned long long)__double_as_longlong(m));
-                redbuf[0] = m;
-            }
-            __syncthreads();
-        }
-        if (redbuf[0] > a.tol_rot) {
-            T* Gcur = Gs;
-            T* Gnxt = Gs2;
-            const int nrr = a.full_inner ? 31 : 16;
-            const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
-            const double tol2 = a.tol_rot * a.tol_rot;
-            for (int rr = 0; rr < nrr; ++rr) {
-                int pa, qa, pb, qb;
-                if (a.full_inner) {
-                    if (ta == 0) { pa = rr; qa = 31; } else { pa = (rr + ta) % 31; qa = (rr - ta + 62) % 31; }
-                    if (pa > qa) { int t = pa; pa = qa; qa = t; }
-                    if (tb == 0) { pb = rr; qb = 31; } else { pb = (rr + tb) % 31; qb = (rr - tb + 62) % 31; }
-                    if (pb > qb) { int t = pb; pb = qb; qb = t; }
-                } else {
-                    // bipartite ordering: only cross pairs (block I x block J); columns inside a block
-                    // were orthogonalised against each other earlier in the sweep
-                    pa = ta; qa = 16 + ((ta + rr) & 15);
-                    pb = tb; qb = 16 + ((tb + rr) & 15);
-                }
-                // 16 threads compute the 16 rotations of this step (pair t = tid):
-                // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]], J^H [[aa,g],[g*,bb]] J diagonal
-                if (tid < 16) {
-                    int pp, qq;
-                    if (a.full_inner) {
-                        if (tid == 0) { pp = rr; qq = 31; } else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
-                        if (pp > qq) { int t = pp; pp = qq; qq = t; }
-                    } else {
-                        pp = tid; qq = 16 + ((tid + rr) & 15);
-                    }
-                    double c = 1.0, sn = 0.0;
-                    T ph = S::one();
-                    const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
-                    const T g = Gcur[pp * GP + qq];
-                    const double g2 = S::abs2(g);
-                    if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
-                        const double inv_absg = rsqrt(g2);
-                        const double absg = g2 * inv_absg;
-                        const double d = 0.5 * (bb - aa);
-                        const double x = d * d + g2;
-                        const double h = x * rsqrt(x);
-                        const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
-                        c = rsqrt(1.0 + t * t);
-                        sn = c * t;
-                        ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
-                    }
-                    rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
-                }
-                __syncthreads();
-                const double ca = rot_c[ta], sa = rot_s[ta], cb = rot_c[tb], sb = rot_s[tb];
-                const T pha = rot_ph[ta], phb = rot_ph[tb];
-                // G' = Ja^H G Jb on the 2 x 2 block owned by this thread
-                const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
-                const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
-                const T cpa = S::conj(pha);
-                const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
-                const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
-                const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
-                const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
-                const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
-                const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
-                Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
-                Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
-                Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
-                Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
-                // W <- W Jb for the two rows owned by this thread (exclusive ownership: in place)
-#pragma unroll
-                for (int rrow = 0; rrow < 2; ++rrow) {
-                    const int i = ta * 2 + rrow;
-                    const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
-                    const T fq = S::mul(wq, phb);
-                    Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
-                    Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
-                }
-                __syncthreads();
-                T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
-            }
-        }
-        // broadcast the flag and W to the peers through distributed shared memory
-        for (int r = 1; r < CS; ++r) {
-            if (redbuf[0] > a.tol_rot) {
-                T* wr = cluster.map_shared_rank(Ws, r);
-                for (int e = tid; e < 32 * WP; e += JT) wr[e] = Ws[e];
-            }
-            if (tid == 0) *cluster.map_shared_rank(redbuf, r) = redbuf[0];
-        }
-    }
-    cluster.sync();   // #2: W and the flag are visible on every CTA; no DSMEM access after this point
-    const double panel_off = redbuf[0];
-    const bool need_rot = panel_off > a.tol_rot;
-    if (need_rot) {
-        // ---- 3. P <- P W on DMMA (all rows: X part and V part) --------------------------------
-        for (int64_t rf = warp; rf < rt / 8; rf += JW) {
-            T av[8];
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) av[ks] = Ps[(size_t)(ks * 4 + tig) * ldp + rf * 8 + grp];
-            T acc[4][2];
-#pragma unroll
-            for (int nf = 0; nf < 4; ++nf) {
-                acc[nf][0] = acc[nf][1] = S::zero();
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    T b = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
-                    mma_frag<CPLX, false>(acc[nf], av[ks], b);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int nf = 0; nf < 4; ++nf)
-#pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2)
-                    Ps[(size_t)(nf * 8 + 2 * tig + c2) * ldp + rf * 8 + grp] = acc[nf][c2];
-        }
-        // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-
-        // ---- TMA bulk write-back -------------------------------------------------------------------
-        if (warp == 0) {
-            const int c = lane;
-            const int64_t col = c < JB ? (int64_t)bi * JB + c : (int64_t)bj * JB + (c - JB);
-            bulk_s2g(Xg + x_lo + col * a.ldx, Ps + c * ldp, (unsigned)(a.rpcx * ES));
-            if (a.rpcv) bulk_s2g(Vg + v_lo + col * a.ldv, Ps + c * ldp + a.rpcx, (unsigned)(a.rpcv * ES));
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        }
-    }
+    return Gcur;
 }
 
 
@@ -454,6 +207,9 @@ struct JPArgs {
     unsigned* done;        // sweep barrier counter
     unsigned long long* flag;   // [max_sweeps] max off-diagonal cosine of the sweep (double bits)
     int* info;             // [0] sweeps executed, [1] converged
+    int inner;             // bipartite inner sweeps per visit
+    double* D;             // [p][16*16] diagonal Gram block carried with every column block
+    double tol_early;      // a sweep that starts below this ends converged (quadratic convergence)
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
 };
 
@@ -514,8 +270,9 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     T* rot_ph = Ws + 32 * WP;
     double* rot_c = reinterpret_cast<double*>(rot_ph + 16);
     double* rot_s = rot_c + 16;
-    double* redbuf = rot_s + 16;                            // JW + 1
+    double* redbuf = rot_s + 16;                            // JW + 2
     uint64_t* bars = reinterpret_cast<uint64_t*>(redbuf + JW + 2);
+    T* Dsm = reinterpret_cast<T*>(bars + 2);                // [2][16*16] carried diagonal blocks of the pair
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -588,12 +345,24 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                     issue_load(nchx - 1, 0);
                     if (nchx > 1) issue_load(nchx - 2, 1);
                     else if (nchv > 0) issue_load(1, 1);       // prefetch the first V chunk
+                    if (!full_inner) {
+                        // diagonal Gram blocks carried with the column blocks (L2 loads: another SM wrote them)
+                        const double* di = a.D + (size_t)bi * 256 * (CPLX ? 2 : 1);
+                        const double* dj = a.D + (size_t)bj * 256 * (CPLX ? 2 : 1);
+                        double* ds = reinterpret_cast<double*>(Dsm);
+                        constexpr int NW = 256 * (CPLX ? 2 : 1);
+#pragma unroll
+                        for (int u = 0; u < NW / 32; ++u) {
+                            ds[lane + 32 * u] = __ldcg(di + lane + 32 * u);
+                            ds[NW + lane + 32 * u] = __ldcg(dj + lane + 32 * u);
+                        }
+                    }
                 }
                 JP_STAMP(0);   // wait for the blocks + issue
 
                 // ---- 1. partial Gram on DMMA ----------------------------------------------------------
                 T* Gp = Gp0 + (item & 1) * 32 * 32;
-                {
+                if (full_inner) {
                     const int fi = warp & 3;
                     const int fj0 = (warp >> 2) * 2;
                     T acc[2][2];
@@ -624,13 +393,41 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                             int row = fi * 8 + grp, col = (fj0 + jj) * 8 + 2 * tig + c2;
                             Gp[col * 32 + row] = acc[jj][c2];
                         }
+                } else {
+                    // cross block only: 4 tiles (block i x block j), the row range split over two warp groups
+                    const int fi = (warp & 3) >> 1;            // 8-row fragment of block i (0..1)
+                    const int fj = 2 + (warp & 1);             // 8-column fragment of block j (2..3)
+                    const int kh = warp >> 2;                  // which half of the k-steps
+                    T acc[2];
+                    acc[0] = acc[1] = S::zero();
+                    for (int i = 0; i < nchx; ++i) {
+                        const int b = i & 1;
+                        wait_load(b);
+                        int nrows = a.rpcx - i * a.ch; if (nrows > a.ch) nrows = a.ch;
+                        const T* Ps = b ? buf1 : buf0;
+                        const T* pa = Ps + (size_t)(fi * 8 + grp) * ldp + tig;
+                        const T* pb = Ps + (size_t)(fj * 8 + grp) * ldp + tig;
+#pragma unroll 4
+                        for (int k0 = kh * 4; k0 < nrows; k0 += 8) mma_frag<CPLX, true>(acc, pa[k0], pb[k0]);
+                        if (i + 2 < nchx) {
+                            __syncthreads();
+                            if (warp == 0) issue_load(nchx - 1 - (i + 2), b);
+                        }
+                    }
+                    // Gp[kh][cj][ri]: ri = row inside block i, cj = column inside block j
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int ri = fi * 8 + grp, cj = (fj - 2) * 8 + 2 * tig + c2;
+                        Gp[kh * 256 + cj * 16 + ri] = acc[c2];
+                    }
                 }
                 JP_STAMP(1);   // load + partial Gram
                 cluster.sync();   // every CTA's partial Gram is visible cluster-wide
                 JP_STAMP(2);   // cluster barrier
                 // every CTA reduces the partial Grams in the same fixed order (bitwise identical G on
                 // every CTA => identical rotations and identical control flow, no broadcast needed)
-                {
+                double mx = 0.0;
+                if (full_inner) {
                     const T* rem[MAXCS];
 #pragma unroll
                     for (int rr = 0; rr < MAXCS; ++rr) rem[rr] = cluster.map_shared_rank(Gp, rr < CS ? rr : 0);
@@ -647,11 +444,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                         Gs[row * GP + col] = gsum;
                         Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
                     }
-                }
-                __syncthreads();
-                // convergence measure: max_{i<j} |G_ij| / sqrt(G_ii G_jj)
-                {
-                    double mx = 0.0;
+                    __syncthreads();
                     for (int e = tid; e < 32 * 32; e += JT) {
                         int row = e & 31, col = e >> 5;
                         if (row < col) {
@@ -663,6 +456,36 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                             }
                         }
                     }
+                } else {
+                    const T* rem[MAXCS];
+#pragma unroll
+                    for (int rr = 0; rr < MAXCS; ++rr) rem[rr] = cluster.map_shared_rank(Gp, rr < CS ? rr : 0);
+                    T v[MAXCS][2];
+#pragma unroll
+                    for (int rr = 0; rr < MAXCS; ++rr) {
+                        v[rr][0] = rr < CS ? rem[rr][tid] : S::zero();
+                        v[rr][1] = rr < CS ? rem[rr][256 + tid] : S::zero();
+                    }
+                    T cx = S::add(v[0][0], v[0][1]);
+#pragma unroll
+                    for (int rr = 1; rr < MAXCS; ++rr) if (rr < CS) cx = S::add(cx, S::add(v[rr][0], v[rr][1]));
+                    const int ri = tid & 15, cj = tid >> 4;
+                    const T dii = Dsm[cj * 16 + ri], djj = Dsm[256 + cj * 16 + ri];   // D_i[ri][cj], D_j[ri][cj]
+                    Gs[ri * GP + 16 + cj] = cx;
+                    Gs[(16 + cj) * GP + ri] = S::conj(cx);
+                    Gs[ri * GP + cj] = dii;
+                    Gs[(16 + ri) * GP + 16 + cj] = djj;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = tid + u * JT;
+                        const int row = e & 31, col = e >> 5;
+                        Ws[col * WP + row] = (row == col) ? S::one() : S::zero();
+                    }
+                    const double gii = S::real(Dsm[ri * 16 + ri]), gjj = S::real(Dsm[256 + cj * 16 + cj]);
+                    const double g2 = S::abs2(cx);
+                    if (gii > 0.0 && gjj > 0.0) mx = g2 / (gii * gjj);
+                }
+                {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         double other = __shfl_xor_sync(0xffffffffu, mx, o);
@@ -682,9 +505,24 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                 const bool need_rot = redbuf[JW] > a.tol_rot;
                 JP_STAMP(3);   // reduce + convergence measure
                 if (need_rot) {
-                    jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid);
+                    const T* Gfin = jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid, a.inner);
+                    if (R == 0) {
+                        // the diagonal blocks of the rotated Gram travel with the column blocks
+                        T* di = reinterpret_cast<T*>(a.D) + (size_t)bi * 256;
+                        T* dj = reinterpret_cast<T*>(a.D) + (size_t)bj * 256;
+                        const int ri = tid & 15, cj = tid >> 4;
+                        di[cj * 16 + ri] = Gfin[ri * GP + cj];
+                        dj[cj * 16 + ri] = Gfin[(16 + ri) * GP + 16 + cj];
+                        __threadfence();
+                    }
                     JP_STAMP(4);   // eig
                     // ---- 3. update pass: P <- P W chunk by chunk, TMA bulk write-back ------------------
+                    // W as DMMA B fragments, held in registers for the whole pass
+                    T wf[4][8];
+#pragma unroll
+                    for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) wf[nf][ks] = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
                     for (int j = 0; j < npos; ++j) {
                         const int b = (nchx - 1 + j) & 1;
                         if (j >= 2 || (j == 1 && nchx == 1)) wait_load(b);
@@ -697,14 +535,11 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                             for (int ks = 0; ks < 8; ++ks) av[ks] = Ps[(size_t)(ks * 4 + tig) * ldp + rf * 8 + grp];
                             T acc[4][2];
 #pragma unroll
-                            for (int nf = 0; nf < 4; ++nf) {
-                                acc[nf][0] = acc[nf][1] = S::zero();
+                            for (int nf = 0; nf < 4; ++nf) acc[nf][0] = acc[nf][1] = S::zero();
 #pragma unroll
-                                for (int ks = 0; ks < 8; ++ks) {
-                                    T bw = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
-                                    mma_frag<CPLX, false>(acc[nf], av[ks], bw);
-                                }
-                            }
+                            for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                                for (int nf = 0; nf < 4; ++nf) mma_frag<CPLX, false>(acc[nf], av[ks], wf[nf][ks]);
                             __syncwarp();
 #pragma unroll
                             for (int nf = 0; nf < 4; ++nf)
@@ -731,8 +566,18 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
                     JP_STAMP(6);   // store completion
-                } else if (nchx == 1 && nchv > 0) {
-                    wait_load(1);   // consume the prefetched V chunk
+                } else {
+                    if (nchx == 1 && nchv > 0) wait_load(1);   // consume the prefetched V chunk
+                    if (full_inner && R == 0) {
+                        // round 0 refreshes the carried diagonal blocks even when nothing is rotated
+                        T* di = reinterpret_cast<T*>(a.D) + (size_t)bi * 256;
+                        T* dj = reinterpret_cast<T*>(a.D) + (size_t)bj * 256;
+                        const int ri = tid & 15, cj = tid >> 4;
+                        di[cj * 16 + ri] = Gs[ri * GP + cj];
+                        dj[cj * 16 + ri] = Gs[(16 + ri) * GP + 16 + cj];
+                        __threadfence();
+                        __syncthreads();
+                    }
                 }
                 // ---- 4. publish: this CTA's rows of both blocks have finished round g ------------------
                 if (warp == 0) {
@@ -759,7 +604,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
         const double off = redbuf[JW + 1];
         __syncthreads();
         JP_STAMP(7);   // publish + sweep barrier
-        if (off <= a.tol) { converged = 1; ++sweep; break; }
+        if (off <= a.tol_early) { converged = 1; ++sweep; break; }
     }
     if (blockIdx.x == 0 && tid == 0) {
         a.info[0] = sweep; a.info[1] = converged;
@@ -875,106 +720,6 @@ Group gg(int64_t dim, int64_t str) {
     return g;
 }
 
-// Launch geometry of the Jacobi rounds for an nx x npad problem (optionally with V rows).
-struct JacobiPlan {
-    int cs = 1;
-    int64_t rpcx = 0, rpcv = 0, ldp = 0, ldx = 0, ldv = 0;
-    size_t smem = 0;
-};
-
-template <bool CPLX>
-JacobiPlan plan_jacobi(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
-    const size_t es = CPLX ? 16 : 8;
-    const int pairs = (int)(npad / JB) / 2;
-    const int64_t nv = with_v ? npad : 0;
-    const size_t fixed = (size_t)(32 * 32 + 2 * 32 * GP + 32 * WP + 16) * es + (32 + JW) * 8 + 64 + 128;
-    const size_t budget = 200 * 1024;
-    auto round8 = [](int64_t v) { return (v + 7) / 8 * 8; };
-    JacobiPlan pl;
-    for (int cs = 1;; cs *= 2) {
-        int64_t rpcx = round8((nx + cs - 1) / cs);
-        int64_t rpcv = nv ? round8((nv + cs - 1) / cs) : 0;
-        int64_t rt = rpcx + rpcv;
-        // pitch: == 4 (mod 16) real, == 2 (mod 8) complex => conflict-free fragment loads, and
-        // every column start stays 16-byte aligned for the TMA bulk copies
-        int64_t ldp = rt;
-        if (CPLX) { while (ldp % 8 != 2) ++ldp; }
-        else { while (ldp % 16 != 4) ++ldp; }
-        size_t smem = (size_t)PW * ldp * es + fixed;
-        bool fits = smem <= budget;
-        bool two_per_sm = smem <= 100 * 1024;   // the eig phase is latency-bound: co-residency hides it
-        bool spread = (int64_t)pairs * cs * 2 > c->num_sms || rt <= 64;
-        if ((fits && two_per_sm && spread) || cs == MAXCS) {
-            if (!fits)
-                throw Error(ST_UNSUPPORTED, "svd: matrix too large for the shared-memory Jacobi panel (n > ~10k)");
-            pl.cs = cs; pl.rpcx = rpcx; pl.rpcv = rpcv; pl.ldp = ldp; pl.smem = smem;
-            pl.ldx = (int64_t)cs * rpcx;
-            pl.ldv = (int64_t)cs * rpcv;
-            return pl;
-        }
-    }
-}
-
-// One-sided block Jacobi on X (ldx x npad, nx live rows); V (ldv x npad) optional.  Returns sweeps.
-template <bool CPLX>
-int jacobi_sweeps(Ctx* c, const JacobiPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
-    const size_t es = CPLX ? 16 : 8;
-    const int p = (int)(npad / JB);
-    const int pairs = p / 2;
-    const int64_t nv = V ? npad : 0;
-    auto kern = jacobi_round_kernel<CPLX>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
-    }
-    unsigned long long* flag = (unsigned long long*)alloc(c, 8);
-    double* hflag = (double*)c->get_pinned(8);
-    const double eps = 2.220446049250313e-16;
-    const double tol = eps * sqrt((double)(nx > 4 ? nx : 4));
-    const int max_sweeps = 40;
-    int sweeps = 0;
-    JacobiArgs a{};
-    a.X = X; a.ldx = pl.ldx; a.nx = nx;
-    a.V = V; a.ldv = pl.ldv; a.nv = nv;
-    a.p = p; a.rpcx = pl.rpcx; a.rpcv = V ? pl.rpcv : 0; a.ldp = pl.ldp;
-    a.tol_rot = tol * 0.25;
-    a.flag = flag;
-    const int rounds = p - 1;
-    for (; sweeps < max_sweeps;) {
-        zero(c, flag, 8);
-        for (int r = 0; r < rounds; ++r) {
-            a.round = r;
-            a.full_inner = (r == 0) ? 1 : 0;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(pairs * pl.cs), 1, 1);
-            cfg.blockDim = dim3(JT, 1, 1);
-            cfg.dynamicSmemBytes = pl.smem;
-            cfg.stream = c->stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = pl.cs;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
-            c->launched("jacobi_round", 2.0 * (double)(nx + nv) * (double)npad * (double)es);  // bytes: panel read + write
-        }
-        ++sweeps;
-        d2h(c, hflag, flag, 8);
-        sync(c);
-        if (getenv("T4B_VERBOSE") && atoi(getenv("T4B_VERBOSE")) > 1) fprintf(stderr, "[t4b]   sweep %d off=%.3e\n", sweeps, *hflag);
-        if (*hflag <= tol) break;
-    }
-    release(c, flag);
-    if (getenv("T4B_VERBOSE"))
-        fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d cs=%d sweeps=%d last_off=%.3e tol=%.3e\n",
-                (long long)nx, (long long)npad, V ? 1 : 0, pl.cs, sweeps, *hflag, tol);
-    return sweeps;
-}
-
 // ---- persistent kernel: launch geometry ------------------------------------------------------------------
 struct JPPlan {
     int cs = 1, nclusters = 1, pairs = 1, rpcx = 0, rpcv = 0, ch = 0, ldp = 0;
@@ -986,7 +731,7 @@ template <bool CPLX>
 size_t jp_smem_bytes(int ldp) {
     const size_t es = CPLX ? 16 : 8;
     return (size_t)2 * PW * ldp * es + (size_t)(2 * 32 * 32 + 2 * 32 * GP + 32 * WP + 16) * es +
-           (size_t)(32 + JW + 2) * 8 + 2 * 8 + 128;
+           (size_t)(32 + JW + 2) * 8 + 2 * 8 + 2 * 256 * es + 128;
 }
 
 template <bool CPLX>
@@ -1064,6 +809,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     // workspace: flag[max_sweeps] (u64) | timing[8] (u64) | ready[p] | done | info[2]
     const bool verbose = getenv("T4B_VERBOSE") != nullptr;
     const size_t ws_bytes = (size_t)(max_sweeps + 8) * 8 + ((size_t)p + 4) * 4;
+    double* Dblk = (double*)alloc(c, (size_t)p * 256 * es);
     unsigned char* ws = (unsigned char*)alloc(c, ws_bytes);
     zero(c, ws, ws_bytes);
     const double eps = 2.220446049250313e-16;
@@ -1075,6 +821,12 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     a.rpcx = pl.rpcx; a.rpcv = V ? pl.rpcv : 0; a.ch = pl.ch; a.ldp = pl.ldp;
     a.max_sweeps = max_sweeps;
     a.tol = tol; a.tol_rot = tol * 0.25;
+    // off_after <~ n * off_before^2 once the iteration converges quadratically: a sweep that starts
+    // below sqrt(0.01 tol / n) leaves the columns orthogonal to working accuracy
+    a.tol_early = sqrt(0.01 * tol / (double)npad);
+    if (a.tol_early < tol) a.tol_early = tol;
+    a.D = Dblk;
+    a.inner = getenv("T4B_JAC_INNER") ? atoi(getenv("T4B_JAC_INNER")) : 1;
     a.flag = (unsigned long long*)ws;
     a.timing = verbose ? (unsigned long long*)ws + max_sweeps : nullptr;
     a.ready = (unsigned*)(ws + (size_t)(max_sweeps + 8) * 8);
@@ -1116,6 +868,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
                 t[0] * 1e-3, t[1] * 1e-3, t[2] * 1e-3, t[3] * 1e-3, t[4] * 1e-3, t[5] * 1e-3, t[6] * 1e-3, t[7] * 1e-3);
     }
     release(c, ws);
+    release(c, Dblk);
 }
 
 // m >= n.  A destroyed.  U (m x n) / Vh (n x n) optional.
