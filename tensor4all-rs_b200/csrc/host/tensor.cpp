@@ -1,6 +1,7 @@
 #include "tensor.h"
 
 #include <algorithm>
+#include <functional>
 #include <atomic>
 #include <limits>
 
@@ -144,23 +145,78 @@ Tensor contract(dla::Ctx* c, const std::vector<const Tensor*>& ts,
         if (out_order) return permute(c, work[0], *out_order);
         return work[0];
     }
-    while (work.size() > 1) {
-        // greedy: cheapest connected pair (cost = product of the union of index dims)
-        double best = std::numeric_limits<double>::infinity();
-        int bi = -1, bj = -1;
-        bool best_connected = false;
-        for (size_t i = 0; i < work.size(); ++i)
-            for (size_t j = i + 1; j < work.size(); ++j) {
-                bool connected = !common_indices(work[i], work[j]).empty();
-                double cost = 1.0;
-                for (auto& ix : work[i].inds) cost *= (double)ix.dim;
-                for (auto& ix : work[j].inds)
-                    if (!work[i].has(ix)) cost *= (double)ix.dim;
-                if ((connected && !best_connected) ||
-                    (connected == best_connected && cost < best)) {
-                    best = cost; bi = (int)i; bj = (int)j; best_connected = connected;
+    // Pairwise order: exhaustive search over contraction sequences for small networks (the reference
+    // hands the order to an einsum optimizer, crates/tensor4all-core/src/defaults/contract.rs:721-849);
+    // cost of a pair = product of the dims of the union of its indices (multiply-adds).  Larger
+    // networks fall back to greedy cheapest-connected-pair.
+    std::vector<std::pair<int, int>> plan;
+    if (work.size() <= 6) {
+        typedef std::vector<std::vector<Index>> Sets;
+        Sets sets;
+        for (auto& t : work) sets.push_back(t.inds);
+        // indices that must survive (appear once overall) are kept by every merge automatically:
+        // merged set = symmetric difference of the two index lists
+        std::vector<std::pair<int, int>> cur, best_plan;
+        double best_cost = std::numeric_limits<double>::infinity();
+        std::function<void(Sets&, double)> dfs = [&](Sets& ss, double cost) {
+            if (cost >= best_cost) return;
+            if (ss.size() == 1) { best_cost = cost; best_plan = cur; return; }
+            for (size_t i = 0; i < ss.size(); ++i)
+                for (size_t j = i + 1; j < ss.size(); ++j) {
+                    bool connected = false;
+                    double pc = 1.0;
+                    for (auto& ix : ss[i]) pc *= (double)ix.dim;
+                    std::vector<Index> merged;
+                    for (auto& ix : ss[i])
+                        if (std::find(ss[j].begin(), ss[j].end(), ix) == ss[j].end()) merged.push_back(ix);
+                    for (auto& ix : ss[j]) {
+                        if (std::find(ss[i].begin(), ss[i].end(), ix) == ss[i].end()) { pc *= (double)ix.dim; merged.push_back(ix); }
+                        else connected = true;
+                    }
+                    // outer products only when nothing is connected any more
+                    if (!connected) {
+                        bool any = false;
+                        for (size_t a = 0; a < ss.size() && !any; ++a)
+                            for (size_t b = a + 1; b < ss.size() && !any; ++b)
+                                for (auto& ix : ss[a])
+                                    if (std::find(ss[b].begin(), ss[b].end(), ix) != ss[b].end()) { any = true; break; }
+                        if (any) continue;
+                    }
+                    Sets next;
+                    for (size_t a = 0; a < ss.size(); ++a)
+                        if (a != i && a != j) next.push_back(ss[a]);
+                    next.insert(next.begin() + i, merged);
+                    cur.push_back({(int)i, (int)j});
+                    dfs(next, cost + pc);
+                    cur.pop_back();
                 }
-            }
+        };
+        dfs(sets, 0.0);
+        plan = best_plan;
+    }
+    size_t step = 0;
+    while (work.size() > 1) {
+        int bi = -1, bj = -1;
+        if (step < plan.size()) {
+            bi = plan[step].first; bj = plan[step].second;
+        } else {
+            // greedy: cheapest connected pair (cost = product of the union of index dims)
+            double best = std::numeric_limits<double>::infinity();
+            bool best_connected = false;
+            for (size_t i = 0; i < work.size(); ++i)
+                for (size_t j = i + 1; j < work.size(); ++j) {
+                    bool connected = !common_indices(work[i], work[j]).empty();
+                    double cost = 1.0;
+                    for (auto& ix : work[i].inds) cost *= (double)ix.dim;
+                    for (auto& ix : work[j].inds)
+                        if (!work[i].has(ix)) cost *= (double)ix.dim;
+                    if ((connected && !best_connected) ||
+                        (connected == best_connected && cost < best)) {
+                        best = cost; bi = (int)i; bj = (int)j; best_connected = connected;
+                    }
+                }
+        }
+        ++step;
         bool last = work.size() == 2;
         Tensor r = contract_pair(c, work[bi], work[bj], false, false, last ? out_order : nullptr);
         work.erase(work.begin() + bj);

@@ -11,6 +11,10 @@
 // conflict-free padded layouts, 64x32 (real) / 32x32 (complex) register-blocked warp tiles.
 // The smem layout of each operand follows its fast axis in global memory (template ALAY/BLAY)
 // so that copies stay coalesced for both "N" and "T" style operands.
+#include <cuda.h>
+
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 namespace t4b {
@@ -259,6 +263,259 @@ gemm_kernel(GemmParams p) {
     }
 }
 
+// =====================================================================================================
+// Warp-specialised variant for operands whose tiles are made of contiguous, 16-byte aligned runs (plain
+// reshapes and composite indices whose fastest axis covers a whole tile - every contraction of the C3
+// sweep): ONE producer warp stages the A/B k-tiles with TMA bulk copies (cp.async.bulk + mbarrier
+// complete_tx) into the same padded, conflict-free layouts, EIGHT consumer warps do nothing but fragment
+// loads and DMMA.  full/empty mbarrier ring of WS_STAGES stages, no __syncthreads in the main loop, no
+// address arithmetic in the MMA warps.
+// =====================================================================================================
+constexpr int WS_STAGES = 4;
+constexpr int WS_BM = 128, WS_BN = 128, WS_WM = 64, WS_WN = 32;
+constexpr int WS_CONSUMERS = (WS_BM / WS_WM) * (WS_BN / WS_WN);   // 8 warps
+constexpr int WS_THREADS = (WS_CONSUMERS + 1) * 32;
+
+// K-fast operands are staged by ONE 2-D..5-D TMA tensor-map copy per k-tile (box = 16 k x 128 rows,
+// 128-byte swizzle); the tile rows are a box of the operand's free-index axes.
+struct TmapCoord {
+    int nk;                 // k axes in the map (1 or 2); tile k-extent lies in axis 0
+    int nm;                 // free-index axes in the map (1..3)
+    int64_t kdim0;          // size of the leading k axis
+    int64_t mdim[3];        // sizes of the free-index axes
+};
+struct GemmWsParams {
+    GemmParams p;
+    Group am, ak, bk, bn;      // simplified operand groups (producer-side address generation)
+    CUtensorMap tmA, tmB;      // valid for K-fast operands only
+    TmapCoord tcA, tcB;
+};
+
+__device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(g_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(g_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(g_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void g_bulk_g2s(void* sdst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(g_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(g_smem_u32(bar)) : "memory");
+}
+
+// one TMA tensor copy: coordinates (k digits, then free-index digits), innermost first
+__device__ __forceinline__ void g_tensor_g2s(void* sdst, const CUtensorMap* tm, const TmapCoord& tc, int64_t k0,
+                                             int64_t r0, uint64_t* bar) {
+    int c[5] = {0, 0, 0, 0, 0};
+    int n = 0;
+    if (tc.nk == 1) { c[n++] = (int)k0; }
+    else { c[n++] = (int)(k0 % tc.kdim0); c[n++] = (int)(k0 / tc.kdim0); }
+    int64_t r = r0;
+    for (int d = 0; d < tc.nm; ++d) {
+        if (d == tc.nm - 1) c[n++] = (int)r;
+        else { c[n++] = (int)(r % tc.mdim[d]); r /= tc.mdim[d]; }
+    }
+    const unsigned dst = g_smem_u32(sdst), mb = g_smem_u32(bar);
+    const unsigned long long tmp = reinterpret_cast<unsigned long long>(tm);
+    if (n == 2)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"(tmp), "r"(mb), "r"(c[0]), "r"(c[1]) : "memory");
+    else if (n == 3)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"(tmp), "r"(mb), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+    else if (n == 4)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst), "l"(tmp), "r"(mb), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                     ::"r"(dst), "l"(tmp), "r"(mb), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+
+// element index inside a K-fast tile: 128-byte rows (16 doubles), 16-byte chunks XOR-swizzled by the row
+__device__ __forceinline__ int kfast_idx(int m, int k) { return m * 16 + ((((k >> 1) ^ (m & 7)) << 1) | (k & 1)); }
+
+template <bool CPLX, int ALAY, int BLAY>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_constant__ GemmWsParams wp) {
+    constexpr int BM = WS_BM, BN = WS_BN, WM = WS_WM, WN = WS_WN;
+    constexpr int ES = CPLX ? 2 : 1;
+    constexpr int PADMN = CPLX ? 2 : 4;
+    static_assert(!CPLX, "the warp-specialised kernel is instantiated for f64 only");
+    constexpr int PITCH_A = ALAY == 0 ? (BM + PADMN) : BK;
+    constexpr int PITCH_B = BLAY == 1 ? (BN + PADMN) : BK;
+    constexpr int A_ELEMS = ALAY == 0 ? BK * PITCH_A : BM * BK;
+    constexpr int B_ELEMS = BLAY == 1 ? BK * PITCH_B : BN * BK;
+    constexpr int B_OFF = (A_ELEMS + 127) / 128 * 128;                       // 1024-byte aligned tiles
+    constexpr int STAGE_DOUBLES = (B_OFF + B_ELEMS + 127) / 128 * 128;
+    constexpr int MF = WM / 8, NF = WN / 8;
+    const GemmParams& p = wp.p;
+
+    extern __shared__ __align__(16) unsigned char ws_smem_raw[];
+    __shared__ uint64_t full_bar[WS_STAGES], empty_bar[WS_STAGES];
+    // swizzled TMA tiles need 1024-byte aligned shared-memory addresses
+    double* smem = reinterpret_cast<double*>(ws_smem_raw + ((1024u - (g_smem_u32(ws_smem_raw) & 1023u)) & 1023u));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t m0 = (tile % p.tiles_m) * BM;
+    const int64_t n0 = (tile / p.tiles_m) * BN;
+    const int64_t KT_all = p.K / BK;
+    const int64_t kt_begin = (int64_t)blockIdx.y * p.kt_per_split;
+    const int64_t kt_stop = (kt_begin + p.kt_per_split < KT_all) ? kt_begin + p.kt_per_split : KT_all;
+    const int64_t KT = kt_stop > kt_begin ? kt_stop - kt_begin : 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < WS_STAGES; ++s) { g_mbar_init(&full_bar[s], 1); g_mbar_init(&empty_bar[s], WS_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == WS_CONSUMERS) {
+        // ================= producer warp =================
+        const int vm = (int)((p.M - m0) < BM ? (p.M - m0) : BM);     // valid rows / columns of this tile
+        const int vn = (int)((p.N - n0) < BN ? (p.N - n0) : BN);
+        // K-fast tiles are full boxes (out-of-range rows are zero-filled by the TMA unit)
+        const unsigned bytes = (unsigned)(((ALAY == 0 ? vm : BM) + (BLAY == 1 ? vn : BN)) * BK) * 8u;
+        const int64_t a_m0 = ALAY == 0 ? group_offset(wp.am, m0) : 0;
+        const int64_t b_n0 = BLAY == 1 ? group_offset(wp.bn, n0) : 0;
+        for (int64_t kt = 0; kt < KT; ++kt) {
+            const int stage = (int)(kt % WS_STAGES);
+            const int64_t round = kt / WS_STAGES;
+            if (round > 0) g_mbar_wait(&empty_bar[stage], (unsigned)((round - 1) & 1));
+            if (lane == 0) g_mbar_expect_tx(&full_bar[stage], bytes);
+            __syncwarp();
+            double* sA = smem + (size_t)stage * STAGE_DOUBLES;
+            double* sB = sA + B_OFF;
+            const int64_t k0 = (kt_begin + kt) * BK;
+            if (ALAY == 0) {
+                if (lane < BK)
+                    g_bulk_g2s(sA + (size_t)lane * PITCH_A, p.A + (a_m0 + group_offset(wp.ak, k0 + lane)),
+                               (unsigned)vm * 8u, &full_bar[stage]);
+            } else if (lane == 0) {
+                g_tensor_g2s(sA, &wp.tmA, wp.tcA, k0, m0, &full_bar[stage]);
+            }
+            if (BLAY == 1) {
+                if (lane < BK)
+                    g_bulk_g2s(sB + (size_t)lane * PITCH_B, p.B + (b_n0 + group_offset(wp.bk, k0 + lane)),
+                               (unsigned)vn * 8u, &full_bar[stage]);
+            } else if (lane == 0) {
+                g_tensor_g2s(sB, &wp.tmB, wp.tcB, k0, n0, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    const int wm0 = (warp % (BM / WM)) * WM;
+    const int wn0 = (warp / (BM / WM)) * WN;
+    const int grp = lane >> 2, tig = lane & 3;
+    double acc[MF][NF][2 * ES];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j)
+#pragma unroll
+            for (int e = 0; e < 2 * ES; ++e) acc[i][j][e] = 0.0;
+    for (int64_t kt = 0; kt < KT; ++kt) {
+        const int stage = (int)(kt % WS_STAGES);
+        g_mbar_wait(&full_bar[stage], (unsigned)((kt / WS_STAGES) & 1));
+        const double* sA = smem + (size_t)stage * STAGE_DOUBLES;
+        const double* sB = sA + B_OFF;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            const int k = ks * 4 + tig;
+            double af[MF], bf[NF];
+#pragma unroll
+            for (int i = 0; i < MF; ++i) {
+                const int m = wm0 + i * 8 + grp;
+                af[i] = sA[ALAY == 0 ? k * PITCH_A + m : kfast_idx(m, k)];
+            }
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+                const int n = wn0 + j * 8 + grp;
+                bf[j] = sB[BLAY == 1 ? k * PITCH_B + n : kfast_idx(n, k)];
+            }
+#pragma unroll
+            for (int i = 0; i < MF; ++i)
+#pragma unroll
+                for (int j = 0; j < NF; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) g_mbar_arrive(&empty_bar[stage]);
+    }
+
+    // epilogue (same as gemm_kernel): thread holds rows (grp) and columns (2*tig, 2*tig+1) of each fragment
+    if (p.ksplit > 1) {
+        double* part = p.partial + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N * ES;
+#pragma unroll
+        for (int i = 0; i < MF; ++i) {
+            int64_t gm = m0 + wm0 + i * 8 + grp;
+            if (gm >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    int64_t gn = n0 + wn0 + j * 8 + 2 * tig + c;
+                    if (gn >= p.N) continue;
+                    size_t o = (size_t)gm + (size_t)gn * (size_t)p.M;
+                    if constexpr (CPLX) {
+                        double2 r;
+                        r.x = acc[i][j][c];
+                        r.y = acc[i][j][2 * ES - 2 + c];
+                        reinterpret_cast<double2*>(part)[o] = r;
+                    } else {
+                        part[o] = acc[i][j][c];
+                    }
+                }
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+        int64_t gm = m0 + wm0 + i * 8 + grp;
+        if (gm >= p.M) continue;
+        int64_t om = off_of(p.tcm, p.scm, gm);
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                int64_t gn = n0 + wn0 + j * 8 + 2 * tig + c;
+                if (gn >= p.N) continue;
+                int64_t o = om + off_of(p.tcn, p.scn, gn);
+                if constexpr (CPLX) {
+                    double2 r;
+                    r.x = p.alpha * acc[i][j][c];
+                    r.y = p.alpha * acc[i][j][2 * ES - 2 + c];
+                    double2* dst = reinterpret_cast<double2*>(p.C) + o;
+                    if (p.beta != 0.0) {
+                        double2 old = *dst;
+                        r.x += p.beta * old.x; r.y += p.beta * old.y;
+                    }
+                    *dst = r;
+                } else {
+                    double r = p.alpha * acc[i][j][c];
+                    if (p.beta != 0.0) r += p.beta * p.C[o];
+                    p.C[o] = r;
+                }
+            }
+        }
+    }
+}
+
 // deterministic split-K reduction: C = alpha * sum_s partial[s] + beta * C
 template <bool CPLX>
 __global__ void splitk_reduce_kernel(const double* __restrict__ partial, int ksplit, int64_t M,
@@ -328,8 +585,12 @@ int64_t min_stride(const Group& g) {
     return s == INT64_MAX ? 1 : s;  // all-ones group: treat as fast
 }
 
+template <bool CPLX>
+bool launch_ws(Ctx* c, GemmParams& p, int alay, int blay, const Group* g);
+
 template <bool CPLX, int BM, int BN, int WM, int WN>
-void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, const Group& cn) {
+void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, const Group& cn,
+                const Group* gops = nullptr) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int ES = CPLX ? 2 : 1;
     constexpr int PADMN = CPLX ? 2 : 4;
@@ -355,7 +616,12 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, cons
         }                                                                                        \
         kern<<<g3, NT, sm, c->stream>>>(p);                                          \
     }
-    if (alay == 0 && blay == 0) T4B_LAUNCH(0, 0)
+    bool done = false;
+    if constexpr (!CPLX && BM == 128 && BN == 128) {
+        if (gops && !getenv("T4B_GEMM_NOWS")) done = launch_ws<false>(c, p, alay, blay, gops);
+    }
+    if (done) {}
+    else if (alay == 0 && blay == 0) T4B_LAUNCH(0, 0)
     else if (alay == 0 && blay == 1) T4B_LAUNCH(0, 1)
     else if (alay == 1 && blay == 0) T4B_LAUNCH(1, 0)
     else T4B_LAUNCH(1, 1)
@@ -369,6 +635,129 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, cons
                                                               p.beta, p.C, cm, cn);
         c->launched("gemm_splitk_reduce");
     }
+}
+
+// The tile rows of an operand are contiguous, 16-byte aligned runs when (fast = the index that is
+// contiguous in memory, other = the index the rows are enumerated by):
+//  * fast.str[0] == 1 and a tile extent `ext` of the fast index never crosses a run boundary
+//    (single axis, or leading axis a multiple of ext),
+//  * every offset is even (real) so that base + offset stays 16-byte aligned.
+bool ws_group_ok(const Group& fast, int64_t ext, const Group& other, bool cplx) {
+    if (fast.nd < 1 || fast.str[0] != 1) return false;
+    if (fast.nd > 1 && fast.dim[0] % ext != 0) return false;
+    if (cplx) return true;
+    if (fast.nd == 1 && fast.dim[0] > ext && ext % 2 != 0) return false;
+    for (int d = 1; d < fast.nd; ++d)
+        if (fast.dim[d] > 1 && fast.str[d] % 2 != 0) return false;
+    for (int d = 0; d < other.nd; ++d)
+        if (other.dim[d] > 1 && other.str[d] % 2 != 0) return false;
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor map for a K-fast f64 operand: axes = (k axes of `fast`, free axes of `other`), box = 16 k x `ext`
+// rows where the rows are a box of the free axes (leading axes fully covered).  Returns false if the operand
+// cannot be described (strides not 16-byte multiples, tile not a box, more than 5 axes).
+bool make_kfast_tmap(const double* base, const Group& fast, const Group& other, int ext, CUtensorMap* tm,
+                     TmapCoord* tc) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if (fast.nd < 1 || fast.nd > 2 || fast.str[0] != 1) return false;
+    if (fast.nd == 2 && fast.dim[0] % BK != 0) return false;
+    if (other.nd < 1 || other.nd > 3) return false;
+    if ((uintptr_t)base % 16) return false;
+    cuuint64_t gdim[5]; cuuint64_t gstr[5]; cuuint32_t box[5]; cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    int n = 0;
+    gdim[n] = (cuuint64_t)fast.dim[0]; box[n] = BK; ++n;
+    if (fast.nd == 2) {
+        if (fast.str[1] % 2) return false;
+        gdim[n] = (cuuint64_t)fast.dim[1]; gstr[n - 1] = (cuuint64_t)fast.str[1] * 8; box[n] = 1; ++n;
+    }
+    int64_t remaining = ext;
+    for (int d = 0; d < other.nd; ++d) {
+        if (other.str[d] % 2 || other.str[d] <= 0) return false;
+        int64_t b;
+        if (remaining == 1) b = 1;
+        else if (other.dim[d] >= remaining) {
+            if (d != other.nd - 1 && other.dim[d] % remaining != 0) return false;
+            b = remaining; remaining = 1;
+        } else {
+            if (remaining % other.dim[d] != 0) return false;
+            b = other.dim[d]; remaining /= other.dim[d];
+        }
+        gdim[n] = (cuuint64_t)other.dim[d]; gstr[n - 1] = (cuuint64_t)other.str[d] * 8; box[n] = (cuuint32_t)b; ++n;
+    }
+    if (remaining != 1) return false;
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)n, (void*)base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    tc->nk = fast.nd; tc->nm = other.nd; tc->kdim0 = fast.dim[0];
+    for (int d = 0; d < 3; ++d) tc->mdim[d] = d < other.nd ? other.dim[d] : 1;
+    return true;
+}
+
+template <bool CPLX>
+bool launch_ws(Ctx* c, GemmParams& p, int alay, int blay, const Group* g) {
+    constexpr int PADMN = 4;
+    if (CPLX) return false;
+    if (p.K % BK != 0 || p.K == 0) return false;
+    if (((uintptr_t)p.A % 16) || ((uintptr_t)p.B % 16)) return false;
+    GemmWsParams wp;
+    // g[0]=am g[1]=ak g[2]=bk g[3]=bn
+    if (alay == 0) {
+        if (!ws_group_ok(g[0], WS_BM, g[1], false) || (p.M % WS_BM) % 2 != 0) return false;
+    } else if (!make_kfast_tmap(p.A, g[1], g[0], WS_BM, &wp.tmA, &wp.tcA)) return false;
+    if (blay == 1) {
+        if (!ws_group_ok(g[3], WS_BN, g[2], false) || (p.N % WS_BN) % 2 != 0) return false;
+    } else if (!make_kfast_tmap(p.B, g[2], g[3], WS_BN, &wp.tmB, &wp.tcB)) return false;
+    auto smem_bytes = [&](int al, int bl) {
+        int a = al == 0 ? BK * (WS_BM + PADMN) : WS_BM * BK;
+        int b = bl == 1 ? BK * (WS_BN + PADMN) : WS_BN * BK;
+        int boff = (a + 127) / 128 * 128;
+        int stage = (boff + b + 127) / 128 * 128;
+        return (size_t)stage * 8 * WS_STAGES + 1024;
+    };
+    p.tiles_m = (int)((p.M + WS_BM - 1) / WS_BM);
+    int64_t tiles_n = (p.N + WS_BN - 1) / WS_BN;
+    wp.p = p; wp.am = g[0]; wp.ak = g[1]; wp.bk = g[2]; wp.bn = g[3];
+    dim3 g3((unsigned)((int64_t)p.tiles_m * tiles_n), (unsigned)p.ksplit, 1);
+    size_t sm = smem_bytes(alay, blay);
+#define T4B_LAUNCH_WS(AL, BL)                                                                    \
+    {                                                                                            \
+        auto kern = gemm_ws_kernel<false, AL, BL>;                                               \
+        static bool attr_set = false;                                                            \
+        if (!attr_set) {                                                                         \
+            T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                (int)smem_bytes(AL, BL)));                       \
+            attr_set = true;                                                                     \
+        }                                                                                        \
+        kern<<<g3, WS_THREADS, sm, c->stream>>>(wp);                                             \
+    }
+    if (alay == 0 && blay == 0) T4B_LAUNCH_WS(0, 0)
+    else if (alay == 0 && blay == 1) T4B_LAUNCH_WS(0, 1)
+    else if (alay == 1 && blay == 0) T4B_LAUNCH_WS(1, 0)
+    else T4B_LAUNCH_WS(1, 1)
+#undef T4B_LAUNCH_WS
+    return true;
 }
 
 }  // namespace
@@ -446,11 +835,15 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
     if (M == 1) alay = 1;   // degenerate free index: follow K
     if (N == 1) blay = 0;
 
+    if (getenv("T4B_GEMM_TRACE"))
+        fprintf(stderr, "[t4b] gemm %s M=%lld N=%lld K=%lld alay=%d blay=%d nd=%d%d%d%d%d%d ksplit=%d class=%s\n",
+                dt == C64 ? "c64" : "f64", (long long)M, (long long)N, (long long)K, alay, blay, g[0].nd, g[1].nd,
+                g[2].nd, g[3].nd, g[4].nd, g[5].nd, ksplit, c->gemm_class);
     if (dt == C64) {
         launch_cfg<true, 64, 64, 32, 32>(c, p, alay, blay, g[4], g[5]);
     } else {
         if (small_tile) launch_cfg<false, 64, 64, 32, 32>(c, p, alay, blay, g[4], g[5]);
-        else launch_cfg<false, 128, 128, 64, 32>(c, p, alay, blay, g[4], g[5]);
+        else launch_cfg<false, 128, 128, 64, 32>(c, p, alay, blay, g[4], g[5], g);
     }
 }
 

@@ -22,6 +22,9 @@ def main():
         "zip_RA_4096x2048x512": ((512, 512, 8), (512, 4, 512), [1], [0]),
         "zip_RAB_262144x32x32": ((512, 8, 4, 512), (8, 4, 4, 8), [1, 2], [0, 1]),
         "absorbR_512x2048x512": ((512, 512), (512, 4, 512), [1], [0]),
+        "UhM_512x4096x2048_tn": ((2048, 512), (2048, 4096), [0], [0]),
+        "UhA_512x512x2048_tn": ((2048, 512), (2048, 512), [0], [0]),
+        "two_site_2048x512x512": ((512, 4, 512), (512, 512), [2], [0]),
         "nn_4096^3": ((4096, 4096), (4096, 4096), [1], [0]),
         "tn_4096^3": ((4096, 4096), (4096, 4096), [0], [0]),
         "nt_4096^3": ((4096, 4096), (4096, 4096), [1], [1]),
