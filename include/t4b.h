@@ -88,6 +88,31 @@ int t4b_qr_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void
 int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* u_dev,
                  double* s_dev, void* vh_dev);
 
+/* Hermitian eigendecomposition g = w diag(lam) w^H: g (n x n, DESTROYED), lam (n f64, non-increasing,
+ * device), w (n x n).  Replaces hermitian_eigendecomposition (tensorbackend/src/matrix.rs:720) as used by
+ * the Gram branch of factorize_auto (core/src/defaults/factorize.rs:153-315). */
+int t4b_eigh(t4b_ctx* ctx, int dtype, int64_t n, void* g_dev, double* lam_dev, void* w_dev);
+
+/* Triangular solve, in place on x: left_side ? x <- op(t)^-1 x (x is n x nrhs) : x <- x op(t)^-1
+ * (x is nrhs x n).  Replaces triangular_solve_matrix (tensorbackend/src/backend.rs:924-937). */
+int t4b_trsm(t4b_ctx* ctx, int dtype, int left_side, int lower, int transpose, int unit_diagonal, int64_t n,
+             int64_t nrhs, const void* t_dev, int64_t ldt, void* x_dev, int64_t ldx);
+
+/* Solve a x = b: a (n x n), b (n x nrhs) preserved, x (n x nrhs).  Full-pivot LU.  Replaces solve_matrix
+ * (tensorbackend/src/backend.rs:865-871; TCI2 fill_site_tensors, tensorci/src/tensorci2.rs:1065-1199).
+ * Returns T4B_NOT_CONVERGED when a is numerically singular. */
+int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_dev, const void* b_dev,
+              void* x_dev);
+
+/* N-ary einsum over numeric labels: operand i is a dense column-major tensor of rank ranks[i] whose shape
+ * and labels are the next ranks[i] entries of shapes / labels.  A label shared by two operands is
+ * contracted, a label that appears once must appear in out_labels (no traces, no batch labels).  The
+ * pairwise order is chosen by exhaustive search for <= 6 operands.  Replaces einsum_native_tensors
+ * (tensorbackend/src/tenferro_bridge.rs:1513) and the N-ary contract (core/src/defaults/contract.rs:283). */
+int t4b_einsum(t4b_ctx* ctx, int dtype, int n_ops, const void* const* ops_dev, const int32_t* ranks,
+               const int64_t* shapes, const uint32_t* labels, int out_rank, const uint32_t* out_labels,
+               void* out_dev);
+
 /* ---- truncation rules (host only, no GPU needed) ----------------------------------------
  * Exact restatements of the reference's rank decisions so that the Rust side and the device
  * sweeps agree: compute_retained_rank (core/src/defaults/svd.rs:151-210), the QR row-norm rule

@@ -4,6 +4,7 @@
 
 #include "../../include/t4b.h"
 #include "capi_common.h"
+#include "host/luci.h"
 #include "dla.h"
 #include "host/tensor.h"
 
@@ -167,6 +168,91 @@ int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, voi
     T4B_REQUIRE(m >= 0 && n >= 0, "svd_thin: negative dimension");
     T4B_REQUIRE(s_dev != nullptr, "svd_thin: s_dev is required");
     dla::svd_thin(ctx->c, to_dtype(dtype), m, n, a_dev, u_dev, s_dev, vh_dev);
+    T4B_CATCH
+}
+
+int t4b_eigh(t4b_ctx* ctx, int dtype, int64_t n, void* g_dev, double* lam_dev, void* w_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && g_dev && lam_dev && w_dev, "eigh: bad arguments");
+    dla::eigh(ctx->c, to_dtype(dtype), n, g_dev, lam_dev, w_dev);
+    T4B_CATCH
+}
+
+int t4b_trsm(t4b_ctx* ctx, int dtype, int left_side, int lower, int transpose, int unit_diagonal, int64_t n,
+             int64_t nrhs, const void* t_dev, int64_t ldt, void* x_dev, int64_t ldx) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && nrhs >= 0 && ldt >= n, "trsm: bad shape");
+    if (n > 0 && nrhs > 0)
+        dla::trsm(ctx->c, to_dtype(dtype), left_side != 0, lower != 0, transpose != 0, unit_diagonal != 0, n, nrhs,
+                  t_dev, ldt, x_dev, ldx);
+    T4B_CATCH
+}
+
+int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_dev, const void* b_dev,
+              void* x_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    solve_matrix(ctx->c, to_dtype(dtype), n, nrhs, a_dev, b_dev, x_dev);
+    T4B_CATCH
+}
+
+int t4b_einsum(t4b_ctx* ctx, int dtype, int n_ops, const void* const* ops_dev, const int32_t* ranks,
+               const int64_t* shapes, const uint32_t* labels, int out_rank, const uint32_t* out_labels,
+               void* out_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    DType dt = to_dtype(dtype);
+    T4B_REQUIRE(n_ops >= 1 && ops_dev && ranks && out_rank >= 0, "einsum: bad arguments");
+    // label -> Index (one fresh id per distinct label), occurrence counts
+    std::vector<std::pair<uint32_t, Index>> table;
+    std::vector<int> count;
+    auto lookup = [&](uint32_t lab, int64_t dim) -> Index {
+        for (size_t i = 0; i < table.size(); ++i)
+            if (table[i].first == lab) {
+                T4B_REQUIRE(table[i].second.dim == dim, "einsum: a label has two different dimensions");
+                ++count[i];
+                return table[i].second;
+            }
+        table.push_back({lab, new_index(dim)});
+        count.push_back(1);
+        return table.back().second;
+    };
+    std::vector<Tensor> ops;
+    size_t off = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        T4B_REQUIRE(ranks[i] >= 0, "einsum: negative rank");
+        std::vector<Index> inds;
+        for (int a = 0; a < ranks[i]; ++a) {
+            Index ix = lookup(labels[off + a], shapes[off + a]);
+            for (auto& prev : inds)
+                if (prev == ix) throw Error(ST_UNSUPPORTED, "einsum: repeated label inside one operand (trace)");
+            inds.push_back(ix);
+        }
+        off += (size_t)ranks[i];
+        ops.push_back(wrap_device(ctx->c, dt, inds, const_cast<void*>(ops_dev[i])));
+    }
+    for (size_t i = 0; i < table.size(); ++i)
+        if (count[i] > 2) throw Error(ST_UNSUPPORTED, "einsum: a label shared by more than two operands");
+    std::vector<Index> out_inds;
+    for (int a = 0; a < out_rank; ++a) {
+        bool found = false;
+        for (size_t i = 0; i < table.size(); ++i)
+            if (table[i].first == out_labels[a]) {
+                T4B_REQUIRE(count[i] == 1, "einsum: an output label is contracted (batch labels unsupported)");
+                out_inds.push_back(table[i].second);
+                found = true;
+            }
+        T4B_REQUIRE(found, "einsum: unknown output label");
+    }
+    size_t n_free = 0;
+    for (size_t i = 0; i < table.size(); ++i) n_free += count[i] == 1 ? 1 : 0;
+    T4B_REQUIRE(n_free == (size_t)out_rank, "einsum: every uncontracted label must appear in the output");
+    std::vector<const Tensor*> ptrs;
+    for (auto& t : ops) ptrs.push_back(&t);
+    Tensor r = contract(ctx->c, ptrs, &out_inds);
+    dla::d2d(ctx->c, out_dev, r.data(), (size_t)r.numel() * dtype_size(dt));
     T4B_CATCH
 }
 

@@ -142,4 +142,20 @@ LuFactors luci_from_rrlu(dla::Ctx* c, const RrLU& lu) {
     return f;
 }
 
+void solve_matrix(dla::Ctx* c, DType dt, int64_t n, int64_t nrhs, const void* A, const void* B, void* X) {
+    T4B_REQUIRE(n > 0 && nrhs >= 0, "solve_matrix: bad shape");
+    if (nrhs == 0) return;
+    const size_t es = dtype_size(dt);
+    RrLUOptions o;
+    o.max_bond_dim = n; o.rel_tol = 0.0; o.abs_tol = 0.0; o.left_orthogonal = true;
+    RrLU lu = rrlu(c, dt, n, n, A, o);
+    if (lu.n_pivot < n) throw Error(ST_NOT_CONVERGED, "solve_matrix: matrix is singular");
+    // A[rp, cp] = L U  =>  L U (X[cp, :]) = B[rp, :]
+    auto Y = std::make_shared<Buffer>(c, (size_t)n * nrhs * es);
+    dla::permute_rows(c, dt, n, nrhs, B, n, Y->p, n, (const int64_t*)lu.d_row_perm->p, false);
+    dla::trsm(c, dt, true, true, false, true, n, nrhs, lu.l->p, n, Y->p, n);     // unit lower
+    dla::trsm(c, dt, true, false, false, false, n, nrhs, lu.u->p, n, Y->p, n);   // upper
+    dla::permute_rows(c, dt, n, nrhs, Y->p, n, X, n, (const int64_t*)lu.d_col_perm->p, true);
+}
+
 }  // namespace t4b

@@ -58,4 +58,9 @@ LuFactors luci_factor_matrix(dla::Ctx*, DType dt, int64_t m, int64_t n, const vo
 // reference factors_from_rrlu (matrix_luci.rs:260-279)
 LuFactors luci_from_rrlu(dla::Ctx*, const RrLU& lu);
 
+// Solve A X = B (A n x n, B n x nrhs, both preserved; X n x nrhs) through the full-pivot LU
+// (reference solve_matrix, crates/tensor4all-tensorbackend/src/backend.rs:865-871).  Throws
+// ST_NOT_CONVERGED when A is numerically singular.
+void solve_matrix(dla::Ctx*, DType dt, int64_t n, int64_t nrhs, const void* A, const void* B, void* X);
+
 }  // namespace t4b

@@ -56,6 +56,14 @@ struct Ctx {
     const char* gemm_class = "gemm";
     std::vector<ProfRec> prof;
     cudaEvent_t prof_start = nullptr;
+    // device-side work counters of kernels whose algorithmic work is only known on the device
+    // ([0] = bytes moved by the persistent Jacobi kernel: sweeps x rounds x panel bytes); valid while profiling
+    double* dev_stats = nullptr;
+    // high-priority side stream + events for look-ahead inside a factorisation (qr.cu); always joined
+    // back into `stream` before the factorisation returns
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_f = nullptr;
+    void ensure_side();
 
     void* get_scratch(size_t bytes);
     void* get_pinned(size_t bytes);

@@ -126,8 +126,65 @@ void set_identity(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t lda) 
     c->launched("set_identity");
 }
 
-void eigh(Ctx*, DType, int64_t, void*, double*, void*) {
-    throw Error(ST_UNSUPPORTED, "eigh: not implemented yet (factorize_auto uses the Jacobi SVD)");
+namespace {
+// out[0] = 2 * max_i sum_j |G_ij| (twice the Gershgorin bound of the spectral radius); one block
+template <bool CPLX>
+__global__ void gershgorin_kernel(const double* __restrict__ G, int64_t n, double* __restrict__ out) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    __shared__ double red[32];
+    const T* g = reinterpret_cast<const T*>(G);
+    double mx = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t j = 0; j < n; ++j) acc += sqrt(S::abs2(g[i + j * n]));
+        if (acc > mx) mx = acc;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double other = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (other > mx) mx = other;
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) if (red[w] > m) m = red[w];
+        out[0] = 2.0 * m;
+    }
+}
+// G[i,i] += shift[0]
+template <bool CPLX>
+__global__ void shift_diag_kernel(double* __restrict__ G, int64_t n, const double* __restrict__ shift) {
+    typedef typename Sc<CPLX>::T T;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T* g = reinterpret_cast<T*>(G) + i + i * n;
+    if constexpr (CPLX) g->x += shift[0]; else *g += shift[0];
+}
+__global__ void unshift_kernel(double* __restrict__ lam, int64_t n, const double* __restrict__ shift) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lam[i] -= shift[0];
+}
+}  // namespace
+
+// Hermitian eigendecomposition through the Jacobi SVD of the shifted matrix G + s I, s = twice the
+// Gershgorin bound: the shifted matrix is positive definite with condition number <= 3, so its left singular
+// vectors are the eigenvectors and sigma_i - s the eigenvalues, accurate to eps * ||G|| (the accuracy class of
+// any backward-stable eigh).  lam comes out non-increasing.
+void eigh(Ctx* c, DType dt, int64_t n, void* G, double* lam, void* W) {
+    if (n == 0) return;
+    double* shift = (double*)alloc(c, 8);
+    if (dt == C64) gershgorin_kernel<true><<<1, 1024, 0, c->stream>>>((const double*)G, n, shift);
+    else gershgorin_kernel<false><<<1, 1024, 0, c->stream>>>((const double*)G, n, shift);
+    c->launched("eigh_shift");
+    const int grid = (int)((n + 255) / 256);
+    if (dt == C64) shift_diag_kernel<true><<<grid, 256, 0, c->stream>>>((double*)G, n, shift);
+    else shift_diag_kernel<false><<<grid, 256, 0, c->stream>>>((double*)G, n, shift);
+    c->launched("eigh_shift");
+    svd_thin(c, dt, n, n, G, W, lam, nullptr);
+    unshift_kernel<<<grid, 256, 0, c->stream>>>(lam, n, shift);
+    c->launched("eigh_shift");
+    release(c, shift);
 }
 
 }  // namespace dla

@@ -1195,7 +1195,7 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
         }
     };
 
-    for (int64_t p = 0; p < npanels; ++p) {
+    auto launch_factor = [&](int64_t p) {
         int64_t j0, rows; int jb, nblocks, h;
         geometry(p, j0, jb, rows, nblocks, h);
         FactorArgs fa{};
@@ -1210,8 +1210,39 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
         const size_t smem = ((size_t)NB * fa.pitch + NB * (NB + 1)) * es;
         fk<<<nblocks, FT, smem, c->stream>>>(fa);
         c->launched("qr_factor", 2.0 * (double)rows * (double)jb * (double)es);   // bytes: panel read + write
+    };
+    // Look-ahead: as soon as panel p has been applied to the columns of panel p+1, that panel is factored
+    // on a high-priority side stream while the rest of the trailing update of panel p runs on the main
+    // stream (disjoint column ranges).  Disabled while profiling (per-kernel events live on one stream).
+    const bool lookahead = !c->profiling && npanels > 1 && !getenv("T4B_QR_NOLOOKAHEAD");
+    if (lookahead) c->ensure_side();
+    launch_factor(0);
+    for (int64_t p = 0; p < npanels; ++p) {
+        const int64_t j0 = p * NB;
+        const int jb = (int)((k - j0) < NB ? (k - j0) : NB);
         const int64_t nt = n - (j0 + jb);
-        if (nt > 0) apply_panel(p, (char*)A + ((size_t)j0 + (size_t)(j0 + jb) * (size_t)m) * es, nt, true);
+        char* At = (char*)A + ((size_t)j0 + (size_t)(j0 + jb) * (size_t)m) * es;   // A[j0:, j0+jb:]
+        if (p + 1 < npanels) {
+            const int64_t j1 = j0 + jb;
+            const int64_t jb1 = (k - j1) < NB ? (k - j1) : NB;      // columns of the next panel
+            apply_panel(p, At, jb1, true);
+            if (lookahead) {
+                T4B_CUDA_CHECK(cudaEventRecord(c->ev_a, c->stream));
+                T4B_CUDA_CHECK(cudaStreamWaitEvent(c->side, c->ev_a, 0));
+                cudaStream_t main_stream = c->stream;
+                c->stream = c->side;
+                launch_factor(p + 1);
+                c->stream = main_stream;
+                T4B_CUDA_CHECK(cudaEventRecord(c->ev_f, c->side));
+                if (nt > jb1) apply_panel(p, At + (size_t)jb1 * (size_t)m * es, nt - jb1, true);
+                T4B_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_f, 0));
+            } else {
+                if (nt > jb1) apply_panel(p, At + (size_t)jb1 * (size_t)m * es, nt - jb1, true);
+                launch_factor(p + 1);
+            }
+        } else if (nt > 0) {
+            apply_panel(p, At, nt, true);
+        }
     }
     if (Rout) {
         int64_t total = k * n;

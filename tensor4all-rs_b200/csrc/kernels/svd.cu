@@ -211,6 +211,8 @@ struct JPArgs {
     double* D;             // [p][16*16] diagonal Gram block carried with every column block
     double tol_early;      // a sweep that starts below this ends converged (quadratic convergence)
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
+    double* stats;         // optional device work counter (bytes), else null
+    double bytes_per_sweep;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -281,6 +283,10 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     }
     __syncthreads();
     unsigned par0 = 0, par1 = 0;
+    // Column c of a chunk buffer starts at c * ldp (+ 4 rows for columns with bit 2 set, real case): with the
+    // pitch == 4 (mod 16) this makes the DMMA fragment loads of both passes AND the accumulator stores of the
+    // update pass (lanes hold columns 2 tig, 2 tig + 1) free of shared-memory bank conflicts.
+    auto cb = [&](int c) -> size_t { return (size_t)c * ldp + (CPLX ? 0 : ((c >> 2) & 1) * 4); };
 
     T* Xg = reinterpret_cast<T*>(a.X);
     T* Vg = reinterpret_cast<T*>(a.V);
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                     T* dst = b ? buf1 : buf0;
                     if (lane == 0) mbar_expect_tx(bar, (unsigned)(PW * nrows) * ES);
                     __syncwarp();
-                    bulk_g2s(dst + (size_t)lane * ldp, base + row0 + col_of(lane) * ld, (unsigned)nrows * ES, bar);
+                    bulk_g2s(dst + cb(lane), base + row0 + col_of(lane) * ld, (unsigned)nrows * ES, bar);
                 };
                 auto wait_load = [&](int b) {
                     if (b) { while (!mbar_try_wait(&bars[1], par1)) {} par1 ^= 1; }
@@ -372,9 +378,9 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                         wait_load(b);
                         int nrows = a.rpcx - i * a.ch; if (nrows > a.ch) nrows = a.ch;
                         const T* Ps = b ? buf1 : buf0;
-                        const T* pa = Ps + (size_t)(fi * 8 + grp) * ldp + tig;
-                        const T* pb0 = Ps + (size_t)(fj0 * 8 + grp) * ldp + tig;
-                        const T* pb1 = Ps + (size_t)((fj0 + 1) * 8 + grp) * ldp + tig;
+                        const T* pa = Ps + cb(fi * 8 + grp) + tig;
+                        const T* pb0 = Ps + cb(fj0 * 8 + grp) + tig;
+                        const T* pb1 = Ps + cb((fj0 + 1) * 8 + grp) + tig;
 #pragma unroll 4
                         for (int k0 = 0; k0 < nrows; k0 += 4) {
                             T av = pa[k0], b0 = pb0[k0], b1 = pb1[k0];
@@ -405,8 +411,8 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                         wait_load(b);
                         int nrows = a.rpcx - i * a.ch; if (nrows > a.ch) nrows = a.ch;
                         const T* Ps = b ? buf1 : buf0;
-                        const T* pa = Ps + (size_t)(fi * 8 + grp) * ldp + tig;
-                        const T* pb = Ps + (size_t)(fj * 8 + grp) * ldp + tig;
+                        const T* pa = Ps + cb(fi * 8 + grp) + tig;
+                        const T* pb = Ps + cb(fj * 8 + grp) + tig;
 #pragma unroll 4
                         for (int k0 = kh * 4; k0 < nrows; k0 += 8) mma_frag<CPLX, true>(acc, pa[k0], pb[k0]);
                         if (i + 2 < nchx) {
@@ -532,7 +538,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                         for (int rf = warp; rf < nrows / 8; rf += JW) {
                             T av[8];
 #pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) av[ks] = Ps[(size_t)(ks * 4 + tig) * ldp + rf * 8 + grp];
+                            for (int ks = 0; ks < 8; ++ks) av[ks] = Ps[cb(ks * 4 + tig) + rf * 8 + grp];
                             T acc[4][2];
 #pragma unroll
                             for (int nf = 0; nf < 4; ++nf) acc[nf][0] = acc[nf][1] = S::zero();
@@ -545,13 +551,13 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                             for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
                                 for (int c2 = 0; c2 < 2; ++c2)
-                                    Ps[(size_t)(nf * 8 + 2 * tig + c2) * ldp + rf * 8 + grp] = acc[nf][c2];
+                                    Ps[cb(nf * 8 + 2 * tig + c2) + rf * 8 + grp] = acc[nf][c2];
                         }
                         // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncthreads();
                         if (warp == 0) {
-                            bulk_s2g(base + row0 + col_of(lane) * ld, Ps + (size_t)lane * ldp, (unsigned)nrows * ES);
+                            bulk_s2g(base + row0 + col_of(lane) * ld, Ps + cb(lane), (unsigned)nrows * ES);
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                             if (j + 2 < npos) {
                                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -608,6 +614,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     }
     if (blockIdx.x == 0 && tid == 0) {
         a.info[0] = sweep; a.info[1] = converged;
+        if (a.stats) atomicAdd(a.stats, (double)sweep * a.bytes_per_sweep);
         if (a.timing)
             for (int k = 0; k < 8; ++k) a.timing[k] = tacc[k];
     }
@@ -756,10 +763,11 @@ int jp_max_clusters(int cs, size_t smem) {
 template <bool CPLX>
 JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
     static bool attr_set = false;
-    const size_t smem_cap = 227 * 1024;
+    const size_t smem_max = 227 * 1024;
+    const size_t smem_cap = getenv("T4B_JAC_SMEMCAP") ? (size_t)atoi(getenv("T4B_JAC_SMEMCAP")) * 1024 : smem_max;
     if (!attr_set) {
         auto kern = jacobi_persistent_kernel<CPLX>;
-        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_set = true;
     }
@@ -826,6 +834,9 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     a.tol_early = sqrt(0.01 * tol / (double)npad);
     if (a.tol_early < tol) a.tol_early = tol;
     a.D = Dblk;
+    // algorithmic bytes of one sweep: every round reads and writes the live rows of X (and V) once
+    a.bytes_per_sweep = (double)(p - 1) * 2.0 * (double)(nx + (V ? npad : 0)) * (double)npad * (double)es;
+    a.stats = c->profiling ? c->dev_stats : nullptr;
     a.inner = getenv("T4B_JAC_INNER") ? atoi(getenv("T4B_JAC_INNER")) : 1;
     a.flag = (unsigned long long*)ws;
     a.timing = verbose ? (unsigned long long*)ws + max_sweeps : nullptr;
@@ -846,9 +857,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     cfg.numAttrs = 1;
     auto kern = jacobi_persistent_kernel<CPLX>;
     T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
-    // bytes: per sweep every round reads and writes the live rows of X (and V) once; the sweep count is
-    // only known on the device, the profile uses the typical 10
-    c->launched("jacobi", 10.0 * (double)(p - 1) * 2.0 * (double)(nx + (V ? npad : 0)) * (double)npad * (double)es);
+    c->launched("jacobi", 0.0);   // work is accumulated on the device (Ctx::dev_stats): the sweep count is data dependent
     if (verbose) {
         unsigned char* h = (unsigned char*)c->get_pinned(128 + 8 * max_sweeps);
         d2h(c, h, a.info, 8);

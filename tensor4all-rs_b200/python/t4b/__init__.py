@@ -169,3 +169,45 @@ class Context:
                                   C.c_void_p(u.ptr if u else 0), C.c_void_p(s.ptr),
                                   C.c_void_p(vh.ptr if vh else 0)))
         return u, s, vh
+
+    def eigh(self, g: DeviceArray):
+        """g (n x n Hermitian) is destroyed.  Returns (lam non-increasing, W) as DeviceArrays."""
+        n = g.shape[0]
+        lam = self.empty((n,), F64)
+        w = self.empty((n, n), g.dt)
+        _check(lib().t4b_eigh(self.h, g.dt, C.c_int64(n), C.c_void_p(g.ptr), C.c_void_p(lam.ptr),
+                              C.c_void_p(w.ptr)))
+        return lam, w
+
+    def solve(self, a: DeviceArray, b: DeviceArray) -> DeviceArray:
+        n, nrhs = a.shape[0], b.shape[1]
+        x = self.empty((n, nrhs), a.dt)
+        _check(lib().t4b_solve(self.h, a.dt, C.c_int64(n), C.c_int64(nrhs), C.c_void_p(a.ptr),
+                               C.c_void_p(b.ptr), C.c_void_p(x.ptr)))
+        return x
+
+    def trsm(self, t: DeviceArray, x: DeviceArray, left_side=True, lower=True, transpose=False,
+             unit_diagonal=False):
+        """In place on x."""
+        n = t.shape[0]
+        nrhs = x.shape[1] if left_side else x.shape[0]
+        _check(lib().t4b_trsm(self.h, t.dt, int(left_side), int(lower), int(transpose), int(unit_diagonal),
+                              C.c_int64(n), C.c_int64(nrhs), C.c_void_p(t.ptr), C.c_int64(t.shape[0]),
+                              C.c_void_p(x.ptr), C.c_int64(x.shape[0])))
+        return x
+
+    def einsum(self, operands, labels, out_labels) -> DeviceArray:
+        """operands: DeviceArrays; labels: one list of ints per operand; out_labels: list of ints."""
+        dims = {}
+        for a, ls in zip(operands, labels):
+            for d, l in zip(a.shape, ls):
+                dims[l] = d
+        out = self.empty([dims[l] for l in out_labels], operands[0].dt)
+        ptrs = (C.c_void_p * len(operands))(*[a.ptr for a in operands])
+        ranks = _i32([len(a.shape) for a in operands])
+        shapes = _i64([d for a in operands for d in a.shape])
+        labs = (C.c_uint32 * sum(len(l) for l in labels))(*[int(x) for l in labels for x in l])
+        outl = (C.c_uint32 * max(len(out_labels), 1))(*[int(x) for x in out_labels])
+        _check(lib().t4b_einsum(self.h, operands[0].dt, len(operands), ptrs, ranks, shapes, labs,
+                                len(out_labels), outl, C.c_void_p(out.ptr)))
+        return out
