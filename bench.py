@@ -149,6 +149,16 @@ def cpu_sample(L, d, chi, w, seed=0x5EED0003):
     return {"sweep_s": sweep, "t_zip": t_zip, "t_two_site": t_two, "t_qr": t_qr}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -162,6 +172,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     L, d, chi, w = args.L, args.d, args.chi, args.w
+    use_all_host_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_sample(L, d, min(chi, 64), w)
     samples = [cpu_sample(L, d, chi, w, seed=0x5EED0003 + i) for i in range(max(1, min(args.steps, 2)))]
@@ -221,6 +232,8 @@ def main():
                          "(use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     ctx = t4b.Context(local_rank, stream.cuda_stream)
@@ -344,6 +357,18 @@ def main():
                 ach = p["work"] / (p["ms"] * 1e-3) / 1e9
                 roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src}
+            # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+            try:
+                ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))
+                if dom == "jacobi":
+                    cap = ncu["jacobi_2048"][0]
+                    roof["traffic"] = cap["dram_bytes"]
+                    roof["traffic_note"] = ("dram__bytes_read+write of one jacobi_persistent_kernel launch on the 2048x2048 "
+                                            "zip-up factor (profiles/ncu_jacobi_2048_r01.csv): the panel is L2-resident, "
+                                            "DRAM sees the matrix once while the algorithmic (L2) traffic of that launch is "
+                                            "~100 GB; DMMA pipe %.1f%% busy" % cap["fp64_tensor_pct"])
+            except Exception:
+                pass
             roof["share_of_step"] = p["ms"] / tot_ms
             roof["launches_per_step"] = p["launches"]
             roof["avg_launch_us"] = 1e3 * p["ms"] / max(p["launches"], 1)
@@ -365,8 +390,12 @@ def main():
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "roofline": roof, "roofline_contraction": roof_gemm,
                 "kernel_profile_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "kernel_profile_note": "per-kernel CUDA-event times of one extra sweep; the QR look-ahead (factor of panel "
+                                       "p+1 on a side stream) is serialised while profiling, so qr_* sum to more than they "
+                                       "cost in the timed region",
                 "result": {"norm_sqr": norm_list, "max_bond": max(bonds) if bonds else 1}}
         if not args.no_cpu_baseline:
+            use_all_host_threads()
             cs = cpu_sample(L, d, chi, w)
             line["cpu_baseline"] = {"value": 1.0 / cs["sweep_s"], "unit": UNIT, "cores": host_threads(),
                                     "kind": "port",
