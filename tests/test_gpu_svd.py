@@ -90,3 +90,24 @@ def test_svd_rank_deficient(ctx):
     assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
     assert np.linalg.norm((u * s) @ vh - a) <= 1e-12 * np.linalg.norm(a)
     assert np.all(np.isfinite(u)) and np.all(np.isfinite(vh))
+
+
+def test_svd_c3_zipup_shape_full_size(ctx):
+    """BASELINE C3 bulk zip-up factorisation at full size: 2048 x 4096 f64, left vectors only (the sweep
+    rebuilds S V^H = U^H M with one contraction).  Spectrum against LAPACK gesdd to the north-star
+    tolerance (1e-12 relative to sigma_max), U orthonormal, and the size-independent identity
+    ||U_r^H M||_F^2 = sum_{i<=r} sigma_i^2 for the retained r = 512."""
+    rng = np.random.default_rng(0x5EED0003)
+    m, n, r = 2048, 4096, 512
+    a = np.asfortranarray(rng.standard_normal((m, n)))
+    da = ctx.upload(a)
+    u, s, _ = ctx.svd_thin(ctx.permute(da, [0, 1]), want_u=True, want_vh=False)
+    u, s = u.get(), s.get()
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
+    assert np.all(np.diff(s) <= 0)
+    assert np.linalg.norm(u.T @ u - np.eye(m)) <= 1e-11
+    b = u[:, :r].T @ a
+    assert abs(np.sum(b * b) - np.sum(s_ref[:r] ** 2)) <= 1e-11 * np.sum(s_ref[:r] ** 2)
+    # the rows of U^H M are sigma_i v_i^H: their norms are the singular values
+    assert np.max(np.abs(np.linalg.norm(b, axis=1) - s_ref[:r])) <= 1e-11 * s_ref[0]

@@ -143,3 +143,48 @@ def test_zipup_c3_reduced_chi64(ctx):
     assert relerr(gpu_chain_dense(out), oracle_chain_dense(ref)) <= TOL
     n_ref = otn.inner(ref, ref).real
     assert abs(out.norm_sqr() - n_ref) <= 1e-10 * n_ref
+
+
+def test_zipup_c3_full_size_properties(ctx):
+    """BASELINE C3 at FULL size (L=64, d=4, chi=512, w=8, cap-only truncation), checked through
+    size-independent properties (the oracle needs minutes per sweep at this size):
+    * every bond of the result is capped at chi and the bulk reaches it;
+    * linearity: contract(2 a, b) = 2 contract(a, b)  =>  <out2|out1> = 2 <out1|out1>, <out2|out2> = 4 <out1|out1>;
+    * the result is already truncated: truncating it again (same cap) leaves <out|out'> = <out|out> to 1e-10
+      and every bond unchanged (idempotence);
+    * determinism: a second sweep on the same operands gives the identical norm."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import make_c3
+    L, d, chi, w = 64, 4, 512, 8
+    mps, mi, mpo, oi = make_c3(0x5EED0003, L, d, chi, w)
+    pol = t4tt.SvdPolicy(0.0)
+    a = t4tt.chain_from_arrays(ctx, mps, mi)
+    b = t4tt.chain_from_arrays(ctx, mpo, oi)
+    out1 = a.contract(b, 0, 0, pol, chi)
+    bonds = out1.bond_dims()
+    assert max(bonds) == chi and all(x <= chi for x in bonds)
+    assert bonds[L // 2] == chi
+    n11 = out1.norm_sqr()
+    assert np.isfinite(n11) and n11 > 0
+    # determinism
+    out1b = a.contract(b, 0, 0, pol, chi)
+    assert out1b.norm_sqr() == n11
+    out1b.release()
+    # linearity
+    mps2 = [x.copy() for x in mps]
+    mps2[0] = 2.0 * mps2[0]
+    a2 = t4tt.chain_from_arrays(ctx, mps2, mi)
+    out2 = a2.contract(b, 0, 0, pol, chi)
+    n22 = out2.norm_sqr()
+    n21 = out2.inner(out1)
+    assert abs(n22 - 4.0 * n11) <= 1e-10 * 4.0 * n11
+    assert abs(n21.real - 2.0 * n11) <= 1e-10 * 2.0 * n11 and abs(n21.imag) <= 1e-10 * n11
+    out2.release(); a2.release()
+    # idempotence of the truncation
+    out3 = out1.clone()
+    out3.truncate(0, pol, chi)
+    assert out3.bond_dims() == bonds
+    n31 = out3.inner(out1)
+    assert abs(n31.real - n11) <= 1e-10 * n11
+    assert abs(out3.norm_sqr() - n11) <= 1e-10 * n11
