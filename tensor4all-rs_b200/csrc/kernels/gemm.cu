@@ -516,6 +516,95 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_con
     }
 }
 
+// =====================================================================================================
+// Tall-skinny contraction (K <= 32, N <= 32, M huge, f64): HBM-bound, e.g. the zip-up step (R A) . B with
+// K = (b, s) = w d and N = (t, b') = d w.  No shared memory: B lives in registers as DMMA fragments for the
+// whole kernel, every warp streams 8-row fragments of A straight from global memory (64-byte row segments,
+// full sectors), 32 DMMA per fragment, results stored straight from the accumulators.
+// =====================================================================================================
+struct GemmSkinnyParams {
+    const double* A; const double* B; double* C;
+    int64_t M; int N, K;
+    Group am, ak, bk, bn, cm, cn;
+    double alpha, beta;
+};
+
+// composite offset of a small index (< 2^31): 32-bit divisions only
+__device__ __forceinline__ int64_t goff32(const Group& g, unsigned i) {
+    int64_t off = 0;
+#pragma unroll
+    for (int d = 0; d < kMaxGroupDims; ++d) {
+        if (d < g.nd) {
+            const unsigned dim = (unsigned)g.dim[d];
+            const unsigned q = i / dim;
+            off += (int64_t)(i - q * dim) * g.str[d];
+            i = q;
+        }
+    }
+    return off;
+}
+
+__global__ void __launch_bounds__(256, 4) gemm_skinny_kernel(const __grid_constant__ GemmSkinnyParams p) {
+    const int lane = threadIdx.x & 31, grp = lane >> 2, tig = lane & 3;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // B as DMMA fragments in shared memory: sB[(nf * 8 + ks) * 32 + lane] = B[k = 4 ks + tig, n = 8 nf + grp]
+    __shared__ double sB[4 * 8 * 32];
+    for (int e = threadIdx.x; e < 4 * 8 * 32; e += blockDim.x) {
+        const int l = e & 31, ks = (e >> 5) & 7, nf = e >> 8;
+        const int k = ks * 4 + (l & 3), n = nf * 8 + (l >> 2);
+        sB[e] = (k < p.K && n < p.N) ? p.B[goff32(p.bk, (unsigned)k) + goff32(p.bn, (unsigned)n)] : 0.0;
+    }
+    int64_t koff[8], coff[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        const int k = ks * 4 + tig;
+        koff[ks] = k < p.K ? goff32(p.ak, (unsigned)k) : -1;
+    }
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int n = nf * 8 + 2 * tig + c2;
+            coff[nf][c2] = n < p.N ? goff32(p.cn, (unsigned)n) : -1;
+        }
+    __syncthreads();
+    const unsigned ad0 = (unsigned)p.am.dim[0], cd0 = (unsigned)p.cm.dim[0];
+    const int64_t as1 = p.am.nd > 1 ? p.am.str[1] : 0, cs1 = p.cm.nd > 1 ? p.cm.str[1] : 0;
+    const int64_t nfrag = (p.M + 7) / 8;
+    for (int64_t mf = warp; mf < nfrag; mf += nwarps) {
+        const int64_t m = mf * 8 + grp;
+        const bool mok = m < p.M;
+        // free index = (d0 fastest with unit stride, d1): one 32-bit division per fragment
+        const unsigned mu = (unsigned)m;
+        const unsigned qa = mu / ad0, qc = mu / cd0;
+        const int64_t abase = (int64_t)(mu - qa * ad0) + (int64_t)qa * as1;
+        double af[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) af[ks] = (mok && koff[ks] >= 0) ? __ldcs(p.A + abase + koff[ks]) : 0.0;
+        double acc[4][2];
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) acc[nf][0] = acc[nf][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) dmma(acc[nf][0], acc[nf][1], af[ks], sB[(nf * 8 + ks) * 32 + lane]);
+        if (mok) {
+            const int64_t cbase = (int64_t)(mu - qc * cd0) + (int64_t)qc * cs1;
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2)
+                    if (coff[nf][c2] >= 0) {
+                        double r = p.alpha * acc[nf][c2];
+                        double* dst = p.C + cbase + coff[nf][c2];
+                        if (p.beta != 0.0) r += p.beta * *dst;
+                        __stcs(dst, r);
+                    }
+        }
+    }
+}
+
 // deterministic split-K reduction: C = alpha * sum_s partial[s] + beta * C
 template <bool CPLX>
 __global__ void splitk_reduce_kernel(const double* __restrict__ partial, int ksplit, int64_t M,
@@ -835,6 +924,24 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
     if (M == 1) alay = 1;   // degenerate free index: follow K
     if (N == 1) blay = 0;
 
+    // tall-skinny HBM-bound case: no tiles, no tables, B in registers
+    if (dt == F64 && K <= 32 && N <= 32 && M >= 4096 && M < (int64_t)1 << 31 && g[0].str[0] == 1 && g[4].str[0] == 1 &&
+        g[0].nd <= 2 && g[4].nd <= 2 &&
+        (g[0].nd == 1 || g[0].dim[0] % 8 == 0) && (g[4].nd == 1 || g[4].dim[0] % 8 == 0) &&
+        !getenv("T4B_GEMM_NOSKINNY")) {
+        GemmSkinnyParams sp;
+        sp.A = (const double*)A; sp.B = (const double*)B; sp.C = (double*)C;
+        sp.M = M; sp.N = (int)N; sp.K = (int)K;
+        sp.am = g[0]; sp.ak = g[1]; sp.bk = g[2]; sp.bn = g[3]; sp.cm = g[4]; sp.cn = g[5];
+        sp.alpha = alpha; sp.beta = beta;
+        const int64_t nfrag = (M + 7) / 8;
+        int64_t blocks = (nfrag + 7) / 8;
+        const int64_t cap = (int64_t)c->num_sms * 4;     // persistent: the per-block set-up (B fragments) is amortised
+        if (blocks > cap) blocks = cap;
+        gemm_skinny_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(sp);
+        c->launched(c->gemm_class, 2.0 * (double)M * (double)N * (double)K);
+        return;
+    }
     if (getenv("T4B_GEMM_TRACE"))
         fprintf(stderr, "[t4b] gemm %s M=%lld N=%lld K=%lld alay=%d blay=%d nd=%d%d%d%d%d%d ksplit=%d class=%s\n",
                 dt == C64 ? "c64" : "f64", (long long)M, (long long)N, (long long)K, alay, blay, g[0].nd, g[1].nd,

@@ -848,15 +848,28 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     cfg.blockDim = dim3(JT, 1, 1);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pl.cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // cooperative launch: the CTAs spin on each other's progress, so the whole grid must be gang-scheduled
+    // (two such kernels from different contexts must never be half resident at the same time)
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static int coop_ok = getenv("T4B_JAC_NOCOOP") ? 0 : 1;
+    cfg.numAttrs = coop_ok ? 2 : 1;
     auto kern = jacobi_persistent_kernel<CPLX>;
-    T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
+    if (le != cudaSuccess && coop_ok) {
+        // cluster + cooperative not accepted by this driver: fall back to the plain cluster launch
+        cudaGetLastError();
+        coop_ok = 0;
+        cfg.numAttrs = 1;
+        le = cudaLaunchKernelEx(&cfg, kern, a);
+    }
+    T4B_CUDA_CHECK(le);
     c->launched("jacobi", 0.0);   // work is accumulated on the device (Ctx::dev_stats): the sweep count is data dependent
     if (verbose) {
         unsigned char* h = (unsigned char*)c->get_pinned(128 + 8 * max_sweeps);

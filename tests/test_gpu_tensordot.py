@@ -88,3 +88,18 @@ def test_permute(ctx):
         if cplx:
             out = ctx.permute(d, [2, 0, 1, 3], conj=True).get()
             assert np.array_equal(out, np.transpose(a, [2, 0, 1, 3]).conj())
+
+
+@pytest.mark.parametrize("shape", [((512, 8, 4, 64), (8, 4, 4, 8), [1, 2], [0, 1]),      # zip-up (R A) . B
+                                   ((4100, 7), (7, 5), [1], [0]),                        # ragged M, odd K and N
+                                   ((64, 9, 128), (9, 3), [1], [0])])                    # composite M around K
+def test_tall_skinny_path(ctx, shape):
+    """K, N <= 32 with a huge free index goes through the register-resident tall-skinny kernel."""
+    sa, sb, xa, xb = shape
+    rng = np.random.default_rng(77)
+    a = np.asfortranarray(rng.standard_normal(sa))
+    b = np.asfortranarray(rng.standard_normal(sb))
+    out = ctx.tensordot(ctx.upload(a), ctx.upload(b), xa, xb).get()
+    ref = np.tensordot(a, b, axes=(xa, xb))
+    assert out.shape == ref.shape
+    assert np.linalg.norm((out - ref).ravel()) <= 1e-13 * np.linalg.norm(ref.ravel())
