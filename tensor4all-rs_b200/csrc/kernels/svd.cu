@@ -180,6 +180,132 @@ __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32(typename Sc<CPLX>:
 }
 
 
+// Rotation of the pivot (aa, g; conj(g), bb): J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]] with J^H (..) J diagonal.
+// Returns tg = t |g| (t = tan of the rotation angle): the rotated diagonal is (aa - tg, bb + tg).
+template <bool CPLX>
+__device__ __forceinline__ void jacobi_rotation(double aa, double bb, typename Sc<CPLX>::T g, double tol2,
+                                                double& c, double& sn, typename Sc<CPLX>::T& ph, double& tg) {
+    typedef Sc<CPLX> S;
+    c = 1.0; sn = 0.0; ph = S::one(); tg = 0.0;
+    const double g2 = S::abs2(g);
+    if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
+        const double d = 0.5 * (bb - aa);
+        if constexpr (CPLX) {
+            const double inv_absg = rsqrt(g2);
+            const double absg = g2 * inv_absg;
+            const double x = d * d + g2;
+            const double h = x * rsqrt(x);
+            const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
+            c = rsqrt(1.0 + t * t);
+            sn = c * t;
+            ph = S::scale(S::conj(g), inv_absg);
+            tg = t * absg;
+        } else {
+            const double ag = fabs(g), ad = fabs(d);
+            const double mx = ag > ad ? ag : ad;
+            const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+            const double sc = __hiloint2double((2046 - ex) << 20, 0);
+            const float fd = (float)(ad * sc), fg = (float)(ag * sc);
+            const float fh = sqrtf(fd * fd + fg * fg);
+            const float ft = __fdividef(fg, fd + fh);
+            const double t = d >= 0.0 ? (double)ft : -(double)ft;
+            const double x = 1.0 + t * t;
+            double y = (double)rsqrtf((float)x);
+            y = y * (1.5 - 0.5 * x * y * y);
+            y = y * (1.5 - 0.5 * x * y * y);
+            c = y;
+            sn = c * t;
+            ph = g >= 0.0 ? 1.0 : -1.0;
+            tg = t * ag;
+        }
+    }
+}
+
+// Bipartite (cross pairs only) inner sweeps with the rotation warp running ONE STEP AHEAD of the apply warps:
+// while warps 1..7 apply the rotations of step r (G' = J^H G J, W <- W J), warp 0 already derives the pivots of
+// step r+1 - G'[p][p] = aa - tg, G'[q'][q'] = bb' + tg' of the neighbouring pair, G'[p][q'] from four entries of
+// G and the two rotations involved - and computes the next rotations.  One __syncthreads per step.
+template <bool CPLX>
+__device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32_pipelined(
+    typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2, typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
+    double* rot_c, double* rot_s, double tol_rot, int tid, int inner) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    T* Gcur = Gs;
+    T* Gnxt = Gs2;
+    const int nrr = 16 * inner;
+    const double tol2 = tol_rot * tol_rot;
+    const int lane = tid & 31, warp = tid >> 5;
+    // rotation state of pair t = lane (warp 0, lanes 0..15)
+    double c = 1.0, sn = 0.0, tg = 0.0, aa = 0.0, bb = 0.0;
+    T ph = S::one();
+    if (warp == 0 && lane < 16) {
+        const int pp = lane, qq = 16 + lane;
+        aa = S::real(Gcur[pp * GP + pp]); bb = S::real(Gcur[qq * GP + qq]);
+        jacobi_rotation<CPLX>(aa, bb, Gcur[pp * GP + qq], tol2, c, sn, ph, tg);
+        rot_c[lane] = c; rot_s[lane] = sn; rot_ph[lane] = ph;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < nrr; ++rr) {
+        const int cur = (rr & 1) * 16, nxt = 16 - cur;
+        if (warp == 0) {
+            if (lane < 16 && rr + 1 < nrr) {
+                // pivots of step rr+1 for pair (p, q'), q' = partner of lane+1 at step rr
+                const int nb = (lane + 1) & 15;
+                const int pp = lane, qq = 16 + ((lane + rr) & 15);
+                const int pn = nb, qn = 16 + ((nb + rr) & 15);
+                const T gpp = Gcur[pp * GP + pn], gpq = Gcur[pp * GP + qn];
+                const T gqp = Gcur[qq * GP + pn], gqq = Gcur[qq * GP + qn];
+                const double cn = __shfl_sync(0x0000ffffu, c, nb), snn = __shfl_sync(0x0000ffffu, sn, nb);
+                const double bbn = __shfl_sync(0x0000ffffu, bb + tg, nb);
+                T phn;
+                if constexpr (CPLX) phn = make_double2(__shfl_sync(0x0000ffffu, ph.x, nb), __shfl_sync(0x0000ffffu, ph.y, nb));
+                else phn = __shfl_sync(0x0000ffffu, ph, nb);
+                // column combination with the neighbour's rotation, then row combination with the own one
+                const T yp = S::add(S::scale(gpp, snn), S::scale(S::mul(gpq, phn), cn));
+                const T yq = S::add(S::scale(gqp, snn), S::scale(S::mul(gqq, phn), cn));
+                const T gnew = S::sub(S::scale(yp, c), S::scale(S::mul(S::conj(ph), yq), sn));
+                aa = aa - tg; bb = bbn;
+                jacobi_rotation<CPLX>(aa, bb, gnew, tol2, c, sn, ph, tg);
+                rot_c[nxt + lane] = c; rot_s[nxt + lane] = sn; rot_ph[nxt + lane] = ph;
+            }
+        } else {
+            // 256 2 x 2 blocks over the 224 threads of warps 1..7
+            for (int blk = tid - 32; blk < 256; blk += 224) {
+                const int ta = blk >> 4, tb = blk & 15;
+                const int pa = ta, qa = 16 + ((ta + rr) & 15);
+                const int pb = tb, qb = 16 + ((tb + rr) & 15);
+                const double ca = rot_c[cur + ta], sa = rot_s[cur + ta], cb = rot_c[cur + tb], sb = rot_s[cur + tb];
+                const T pha = rot_ph[cur + ta], phb = rot_ph[cur + tb];
+                const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
+                const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
+                const T cpa = S::conj(pha);
+                const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
+                const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
+                const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
+                const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
+                const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
+                const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
+                Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
+                Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
+                Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
+                Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
+#pragma unroll
+                for (int rrow = 0; rrow < 2; ++rrow) {
+                    const int i = ta * 2 + rrow;
+                    const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
+                    const T fq = S::mul(wq, phb);
+                    Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
+                    Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
+                }
+            }
+        }
+        __syncthreads();
+        T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
+    }
+    return Gcur;
+}
+
 // =====================================================================================================
 // Persistent data-flow Jacobi: ONE launch runs every round of every sweep.
 //
@@ -208,6 +334,7 @@ struct JPArgs {
     unsigned long long* flag;   // [max_sweeps] max off-diagonal cosine of the sweep (double bits)
     int* info;             // [0] sweeps executed, [1] converged
     int inner;             // bipartite inner sweeps per visit
+    int eig_serial;        // 1: two-barrier reference form of the inner eigen-solve (debug / A-B)
     double* D;             // [p][16*16] diagonal Gram block carried with every column block
     double tol_early;      // a sweep that starts below this ends converged (quadratic convergence)
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
@@ -269,10 +396,10 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     T* Gs = Gp0 + 2 * 32 * 32;                              // [32][GP]
     T* Gs2 = Gs + 32 * GP;
     T* Ws = Gs2 + 32 * GP;                                  // [32 cols][WP]
-    T* rot_ph = Ws + 32 * WP;
-    double* rot_c = reinterpret_cast<double*>(rot_ph + 16);
-    double* rot_s = rot_c + 16;
-    double* redbuf = rot_s + 16;                            // JW + 2
+    T* rot_ph = Ws + 32 * WP;                               // [2][16] (double buffered by the pipelined eig)
+    double* rot_c = reinterpret_cast<double*>(rot_ph + 32); // [2][16]
+    double* rot_s = rot_c + 32;                             // [2][16]
+    double* redbuf = rot_s + 32;                            // JW + 2
     uint64_t* bars = reinterpret_cast<uint64_t*>(redbuf + JW + 2);
     T* Dsm = reinterpret_cast<T*>(bars + 2);                // [2][16*16] carried diagonal blocks of the pair
 
@@ -511,7 +638,9 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                 const bool need_rot = redbuf[JW] > a.tol_rot;
                 JP_STAMP(3);   // reduce + convergence measure
                 if (need_rot) {
-                    const T* Gfin = jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid, a.inner);
+                    const T* Gfin = (full_inner || a.eig_serial)
+                                        ? jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid, a.inner)
+                                        : jacobi_eig32_pipelined<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, a.tol_rot, tid, a.inner);
                     if (R == 0) {
                         // the diagonal blocks of the rotated Gram travel with the column blocks
                         T* di = reinterpret_cast<T*>(a.D) + (size_t)bi * 256;
@@ -737,8 +866,8 @@ struct JPPlan {
 template <bool CPLX>
 size_t jp_smem_bytes(int ldp) {
     const size_t es = CPLX ? 16 : 8;
-    return (size_t)2 * PW * ldp * es + (size_t)(2 * 32 * 32 + 2 * 32 * GP + 32 * WP + 16) * es +
-           (size_t)(32 + JW + 2) * 8 + 2 * 8 + 2 * 256 * es + 128;
+    return (size_t)2 * PW * ldp * es + (size_t)(2 * 32 * 32 + 2 * 32 * GP + 32 * WP + 32) * es +
+           (size_t)(64 + JW + 2) * 8 + 2 * 8 + 2 * 256 * es + 128;
 }
 
 template <bool CPLX>
@@ -838,6 +967,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     a.bytes_per_sweep = (double)(p - 1) * 2.0 * (double)(nx + (V ? npad : 0)) * (double)npad * (double)es;
     a.stats = c->profiling ? c->dev_stats : nullptr;
     a.inner = getenv("T4B_JAC_INNER") ? atoi(getenv("T4B_JAC_INNER")) : 1;
+    a.eig_serial = getenv("T4B_JAC_EIG_SERIAL") ? 1 : 0;
     a.flag = (unsigned long long*)ws;
     a.timing = verbose ? (unsigned long long*)ws + max_sweeps : nullptr;
     a.ready = (unsigned*)(ws + (size_t)(max_sweeps + 8) * 8);
