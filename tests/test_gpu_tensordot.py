@@ -103,3 +103,36 @@ def test_tall_skinny_path(ctx, shape):
     ref = np.tensordot(a, b, axes=(xa, xb))
     assert out.shape == ref.shape
     assert np.linalg.norm((out - ref).ravel()) <= 1e-13 * np.linalg.norm(ref.ravel())
+
+
+WS_CASES = [
+    # shapes that take the warp-specialised TMA kernel (f64, K % 16 == 0, M and N > 64, aligned runs)
+    ((258, 48), (48, 130), [1], [0]),                 # NN, partial edge tiles (even remainders)
+    ((48, 258), (48, 130), [0], [0]),                 # TN: both operands K-fast -> tensor maps, OOB rows zero-filled
+    ((258, 48), (130, 48), [1], [1]),                 # NT: both operands staged by 1-D bulk copies
+    ((48, 258), (130, 48), [0], [1]),                 # TT
+    ((128, 32, 6), (32, 4, 96), [1], [0]),            # zip-up R.A: composite M (n, b), composite N (s, a')
+    ((32, 4, 96), (32, 4, 70), [0, 1], [0, 1]),       # K composite and K-fast in both operands: U^H M style
+    ((96, 4, 32), (32, 4, 80), [2], [0]),             # two-site A.B
+    ((640, 512), (512, 384), [1], [0]),               # several k-tiles beyond the ring depth, multi-tile grid
+    ((256, 2048), (2048, 128), [1], [0]),             # long K with few tiles: split-K through the same kernel
+]
+
+
+@pytest.mark.parametrize("case", WS_CASES)
+def test_tensordot_warp_specialised_path(ctx, case):
+    sa, sb, xa, xb = case
+    rng = np.random.default_rng(4321 + sum(sa) + sum(sb))
+    a, b = _rand(rng, sa, False), _rand(rng, sb, False)
+    ref = np.tensordot(a, b, axes=(xa, xb))
+    out = ctx.tensordot(ctx.upload(a), ctx.upload(b), xa, xb).get()
+    assert out.shape == ref.shape
+    assert _relerr(out, ref) <= TOL
+
+
+def test_tensordot_odd_alignment_falls_back(ctx):
+    """Odd leading dimensions break the 16-byte alignment the TMA paths need: the general kernel must take over."""
+    rng = np.random.default_rng(99)
+    a, b = _rand(rng, (129, 80), False), _rand(rng, (80, 131), False)
+    out = ctx.tensordot(ctx.upload(a), ctx.upload(b), [1], [0]).get()
+    assert _relerr(out, a @ b) <= TOL
