@@ -165,6 +165,11 @@ int t4b_tci_update_rank(const t4b_tci_update* u, int64_t* rank, int64_t* new_bon
 int t4b_tci_update_indices(const t4b_tci_update* u, int64_t* rows_host, int64_t* cols_host, int64_t* n);
 int t4b_tci_update_tensors(t4b_ctx* ctx, const t4b_tci_update* u, void* tensor_b_host, void* tensor_bp1_host);
 int t4b_tci_update_release(t4b_tci_update* u);
+/* One-site tensor of fill_site_tensors (tensorci/src/tensorci2.rs:1065-1199): out[l, s, r] = (Pi1 P^-1)[l*d + s, r],
+ * Pi1 ((left_dim*site_dim) x nj device matrix, rows l*d + s), P (nj x nj pivot matrix); a numerically zero P gives
+ * a zero tensor.  p_dev == NULL: last site (nj == 1), Pi1 is stored directly.  out: [left_dim, site_dim, nj]. */
+int t4b_tci2_site_tensor(t4b_ctx* ctx, int dtype, int64_t left_dim, int64_t site_dim, int64_t nj,
+                         const void* pi1_dev, const void* p_dev, void* out_dev);
 
 /* ---- chain tensor networks (tensor4all-treetn, chain topology) ------------------------------
  * A site is a dense tensor whose axes carry caller-chosen non-negative index ids; equal ids on

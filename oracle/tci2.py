@@ -30,6 +30,28 @@ def update_from_pi(pi, left_dim, d_b, d_bp1, right_dim, max_bond_dim=None, toler
     return rank, rows, cols, tb, tp, float(errs[-1])
 
 
+def site_tensor_from_pi1(pi1, p, left_dim, site_dim):
+    """One site of fill_site_tensors (tensorci2.rs:1065-1199): Tmat = Pi1 P^-1 through the transposed solve
+    P^T X_t = Pi1^T (:1163-1168), out[l, s, r] = X_t[r, l*d + s] (:1171-1186); a numerically zero pivot matrix
+    gives a zero core (:1155-1160); the last site (p is None) stores Pi1 directly (:1110-1131)."""
+    ni = left_dim * site_dim
+    if p is None:
+        out = np.zeros((left_dim, site_dim, 1), dtype=pi1.dtype)
+        for l in range(left_dim):
+            for s in range(site_dim):
+                out[l, s, 0] = pi1[l * site_dim + s, 0]
+        return out
+    np_ = p.shape[0]
+    out = np.zeros((left_dim, site_dim, np_), dtype=pi1.dtype)
+    if np.all(np.abs(p) < np.finfo(np.float64).eps):
+        return out
+    x_t = np.linalg.solve(p.T, pi1.T)
+    for l in range(left_dim):
+        for s in range(site_dim):
+            out[l, s, :] = x_t[:, l * site_dim + s]
+    return out
+
+
 class TCI2:
     """Minimal TensorCI2 state: nested index sets and site tensors."""
 

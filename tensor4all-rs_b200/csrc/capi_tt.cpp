@@ -445,6 +445,13 @@ int t4b_tci_update_release(t4b_tci_update* u) {
     delete u;
     T4B_CATCH
 }
+int t4b_tci2_site_tensor(t4b_ctx* ctx, int dtype, int64_t left_dim, int64_t site_dim, int64_t nj,
+                         const void* pi1_dev, const void* p_dev, void* out_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    tci2_site_tensor(ctx->c, to_dtype(dtype), left_dim, site_dim, nj, pi1_dev, p_dev, out_dev);
+    T4B_CATCH
+}
 }
 
 // ---- partitioned adaptive truncation -----------------------------------------------------------------

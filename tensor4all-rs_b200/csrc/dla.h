@@ -116,6 +116,8 @@ void scale_rows(Ctx*, DType dt, int64_t m, int64_t n, void* A, int64_t lda, cons
 void upper_row_norms(Ctx*, DType dt, int64_t k, int64_t n, const void* R, int64_t ldr, double* out);
 // *out (device scalar, f64) = sum |x_i|^2
 void sumsq(Ctx*, DType dt, int64_t n, const void* x, double* out);
+// *out (device scalar, f64, must be zero on entry is NOT required) = max_i |x_i|
+void maxabs(Ctx*, DType dt, int64_t n, const void* x, double* out);
 // x *= alpha
 void scal(Ctx*, DType dt, int64_t n, void* x, double alpha);
 // y += alpha * x

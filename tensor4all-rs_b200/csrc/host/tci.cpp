@@ -52,4 +52,46 @@ TciUpdate tci2_update_pivots(dla::Ctx* c, DType dt, const void* pi_dev, int64_t 
     return u;
 }
 
+void tci2_site_tensor(dla::Ctx* c, DType dt, int64_t left_dim, int64_t site_dim, int64_t nj, const void* pi1_dev,
+                      const void* p_dev, void* out_dev) {
+    T4B_REQUIRE(left_dim > 0 && site_dim > 0 && nj > 0 && pi1_dev && out_dev, "tci2_site_tensor: bad arguments");
+    const size_t es = dtype_size(dt);
+    const int64_t ni = left_dim * site_dim;
+    auto transpose_into = [&](void* dst, const void* src, int64_t rows, int64_t cols) {
+        Group g;   // dst (cols x rows): dst[j + cols*i] = src[i + rows*j]
+        g.nd = 2; g.dim[0] = cols; g.str[0] = rows; g.dim[1] = rows; g.str[1] = 1;
+        dla::permute(c, dt, dst, src, g, false);
+    };
+    if (!p_dev) {
+        T4B_REQUIRE(nj == 1, "tci2_site_tensor: the last site has a single column");
+        // out[l, s, 0] = Pi1[l*d + s]: [s, l] -> [l, s]
+        transpose_into(out_dev, pi1_dev, site_dim, left_dim);
+        return;
+    }
+    // numerically zero pivot matrix -> zero core (the solve would fail)
+    double* dmax = (double*)dla::alloc(c, 8);
+    dla::maxabs(c, dt, nj * nj, p_dev, dmax);
+    double hmax = 0.0;
+    dla::d2h(c, &hmax, dmax, 8);
+    dla::sync(c);
+    dla::release(c, dmax);
+    if (hmax < 2.220446049250313e-16) {
+        dla::zero(c, out_dev, (size_t)ni * nj * es);
+        return;
+    }
+    // P^T X_t = Pi1^T  (X_t: nj x ni), then out[l, s, r] = X_t[r, l*d + s]
+    auto pt = std::make_shared<Buffer>(c, (size_t)nj * nj * es);
+    auto pi1t = std::make_shared<Buffer>(c, (size_t)nj * ni * es);
+    auto xt = std::make_shared<Buffer>(c, (size_t)nj * ni * es);
+    transpose_into(pt->p, p_dev, nj, nj);
+    transpose_into(pi1t->p, pi1_dev, ni, nj);
+    solve_matrix(c, dt, nj, ni, pt->p, pi1t->p, xt->p);
+    Group g;   // X_t as [r, s, l] (r fastest) -> out [l, s, r]
+    g.nd = 3;
+    g.dim[0] = left_dim; g.str[0] = nj * site_dim;
+    g.dim[1] = site_dim; g.str[1] = nj;
+    g.dim[2] = nj;       g.str[2] = 1;
+    dla::permute(c, dt, out_dev, xt->p, g, false);
+}
+
 }  // namespace t4b

@@ -29,4 +29,10 @@ TciUpdate tci2_update_pivots(dla::Ctx*, DType dt, const void* pi_dev, int64_t le
                              std::optional<int64_t> max_bond_dim, double tolerance,
                              bool left_orthogonal);
 
+// One-site tensor of fill_site_tensors (reference tensorci2.rs:1065-1199): out[l, s, r] = (Pi1 P^-1)[l*d + s, r]
+// with Pi1 ((left_dim*site_dim) x nj, rows l*d + s) and the pivot matrix P (nj x nj); a numerically zero P
+// (every |P_ij| < eps) gives a zero tensor.  p_dev == null: last site (nj == 1), Pi1 is stored directly.
+void tci2_site_tensor(dla::Ctx*, DType dt, int64_t left_dim, int64_t site_dim, int64_t nj, const void* pi1_dev,
+                      const void* p_dev, void* out_dev);
+
 }  // namespace t4b

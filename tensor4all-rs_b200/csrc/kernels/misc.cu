@@ -171,6 +171,35 @@ __global__ void unshift_kernel(double* __restrict__ lam, int64_t n, const double
 // Gershgorin bound: the shifted matrix is positive definite with condition number <= 3, so its left singular
 // vectors are the eigenvectors and sigma_i - s the eigenvalues, accurate to eps * ||G|| (the accuracy class of
 // any backward-stable eigh).  lam comes out non-increasing.
+namespace {
+template <bool CPLX>
+__global__ void maxabs_kernel(const double* __restrict__ x, int64_t n, unsigned long long* __restrict__ out) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const T* v = reinterpret_cast<const T*>(x);
+    double mx = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a2 = S::abs2(v[i]);
+        if (a2 > mx) mx = a2;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (other > mx) mx = other;
+    }
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(sqrt(mx)));
+}
+}  // namespace
+
+void maxabs(Ctx* c, DType dt, int64_t n, const void* x, double* out) {
+    zero(c, out, 8);
+    if (n == 0) return;
+    const int grid = grid_of(c, n);
+    if (dt == C64) maxabs_kernel<true><<<grid, 256, 0, c->stream>>>((const double*)x, n, (unsigned long long*)out);
+    else maxabs_kernel<false><<<grid, 256, 0, c->stream>>>((const double*)x, n, (unsigned long long*)out);
+    c->launched("maxabs", (double)n * (double)dtype_size(dt));
+}
+
 void eigh(Ctx* c, DType dt, int64_t n, void* G, double* lam, void* W) {
     if (n == 0) return;
     double* shift = (double*)alloc(c, 8);

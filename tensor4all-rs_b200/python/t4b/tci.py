@@ -35,3 +35,13 @@ class TciUpdate:
                                             self.tensor_bp1.ctypes.data_as(C.c_void_p)))
         lib().t4b_tci_update_release(h)
         self.h = None
+
+
+def site_tensor(ctx, pi1, p, left_dim, site_dim):
+    """fill_site_tensors for one site: pi1 ((left*site) x nj) and p (nj x nj or None) are DeviceArrays."""
+    nj = pi1.shape[1]
+    out = ctx.empty((left_dim, site_dim, nj), pi1.dt)
+    _check(lib().t4b_tci2_site_tensor(ctx.h, pi1.dt, C.c_int64(left_dim), C.c_int64(site_dim), C.c_int64(nj),
+                                      C.c_void_p(pi1.ptr), C.c_void_p(p.ptr if p is not None else 0),
+                                      C.c_void_p(out.ptr)))
+    return out

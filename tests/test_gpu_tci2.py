@@ -71,3 +71,33 @@ def test_config4_shape_update(ctx):
     assert got.rank == rank and list(got.row_indices) == rows and list(got.col_indices) == cols
     assert got.bond_error == err
     assert np.abs(got.tensor_b - tb).max() <= 1e-9 and np.abs(got.tensor_bp1 - tp).max() <= 1e-9 * np.abs(tp).max()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("dims", [(1, 2, 3), (7, 2, 14), (30, 8, 40), (300, 2, 300)])
+def test_fill_site_tensor_matches_oracle(ctx, dims, cplx):
+    """One site of fill_site_tensors (tensorci2.rs:1065-1199) against the oracle restatement; the last shape is
+    BASELINE C4's bond (max bond 300, d = 2)."""
+    from t4b import tci as ttci
+    left, d, nj = dims
+    rng = np.random.default_rng(left * 100 + nj)
+    def rnd(shape):
+        a = rng.standard_normal(shape)
+        return np.asfortranarray(a + 1j * rng.standard_normal(shape) if cplx else a)
+    pi1 = rnd((left * d, nj))
+    p = rnd((nj, nj)) + nj * np.eye(nj)
+    out = ttci.site_tensor(ctx, ctx.upload(pi1), ctx.upload(p), left, d).get()
+    ref = otci.site_tensor_from_pi1(pi1, p, left, d)
+    assert out.shape == ref.shape
+    assert np.linalg.norm((out - ref).ravel()) <= 1e-11 * np.linalg.norm(ref.ravel())
+    # numerically zero pivot matrix -> zero core
+    z = ttci.site_tensor(ctx, ctx.upload(pi1), ctx.upload(np.asfortranarray(p * 1e-300)), left, d).get()
+    assert np.all(z == 0)
+
+
+def test_fill_site_tensor_last_site(ctx):
+    from t4b import tci as ttci
+    rng = np.random.default_rng(5)
+    pi1 = np.asfortranarray(rng.standard_normal((6 * 2, 1)))
+    out = ttci.site_tensor(ctx, ctx.upload(pi1), None, 6, 2).get()
+    assert np.array_equal(out, otci.site_tensor_from_pi1(pi1, None, 6, 2))
