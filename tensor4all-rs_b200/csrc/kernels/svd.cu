@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     int item = 0;
     int sweep = 0;
     int converged = 0;
+    double prev_off = 1.0;
 
     for (; sweep < a.max_sweeps; ++sweep) {
         for (int r = 0; r < rounds; ++r) {
@@ -739,7 +740,12 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
         const double off = redbuf[JW + 1];
         __syncthreads();
         JP_STAMP(7);   // publish + sweep barrier
-        if (off <= a.tol_early) { converged = 1; ++sweep; break; }
+        // converged: the sweep found every pair orthogonal to working accuracy, or it started so far inside the
+        // quadratic regime (off <= tol_early AND off <= off_prev^1.5, i.e. the previous sweep contracted
+        // super-linearly) that its own rotations finished the job.  Degenerate clusters, which only contract
+        // linearly, never take the early exit.
+        if (off <= a.tol || (off <= a.tol_early && off <= prev_off * sqrt(prev_off))) { converged = 1; ++sweep; break; }
+        prev_off = off;
     }
     if (blockIdx.x == 0 && tid == 0) {
         a.info[0] = sweep; a.info[1] = converged;

@@ -111,3 +111,22 @@ def test_svd_c3_zipup_shape_full_size(ctx):
     assert abs(np.sum(b * b) - np.sum(s_ref[:r] ** 2)) <= 1e-11 * np.sum(s_ref[:r] ** 2)
     # the rows of U^H M are sigma_i v_i^H: their norms are the singular values
     assert np.max(np.abs(np.linalg.norm(b, axis=1) - s_ref[:r])) <= 1e-11 * s_ref[0]
+
+
+def test_svd_degenerate_clusters(ctx):
+    """Repeated singular values (only linear contraction inside the cluster): the early-exit heuristic of the
+    Jacobi iteration must not fire; U and V stay orthonormal to working accuracy."""
+    rng = np.random.default_rng(31)
+    m, n = 300, 160
+    qa, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    qb, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sv = np.repeat([3.0, 2.0, 1.0, 0.5], n // 4)
+    a = np.asfortranarray((qa * sv) @ qb.T)
+    a += 1e-9 * rng.standard_normal(a.shape)          # nearly (not exactly) degenerate
+    u, s, vh = ctx.svd_thin(ctx.upload(a))
+    u, s, vh = u.get(), s.get(), vh.get()
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
+    assert np.linalg.norm(u.T @ u - np.eye(n)) <= 1e-12 * n
+    assert np.linalg.norm(vh @ vh.T - np.eye(n)) <= 1e-12 * n
+    assert np.linalg.norm((u * s) @ vh - a) <= 1e-12 * np.linalg.norm(a)
