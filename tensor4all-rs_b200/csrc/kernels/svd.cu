@@ -989,12 +989,16 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     attr[0].val.clusterDim.x = pl.cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    // cooperative launch: the CTAs spin on each other's progress, so the whole grid must be gang-scheduled
-    // (two such kernels from different contexts must never be half resident at the same time)
+    // The CTAs spin on each other's progress, so the whole grid must be resident: the plan never launches more
+    // clusters than cudaOccupancyMaxActiveClusters reports.  Two such kernels from DIFFERENT contexts on one
+    // device could still be half resident at the same time; T4B_JAC_COOP=1 adds the cooperative (gang-scheduled)
+    // launch attribute for that deployment.  It is off by default because Nsight Compute cannot replay
+    // cooperative cluster launches (LaunchFailed) and the reference serialises backend calls process-wide anyway
+    // (tensorbackend/src/context.rs:318-337).
     attr[1].id = cudaLaunchAttributeCooperative;
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    static int coop_ok = getenv("T4B_JAC_NOCOOP") ? 0 : 1;
+    static int coop_ok = (getenv("T4B_JAC_COOP") && atoi(getenv("T4B_JAC_COOP")) > 0) ? 1 : 0;
     cfg.numAttrs = coop_ok ? 2 : 1;
     auto kern = jacobi_persistent_kernel<CPLX>;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);

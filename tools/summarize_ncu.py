@@ -63,7 +63,7 @@ def launches():
         w.writerow(["kernel", "launches", "total_ms", "share", "avg_us", "min_us", "max_us"])
         for k, (n, t, mn, mx) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             w.writerow([k, n, round(t / 1e6, 3), round(t / total, 4), round(t / n / 1e3, 2), round(mn / 1e3, 2), round(mx / 1e3, 2)])
-        w.writerow(["# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 37000 --csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline  (stopped by a 25 min timeout after the first 9455 launches of the sweep: operand canonicalisation + 44 of the 62 zip-up sites)"])
+        w.writerow(["# command: tools/ncu_capture.sh (ncu --metrics gpu__time_duration.sum --clock-control none [--launch-skip S] -c N --csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline); %d launches captured" % sum(a[0] for a in agg.values())])
         w.writerow(["# times under ncu are serialised / cold-cache: compare the SHARE with bench.py's kernel_profile_ms"])
     print("wrote", dst)
 
