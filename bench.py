@@ -359,12 +359,13 @@ def main():
                         "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src}
             # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
             try:
-                ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))
+                cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("ncu_summary_"))
+                ncu = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
                 if dom == "jacobi":
                     cap = ncu["jacobi_2048"][0]
                     roof["traffic"] = cap["dram_bytes"]
                     roof["traffic_note"] = ("dram__bytes_read+write of one jacobi_persistent_kernel launch on the 2048x2048 "
-                                            "zip-up factor (profiles/ncu_jacobi_2048_r01.csv): the panel is L2-resident, "
+                                            "zip-up factor (profiles/ncu_jacobi_2048_*.csv): the panel is L2-resident, "
                                             "DRAM sees the matrix once while the algorithmic (L2) traffic of that launch is "
                                             "~100 GB; DMMA pipe %.1f%% busy" % cap["fp64_tensor_pct"])
             except Exception:
