@@ -63,6 +63,8 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         T4B_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
     }
+    T4B_CUDA_CHECK(cudaMalloc((void**)&c->fail_dev, sizeof(unsigned)));
+    T4B_CUDA_CHECK(cudaMemset(c->fail_dev, 0, sizeof(unsigned)));
     // keep freed blocks cached in the default pool: sweeps re-allocate the same shapes
     cudaMemPool_t pool;
     T4B_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -77,6 +79,7 @@ void ctx_destroy(Ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_f); }
     if (c->dev_stats) cudaFree(c->dev_stats);
+    if (c->fail_dev) cudaFree(c->fail_dev);
     if (c->scratch) cudaFreeAsync(c->scratch, c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& kv : c->free_lists)
@@ -170,6 +173,15 @@ void sync(Ctx* c) {
     HostTimer t(c->host_sync_s);
     ++c->host_sync_n;
     T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->fail_dev) {
+        unsigned h = 0;
+        T4B_CUDA_CHECK(cudaMemcpy(&h, c->fail_dev, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (h) {
+            cudaMemset(c->fail_dev, 0, sizeof(unsigned));
+            throw Error(ST_NOT_CONVERGED, "svd: the Jacobi iteration did not converge within its sweep limit (" +
+                                              std::to_string(h) + " factorisation(s))");
+        }
+    }
 }
 std::string host_stats(Ctx* c) {
     char buf[256];

@@ -59,6 +59,8 @@ struct Ctx {
     // device-side work counters of kernels whose algorithmic work is only known on the device
     // ([0] = bytes moved by the persistent Jacobi kernel: sweeps x rounds x panel bytes); valid while profiling
     double* dev_stats = nullptr;
+    // sticky device-side failure counter (e.g. a Jacobi iteration that hit its sweep limit); checked by sync()
+    unsigned* fail_dev = nullptr;
     // high-priority side stream + events for look-ahead inside a factorisation (qr.cu); always joined
     // back into `stream` before the factorisation returns
     cudaStream_t side = nullptr;

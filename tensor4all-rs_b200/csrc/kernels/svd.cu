@@ -330,6 +330,7 @@ struct JPArgs {
     double tol_early;      // a sweep that starts below this ends converged (quadratic convergence)
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
     double* stats;         // optional device work counter (bytes), else null
+    unsigned* fail;        // sticky failure counter of the context (sweep limit reached)
     double bytes_per_sweep;
 };
 
@@ -741,6 +742,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     if (blockIdx.x == 0 && tid == 0) {
         a.info[0] = sweep; a.info[1] = converged;
         if (a.stats) atomicAdd(a.stats, (double)sweep * a.bytes_per_sweep);
+        if (!converged && a.fail) atomicAdd(a.fail, 1u);
         if (a.timing)
             for (int k = 0; k < 8; ++k) a.timing[k] = tacc[k];
     }
@@ -939,7 +941,7 @@ template <bool CPLX>
 void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
     const size_t es = CPLX ? 16 : 8;
     const int p = (int)(npad / JB);
-    const int max_sweeps = 40;
+    const int max_sweeps = getenv("T4B_JAC_MAXSWEEPS") ? atoi(getenv("T4B_JAC_MAXSWEEPS")) : 40;
     // workspace: flag[max_sweeps] (u64) | timing[8] (u64) | ready[p] | done | info[2]
     const bool verbose = getenv("T4B_VERBOSE") != nullptr;
     const size_t ws_bytes = (size_t)(max_sweeps + 8) * 8 + ((size_t)p + 4) * 4;
@@ -963,6 +965,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     // algorithmic bytes of one sweep: every round reads and writes the live rows of X (and V) once
     a.bytes_per_sweep = (double)(p - 1) * 2.0 * (double)(nx + (V ? npad : 0)) * (double)npad * (double)es;
     a.stats = c->profiling ? c->dev_stats : nullptr;
+    a.fail = c->fail_dev;
     a.inner = getenv("T4B_JAC_INNER") ? atoi(getenv("T4B_JAC_INNER")) : 1;
     a.eig_serial = getenv("T4B_JAC_EIG_SERIAL") ? 1 : 0;
     a.flag = (unsigned long long*)ws;
