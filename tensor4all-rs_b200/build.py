@@ -1,7 +1,6 @@
 """In-tree build of libt4b.so (sm_100a only) and of the test/oracle helper libraries.
 
     python tensor4all-rs_b200/build.py            # product library
-    python tensor4all-rs_b200/build.py --hostsim  # + tests/hostsim test double (CPU, tests only)
     python tensor4all-rs_b200/build.py --oracle   # + oracle/_build/liboracle.so (C restatement)
 
 nvcc cross-compiles without a GPU.  Objects are cached under build/ by mtime.
@@ -100,31 +99,6 @@ def build_product(verbose=True):
     return lib
 
 
-def build_hostsim(verbose=True):
-    """Test double of csrc/dla.h on the CPU + the real host drivers (tests only)."""
-    os.makedirs(BUILD, exist_ok=True)
-    sim_dir = os.path.join(ROOT, "tests", "hostsim")
-    _, cpp = _sources()
-    srcs = cpp + [os.path.join(sim_dir, f) for f in sorted(os.listdir(sim_dir)) if f.endswith(".cpp")]
-    hm = _headers_mtime()
-    objs = []
-    cxx = os.environ.get("CXX", "g++")
-    for s in srcs:
-        o = _obj_for(s, "hostsim_")
-        objs.append(o)
-        if os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hm):
-            continue
-        _run([cxx] + CXX_FLAGS + ["-DT4B_HOSTSIM", "-I", CSRC, "-c", s, "-o", o])
-        if verbose:
-            print("compiled(hostsim)", os.path.relpath(s, ROOT))
-    lib = os.path.join(sim_dir, "libt4b_hostsim.so")
-    if (not os.path.exists(lib)) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
-        _run([cxx, "-shared", "-o", lib] + objs)
-        if verbose:
-            print("linked", os.path.relpath(lib, ROOT))
-    return lib
-
-
 def build_oracle(verbose=True):
     odir = os.path.join(ROOT, "oracle")
     out_dir = os.path.join(odir, "_build")
@@ -143,12 +117,9 @@ def build_oracle(verbose=True):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--hostsim", action="store_true")
     ap.add_argument("--oracle", action="store_true")
     ap.add_argument("--all", action="store_true")
     a = ap.parse_args()
     build_product()
-    if a.hostsim or a.all:
-        build_hostsim()
     if a.oracle or a.all:
         build_oracle()

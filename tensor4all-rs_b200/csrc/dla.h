@@ -5,9 +5,7 @@
 // Complex64 = interleaved (re,im) f64 pairs (reference docs/CAPI_DESIGN.md:128-134).
 //
 // The product implementation is csrc/kernels/ (CUDA only; there is no CPU
-// fallback: ctx_create throws if no CUDA device is usable).  tests/hostsim/
-// holds a test double of this interface used ONLY by the `-m "not gpu"` tests
-// to exercise the host drivers; it is never linked into libt4b.so.
+// fallback: ctx_create throws if no CUDA device is usable).
 #pragma once
 #include "common.h"
 

@@ -1,6 +1,7 @@
 """pytest configuration: `-m gpu` tests need a B200 and call through the C ABI (libt4b.so);
-`-m "not gpu"` tests run on CPU (oracle vs golden vectors, host logic through the hostsim test
-double, C-ABI symbol export)."""
+`-m "not gpu"` tests run on CPU (oracle vs golden vectors, the host-only entry points of the C ABI - rank
+rules, sweep plans, adaptive cutoffs -, the world-size-2 gloo run of the sharded patch driver, C-ABI symbol
+export)."""
 import os
 import sys
 
