@@ -462,18 +462,28 @@ __device__ void house_factor_regs(typename Sc<CPLX>::T* P, int pitch, int r, int
             const T* pc = P + (size_t)c * pitch;
             const T tau = tau_s[c];
             if (S::abs2(tau) != 0.0) {
-                T v[RPL];
+                // short columns keep the reflector in registers between the two passes; longer ones re-read it
+                // from shared memory (the register file is 64 per thread at 1024 threads per CTA)
+                constexpr bool KEEPV = RPL <= 8;
+                T v[KEEPV ? RPL : 1];
                 T dot = S::zero();
 #pragma unroll
                 for (int j = 0; j < RPL; ++j) {
                     const int i = lane + 32 * j;
-                    v[j] = (i > c && i < r) ? pc[i] : ((i == c) ? S::one() : S::zero());
-                    dot = S::add(dot, S::mul(S::conj(v[j]), x[j]));
+                    const T vj = (i > c && i < r) ? pc[i] : ((i == c) ? S::one() : S::zero());
+                    if constexpr (KEEPV) v[j] = vj;
+                    dot = S::add(dot, S::mul(S::conj(vj), x[j]));
                 }
                 dot = warp_sum_t<CPLX>(dot);
                 const T f = S::mul(S::conj(tau), dot);
 #pragma unroll
-                for (int j = 0; j < RPL; ++j) x[j] = S::sub(x[j], S::mul(f, v[j]));
+                for (int j = 0; j < RPL; ++j) {
+                    const int i = lane + 32 * j;
+                    T vj;
+                    if constexpr (KEEPV) vj = v[j];
+                    else vj = (i > c && i < r) ? pc[i] : ((i == c) ? S::one() : S::zero());
+                    x[j] = S::sub(x[j], S::mul(f, vj));
+                }
             }
             if (warp == c + 1) publish(c + 1);
         } else if (c < jb && warp < c) {
