@@ -192,22 +192,26 @@ __device__ __forceinline__ void jacobi_rotation(double aa, double bb, typename S
             ph = S::scale(S::conj(g), inv_absg);
             tg = t * absg;
         } else {
+            // (c, s) = (u, |g|) / sqrt(u^2 + g^2), u = |d| + sqrt(d^2 + g^2), evaluated in fp32 on exponent-
+            // normalised operands (two MUFU ops, no division): the angle only steers the convergence.  The
+            // pair is then renormalised in fp64, (c, s) *= 1 - e/2 + 3 e^2 / 8 with e = c^2 + s^2 - 1 ~ 1e-7,
+            // which makes the rotation orthogonal to ~e^3.
             const double ag = fabs(g), ad = fabs(d);
             const double mx = ag > ad ? ag : ad;
             const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
-            const double sc = __hiloint2double((2046 - ex) << 20, 0);
+            const double sc = __hiloint2double((2046 - ex) << 20, 0);     // mx * sc in [1, 2)
             const float fd = (float)(ad * sc), fg = (float)(ag * sc);
-            const float fh = sqrtf(fd * fd + fg * fg);
-            const float ft = __fdividef(fg, fd + fh);
-            const double t = d >= 0.0 ? (double)ft : -(double)ft;
-            const double x = 1.0 + t * t;
-            double y = (double)rsqrtf((float)x);
-            y = y * (1.5 - 0.5 * x * y * y);
-            y = y * (1.5 - 0.5 * x * y * y);
-            c = y;
-            sn = c * t;
+            const float fu = fd + sqrtf(fd * fd + fg * fg);
+            const float rho = rsqrtf(fu * fu + fg * fg);
+            double cd = (double)(fu * rho), sd = (double)(fg * rho);
+            if (fg == 0.0f) { cd = 1.0; sd = ag / (2.0 * ad); }          // |g| / |d| below fp32 range: tiny angle
+            const double e = fma(cd, cd, fma(sd, sd, -1.0));
+            const double corr = fma(e, fma(e, 0.375, -0.5), 1.0);
+            cd *= corr; sd *= corr;
+            c = cd;
+            sn = d >= 0.0 ? sd : -sd;
             ph = g >= 0.0 ? 1.0 : -1.0;
-            tg = t * ag;
+            tg = fma(sn * sn, aa - bb, 2.0 * c * sn * ag);               // aa - (c^2 aa - 2 c s |g| + s^2 bb)
         }
     }
 }
