@@ -140,3 +140,12 @@ def test_treetn_truncate_is_idempotent_and_canonical():
     d1 = oracle_chain_dense(tn)
     otn.truncate(tn, 0, SvdTruncationPolicy(0.0), 3)
     assert relerr(oracle_chain_dense(tn), d1) <= 1e-12
+
+
+def test_rrlu_fixture_pivots_agree_with_exact_rational_scan():
+    """The expected pivot sets are independent of any floating-point implementation
+    (tests/golden/check_rrlu_fixtures.py: fractions.Fraction full-pivot LU with the reference's scan order)."""
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(GOLD, "check_rrlu_fixtures.py")], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
