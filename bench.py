@@ -289,17 +289,32 @@ def main():
     bonds = last.bond_dims()
 
     # ---- e2e: host buffers in, host buffers out ----------------------------------------------------
+    # pinned result buffers (the shapes of the result are fixed by the cap-only truncation)
+    out_pin = []
+    for i in range(L):
+        shp, _ = last.site_shape(i)
+        t = torch.empty(int(np.prod(shp)), dtype=torch.float64, pin_memory=True)
+        out_pin.append(t.numpy().reshape(shp, order="F"))
     d2h_bytes = 0
+
+    def e2e_step():
+        ta = t4tt.chain_from_arrays(ctx, [v for _, v in mps_pin], mps_ids)
+        tb = t4tt.chain_from_arrays(ctx, [v for _, v in mpo_pin], mpo_ids)
+        out = ta.contract(tb, 0, 0, policy, chi)
+        for i in range(L):
+            shp, _ = out.site_shape(i)
+            if tuple(shp) != out_pin[i].shape:      # never the case for C3; keep the path general
+                out_pin[i] = np.empty(shp, dtype=np.float64, order="F")
+            out.site_into(i, out_pin[i])
+        ta.release(); tb.release(); out.release()
+        return sum(a.nbytes for a in out_pin)
+
+    e2e_step()          # untimed warm-up of the end-to-end path (allocator, pinned pages)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     for _ in range(args.steps):
-        ta = t4tt.chain_from_arrays(ctx, [v for _, v in mps_pin], mps_ids)
-        tb = t4tt.chain_from_arrays(ctx, [v for _, v in mpo_pin], mpo_ids)
-        out = ta.contract(tb, 0, 0, policy, chi)
-        res = out.sites()
-        d2h_bytes = sum(a.nbytes for a, _ in res)
-        ta.release(); tb.release(); out.release()
+        d2h_bytes = e2e_step()
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)

@@ -104,6 +104,11 @@ int t4b_trsm(t4b_ctx* ctx, int dtype, int left_side, int lower, int transpose, i
 int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_dev, const void* b_dev,
               void* x_dev);
 
+/* Batched matrix product c[:, :, b] = a[:, :, b] * b[:, :, b]: a (m x k x batch), b (k x n x batch), c (m x n x batch),
+ * dense column-major, one launch.  Replaces batched_mat_mul_same_shape (tensorbackend/src/matrix.rs:1538-1584). */
+int t4b_batched_matmul(t4b_ctx* ctx, int dtype, int64_t batch, int64_t m, int64_t k, int64_t n, const void* a_dev,
+                       const void* b_dev, void* c_dev);
+
 /* N-ary einsum over numeric labels: operand i is a dense column-major tensor of rank ranks[i] whose shape
  * and labels are the next ranks[i] entries of shapes / labels.  A label shared by two operands is
  * contracted, a label that appears once must appear in out_labels (no traces, no batch labels).  The

@@ -198,6 +198,22 @@ int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_de
     T4B_CATCH
 }
 
+int t4b_batched_matmul(t4b_ctx* ctx, int dtype, int64_t batch, int64_t m, int64_t k, int64_t n, const void* a_dev,
+                       const void* b_dev, void* c_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(batch >= 0 && m >= 0 && k >= 0 && n >= 0, "batched_matmul: negative dimension");
+    T4B_REQUIRE(batch * m * n == 0 || (a_dev && b_dev && c_dev), "batched_matmul: null buffer");
+    // split very large batches over several launches (grid z limit)
+    const size_t es = dtype_size(to_dtype(dtype));
+    for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+        const int64_t nb = batch - b0 < 32768 ? batch - b0 : 32768;
+        dla::gemm_batched(ctx->c, to_dtype(dtype), nb, m, n, k, (const char*)a_dev + (size_t)b0 * m * k * es,
+                          (const char*)b_dev + (size_t)b0 * k * n * es, (char*)c_dev + (size_t)b0 * m * n * es);
+    }
+    T4B_CATCH
+}
+
 int t4b_einsum(t4b_ctx* ctx, int dtype, int n_ops, const void* const* ops_dev, const int32_t* ranks,
                const int64_t* shapes, const uint32_t* labels, int out_rank, const uint32_t* out_labels,
                void* out_dev) {

@@ -52,6 +52,11 @@ void gemm(Ctx*, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const v
           const Group& am, const Group& ak, bool conjA, const void* B, const Group& bk,
           const Group& bn, bool conjB, double beta, void* C, const Group& cm, const Group& cn);
 
+// C[:, :, b] = A[:, :, b] * B[:, :, b], b < batch; dense column-major [m,k,batch] x [k,n,batch] -> [m,n,batch]
+// (reference batched_mat_mul_same_shape, crates/tensor4all-tensorbackend/src/matrix.rs:1538-1584).
+void gemm_batched(Ctx*, DType dt, int64_t batch, int64_t M, int64_t N, int64_t K, const void* A, const void* B,
+                  void* C);
+
 // out[i] (contiguous, i over g.dim first-fastest) = op(in[offset_g(i)])
 // (materialised permute; reference idx_tensor.rs:3389,3445).
 void permute(Ctx*, DType dt, void* out, const void* in, const Group& g, bool conj);

@@ -42,6 +42,8 @@ struct GemmParams {
     int ksplit;
     int64_t kt_per_split;
     double* partial;
+    // batched mode (blockIdx.z = batch entry): element strides between consecutive problems, 0 = not batched
+    int64_t batch_a, batch_b, batch_c;
 };
 
 __device__ __forceinline__ int64_t off_of(const int64_t* tbl, int64_t stride, int64_t i) {
@@ -97,6 +99,10 @@ gemm_kernel(GemmParams p) {
     const int64_t tile = blockIdx.x;
     const int64_t m0 = (tile % p.tiles_m) * BM;
     const int64_t n0 = (tile / p.tiles_m) * BN;
+    // batched mode: this CTA works on problem blockIdx.z
+    p.A += (int64_t)blockIdx.z * p.batch_a * ES;
+    p.B += (int64_t)blockIdx.z * p.batch_b * ES;
+    p.C += (int64_t)blockIdx.z * p.batch_c * ES;
 
     double acc[MF][NF][2 * ES];
 #pragma unroll
@@ -952,6 +958,36 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
         if (small_tile) launch_cfg<false, 64, 64, 32, 32>(c, p, alay, blay, g[4], g[5]);
         else launch_cfg<false, 128, 128, 64, 32>(c, p, alay, blay, g[4], g[5], g);
     }
+}
+
+// C[:, :, b] = A[:, :, b] * B[:, :, b] for b < batch: A (m x k x batch), B (k x n x batch), C (m x n x batch), all
+// dense column-major (reference batched_mat_mul_same_shape, crates/tensor4all-tensorbackend/src/matrix.rs:1538-1584).
+// One launch: blockIdx.z enumerates the batch.
+void gemm_batched(Ctx* c, DType dt, int64_t batch, int64_t M, int64_t N, int64_t K, const void* A, const void* B,
+                  void* C) {
+    if (batch == 0 || M == 0 || N == 0) return;
+    T4B_REQUIRE(batch <= 65535, "gemm_batched: batch exceeds the grid z limit (split the call)");
+    GemmParams p{};
+    p.A = (const double*)A; p.B = (const double*)B; p.C = (double*)C;
+    p.M = M; p.N = N; p.K = K;
+    p.alpha = 1.0; p.beta = 0.0;
+    p.sam = 1; p.sak = M; p.sbk = 1; p.sbn = K; p.scm = 1; p.scn = M;
+    p.ksplit = 1;
+    p.kt_per_split = (K + BK - 1) / BK;
+    if (p.kt_per_split < 1) p.kt_per_split = 1;
+    p.batch_a = M * K; p.batch_b = K * N; p.batch_c = M * N;
+    constexpr int BMs = 64, BNs = 64;
+    p.tiles_m = (int)((M + BMs - 1) / BMs);
+    const int64_t tiles_n = (N + BNs - 1) / BNs;
+    dim3 grid((unsigned)((int64_t)p.tiles_m * tiles_n), 1, (unsigned)batch);
+    auto launch = [&](auto kern, size_t smem) {
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, c->stream>>>(p);
+    };
+    // A is M-fast (ALAY 0), B is K-fast (BLAY 0)
+    if (dt == C64) launch(gemm_kernel<true, 64, 64, 32, 32, 0, 0>, (size_t)(BK * (64 + 2) + 64 * (BK + 4)) * 2 * 8 * STAGES);
+    else launch(gemm_kernel<false, 64, 64, 32, 32, 0, 0>, (size_t)(BK * (64 + 4) + 64 * (BK + 4)) * 8 * STAGES);
+    c->launched(c->gemm_class, (dt == C64 ? 8.0 : 2.0) * (double)batch * (double)M * (double)N * (double)K);
 }
 
 }  // namespace dla

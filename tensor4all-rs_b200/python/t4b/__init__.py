@@ -211,3 +211,12 @@ class Context:
         _check(lib().t4b_einsum(self.h, operands[0].dt, len(operands), ptrs, ranks, shapes, labs,
                                 len(out_labels), outl, C.c_void_p(out.ptr)))
         return out
+
+    def batched_matmul(self, a: DeviceArray, b: DeviceArray) -> DeviceArray:
+        """a [m, k, batch], b [k, n, batch] -> [m, n, batch]."""
+        m, k, batch = a.shape
+        n = b.shape[1]
+        out = self.empty((m, n, batch), a.dt)
+        _check(lib().t4b_batched_matmul(self.h, a.dt, C.c_int64(batch), C.c_int64(m), C.c_int64(k), C.c_int64(n),
+                                        C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(out.ptr)))
+        return out

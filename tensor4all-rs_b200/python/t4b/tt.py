@@ -146,6 +146,18 @@ class ChainTN:
         _check(lib().t4b_tn_download_site(self.ctx.h, self.h, i, out.ctypes.data_as(C.c_void_p)))
         return out, list(ids)
 
+    def site_shape(self, i):
+        r = C.c_int()
+        _check(lib().t4b_tn_site_rank(self.h, i, C.byref(r)))
+        shape = (C.c_int64 * r.value)()
+        ids = (C.c_int64 * r.value)()
+        _check(lib().t4b_tn_site_shape(self.h, i, shape, ids))
+        return tuple(shape), list(ids)
+
+    def site_into(self, i, out):
+        """Download site i into a caller-owned (e.g. pinned) column-major buffer of the right size."""
+        _check(lib().t4b_tn_download_site(self.ctx.h, self.h, i, out.ctypes.data_as(C.c_void_p)))
+
     def dtype(self):
         return self._dt
 

@@ -118,3 +118,22 @@ def test_einsum_rejects_trace(ctx):
     a = ctx.upload(np.ones((3, 3)))
     with pytest.raises(t4b.T4BError):
         ctx.einsum([a], [[0, 0]], [])
+
+
+def test_batched_matmul_reference_doc_example(ctx):
+    # batched_mat_mul_same_shape(1, 2, 2, 2, a, b) == [19, 43, 22, 50] (tensorbackend/src/matrix.rs:1530-1536)
+    a = np.asfortranarray(np.array([1.0, 3.0, 2.0, 4.0]).reshape((2, 2, 1), order="F"))
+    b = np.asfortranarray(np.array([5.0, 7.0, 6.0, 8.0]).reshape((2, 2, 1), order="F"))
+    out = ctx.batched_matmul(ctx.upload(a), ctx.upload(b)).get()
+    assert list(out.ravel(order="F")) == [19.0, 43.0, 22.0, 50.0]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("shape", [(3, 5, 4, 7), (64, 64, 64, 33), (70, 9, 130, 300), (1, 1, 1, 1000)])
+def test_batched_matmul_matches_numpy(ctx, shape, cplx):
+    m, k, n, batch = shape
+    rng = np.random.default_rng(m + 10 * k + 100 * n)
+    a, b = _rand(rng, (m, k, batch), cplx), _rand(rng, (k, n, batch), cplx)
+    out = ctx.batched_matmul(ctx.upload(a), ctx.upload(b)).get()
+    ref = np.einsum("mkb,knb->mnb", a, b)
+    assert np.linalg.norm((out - ref).ravel()) <= 1e-13 * np.linalg.norm(ref.ravel())
