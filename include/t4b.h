@@ -104,6 +104,13 @@ int t4b_trsm(t4b_ctx* ctx, int dtype, int left_side, int lower, int transpose, i
 int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_dev, const void* b_dev,
               void* x_dev);
 
+/* Host only (no GPU needed): optimal pairwise order for t4b_einsum-style operands (n_ops <= 8).  pairs_out receives
+ * 2 * (n_ops - 1) ints: step s contracts the operands at positions (pairs_out[2s], pairs_out[2s+1]) of the current
+ * operand list, the result takes the first position and the second is removed.  cost_out = sum over steps of the
+ * product of the dims of the union of the two label sets (multiply-adds). */
+int t4b_contraction_order(int n_ops, const int32_t* ranks, const int64_t* shapes, const uint32_t* labels,
+                          int32_t* pairs_out, double* cost_out);
+
 /* Batched matrix product c[:, :, b] = a[:, :, b] * b[:, :, b]: a (m x k x batch), b (k x n x batch), c (m x n x batch),
  * dense column-major, one launch.  Replaces batched_mat_mul_same_shape (tensorbackend/src/matrix.rs:1538-1584). */
 int t4b_batched_matmul(t4b_ctx* ctx, int dtype, int64_t batch, int64_t m, int64_t k, int64_t n, const void* a_dev,

@@ -198,6 +198,31 @@ int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_de
     T4B_CATCH
 }
 
+int t4b_contraction_order(int n_ops, const int32_t* ranks, const int64_t* shapes, const uint32_t* labels,
+                          int32_t* pairs_out, double* cost_out) {
+    T4B_TRY
+    T4B_REQUIRE(n_ops >= 1 && n_ops <= 8 && ranks && (n_ops == 1 || pairs_out), "contraction_order: bad arguments");
+    std::vector<std::vector<Index>> sets;
+    size_t off = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        std::vector<Index> inds;
+        for (int a = 0; a < ranks[i]; ++a) {
+            Index ix;
+            ix.id = (int64_t)labels[off + a];
+            ix.dim = shapes[off + a];
+            inds.push_back(ix);
+        }
+        off += (size_t)ranks[i];
+        sets.push_back(inds);
+    }
+    double cost = 0.0;
+    auto plan = plan_contraction_order(sets, &cost);
+    T4B_REQUIRE((int)plan.size() == n_ops - 1, "contraction_order: the operands do not form one network");
+    for (size_t s = 0; s < plan.size(); ++s) { pairs_out[2 * s] = plan[s].first; pairs_out[2 * s + 1] = plan[s].second; }
+    if (cost_out) *cost_out = cost;
+    T4B_CATCH
+}
+
 int t4b_batched_matmul(t4b_ctx* ctx, int dtype, int64_t batch, int64_t m, int64_t k, int64_t n, const void* a_dev,
                        const void* b_dev, void* c_dev) {
     T4B_TRY

@@ -136,6 +136,54 @@ Tensor contract_pair(dla::Ctx* c, const Tensor& a, const Tensor& b, bool conj_a,
     return out;
 }
 
+// Optimal pairwise order of a small network by exhaustive search: `sets` holds the index list of every operand;
+// a step (i, j) (positions in the CURRENT operand list, i < j) replaces operand i by the contraction of i and j
+// (indices = those of i not in j, then those of j not in i) and removes operand j.  Cost of a step = product
+// of the dims of the union of the two index lists.  Outer products are only taken once nothing is connected.
+std::vector<std::pair<int, int>> plan_contraction_order(const std::vector<std::vector<Index>>& sets_in,
+                                                        double* total_cost) {
+    typedef std::vector<std::vector<Index>> Sets;
+    Sets sets = sets_in;
+    std::vector<std::pair<int, int>> cur, best_plan;
+    double best_cost = std::numeric_limits<double>::infinity();
+    std::function<void(Sets&, double)> dfs = [&](Sets& ss, double cost) {
+        if (cost >= best_cost) return;
+        if (ss.size() == 1) { best_cost = cost; best_plan = cur; return; }
+        for (size_t i = 0; i < ss.size(); ++i)
+            for (size_t j = i + 1; j < ss.size(); ++j) {
+                bool connected = false;
+                double pc = 1.0;
+                for (auto& ix : ss[i]) pc *= (double)ix.dim;
+                std::vector<Index> merged;
+                for (auto& ix : ss[i])
+                    if (std::find(ss[j].begin(), ss[j].end(), ix) == ss[j].end()) merged.push_back(ix);
+                for (auto& ix : ss[j]) {
+                    if (std::find(ss[i].begin(), ss[i].end(), ix) == ss[i].end()) { pc *= (double)ix.dim; merged.push_back(ix); }
+                    else connected = true;
+                }
+                if (!connected) {
+                    bool any = false;
+                    for (size_t a = 0; a < ss.size() && !any; ++a)
+                        for (size_t b = a + 1; b < ss.size() && !any; ++b)
+                            for (auto& ix : ss[a])
+                                if (std::find(ss[b].begin(), ss[b].end(), ix) != ss[b].end()) { any = true; break; }
+                    if (any) continue;
+                }
+                Sets next;
+                for (size_t a = 0; a < ss.size(); ++a)
+                    if (a != i && a != j) next.push_back(ss[a]);
+                next.insert(next.begin() + i, merged);
+                cur.push_back({(int)i, (int)j});
+                dfs(next, cost + pc);
+                cur.pop_back();
+            }
+    };
+    if (sets.size() <= 1) { if (total_cost) *total_cost = 0.0; return {}; }
+    dfs(sets, 0.0);
+    if (total_cost) *total_cost = best_cost;
+    return best_plan;
+}
+
 Tensor contract(dla::Ctx* c, const std::vector<const Tensor*>& ts,
                 const std::vector<Index>* out_order) {
     T4B_REQUIRE(!ts.empty(), "contract: no tensors");
@@ -151,48 +199,9 @@ Tensor contract(dla::Ctx* c, const std::vector<const Tensor*>& ts,
     // networks fall back to greedy cheapest-connected-pair.
     std::vector<std::pair<int, int>> plan;
     if (work.size() <= 6) {
-        typedef std::vector<std::vector<Index>> Sets;
-        Sets sets;
+        std::vector<std::vector<Index>> sets;
         for (auto& t : work) sets.push_back(t.inds);
-        // indices that must survive (appear once overall) are kept by every merge automatically:
-        // merged set = symmetric difference of the two index lists
-        std::vector<std::pair<int, int>> cur, best_plan;
-        double best_cost = std::numeric_limits<double>::infinity();
-        std::function<void(Sets&, double)> dfs = [&](Sets& ss, double cost) {
-            if (cost >= best_cost) return;
-            if (ss.size() == 1) { best_cost = cost; best_plan = cur; return; }
-            for (size_t i = 0; i < ss.size(); ++i)
-                for (size_t j = i + 1; j < ss.size(); ++j) {
-                    bool connected = false;
-                    double pc = 1.0;
-                    for (auto& ix : ss[i]) pc *= (double)ix.dim;
-                    std::vector<Index> merged;
-                    for (auto& ix : ss[i])
-                        if (std::find(ss[j].begin(), ss[j].end(), ix) == ss[j].end()) merged.push_back(ix);
-                    for (auto& ix : ss[j]) {
-                        if (std::find(ss[i].begin(), ss[i].end(), ix) == ss[i].end()) { pc *= (double)ix.dim; merged.push_back(ix); }
-                        else connected = true;
-                    }
-                    // outer products only when nothing is connected any more
-                    if (!connected) {
-                        bool any = false;
-                        for (size_t a = 0; a < ss.size() && !any; ++a)
-                            for (size_t b = a + 1; b < ss.size() && !any; ++b)
-                                for (auto& ix : ss[a])
-                                    if (std::find(ss[b].begin(), ss[b].end(), ix) != ss[b].end()) { any = true; break; }
-                        if (any) continue;
-                    }
-                    Sets next;
-                    for (size_t a = 0; a < ss.size(); ++a)
-                        if (a != i && a != j) next.push_back(ss[a]);
-                    next.insert(next.begin() + i, merged);
-                    cur.push_back({(int)i, (int)j});
-                    dfs(next, cost + pc);
-                    cur.pop_back();
-                }
-        };
-        dfs(sets, 0.0);
-        plan = best_plan;
+        plan = plan_contraction_order(sets, nullptr);
     }
     size_t step = 0;
     while (work.size() > 1) {

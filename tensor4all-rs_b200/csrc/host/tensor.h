@@ -78,6 +78,10 @@ Tensor contract_pair(dla::Ctx*, const Tensor& a, const Tensor& b, bool conj_a = 
 // (reference `contract`, core/defaults/contract.rs:283,721-849).
 Tensor contract(dla::Ctx*, const std::vector<const Tensor*>& ts,
                 const std::vector<Index>* out_order = nullptr);
+// Optimal pairwise contraction order of <= ~8 operands (exhaustive search; host only).  Steps (i, j) refer to
+// positions in the current operand list: operand i <- contract(i, j), operand j removed.
+std::vector<std::pair<int, int>> plan_contraction_order(const std::vector<std::vector<Index>>& sets,
+                                                        double* total_cost);
 // Materialised axis permutation (reference permute_indices, idx_tensor.rs:3389).
 Tensor permute(dla::Ctx*, const Tensor& t, const std::vector<Index>& new_order, bool conj = false);
 // sum |t|^2 (synchronises)

@@ -93,3 +93,60 @@ def test_sweep_plan_and_zipup_order():
     # end-of-chain centre: out and back, 2(L-1) steps (localupdate.rs:126-152)
     assert t4tt.sweep_plan(4, 0) == [(0, 1), (1, 2), (2, 3), (3, 2), (2, 1), (1, 0)]
     assert t4tt.zipup_order(4, 0) == [3, 2, 1, 0] and t4tt.zipup_order(4, 2) == [0, 1, 2, 3]
+
+
+def _order(shapes, labels):
+    import ctypes as C
+    import t4b
+    n = len(shapes)
+    ranks = (C.c_int32 * n)(*[len(s) for s in shapes])
+    flat_s = [d for s in shapes for d in s]
+    flat_l = [l for ls in labels for l in ls]
+    sh = (C.c_int64 * len(flat_s))(*flat_s)
+    lb = (C.c_uint32 * len(flat_l))(*flat_l)
+    pairs = (C.c_int32 * (2 * max(n - 1, 1)))()
+    cost = C.c_double()
+    rc = t4b.lib().t4b_contraction_order(n, ranks, sh, lb, pairs, C.byref(cost))
+    assert rc == 0, t4b.lib().t4b_last_error()
+    return [(pairs[2 * s], pairs[2 * s + 1]) for s in range(n - 1)], cost.value
+
+
+def test_contraction_order_zipup_site():
+    """The C3 zip-up site R[n,a,b] A[a,s,a'] B[b,s,t,b']: contracting R.A first (8.6 GF) then .B (0.54 GF) beats
+    R.B first (34.9 GF) - host-only planner, no GPU needed."""
+    n_, a_, b_, s_, a2, t_, b2 = range(7)
+    shapes = [(512, 512, 8), (512, 4, 512), (8, 4, 4, 8)]
+    labels = [(n_, a_, b_), (a_, s_, a2), (b_, s_, t_, b2)]
+    plan, cost = _order(shapes, labels)
+    assert plan[0] == (0, 1)                       # R.A first
+    assert plan[1] == (0, 1)                       # then (RA).B
+    ra = 512 * 512 * 8 * 4 * 512                   # n a b s a'
+    rab = 512 * 8 * 4 * 512 * 4 * 8                # n b s a' t b'
+    assert cost == float(ra + rab)
+
+
+def test_contraction_order_chain_is_optimal():
+    """Matrix chain 3x40 40x2 2x50 50x4: brute-force optimum over all pairwise orders equals the planner's cost."""
+    import itertools
+    dims = [3, 40, 2, 50, 4]
+    shapes = [(dims[i], dims[i + 1]) for i in range(4)]
+    labels = [(i, i + 1) for i in range(4)]
+    plan, cost = _order(shapes, labels)
+
+    def brute(sets):
+        if len(sets) == 1:
+            return 0.0
+        best = float("inf")
+        for i, j in itertools.combinations(range(len(sets)), 2):
+            if not (set(sets[i]) & set(sets[j])):
+                continue
+            union = set(sets[i]) | set(sets[j])
+            c = 1.0
+            for l in union:
+                c *= dims[l]
+            merged = tuple(sorted(set(sets[i]) ^ set(sets[j])))
+            rest = [s for k, s in enumerate(sets) if k not in (i, j)]
+            best = min(best, c + brute(rest[:i] + [merged] + rest[i:]))
+        return best
+    assert cost == brute([tuple(l) for l in labels])
+    assert len(plan) == 3
