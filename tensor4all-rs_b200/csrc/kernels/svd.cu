@@ -962,8 +962,8 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     a.max_sweeps = max_sweeps;
     a.tol = tol; a.tol_rot = tol * 0.25;
     // off_after <~ n * off_before^2 once the iteration converges quadratically: a sweep that starts
-    // below sqrt(0.01 tol / n) leaves the columns orthogonal to working accuracy
-    a.tol_early = sqrt(0.01 * tol / (double)npad);
+    // below sqrt(0.1 tol / n) leaves the columns orthogonal to working accuracy (n off^2 <= 0.1 tol)
+    a.tol_early = sqrt(0.1 * tol / (double)npad);
     if (a.tol_early < tol) a.tol_early = tol;
     a.D = Dblk;
     // algorithmic bytes of one sweep: every round reads and writes the live rows of X (and V) once
