@@ -643,22 +643,39 @@ __global__ void __launch_bounds__(AT) tsqr_apply_kernel(ApplyArgs a) {
     auto crow = [&](int i) -> int64_t {      // physical row of C for logical block row i
         return a.gather ? (int64_t)(i >> 5) * a.h + (i & 31) : blk0 + i;
     };
+    // global -> registers -> shared, all loads of a thread issued before the first store so that their latencies
+    // overlap (a warp owns columns warp, warp + 8, ...; lanes run over the 64 rows of the chunk)
     auto load_chunk = [&](int q0) {
-        for (int c = warp; c < NB + NT; c += AT / 32) {
+        constexpr int NCOL = (NB + NT) / (AT / 32);
+        T regs[NCOL][CHR / 32];
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+            const int c = warp + k * (AT / 32);
 #pragma unroll
             for (int u = 0; u < CHR / 32; ++u) {
-                const int q = lane + u * 32, i = q0 + q;
+                const int i = q0 + lane + u * 32;
                 T v = S::zero();
                 if (c < NB) {
-                    if (c < jb && i < r) {
-                        if (a.v_implicit && i <= c) v = (i == c) ? S::one() : S::zero();
-                        else v = Vg[i + (int64_t)c * a.ldv];
-                    }
-                    Vs[c * CP + q] = v;
+                    if (c < jb && i < r && !(a.v_implicit && i <= c)) v = Vg[i + (int64_t)c * a.ldv];
                 } else {
                     const int cc = c - NB;
                     if (n0 + cc < a.ncols && i < r) v = Cg[crow(i) + (int64_t)cc * a.ldc];
-                    Cs[cc * CP + q] = v;
+                }
+                regs[k][u] = v;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NCOL; ++k) {
+            const int c = warp + k * (AT / 32);
+#pragma unroll
+            for (int u = 0; u < CHR / 32; ++u) {
+                const int q = lane + u * 32, i = q0 + q;
+                T v = regs[k][u];
+                if (c < NB) {
+                    if (a.v_implicit && c < jb && i == c) v = S::one();
+                    Vs[c * CP + q] = v;
+                } else {
+                    Cs[(c - NB) * CP + q] = v;
                 }
             }
         }
