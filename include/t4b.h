@@ -209,6 +209,10 @@ int t4b_tn_truncate(t4b_ctx* ctx, t4b_tn* tn, int center, const t4b_svd_policy* 
 int t4b_tn_contract(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, int center, int method,
                     const t4b_svd_policy* policy, int64_t max_bond_dim, int nfullsweeps,
                     t4b_tn** out);
+/* Strict direct-sum addition out = a + b (TreeTN::add, treetn/src/treetn/addition.rs:322): same site indices on
+ * every site, bond dimensions add, fresh (negative-id) bonds.  Used by PartitionedTreeTN::contract to sum the
+ * contributions of one output projector before a single truncation (partitioned_tree_tn.rs:447-466). */
+int t4b_tn_add(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, t4b_tn** out);
 int t4b_tn_norm_sqr(t4b_ctx* ctx, const t4b_tn* tn, double* out);
 int t4b_tn_inner(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, double* re, double* im);
 

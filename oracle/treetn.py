@@ -293,3 +293,37 @@ def contract_fit(a, b, center, policy=None, max_bond_dim=None, nfullsweeps=1):
 def inner(a, b):
     a2 = a.sim_bonds()
     return complex(contract([s.conj() for s in a2.sites] + list(b.sites)).arr)
+
+
+def add(a, b):
+    """Strict direct-sum addition (treetn/addition.rs:322-...): same site labels on every site, bond dimensions
+    add, fresh bond labels; site tensors are block diagonal in the bonds (axis order follows `a`)."""
+    L = len(a)
+    assert L == len(b)
+    if L == 1:
+        return Chain([LT(a.sites[0].arr + b.sites[0].permute(a.sites[0].labels).arr, a.sites[0].labels)])
+    merged = [new_label() for _ in range(L - 1)]
+    sites = []
+    for i in range(L):
+        ta, tb = a.sites[i], b.sites[i]
+        labels, shape, off_a, off_b = [], [], [], []
+        mapping_b = {}
+        for ax, l in enumerate(ta.labels):
+            e = None
+            if i > 0 and l == a.bonds[i - 1]:
+                e = i - 1
+            if i < L - 1 and l == a.bonds[i]:
+                e = i
+            if e is None:
+                labels.append(l); shape.append(ta.arr.shape[ax]); off_b.append(0)
+                mapping_b[l] = l
+            else:
+                da, db = ta.arr.shape[ax], b.sites[i].dim(b.bonds[e])
+                labels.append(merged[e]); shape.append(da + db); off_b.append(da)
+                mapping_b[b.bonds[e]] = merged[e]
+        out = np.zeros(shape, dtype=np.result_type(ta.arr.dtype, tb.arr.dtype))
+        out[tuple(slice(0, n) for n in ta.arr.shape)] = ta.arr
+        tbp = tb.permute([next(k for k, v in mapping_b.items() if v == l) for l in labels])
+        out[tuple(slice(o, o + n) for o, n in zip(off_b, tbp.arr.shape))] = tbp.arr
+        sites.append(LT(out, labels))
+    return Chain(sites)

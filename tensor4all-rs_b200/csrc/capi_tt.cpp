@@ -196,6 +196,13 @@ int t4b_tn_clone(t4b_ctx* ctx, const t4b_tn* tn, t4b_tn** out) {
     *out = new t4b_tn{clone_chain(ctx->c, tn->tn)};
     T4B_CATCH
 }
+int t4b_tn_add(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, t4b_tn** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(a && b && out, "null argument");
+    *out = new t4b_tn{add(ctx->c, a->tn, b->tn)};
+    T4B_CATCH
+}
 int t4b_tn_release(t4b_tn* tn) {
     T4B_TRY
     delete tn;

@@ -61,6 +61,10 @@ void gemm_batched(Ctx*, DType dt, int64_t batch, int64_t M, int64_t N, int64_t K
 // (materialised permute; reference idx_tensor.rs:3389,3445).
 void permute(Ctx*, DType dt, void* out, const void* in, const Group& g, bool conj);
 
+// out[offset_g(i)] = in[i], i contiguous over g.dim first-fastest (block placement of a direct sum; reference
+// TreeTN::add, crates/tensor4all-treetn/src/treetn/addition.rs:322-...).
+void scatter(Ctx*, DType dt, void* out, const void* in, const Group& g);
+
 // A (m x n, ld = m) -> Q (m x k, ld = m), R (k x n, ld = k, upper trapezoidal), k = min(m,n).
 // Householder; A is destroyed.  Q may be null (R only).
 // Replaces tenferro `.qr()` (reference crates/tensor4all-core/src/defaults/qr.rs:258-260,

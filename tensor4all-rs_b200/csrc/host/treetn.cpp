@@ -393,4 +393,81 @@ Tensor to_dense(dla::Ctx* c, const ChainTN& tn) {
     return t;
 }
 
+static std::vector<int64_t> col_major_strides(const std::vector<Index>& inds) {
+    std::vector<int64_t> st(inds.size());
+    int64_t acc = 1;
+    for (size_t i = 0; i < inds.size(); ++i) { st[i] = acc; acc *= inds[i].dim; }
+    return st;
+}
+
+ChainTN add(dla::Ctx* c, const ChainTN& a, const ChainTN& b) {
+    const int L = (int)a.length();
+    T4B_REQUIRE(L == (int)b.length(), "add: the networks have different lengths");
+    T4B_REQUIRE(L >= 1, "add: empty network");
+    if (L == 1) {
+        // no bonds: plain tensor sum (b permuted to a's axis order)
+        Tensor pb = permute(c, b.sites[0], a.sites[0].inds);
+        Tensor r = clone(c, a.sites[0]);
+        dla::axpy(c, r.dt, r.numel(), 1.0, pb.data(), r.data());
+        return make_chain({r});
+    }
+    std::vector<Index> merged(L - 1);
+    for (int e = 0; e + 1 < L; ++e) merged[e] = new_index(a.bonds[e].dim + b.bonds[e].dim);
+    std::vector<Tensor> sites;
+    for (int i = 0; i < L; ++i) {
+        const Tensor& ta = a.sites[i];
+        const Tensor& tb = b.sites[i];
+        T4B_REQUIRE(ta.dt == tb.dt, "add: dtype mismatch");
+        // result indices: a's axis order with its bonds replaced by the merged ones
+        std::vector<Index> rinds = ta.inds;
+        std::vector<int64_t> off_b(rinds.size(), 0);     // offset of b's block along every result axis
+        for (size_t ax = 0; ax < rinds.size(); ++ax) {
+            for (int e = std::max(i - 1, 0); e <= std::min(i, L - 2); ++e)
+                if (rinds[ax] == a.bonds[e]) { rinds[ax] = merged[e]; off_b[ax] = a.bonds[e].dim; }
+        }
+        // site spaces must agree
+        std::vector<Index> sa = a.site_inds(i), sb = b.site_inds(i);
+        T4B_REQUIRE(sa.size() == sb.size(), "add: site index sets differ");
+        for (auto& ix : sa) {
+            int pos = tb.find(ix);
+            T4B_REQUIRE(pos >= 0 && tb.inds[pos].dim == ix.dim, "add: site index sets differ");
+        }
+        Tensor r = empty_tensor(c, ta.dt, rinds);
+        dla::zero(c, r.data(), (size_t)r.numel() * dtype_size(r.dt));
+        auto rs = col_major_strides(rinds);
+        // a's block at offset 0 in every bond axis
+        {
+            Group g;
+            g.nd = (int)ta.inds.size();
+            T4B_REQUIRE(g.nd <= kMaxGroupDims, "add: tensor rank exceeds the group limit");
+            for (int ax = 0; ax < g.nd; ++ax) { g.dim[ax] = ta.inds[ax].dim; g.str[ax] = rs[ax]; }
+            dla::scatter(c, ta.dt, r.data(), ta.data(), g);
+        }
+        // b's block at offset dim_a in every bond axis; b's axes are matched to the result axes by index id
+        {
+            Group g;
+            g.nd = (int)tb.inds.size();
+            T4B_REQUIRE(g.nd == (int)rinds.size() && g.nd <= kMaxGroupDims, "add: tensor ranks differ");
+            int64_t base = 0;
+            for (int axb = 0; axb < g.nd; ++axb) {
+                int target = -1;
+                for (int e = std::max(i - 1, 0); e <= std::min(i, L - 2); ++e)
+                    if (tb.inds[axb] == b.bonds[e])
+                        for (size_t ax = 0; ax < rinds.size(); ++ax)
+                            if (rinds[ax] == merged[e]) target = (int)ax;
+                if (target < 0)
+                    for (size_t ax = 0; ax < rinds.size(); ++ax)
+                        if (rinds[ax] == tb.inds[axb]) target = (int)ax;
+                T4B_REQUIRE(target >= 0, "add: an index of the second operand has no counterpart");
+                g.dim[axb] = tb.inds[axb].dim;
+                g.str[axb] = rs[target];
+                base += off_b[target] * rs[target];
+            }
+            dla::scatter(c, tb.dt, (char*)r.data() + (size_t)base * dtype_size(r.dt), tb.data(), g);
+        }
+        sites.push_back(r);
+    }
+    return make_chain(sites);
+}
+
 }  // namespace t4b

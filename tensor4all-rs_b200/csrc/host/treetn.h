@@ -50,6 +50,11 @@ ChainTN contract_fit(dla::Ctx*, const ChainTN& a, const ChainTN& b, int center,
 ChainTN contract(dla::Ctx*, const ChainTN& a, const ChainTN& b, int center,
                  const ContractionOptions& opts);
 
+// Strict direct-sum addition a + b (reference TreeTN::add, treetn/addition.rs:322-...): same length, same site
+// indices on every site; every bond becomes a fresh index of dimension dim_a + dim_b, site tensors are block
+// diagonal in the bonds (the end sites concatenate along their single bond).  Axis order follows a.
+ChainTN add(dla::Ctx*, const ChainTN& a, const ChainTN& b);
+
 // <a|b> over all matching site indices (conjugating a); sum |tn|^2
 void inner(dla::Ctx*, const ChainTN& a, const ChainTN& b, double* re, double* im);
 double norm_sqr(dla::Ctx*, const ChainTN& tn);

@@ -210,12 +210,32 @@ __global__ void permute_kernel(double* __restrict__ out, const double* __restric
     }
 }
 
+// scatter: in contiguous, out addressed through the group (direct-sum block placement)
+template <bool CPLX>
+__global__ void scatter_kernel(double* __restrict__ out, const double* __restrict__ in, Group g, int64_t total) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        int64_t off = group_offset(g, i);
+        if (CPLX) reinterpret_cast<double2*>(out)[off] = reinterpret_cast<const double2*>(in)[i];
+        else out[off] = in[i];
+    }
+}
+
 static int grid_for(Ctx* c, int64_t total, int threads, int per_sm = 8) {
     int64_t blocks = (total + threads - 1) / threads;
     int64_t cap = (int64_t)c->num_sms * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+
+void scatter(Ctx* c, DType dt, void* out, const void* in, const Group& g) {
+    int64_t total = g.size();
+    if (total == 0) return;
+    int grid = grid_for(c, total, 256);
+    if (dt == C64) scatter_kernel<true><<<grid, 256, 0, c->stream>>>((double*)out, (const double*)in, g, total);
+    else scatter_kernel<false><<<grid, 256, 0, c->stream>>>((double*)out, (const double*)in, g, total);
+    c->launched("scatter", 2.0 * (double)total * (double)dtype_size(dt));
 }
 
 void permute(Ctx* c, DType dt, void* out, const void* in, const Group& g, bool conj) {

@@ -70,7 +70,7 @@ template <bool CPLX>
 __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32(typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2,
                                              typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
                                              double* rot_c, double* rot_s, int full_inner, double tol_rot,
-                                             int tid, int inner = 1) {
+                                             int tid, int inner = 1, double zthr = 0.0) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     T* Gcur = Gs;
@@ -104,7 +104,7 @@ __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32(typename Sc<CPLX>:
             const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
             const T g = Gcur[pp * GP + qq];
             const double g2 = S::abs2(g);
-            if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
+            if (g2 > 0.0 && aa > zthr && bb > zthr && g2 > tol2 * aa * bb) {
                 const double d = 0.5 * (bb - aa);
                 if constexpr (CPLX) {
                     const double inv_absg = rsqrt(g2);
@@ -175,11 +175,12 @@ __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32(typename Sc<CPLX>:
 // Returns tg = t |g| (t = tan of the rotation angle): the rotated diagonal is (aa - tg, bb + tg).
 template <bool CPLX>
 __device__ __forceinline__ void jacobi_rotation(double aa, double bb, typename Sc<CPLX>::T g, double tol2,
-                                                double& c, double& sn, typename Sc<CPLX>::T& ph, double& tg) {
+                                                double& c, double& sn, typename Sc<CPLX>::T& ph, double& tg,
+                                                double zthr = 0.0) {
     typedef Sc<CPLX> S;
     c = 1.0; sn = 0.0; ph = S::one(); tg = 0.0;
     const double g2 = S::abs2(g);
-    if (g2 > 0.0 && aa > 0.0 && bb > 0.0 && g2 > tol2 * aa * bb) {
+    if (g2 > 0.0 && aa > zthr && bb > zthr && g2 > tol2 * aa * bb) {
         const double d = 0.5 * (bb - aa);
         if constexpr (CPLX) {
             const double inv_absg = rsqrt(g2);
@@ -223,7 +224,7 @@ __device__ __forceinline__ void jacobi_rotation(double aa, double bb, typename S
 template <bool CPLX>
 __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32_pipelined(
     typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2, typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
-    double* rot_c, double* rot_s, double tol_rot, int tid, int inner) {
+    double* rot_c, double* rot_s, double tol_rot, int tid, int inner, double zthr) {
     typedef Sc<CPLX> S;
     typedef typename S::T T;
     T* Gcur = Gs;
@@ -237,7 +238,7 @@ __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32_pipelined(
     if (warp == 0 && lane < 16) {
         const int pp = lane, qq = 16 + lane;
         aa = S::real(Gcur[pp * GP + pp]); bb = S::real(Gcur[qq * GP + qq]);
-        jacobi_rotation<CPLX>(aa, bb, Gcur[pp * GP + qq], tol2, c, sn, ph, tg);
+        jacobi_rotation<CPLX>(aa, bb, Gcur[pp * GP + qq], tol2, c, sn, ph, tg, zthr);
         rot_c[lane] = c; rot_s[lane] = sn; rot_ph[lane] = ph;
     }
     __syncthreads();
@@ -261,7 +262,7 @@ __device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32_pipelined(
                 const T yq = S::add(S::scale(gqp, snn), S::scale(S::mul(gqq, phn), cn));
                 const T gnew = S::sub(S::scale(yp, c), S::scale(S::mul(S::conj(ph), yq), sn));
                 aa = aa - tg; bb = bbn;
-                jacobi_rotation<CPLX>(aa, bb, gnew, tol2, c, sn, ph, tg);
+                jacobi_rotation<CPLX>(aa, bb, gnew, tol2, c, sn, ph, tg, zthr);
                 rot_c[nxt + lane] = c; rot_s[nxt + lane] = sn; rot_ph[nxt + lane] = ph;
             }
         } else {
@@ -335,6 +336,7 @@ struct JPArgs {
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
     double* stats;         // optional device work counter (bytes), else null
     unsigned* fail;        // sticky failure counter of the context (sweep limit reached)
+    const double* fro2;    // ||X||_F^2 (device scalar): columns below (16 eps)^2 ||X||_F^2 are numerically zero
     double bytes_per_sweep;
 };
 
@@ -406,6 +408,10 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     }
     __syncthreads();
     unsigned par0 = 0, par1 = 0;
+    // Columns whose squared norm is below (16 eps)^2 ||X||_F^2 are rounding residue of a rank-deficient input (two
+    // parallel columns leave such a residue that stays parallel - cosine 1 - to its partner however often it is
+    // rotated): they neither rotate nor count in the convergence measure.
+    const double zthr = 1.2621774483536189e-29 * __ldg(a.fro2);
     // Column c of a chunk buffer starts at c * ldp (+ 4 rows for columns with bit 2 set, real case): with the
     // pitch == 4 (mod 16) this makes the DMMA fragment loads of both passes AND the accumulator stores of the
     // update pass (lanes hold columns 2 tig, 2 tig + 1) free of shared-memory bank conflicts.
@@ -580,7 +586,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                         if (row < col) {
                             double gii = S::real(Gs[row * GP + row]), gjj = S::real(Gs[col * GP + col]);
                             double g2 = S::abs2(Gs[row * GP + col]);
-                            if (gii > 0.0 && gjj > 0.0) {
+                            if (gii > zthr && gjj > zthr) {
                                 double r2 = g2 / (gii * gjj);
                                 if (r2 > mx) mx = r2;
                             }
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                     }
                     const double gii = S::real(Dsm[ri * 16 + ri]), gjj = S::real(Dsm[256 + cj * 16 + cj]);
                     const double g2 = S::abs2(cx);
-                    if (gii > 0.0 && gjj > 0.0) mx = g2 / (gii * gjj);
+                    if (gii > zthr && gjj > zthr) mx = g2 / (gii * gjj);
                 }
                 {
 #pragma unroll
@@ -636,8 +642,8 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                 JP_STAMP(3);   // reduce + convergence measure
                 if (need_rot) {
                     const T* Gfin = (full_inner || a.eig_serial)
-                                        ? jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid, a.inner)
-                                        : jacobi_eig32_pipelined<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, a.tol_rot, tid, a.inner);
+                                        ? jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid, a.inner, zthr)
+                                        : jacobi_eig32_pipelined<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, a.tol_rot, tid, a.inner, zthr);
                     if (R == 0) {
                         // the diagonal blocks of the rotated Gram travel with the column blocks
                         T* di = reinterpret_cast<T*>(a.D) + (size_t)bi * 256;
@@ -740,7 +746,12 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
         // quadratic regime (off <= tol_early AND off <= off_prev^1.5, i.e. the previous sweep contracted
         // super-linearly) that its own rotations finished the job.  Degenerate clusters, which only contract
         // linearly, never take the early exit.
-        if (off <= a.tol || (off <= a.tol_early && off <= prev_off * sqrt(prev_off))) { converged = 1; ++sweep; break; }
+        // A plateau at the rounding floor (no further contraction although off is already tiny) is convergence too:
+        // the remaining cosines are noise of the Gram computation, not rotations that are still owed.
+        const bool plateau = off <= 1024.0 * a.tol && off >= 0.25 * prev_off;
+        if (off <= a.tol || plateau || (off <= a.tol_early && off <= prev_off * sqrt(prev_off))) {
+            converged = 1; ++sweep; break;
+        }
         prev_off = off;
     }
     if (blockIdx.x == 0 && tid == 0) {
@@ -953,14 +964,17 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     unsigned char* ws = (unsigned char*)alloc(c, ws_bytes);
     zero(c, ws, ws_bytes);
     const double eps = 2.220446049250313e-16;
-    const double tol = eps * sqrt((double)(nx > 4 ? nx : 4));
+    // |x_i^H x_j| <= tol ||x_i|| ||x_j||.  The cosines come from DMMA Gram blocks (and diagonal blocks carried
+    // across rounds), whose rounding noise sits at a few eps sqrt(nx): the factor 4 keeps the target above that
+    // floor (measured plateaus: 2.6e-15 at n = 2048, 8.3e-15 at n = 512).
+    const double tol = 4.0 * eps * sqrt((double)(nx > 4 ? nx : 4));
     JPArgs a{};
     a.X = X; a.ldx = pl.ldx;
     a.V = V; a.ldv = pl.ldv;
     a.p = p; a.cs = pl.cs; a.nclusters = pl.nclusters; a.pairs = pl.pairs;
     a.rpcx = pl.rpcx; a.rpcv = V ? pl.rpcv : 0; a.ch = pl.ch; a.ldp = pl.ldp;
     a.max_sweeps = max_sweeps;
-    a.tol = tol; a.tol_rot = tol * 0.25;
+    a.tol = tol; a.tol_rot = tol * 0.0625;
     // off_after <~ n * off_before^2 once the iteration converges quadratically: a sweep that starts
     // below sqrt(0.1 tol / n) leaves the columns orthogonal to working accuracy (n off^2 <= 0.1 tol)
     a.tol_early = sqrt(0.1 * tol / (double)npad);
@@ -970,6 +984,9 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     a.bytes_per_sweep = (double)(p - 1) * 2.0 * (double)(nx + (V ? npad : 0)) * (double)npad * (double)es;
     a.stats = c->profiling ? c->dev_stats : nullptr;
     a.fail = c->fail_dev;
+    double* fro2 = (double*)alloc(c, 8);
+    sumsq(c, CPLX ? C64 : F64, pl.ldx * npad, X, fro2);
+    a.fro2 = fro2;
     a.inner = getenv("T4B_JAC_INNER") ? atoi(getenv("T4B_JAC_INNER")) : 1;
     a.eig_serial = getenv("T4B_JAC_EIG_SERIAL") ? 1 : 0;
     a.flag = (unsigned long long*)ws;
@@ -1014,7 +1031,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
         d2h(c, h, a.info, 8);
         d2h(c, h + 64, a.timing, 64);
         d2h(c, h + 128, a.flag, 8 * max_sweeps);
-        sync(c);
+        T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // not dla::sync: a failed iteration must still be printed
         if (atoi(getenv("T4B_VERBOSE")) > 1) {
             fprintf(stderr, "[t4b]   off per sweep:");
             for (int i = 0; i < ((const int*)h)[0]; ++i) fprintf(stderr, " %.1e", ((const double*)(h + 128))[i]);
@@ -1029,6 +1046,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     }
     release(c, ws);
     release(c, Dblk);
+    release(c, fro2);
 }
 
 // m >= n.  A destroyed.  U (m x n) / Vh (n x n) optional.

@@ -89,3 +89,56 @@ def run_truncate_adaptive(rank, world, owner, my_patches, volumes, center, cutof
         dist.all_reduce(res)
     res = res.cpu().numpy()
     return keep, [[int(x) for x in row[1:] if x > 0] for row in res], res[:, 0]
+
+
+# ---- PartitionedTreeTN::contract (partitionedtreetn/src/partitioned_tree_tn.rs:407-483) ---------------------------
+def projectors_compatible(p, q):
+    return all(q[k] == v for k, v in p.items() if k in q)
+
+
+def projector_key(p):
+    return tuple(sorted(p.items()))
+
+
+def contract_partitioned(left, right, center, policy=None, max_bond_dim=0, rank=0, world=1):
+    """left / right: lists of (projector dict {site index id: value}, ChainTN) with already masked data on this
+    rank's GPU.  All compatible pairs are contracted (zip-up), grouped by output projector, summed with the strict
+    direct-sum addition and truncated once per multi-contribution group.  Sharding: the grouping is decided on the
+    host from the projectors alone, so rank r computes exactly the groups g with g % world == r - no tensor ever
+    crosses ranks (the results stay where they were produced).  Returns [(projector, ChainTN)] of this rank's
+    groups in canonical projector order."""
+    left = sorted(left, key=lambda pc: projector_key(pc[0]))
+    right = sorted(right, key=lambda pc: projector_key(pc[0]))
+    # host-side plan: which pairs feed which output projector
+    plan, order = {}, []
+    for il, (pl, cl) in enumerate(left):
+        ext_l = set(i for k in range(cl.length()) for i in cl.site_shape(k)[1] if i >= 0)
+        for ir, (pr, cr) in enumerate(right):
+            if not projectors_compatible(pl, pr):
+                continue
+            ext_r = set(i for k in range(cr.length()) for i in cr.site_shape(k)[1] if i >= 0)
+            surviving = ext_l ^ ext_r                      # shared site indices are contracted away
+            proj = {k: v for k, v in {**pl, **pr}.items() if k in surviving}
+            key = projector_key(proj)
+            if key not in plan:
+                plan[key] = (proj, [])
+                order.append(key)
+            plan[key][1].append((il, ir))
+    result = []
+    for g, key in enumerate(sorted(order)):
+        if g % world != rank:
+            continue
+        proj, pairs = plan[key]
+        combined = None
+        for il, ir in pairs:
+            out = left[il][1].contract(right[ir][1], center, 0, policy, max_bond_dim)
+            if combined is None:
+                combined = out
+            else:
+                s = combined.add(out)
+                combined.release(); out.release()
+                combined = s
+        if len(pairs) > 1:
+            combined.truncate(center, policy, max_bond_dim)
+        result.append((proj, combined))
+    return result

@@ -129,6 +129,12 @@ class ChainTN:
         _check(lib().t4b_tn_clone(self.ctx.h, self.h, C.byref(h)))
         return ChainTN(self.ctx, h, self._dt)
 
+    def add(self, other):
+        """Strict direct-sum addition (TreeTN::add)."""
+        h = C.c_void_p()
+        _check(lib().t4b_tn_add(self.ctx.h, self.h, other.h, C.byref(h)))
+        return ChainTN(self.ctx, h, self._dt)
+
     def length(self):
         n = C.c_int()
         _check(lib().t4b_tn_length(self.h, C.byref(n)))

@@ -1,0 +1,117 @@
+"""PartitionedTreeTN::contract (crates/tensor4all-partitionedtreetn/src/partitioned_tree_tn.rs:407-483) and the
+strict TreeTN addition it relies on (treetn/src/treetn/addition.rs:322):
+ * CPU: the oracle restatement against dense arithmetic (sum over compatible patch pairs == O psi);
+ * GPU: t4b_tn_add and t4b.patches.contract_partitioned through the C ABI against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import patching as opatch
+from oracle import treetn as otn
+from oracle.truncation import SvdTruncationPolicy
+
+from util import oracle_chain_dense, random_mpo, random_mps, relerr, to_oracle_chain
+
+
+def _masked(arrays, ids, fixed):
+    """Copy of the site arrays with every slice that violates `fixed` {index id: value} zeroed."""
+    out = []
+    for a, sid in zip(arrays, ids):
+        b = a.copy()
+        for ax, i in enumerate(sid):
+            if i in fixed:
+                sl = [slice(None)] * b.ndim
+                for v in range(b.shape[ax]):
+                    if v != fixed[i]:
+                        sl[ax] = v
+                        b[tuple(sl)] = 0
+        out.append(np.asfortranarray(b))
+    return out
+
+
+def _problem(cplx=False):
+    rng = np.random.default_rng(17)
+    L, d, chi, w = 5, 2, 4, 3
+    ma, mi = random_mps(rng, L, d, chi, cplx)          # site ids 100 + i
+    oa, oi = random_mpo(rng, L, d, w, cplx)            # out ids 200 + i, in ids 100 + i
+    left = [({100: v}, _masked(ma, mi, {100: v})) for v in range(d)]
+    right = [({200: o, 100: v}, _masked(oa, oi, {200: o, 100: v})) for o in range(d) for v in range(d)]
+    return (ma, mi), (oa, oi), left, right
+
+
+def _dense_by_id(chain):
+    return oracle_chain_dense(chain)
+
+
+def _olab(p):
+    """projector keyed by the oracle's labels ("x", id)"""
+    return {("x", k): v for k, v in p.items()}
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_oracle_add_is_dense_sum(cplx):
+    rng = np.random.default_rng(3)
+    a, ai = random_mps(rng, 4, 3, 5, cplx)
+    b, _ = random_mps(rng, 4, 3, 2, cplx, bond_id0=5000)
+    ca, cb = to_oracle_chain(a, ai), to_oracle_chain(b, [[(5000 + (i - 1000)) if i >= 1000 else i for i in s] for s in ai])
+    s = otn.add(ca, cb)
+    assert s.bond_dims() == [x + y for x, y in zip(ca.bond_dims(), cb.bond_dims())]
+    assert relerr(_dense_by_id(s), _dense_by_id(ca) + _dense_by_id(cb)) <= 1e-13
+
+
+def test_oracle_partitioned_contract_equals_dense():
+    (ma, mi), (oa, oi), left, right = _problem()
+    full = otn.contract_zipup(to_oracle_chain(ma, mi), to_oracle_chain(oa, oi), 0, SvdTruncationPolicy(0.0), None)
+    res = opatch.contract_partitioned([(_olab(p), to_oracle_chain(a, mi)) for p, a in left],
+                                      [(_olab(p), to_oracle_chain(a, oi)) for p, a in right], 0,
+                                      SvdTruncationPolicy(0.0), None)
+    assert [p for p, _ in res] == [{("x", 200): 0}, {("x", 200): 1}]   # grouped by the surviving projected index
+    total = sum(_dense_by_id(c) for _, c in res)
+    assert relerr(total, _dense_by_id(full)) <= 1e-12
+    # every group lives on its own slice of the projected output index
+    for p, c in res:
+        dn = _dense_by_id(c)                                   # axes sorted by id: 200 first
+        other = 1 - p[("x", 200)]
+        assert np.abs(np.take(dn, other, axis=0)).max() <= 1e-13 * np.abs(dn).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gpu_add_matches_oracle(ctx, cplx):
+    from t4b import tt as t4tt
+    from util import gpu_chain_dense
+    rng = np.random.default_rng(4)
+    a, ai = random_mps(rng, 5, 2, 6, cplx)
+    b, _ = random_mps(rng, 5, 2, 3, cplx, bond_id0=5000)
+    bi = [[(5000 + (i - 1000)) if i >= 1000 else i for i in s] for s in ai]
+    ga, gb = t4tt.chain_from_arrays(ctx, a, ai), t4tt.chain_from_arrays(ctx, b, bi)
+    gs = ga.add(gb)
+    ref = otn.add(to_oracle_chain(a, ai), to_oracle_chain(b, bi))
+    assert gs.bond_dims() == ref.bond_dims()
+    assert relerr(gpu_chain_dense(gs), oracle_chain_dense(ref)) <= 1e-13
+    # adding a network to itself doubles it (TreeTN::add doc example, addition.rs:317-320)
+    assert relerr(gpu_chain_dense(ga.add(ga)), 2.0 * gpu_chain_dense(ga)) <= 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gpu_partitioned_contract_matches_oracle(ctx, cplx):
+    from t4b import patches as tpatch
+    from t4b import tt as t4tt
+    from util import gpu_chain_dense
+    (ma, mi), (oa, oi), left, right = _problem(cplx)
+    # masked patches are exactly rank deficient: a threshold of exactly 0 would keep rounding-noise singular
+    # values (ill-defined rank); the reference's default relative 1e-12 drops them in every implementation
+    pol = SvdTruncationPolicy(1e-12)
+    ref = opatch.contract_partitioned([(_olab(p), to_oracle_chain(a, mi)) for p, a in left],
+                                      [(_olab(p), to_oracle_chain(a, oi)) for p, a in right], 0, pol, 6)
+    gl = [(p, t4tt.chain_from_arrays(ctx, a, mi)) for p, a in left]
+    gr = [(p, t4tt.chain_from_arrays(ctx, a, oi)) for p, a in right]
+    got = tpatch.contract_partitioned(gl, gr, 0, t4tt.SvdPolicy(1e-12), 6)
+    assert [_olab(p) for p, _ in got] == [p for p, _ in ref]
+    for (_, g), (_, r) in zip(got, ref):
+        assert g.bond_dims() == r.bond_dims()
+        assert relerr(gpu_chain_dense(g), oracle_chain_dense(r)) <= 1e-10
+    # sharded over two ranks: the union of the ranks' groups is the single-rank result
+    parts = [tpatch.contract_partitioned(gl, gr, 0, t4tt.SvdPolicy(1e-12), 6, rank=r, world=2) for r in range(2)]
+    assert sorted(tpatch.projector_key(_olab(p)) for part in parts for p, _ in part) == \
+        sorted(tpatch.projector_key(p) for p, _ in ref)
