@@ -115,3 +115,57 @@ def test_gpu_partitioned_contract_matches_oracle(ctx, cplx):
     parts = [tpatch.contract_partitioned(gl, gr, 0, t4tt.SvdPolicy(1e-12), 6, rank=r, world=2) for r in range(2)]
     assert sorted(tpatch.projector_key(_olab(p)) for part in parts for p, _ in part) == \
         sorted(tpatch.projector_key(p) for p, _ in ref)
+
+
+class _FakeChain:
+    """Host-only stand-in with the ChainTN methods the partitioned driver touches: records what was asked."""
+
+    def __init__(self, site_ids, log, name):
+        self.site_ids, self.log, self.name = site_ids, log, name
+
+    def length(self):
+        return len(self.site_ids)
+
+    def site_shape(self, k):
+        return (2,) * len(self.site_ids[k]), list(self.site_ids[k])
+
+    def contract(self, other, center, method, policy, max_bond_dim):
+        self.log.append(("contract", self.name, other.name))
+        ids = [sorted(set(a) ^ set(b)) for a, b in zip(self.site_ids, other.site_ids)]
+        return _FakeChain(ids, self.log, f"({self.name}*{other.name})")
+
+    def add(self, other):
+        self.log.append(("add", self.name, other.name))
+        return _FakeChain(self.site_ids, self.log, f"[{self.name}+{other.name}]")
+
+    def truncate(self, center, policy, max_bond_dim):
+        self.log.append(("truncate", self.name))
+
+    def release(self):
+        pass
+
+
+def test_partitioned_driver_grouping_and_sharding_host_logic():
+    """The pair list, the grouping by output projector, the add order (canonical projector order) and the
+    rank sharding of t4b.patches.contract_partitioned are pure host logic: checked here without a GPU."""
+    from t4b import patches as tpatch
+    log = []
+    state_ids = [[100], [101], [102]]
+    op_ids = [[200, 100], [201, 101], [202, 102]]
+    left = [({100: v}, _FakeChain(state_ids, log, f"s{v}")) for v in (1, 0)]          # deliberately unsorted
+    right = [({200: o, 100: v}, _FakeChain(op_ids, log, f"o{o}{v}")) for o in (1, 0) for v in (0, 1)]
+    res = tpatch.contract_partitioned(left, right, 0, None, 0)
+    assert [p for p, _ in res] == [{200: 0}, {200: 1}]
+    contracts = [e for e in log if e[0] == "contract"]
+    # only projector-compatible pairs (same value of the contracted index 100); the driver works group by group,
+    # within a group in the reference's left-major canonical order (which fixes the order of the exact adds)
+    assert contracts == [("contract", "s0", "o00"), ("contract", "s1", "o01"),
+                         ("contract", "s0", "o10"), ("contract", "s1", "o11")]
+    assert [e for e in log if e[0] == "add"] == [("add", "(s0*o00)", "(s1*o01)"), ("add", "(s0*o10)", "(s1*o11)")]
+    assert len([e for e in log if e[0] == "truncate"]) == 2          # one truncation per multi-contribution group
+    # sharding: each rank owns every second group and contracts only the pairs that feed it
+    for r in range(2):
+        log.clear()
+        part = tpatch.contract_partitioned(left, right, 0, None, 0, rank=r, world=2)
+        assert [p for p, _ in part] == [{200: r}]
+        assert len([e for e in log if e[0] == "contract"]) == 2
