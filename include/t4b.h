@@ -54,6 +54,14 @@ int t4b_ctx_profile_begin(t4b_ctx* ctx);
 /* Host-side overhead counters of this context (allocator / synchronisation time) as text. */
 int t4b_ctx_host_stats(t4b_ctx* ctx, char* buf, size_t cap);
 int t4b_ctx_profile_end(t4b_ctx* ctx, char* buf, size_t cap, size_t* needed);
+/* Retained-spectrum log (parity instrumentation): between begin and end every truncated factorisation run through
+ * this context appends the singular values it retained - the `singular_values` field of the reference's
+ * FactorizeResult (crates/tensor4all-core/src/defaults/factorize.rs:507-558,304-311), in call order.  end reports
+ * the counts; t4b_ctx_spectra_get then fills lens_out[n_spectra] and values_out[n_values] (concatenated) on the
+ * calling thread. */
+int t4b_ctx_spectra_begin(t4b_ctx* ctx);
+int t4b_ctx_spectra_end(t4b_ctx* ctx, int64_t* n_spectra, int64_t* n_values);
+int t4b_ctx_spectra_get(int64_t* lens_out, double* values_out);
 int t4b_malloc(t4b_ctx* ctx, size_t bytes, void** dev);
 int t4b_free(t4b_ctx* ctx, void* dev);
 int t4b_upload(t4b_ctx* ctx, void* dev, const void* host, size_t bytes);   /* async */
@@ -103,6 +111,28 @@ int t4b_trsm(t4b_ctx* ctx, int dtype, int left_side, int lower, int transpose, i
  * Returns T4B_NOT_CONVERGED when a is numerically singular. */
 int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_dev, const void* b_dev,
               void* x_dev);
+
+/* a (m x n, ld = lda) scaled in place by the real diagonal s (device): side 0 rows (a[i,j] *= s[i]), side 1 columns
+ * (a[i,j] *= s[j]); invert != 0 divides.  The S*Vh / U*S products of factorize (core/src/defaults/factorize.rs:
+ * 507-558, scale_bond :317-345), which the reference routes through a diag-storage einsum. */
+int t4b_scale_by_diag(t4b_ctx* ctx, int dtype, int side, int invert, int64_t m, int64_t n, void* a_dev, int64_t lda,
+                      const double* s_dev);
+/* Reductions over a dense buffer of n elements (synchronise): Frobenius norm, sum (re, im; im may be NULL for f64),
+ * max |x_i|.  Replace norm / sum_native_tensor / maxabs of the bridge (tensorbackend/src/tenferro_bridge.rs). */
+int t4b_norm2(t4b_ctx* ctx, int dtype, int64_t n, const void* x_dev, double* out);
+int t4b_sum(t4b_ctx* ctx, int dtype, int64_t n, const void* x_dev, double* re, double* im);
+int t4b_maxabs(t4b_ctx* ctx, int dtype, int64_t n, const void* x_dev, double* out);
+
+/* Complete-pivoting LU of a square matrix a (n x n, preserved): permutation MATRICES p, q (n x n) with
+ * p[k, row_perm[k]] = 1, q[k, col_perm[k]] = 1 (the convention read back by core/src/matrixluci/dense.rs:119-141),
+ * l unit lower, u upper, p a q^T = l u.  Replaces full_piv_lu_matrix (tensorbackend/src/backend.rs:980-1036); pivot
+ * order bit-compatible with rrlu (core/src/matrixluci/dense/tests.rs:119-216 pins the two together). */
+int t4b_full_piv_lu(t4b_ctx* ctx, int dtype, int64_t n, const void* a_dev, void* p_dev, void* l_dev, void* u_dev,
+                    void* q_dev);
+/* out (lhs_rows x pivot_cols) = lhs * pivot^-1, i.e. T P = Pi1 solved for T through the complete-pivoting LU.
+ * Replaces FullPivLuScalar::solve_right_full_piv_lu (tensorbackend/src/backend.rs:181-249), same shape errors. */
+int t4b_solve_right_full_piv_lu(t4b_ctx* ctx, int dtype, int64_t lhs_rows, int64_t lhs_cols, const void* lhs_dev,
+                                int64_t pivot_rows, int64_t pivot_cols, const void* pivot_dev, void* out_dev);
 
 /* Host only (no GPU needed): optimal pairwise order for t4b_einsum-style operands (n_ops <= 8).  pairs_out receives
  * 2 * (n_ops - 1) ints: step s contracts the operands at positions (pairs_out[2s], pairs_out[2s+1]) of the current
@@ -205,10 +235,24 @@ int t4b_tn_bond_dims(const t4b_tn* tn, int64_t* out /* length-1 */);
 int t4b_tn_canonicalize(t4b_ctx* ctx, t4b_tn* tn, int center);
 int t4b_tn_truncate(t4b_ctx* ctx, t4b_tn* tn, int center, const t4b_svd_policy* policy,
                     int64_t max_bond_dim);
-/* contract dispatcher (treetn/contraction.rs:1576-1645): method 0 Zipup, 1 Fit, 2 Naive. */
+/* contract dispatcher (treetn/contraction.rs:1576-1645): method 0 Zipup, 1 Fit, 2 Naive.  Both operands get fresh bond
+ * ids first (sim_internal_inds, contraction.rs:470-471), so shared bond ids between a and b are harmless.  Zip-up uses
+ * ZipupTopologyMode::PruneScalarSubtrees like the public reference entry (contraction.rs:340-358): a site whose
+ * contraction leaves no external index is absorbed into its neighbour and the result has fewer sites.  SVD policies
+ * with an effective cutoff > 1e-12 take the Gram + eigh route of factorize_auto (core/defaults/factorize.rs:119-315). */
 int t4b_tn_contract(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, int center, int method,
                     const t4b_svd_policy* policy, int64_t max_bond_dim, int nfullsweeps,
                     t4b_tn** out);
+/* apply_linear_operator (treetn/src/operator/apply.rs:306-398) for chain networks: the state's true site index
+ * in_true[i] at node in_nodes[i] is rebound to the operator's internal input index in_internal[i]
+ * (transform_state_to_input), state x operator goes through the contract dispatcher with centre = node 0 (the first
+ * node in sorted order, apply.rs:352-357), and the operator's internal output index out_internal[i] at node
+ * out_nodes[i] is rebound to out_true[i] (transform_output_to_true).  Unmapped operator indices pass through. */
+int t4b_apply_linear_operator(t4b_ctx* ctx, const t4b_tn* op, const t4b_tn* state, int n_in, const int32_t* in_nodes,
+                              const int64_t* in_true, const int64_t* in_internal, int n_out,
+                              const int32_t* out_nodes, const int64_t* out_internal, const int64_t* out_true,
+                              int method, const t4b_svd_policy* policy, int64_t max_bond_dim, int nfullsweeps,
+                              t4b_tn** out);
 /* Strict direct-sum addition out = a + b (TreeTN::add, treetn/src/treetn/addition.rs:322): same site indices on
  * every site, bond dimensions add, fresh (negative-id) bonds.  Used by PartitionedTreeTN::contract to sum the
  * contributions of one output projector before a single truncation (partitioned_tree_tn.rs:447-466). */

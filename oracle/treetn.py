@@ -9,6 +9,8 @@
   LocalUpdateSweepPlan (nsite=2), TruncateUpdater   .../treetn/localupdate.rs:103-160,526-645
   contract_zipup_chain         crates/tensor4all-treetn/src/treetn/contraction.rs:438-766
   contract_fit                 crates/tensor4all-treetn/src/treetn/fit.rs:648-1054,1664-1739
+  factorize_auto / _gram       crates/tensor4all-core/src/defaults/factorize.rs:119-315
+  apply_linear_operator        crates/tensor4all-treetn/src/operator/apply.rs:306-398
 
 Tensors carry labelled axes (any hashable label) exactly like IdxTensor carries DynIndex ids.
 Dense SVD/QR are LAPACK gesdd/geqrf (the reference forwards them to tenferro/faer): factor values
@@ -90,6 +92,54 @@ def factorize_svd(t, left, canonical="left", policy=None, max_bond_dim=None, tru
         lt = LT((u * s_r[None, :]).reshape(*ldims, r, order="F"), left + [bond])
         rt = LT(vh.reshape(r, *rdims, order="F"), [bond] + right)
     return lt, rt, bond, s_r, s
+
+
+def factorize_auto(t, left, canonical="left", policy=None, max_bond_dim=None):
+    """factorize_auto / factorize_gram (core/src/defaults/factorize.rs:119-151,153-315): Gram matrix of the smaller
+    side + Hermitian eigendecomposition when the policy's effective cutoff on sigma^2/sigma_max^2 exceeds 1e-12,
+    otherwise (and on every failure of the Gram route) the SVD."""
+    from .truncation import compute_retained_rank
+    if policy is None:
+        return factorize_svd(t, left, canonical, policy, max_bond_dim)
+    eff = 0.0
+    if policy.scale == 0 and policy.measure == 1:
+        eff = policy.threshold
+    elif policy.scale == 0 and policy.measure == 0 and policy.rule == 0:
+        eff = policy.threshold * policy.threshold
+    if eff <= 1.0e-12:
+        return factorize_svd(t, left, canonical, policy, max_bond_dim)
+    mat, left, right, shape = _unfold(t, left)
+    m, n = mat.shape
+    eig_left = m <= n
+    gram = mat @ mat.conj().T if eig_left else mat.conj().T @ mat
+    lam, w = np.linalg.eigh(gram)
+    scale = float(np.max(np.abs(lam)))
+    if scale == 0.0 or not np.all(np.isfinite(lam)) or np.any(lam < -1e-12 * scale):
+        return factorize_svd(t, left, canonical, policy, max_bond_dim)
+    lam = np.where(lam < 0.0, 0.0, lam)
+    order = np.argsort(-lam, kind="stable")
+    sv = np.sqrt(lam[order])
+    r = compute_retained_rank(list(sv), policy)
+    if max_bond_dim is not None:
+        r = min(r, max_bond_dim)
+    r = min(max(r, 1), min(m, n))
+    s_r = sv[:r]
+    if np.any(s_r == 0.0):
+        return factorize_svd(t, left, canonical, policy, max_bond_dim)
+    basis = w[:, order[:r]]
+    if eig_left:
+        lm, rm = basis, basis.conj().T @ mat
+        if canonical == "right":
+            lm, rm = lm * s_r[None, :], rm / s_r[:, None]
+    else:
+        lm, rm = mat @ basis, basis.conj().T
+        if canonical == "left":
+            lm, rm = lm / s_r[None, :], rm * s_r[:, None]
+    bond = new_label()
+    ldims, rdims = shape[: len(left)], shape[len(left):]
+    lt = LT(lm.reshape(*ldims, r, order="F"), left + [bond])
+    rt = LT(rm.reshape(r, *rdims, order="F"), [bond] + right)
+    return lt, rt, bond, s_r, sv
 
 
 def factorize_qr(t, left, rtol=1e-15, truncate=True):
@@ -207,6 +257,9 @@ def zipup_chain_order(L, center):
 
 
 def contract_zipup(a, b, center, policy=None, max_bond_dim=None, final_truncate=True, spectra=None):
+    """contract_zipup_chain (treetn/contraction.rs:438-766) in ZipupTopologyMode::PruneScalarSubtrees (the mode of the
+    public entry, :340-358): a site whose contraction leaves no external label is absorbed into the remainder and
+    the result has fewer sites (:540-544, 636-645); the final pass is skipped when the centre itself was pruned."""
     L = len(a)
     assert L == len(b)
     chain = zipup_chain_order(L, center)
@@ -215,7 +268,7 @@ def contract_zipup(a, b, center, policy=None, max_bond_dim=None, final_truncate=
     canonicalize(b, chain[0])
     if L == 1:
         return Chain([contract([a.sites[0], b.sites[0]])])
-    res_sites = [None] * L
+    kept = {}
     rem = None
     for k in range(L - 2):
         s, nx = chain[k], chain[k + 1]
@@ -223,10 +276,13 @@ def contract_zipup(a, b, center, policy=None, max_bond_dim=None, final_truncate=
         ts = [a.sites[s], b.sites[s]] if rem is None else [rem, a.sites[s], b.sites[s]]
         contracted = contract(ts)
         left = [l for l in contracted.labels if l not in (ra, rb)]
-        lt, rt, nb, s_r, _ = factorize_svd(contracted, left, "left", policy, max_bond_dim)
+        if not left:
+            rem = contracted
+            continue
+        lt, rt, nb, s_r, _ = factorize_auto(contracted, left, "left", policy, max_bond_dim)
         if spectra is not None:
             spectra.append(np.array(s_r))
-        res_sites[s] = lt
+        kept[s] = lt
         rem = rt
     pen, last = chain[L - 2], chain[L - 1]
     ts = [a.sites[pen], b.sites[pen], a.sites[last], b.sites[last]]
@@ -235,16 +291,42 @@ def contract_zipup(a, b, center, policy=None, max_bond_dim=None, final_truncate=
     block = contract(ts)
     last_sites = a.site_labels(last) + b.site_labels(last)
     left = [l for l in block.labels if l not in last_sites]
-    lt, rt, nb, s_r, _ = factorize_svd(block, left, "right", policy, max_bond_dim)
-    if spectra is not None:
-        spectra.append(np.array(s_r))
-    res_sites[pen], res_sites[last] = lt, rt
-    res = Chain(res_sites)
-    if final_truncate:
-        truncate(res, center, policy, max_bond_dim, spectra)
+    right_exist = any(l in last_sites for l in block.labels)
+    if not left or not right_exist:
+        kept[last if not left else pen] = block
     else:
-        canonicalize(res, center)
+        lt, rt, nb, s_r, _ = factorize_auto(block, left, "right", policy, max_bond_dim)
+        if spectra is not None:
+            spectra.append(np.array(s_r))
+        kept[pen], kept[last] = lt, rt
+    positions = sorted(kept)
+    res = Chain([kept[p] for p in positions])
+    if center not in positions:
+        return res
+    target = positions.index(center)
+    if final_truncate:
+        truncate(res, target, policy, max_bond_dim, spectra)
+    else:
+        canonicalize(res, target)
     return res
+
+
+def apply_linear_operator(mpo, input_mapping, output_mapping, state, method="zipup", policy=None, max_bond_dim=None,
+                          nfullsweeps=1):
+    """apply_linear_operator (treetn/src/operator/apply.rs:306-398): mappings are lists of (node, true_label,
+    internal_label); state true -> internal input, contract with centre = first node, internal output -> true."""
+    st = state.copy()
+    for node, true, internal in input_mapping:
+        st.sites[node] = st.sites[node].replace(true, internal)
+    if method == "zipup":
+        out = contract_zipup(st, mpo, 0, policy, max_bond_dim)
+    elif method == "fit":
+        out = contract_fit(st, mpo, 0, policy, max_bond_dim, nfullsweeps)
+    else:
+        raise ValueError(method)
+    for node, internal, true in output_mapping:
+        out.sites[node] = out.sites[node].replace(internal, true)
+    return out
 
 
 def contract_fit(a, b, center, policy=None, max_bond_dim=None, nfullsweeps=1):

@@ -1,6 +1,8 @@
 // extern "C" boundary of libt4b.so (declared in include/t4b.h).
+#include <cmath>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/t4b.h"
 #include "capi_common.h"
@@ -294,6 +296,116 @@ int t4b_einsum(t4b_ctx* ctx, int dtype, int n_ops, const void* const* ops_dev, c
     for (auto& t : ops) ptrs.push_back(&t);
     Tensor r = contract(ctx->c, ptrs, &out_inds);
     dla::d2d(ctx->c, out_dev, r.data(), (size_t)r.numel() * dtype_size(dt));
+    T4B_CATCH
+}
+
+
+// ---- parity instrumentation: retained-spectrum log ------------------------------------------------------
+int t4b_ctx_spectra_begin(t4b_ctx* ctx) {
+    T4B_TRY
+    require_ctx(ctx);
+    dla::spectra_begin(ctx->c);
+    T4B_CATCH
+}
+static thread_local std::vector<std::vector<double>> g_spectra;
+int t4b_ctx_spectra_end(t4b_ctx* ctx, int64_t* n_spectra, int64_t* n_values) {
+    T4B_TRY
+    require_ctx(ctx);
+    g_spectra = dla::spectra_end(ctx->c);
+    int64_t tot = 0;
+    for (auto& v : g_spectra) tot += (int64_t)v.size();
+    if (n_spectra) *n_spectra = (int64_t)g_spectra.size();
+    if (n_values) *n_values = tot;
+    T4B_CATCH
+}
+int t4b_ctx_spectra_get(int64_t* lens_out, double* values_out) {
+    T4B_TRY
+    size_t off = 0;
+    for (size_t i = 0; i < g_spectra.size(); ++i) {
+        if (lens_out) lens_out[i] = (int64_t)g_spectra[i].size();
+        if (values_out) std::memcpy(values_out + off, g_spectra[i].data(), g_spectra[i].size() * sizeof(double));
+        off += g_spectra[i].size();
+    }
+    T4B_CATCH
+}
+
+// ---- seam leftovers: diagonal scaling, reductions, complete-pivoting LU ------------------------------------
+int t4b_scale_by_diag(t4b_ctx* ctx, int dtype, int side, int invert, int64_t m, int64_t n, void* a_dev, int64_t lda,
+                      const double* s_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(m >= 0 && n >= 0 && lda >= m && (side == 0 || side == 1), "scale_by_diag: bad arguments");
+    if (side == 0) dla::scale_rows(ctx->c, to_dtype(dtype), m, n, a_dev, lda, s_dev, invert != 0);
+    else dla::scale_cols(ctx->c, to_dtype(dtype), m, n, a_dev, lda, s_dev, invert != 0);
+    T4B_CATCH
+}
+int t4b_norm2(t4b_ctx* ctx, int dtype, int64_t n, const void* x_dev, double* out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && out, "norm2: bad arguments");
+    double h = 0.0;
+    if (n > 0) {
+        double* d = (double*)dla::alloc(ctx->c, 8);
+        dla::sumsq(ctx->c, to_dtype(dtype), n, x_dev, d);
+        dla::d2h(ctx->c, &h, d, 8);
+        dla::sync(ctx->c);
+        dla::release(ctx->c, d);
+    }
+    *out = std::sqrt(h);
+    T4B_CATCH
+}
+int t4b_sum(t4b_ctx* ctx, int dtype, int64_t n, const void* x_dev, double* re, double* im) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && re, "sum: bad arguments");
+    double h[2] = {0.0, 0.0};
+    if (n > 0) {
+        double* d = (double*)dla::alloc(ctx->c, 16);
+        dla::sum(ctx->c, to_dtype(dtype), n, x_dev, d);
+        dla::d2h(ctx->c, h, d, 16);
+        dla::sync(ctx->c);
+        dla::release(ctx->c, d);
+    }
+    *re = h[0];
+    if (im) *im = h[1];
+    T4B_CATCH
+}
+int t4b_maxabs(t4b_ctx* ctx, int dtype, int64_t n, const void* x_dev, double* out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && out, "maxabs: bad arguments");
+    double h = 0.0;
+    if (n > 0) {
+        double* d = (double*)dla::alloc(ctx->c, 8);
+        dla::maxabs(ctx->c, to_dtype(dtype), n, x_dev, d);
+        dla::d2h(ctx->c, &h, d, 8);
+        dla::sync(ctx->c);
+        dla::release(ctx->c, d);
+    }
+    *out = h;
+    T4B_CATCH
+}
+int t4b_full_piv_lu(t4b_ctx* ctx, int dtype, int64_t n, const void* a_dev, void* p_dev, void* l_dev, void* u_dev,
+                    void* q_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(a_dev && p_dev && l_dev && u_dev && q_dev, "full_piv_lu: null argument");
+    full_piv_lu(ctx->c, to_dtype(dtype), n, a_dev, p_dev, l_dev, u_dev, q_dev);
+    T4B_CATCH
+}
+int t4b_solve_right_full_piv_lu(t4b_ctx* ctx, int dtype, int64_t lhs_rows, int64_t lhs_cols, const void* lhs_dev,
+                                int64_t pivot_rows, int64_t pivot_cols, const void* pivot_dev, void* out_dev) {
+    T4B_TRY
+    require_ctx(ctx);
+    // same argument checks (and messages) as backend.rs:199-215
+    if (pivot_rows != pivot_cols)
+        throw Error(t4b::ST_INVALID_ARGUMENT, "full-pivot solve requires a square pivot matrix, got " +
+                                                  std::to_string(pivot_rows) + "x" + std::to_string(pivot_cols));
+    if (lhs_cols != pivot_rows)
+        throw Error(t4b::ST_INVALID_ARGUMENT, "cannot solve T * P = Pi1 with Pi1 shape " + std::to_string(lhs_rows) + "x" +
+                                                  std::to_string(lhs_cols) + " and P shape " + std::to_string(pivot_rows) +
+                                                  "x" + std::to_string(pivot_cols));
+    solve_right_full_piv_lu(ctx->c, to_dtype(dtype), lhs_rows, pivot_rows, lhs_dev, pivot_dev, out_dev);
     T4B_CATCH
 }
 

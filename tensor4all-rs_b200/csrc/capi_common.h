@@ -29,6 +29,8 @@ std::string& t4b_last_error_ref();
 
 inline void require_ctx(t4b_ctx* ctx) {
     if (!ctx || !ctx->c) throw t4b::Error(t4b::ST_INVALID_ARGUMENT, "null context");
+    // contexts are per device: make that device current for everything this call launches or allocates
+    t4b::dla::make_current(ctx->c);
 }
 inline t4b::DType to_dtype(int d) {
     if (d == 0) return t4b::F64;

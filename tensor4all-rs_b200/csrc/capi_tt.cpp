@@ -281,6 +281,48 @@ int t4b_tn_contract(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, int center, 
     *out = new t4b_tn{contract(ctx->c, a->tn, b->tn, center, o)};
     T4B_CATCH
 }
+int t4b_apply_linear_operator(t4b_ctx* ctx, const t4b_tn* op, const t4b_tn* state, int n_in, const int32_t* in_nodes,
+                              const int64_t* in_true, const int64_t* in_internal, int n_out,
+                              const int32_t* out_nodes, const int64_t* out_internal, const int64_t* out_true,
+                              int method, const t4b_svd_policy* policy, int64_t max_bond_dim, int nfullsweeps,
+                              t4b_tn** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(op && state && out, "null argument");
+    T4B_REQUIRE(n_in >= 0 && n_out >= 0 && (n_in == 0 || (in_nodes && in_true && in_internal)) &&
+                    (n_out == 0 || (out_nodes && out_internal && out_true)),
+                "apply_linear_operator: bad mapping arrays");
+    T4B_REQUIRE(method >= 0 && method <= 2, "method must be 0 (zipup), 1 (fit) or 2 (naive)");
+    auto find_dim = [](const ChainTN& tn, int node, int64_t id) -> int64_t {
+        if (node < 0 || node >= (int)tn.length()) return -1;
+        for (auto& ix : tn.sites[node].inds) if (ix.id == id) return ix.dim;
+        return -1;
+    };
+    std::vector<IndexMapping> im(n_in), om(n_out);
+    for (int i = 0; i < n_in; ++i) {
+        im[i].node = in_nodes[i];
+        im[i].true_index.id = ext_to_int(in_true[i]);
+        im[i].true_index.dim = find_dim(state->tn, in_nodes[i], im[i].true_index.id);
+        im[i].internal_index.id = ext_to_int(in_internal[i]);
+        im[i].internal_index.dim = find_dim(op->tn, in_nodes[i], im[i].internal_index.id);
+        T4B_REQUIRE(im[i].true_index.dim > 0 && im[i].internal_index.dim > 0, "apply_linear_operator: unknown input index id");
+    }
+    for (int i = 0; i < n_out; ++i) {
+        om[i].node = out_nodes[i];
+        om[i].internal_index.id = ext_to_int(out_internal[i]);
+        om[i].internal_index.dim = find_dim(op->tn, out_nodes[i], om[i].internal_index.id);
+        T4B_REQUIRE(om[i].internal_index.dim > 0, "apply_linear_operator: unknown output index id");
+        om[i].true_index.id = ext_to_int(out_true[i]);
+        om[i].true_index.dim = om[i].internal_index.dim;
+    }
+    ContractionOptions o;
+    o.method = method == 0 ? ContractMethod::Zipup : method == 1 ? ContractMethod::Fit : ContractMethod::Naive;
+    o.svd_policy = opt_policy(policy);
+    o.max_bond_dim = opt_bond(max_bond_dim);
+    o.nfullsweeps = nfullsweeps;
+    *out = new t4b_tn{apply_linear_operator(ctx->c, op->tn, im, om, state->tn, o)};
+    T4B_CATCH
+}
 int t4b_tn_norm_sqr(t4b_ctx* ctx, const t4b_tn* tn, double* out) {
     T4B_TRY
     require_ctx(ctx);

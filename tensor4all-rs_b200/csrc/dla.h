@@ -24,8 +24,16 @@ int64_t ctx_launch_count(Ctx*);
 }  // namespace dla
 }  // namespace t4b
 #include <string>
+#include <vector>
 namespace t4b {
 namespace dla {
+// Makes the context's device the calling thread's current CUDA device (every C-ABI entry point calls this).
+void make_current(Ctx*);
+// Retained-spectrum log: while enabled, every truncated-SVD factorisation of the sweep drivers appends the
+// singular values it retained (the `singular_values` of the reference's FactorizeResult, in call order).
+void spectra_begin(Ctx*);
+void spectra_push(Ctx*, const double* s, int64_t n);
+std::vector<std::vector<double>> spectra_end(Ctx*);
 // Per-kernel-class device timing (CUDA events on the launching stream) used by bench.py for
 // the roofline: profile_end returns lines "kernel launches total_ms algorithmic_work".
 void profile_begin(Ctx*);
@@ -125,6 +133,8 @@ void upper_row_norms(Ctx*, DType dt, int64_t k, int64_t n, const void* R, int64_
 void sumsq(Ctx*, DType dt, int64_t n, const void* x, double* out);
 // *out (device scalar, f64, must be zero on entry is NOT required) = max_i |x_i|
 void maxabs(Ctx*, DType dt, int64_t n, const void* x, double* out);
+// out[0], out[1] (device f64) = real / imaginary part of sum_i x_i (deterministic two-pass tree)
+void sum(Ctx*, DType dt, int64_t n, const void* x, double* out);
 // x *= alpha
 void scal(Ctx*, DType dt, int64_t n, void* x, double alpha);
 // y += alpha * x

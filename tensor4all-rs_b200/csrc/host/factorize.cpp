@@ -195,6 +195,7 @@ FactorizeResult factorize_svd(dla::Ctx* c, const Tensor& t, const std::vector<In
         return std::max<int64_t>(r, 1);
     };
     MatrixFactors f = svd_factor_matrix(c, t.dt, u.m, u.n, u.mat.data(), o.canonical, rank_fn);
+    dla::spectra_push(c, f.singular_values.data(), (int64_t)f.singular_values.size());
     FactorizeResult res;
     res.bond = new_index(f.rank);
     std::vector<Index> li = u.left;
@@ -287,11 +288,131 @@ FactorizeResult factorize(dla::Ctx* c, const Tensor& t, const std::vector<Index>
     throw Error(ST_INTERNAL, "factorize: unknown algorithm");
 }
 
+namespace {
+
+struct GramFallback {};   // the reference's `.or_else(|_| factorize(..))`: any failure of the Gram route
+
+// reference factorize_gram (core/src/defaults/factorize.rs:153-315): Gram matrix of the smaller side through the
+// contraction path, Hermitian eigendecomposition, sigma = sqrt(max(lambda, 0)) sorted descending, rank from the
+// policy, retained eigenvectors as the isometric factor, the other factor by back-multiplication (and a diagonal
+// scaling when the canonical side is the back-multiplied one).
+FactorizeResult factorize_gram(dla::Ctx* c, const Tensor& t, const std::vector<Index>& left_inds,
+                               const FactorizeOptions& o, const SvdTruncationPolicy& policy) {
+    Unfolded u = unfold(c, t, left_inds);
+    const DType dt = t.dt;
+    const size_t es = dtype_size(dt);
+    const int64_t m = u.m, n = u.n;
+    T4B_REQUIRE(m > 0 && n > 0, "cannot factorize a matrix with an empty dimension");
+    const bool eig_left = m <= n;
+    const int64_t g = eig_left ? m : n;
+    const void* M = u.mat.data();
+    auto G = std::make_shared<Buffer>(c, (size_t)g * g * es);
+    if (eig_left)   // G = M M^H
+        dla::gemm(c, dt, m, m, n, 1.0, M, g1(m, 1), g1(n, m), false, M, g1(n, m), g1(m, 1), true, 0.0, G->p,
+                  g1(m, 1), g1(m, m));
+    else            // G = M^H M
+        dla::gemm(c, dt, n, n, m, 1.0, M, g1(n, m), g1(m, 1), true, M, g1(m, 1), g1(n, m), false, 0.0, G->p,
+                  g1(n, 1), g1(n, n));
+    auto lam_dev = std::make_shared<Buffer>(c, (size_t)g * sizeof(double));
+    auto W = std::make_shared<Buffer>(c, (size_t)g * g * es);
+    dla::eigh(c, dt, g, G->p, (double*)lam_dev->p, W->p);
+    std::vector<double> lam(g);
+    dla::d2h(c, lam.data(), lam_dev->p, (size_t)g * sizeof(double));
+    dla::sync(c);
+    double scale = 0.0;
+    for (double v : lam) scale = std::fmax(scale, std::fabs(v));
+    if (scale == 0.0) throw GramFallback{};                       // :204-208 zero Gram matrix
+    const double negtol = 1e-12 * scale;
+    std::vector<std::pair<double, int64_t>> pairs(g);
+    for (int64_t i = 0; i < g; ++i) {
+        double v = lam[i];
+        if (!std::isfinite(v) || v < -negtol) throw GramFallback{};   // :216-226
+        if (v < 0.0) v = 0.0;
+        pairs[i] = {v, i};
+    }
+    std::stable_sort(pairs.begin(), pairs.end(),
+                     [](const std::pair<double, int64_t>& a, const std::pair<double, int64_t>& b) { return a.first > b.first; });
+    std::vector<double> sv(g);
+    for (int64_t i = 0; i < g; ++i) sv[i] = std::sqrt(pairs[i].first);
+    int64_t rank = compute_retained_rank(sv, policy);
+    if (o.max_bond_dim) rank = std::min<int64_t>(rank, *o.max_bond_dim);
+    rank = std::min<int64_t>(std::max<int64_t>(rank, 1), std::min(m, n));
+    for (int64_t i = 0; i < rank; ++i)
+        if (sv[i] == 0.0) throw GramFallback{};                   // :245-249
+    // basis = W[:, retained columns] (g x rank)
+    auto basis = std::make_shared<Buffer>(c, (size_t)g * rank * es);
+    {
+        std::vector<int64_t> cols(rank);
+        for (int64_t i = 0; i < rank; ++i) cols[i] = pairs[i].second;
+        auto cols_dev = std::make_shared<Buffer>(c, (size_t)rank * sizeof(int64_t));
+        dla::h2d(c, cols_dev->p, cols.data(), (size_t)rank * sizeof(int64_t));
+        dla::permute_cols(c, dt, g, rank, W->p, g, basis->p, g, (const int64_t*)cols_dev->p, /*scatter=*/false);
+        dla::sync(c);   // `cols` is a host temporary
+    }
+    auto sdev = std::make_shared<Buffer>(c, (size_t)rank * sizeof(double));
+    dla::h2d(c, sdev->p, sv.data(), (size_t)rank * sizeof(double));
+    std::shared_ptr<Buffer> left, right;
+    if (eig_left) {
+        // sigma_vh = basis^H M (rank x n)
+        right = std::make_shared<Buffer>(c, (size_t)rank * n * es);
+        dla::gemm(c, dt, rank, n, m, 1.0, basis->p, g1(rank, m), g1(m, 1), true, M, g1(m, 1), g1(n, m), false, 0.0,
+                  right->p, g1(rank, 1), g1(n, rank));
+        left = basis;
+        if (o.canonical == Canonical::Right) {
+            dla::scale_cols(c, dt, m, rank, left->p, m, (const double*)sdev->p, false);
+            dla::scale_rows(c, dt, rank, n, right->p, rank, (const double*)sdev->p, true);
+        }
+    } else {
+        // u_sigma = M basis (m x rank), vh = basis^H (rank x n)
+        left = std::make_shared<Buffer>(c, (size_t)m * rank * es);
+        dla::gemm(c, dt, m, rank, n, 1.0, M, g1(m, 1), g1(n, m), false, basis->p, g1(n, 1), g1(rank, n), false, 0.0,
+                  left->p, g1(m, 1), g1(rank, m));
+        right = std::make_shared<Buffer>(c, (size_t)rank * n * es);
+        Group gt;
+        gt.nd = 2; gt.dim[0] = rank; gt.str[0] = n; gt.dim[1] = n; gt.str[1] = 1;   // vh[r, j] = conj(basis[j, r])
+        dla::permute(c, dt, right->p, basis->p, gt, true);
+        if (o.canonical == Canonical::Left) {
+            dla::scale_cols(c, dt, m, rank, left->p, m, (const double*)sdev->p, true);
+            dla::scale_rows(c, dt, rank, n, right->p, rank, (const double*)sdev->p, false);
+        }
+    }
+    dla::sync(c);   // sv (host) feeds an asynchronous upload
+    FactorizeResult res;
+    res.bond = new_index(rank);
+    std::vector<Index> li = u.left;
+    li.push_back(res.bond);
+    std::vector<Index> ri = {res.bond};
+    ri.insert(ri.end(), u.right.begin(), u.right.end());
+    res.left = make_tensor(dt, li, left);
+    res.right = make_tensor(dt, ri, right);
+    res.singular_values.assign(sv.begin(), sv.begin() + rank);
+    res.rank = rank;
+    dla::spectra_push(c, res.singular_values.data(), rank);
+    return res;
+}
+
+}  // namespace
+
+// reference factorize_auto (core/src/defaults/factorize.rs:119-151): the Gram + eigh route only for SVD
+// policies whose effective cutoff on sigma^2 / sigma_max^2 exceeds 1e-12; everything else (and every failure of the
+// Gram route) takes the SVD.
 FactorizeResult factorize_auto(dla::Ctx* c, const Tensor& t, const std::vector<Index>& left_inds,
                                const FactorizeOptions& o) {
     if (o.alg != FactorizeAlg::SVD)
         throw Error(ST_INVALID_ARGUMENT, "automatic factorization only supports SVD options");
-    return factorize(c, t, left_inds, o);
+    if (!o.full_rank) validate_svd_truncation_options(o.max_bond_dim, o.svd_policy);
+    if (!o.svd_policy || o.full_rank) return factorize(c, t, left_inds, o);
+    const SvdTruncationPolicy& p = *o.svd_policy;
+    double effective_cutoff = 0.0;
+    if (p.scale == ThresholdScale::Relative && p.measure == SingularValueMeasure::SquaredValue) effective_cutoff = p.threshold;
+    else if (p.scale == ThresholdScale::Relative && p.measure == SingularValueMeasure::Value &&
+             p.rule == TruncationRule::PerValue) effective_cutoff = p.threshold * p.threshold;
+    if (effective_cutoff <= 1.0e-12) return factorize(c, t, left_inds, o);
+    try {
+        return factorize_gram(c, t, left_inds, o, p);
+    } catch (const GramFallback&) {
+        return factorize(c, t, left_inds, o);
+    }
 }
 
 }  // namespace t4b

@@ -158,4 +158,55 @@ void solve_matrix(dla::Ctx* c, DType dt, int64_t n, int64_t nrhs, const void* A,
     dla::permute_rows(c, dt, n, nrhs, Y->p, n, X, n, (const int64_t*)lu.d_col_perm->p, true);
 }
 
+void full_piv_lu(dla::Ctx* c, DType dt, int64_t n, const void* A, void* P, void* L, void* U, void* Q) {
+    T4B_REQUIRE(n > 0, "full_piv_lu: empty matrix");
+    const size_t es = dtype_size(dt);
+    RrLUOptions o;
+    o.max_bond_dim = n; o.rel_tol = 0.0; o.abs_tol = 0.0; o.left_orthogonal = true;
+    RrLU lu = rrlu(c, dt, n, n, A, o);
+    const int64_t r = lu.n_pivot;
+    // l = [L (n x r) | unit vectors], u = [U (r x n); 0]
+    dla::zero(c, L, (size_t)n * n * es);
+    dla::set_identity(c, dt, n, n, L, n);
+    if (r > 0) dla::d2d(c, L, lu.l->p, (size_t)n * r * es);
+    dla::zero(c, U, (size_t)n * n * es);
+    if (r > 0) {
+        Group g;   // U[0:r, :] <- lu.u (r x n, ld = r): scatter with row stride 1, column stride n
+        g.nd = 2; g.dim[0] = r; g.str[0] = 1; g.dim[1] = n; g.str[1] = n;
+        dla::scatter(c, dt, U, lu.u->p, g);
+    }
+    // permutation matrices: row k has its single 1 in column perm[k]
+    auto perm_matrix = [&](void* out, const std::vector<int64_t>& perm) {
+        std::vector<double> h((size_t)n * n * (dt == C64 ? 2 : 1), 0.0);
+        for (int64_t k = 0; k < n; ++k) {
+            const size_t e = (size_t)k + (size_t)n * (size_t)perm[k];
+            h[dt == C64 ? 2 * e : e] = 1.0;
+        }
+        dla::h2d(c, out, h.data(), (size_t)n * n * es);
+        dla::sync(c);   // h is a host temporary
+    };
+    perm_matrix(P, lu.row_permutation);
+    perm_matrix(Q, lu.col_permutation);
+}
+
+void solve_right_full_piv_lu(dla::Ctx* c, DType dt, int64_t lhs_rows, int64_t n, const void* Pi1, const void* P,
+                             void* T) {
+    T4B_REQUIRE(n > 0 && lhs_rows >= 0, "solve_right_full_piv_lu: bad shape");
+    if (lhs_rows == 0) return;
+    const size_t es = dtype_size(dt);
+    // the reference transposes both operands, solves P^T X = Pi1^T and transposes back (backend.rs:219-246)
+    auto transpose_into = [&](void* dst, const void* src, int64_t rows, int64_t cols) {
+        Group g;   // dst (cols x rows): dst[j + cols*i] = src[i + rows*j]
+        g.nd = 2; g.dim[0] = cols; g.str[0] = rows; g.dim[1] = rows; g.str[1] = 1;
+        dla::permute(c, dt, dst, src, g, false);
+    };
+    auto pt = std::make_shared<Buffer>(c, (size_t)n * n * es);
+    auto bt = std::make_shared<Buffer>(c, (size_t)n * lhs_rows * es);
+    auto xt = std::make_shared<Buffer>(c, (size_t)n * lhs_rows * es);
+    transpose_into(pt->p, P, n, n);
+    transpose_into(bt->p, Pi1, lhs_rows, n);
+    solve_matrix(c, dt, n, lhs_rows, pt->p, bt->p, xt->p);
+    transpose_into(T, xt->p, n, lhs_rows);
+}
+
 }  // namespace t4b

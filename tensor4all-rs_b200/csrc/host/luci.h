@@ -63,4 +63,14 @@ LuFactors luci_from_rrlu(dla::Ctx*, const RrLU& lu);
 // ST_NOT_CONVERGED when A is numerically singular.
 void solve_matrix(dla::Ctx*, DType dt, int64_t n, int64_t nrhs, const void* A, const void* B, void* X);
 
+// Complete-pivoting LU of a square matrix in the layout of the reference's full_piv_lu_matrix
+// (crates/tensor4all-tensorbackend/src/backend.rs:980-1036): permutation MATRICES p, q (n x n) with
+// p[k, row_perm[k]] = 1 and q[k, col_perm[k]] = 1 (the convention core/src/matrixluci/dense.rs:119-141 reads back),
+// l (n x n unit lower), u (n x n upper), p a q^T = l u.  Pivots below eps end the elimination (rrLU rule); the
+// remaining columns of l are unit vectors and the remaining rows of u zero.  All outputs are device buffers.
+void full_piv_lu(dla::Ctx*, DType dt, int64_t n, const void* A, void* P, void* L, void* U, void* Q);
+// T P = Pi1 for T (lhs_rows x n), P (n x n), Pi1 (lhs_rows x n): reference solve_right_full_piv_lu
+// (backend.rs:181-249).  Throws ST_NOT_CONVERGED for a singular P.
+void solve_right_full_piv_lu(dla::Ctx*, DType dt, int64_t lhs_rows, int64_t n, const void* Pi1, const void* P, void* T);
+
 }  // namespace t4b

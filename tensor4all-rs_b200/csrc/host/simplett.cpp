@@ -23,19 +23,17 @@ static Group g3(int64_t d0, int64_t s0, int64_t d1, int64_t s1, int64_t d2, int6
 }
 
 // reference compression.rs:286-306 / mpo/factorize.rs:206-250: keep while sv >= threshold
-// (non-strict), stop at the cap, floor 1.
+// (non-strict), stop at the cap, floor 1.  An all-zero spectrum has threshold = tolerance * 0 = 0, so every
+// value is kept (`0 < 0` is false) up to the cap - exactly what the reference loop does.
 int64_t simplett_rank(const std::vector<double>& s, double tolerance, bool normalize_error,
                       std::optional<int64_t> max_bond_dim) {
-    double s_max = 0.0;
-    for (double v : s) s_max = std::fmax(s_max, v);
+    const double s_max = s.empty() ? 0.0 : s[0];      // compression.rs:288 (spectra are non-increasing)
     const double threshold = normalize_error ? tolerance * s_max : tolerance;
     int64_t rank = 0;
-    if (!(normalize_error && s_max == 0.0 && tolerance > 0.0)) {
-        for (double sv : s) {
-            if (max_bond_dim && rank >= *max_bond_dim) break;
-            if (sv < threshold) break;
-            ++rank;
-        }
+    for (double sv : s) {
+        if (max_bond_dim && rank >= *max_bond_dim) break;
+        if (sv < threshold) break;
+        ++rank;
     }
     return std::max<int64_t>(rank, 1);
 }

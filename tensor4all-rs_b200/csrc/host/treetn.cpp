@@ -37,6 +37,20 @@ ChainTN clone_chain(dla::Ctx* c, const ChainTN& tn) {
     return r;
 }
 
+// reference sim_internal_inds (treetn/contraction.rs:470-471): every bond gets a fresh index id on both adjacent
+// sites, so that two operands that happen to share bond ids (a clone, the same handle twice, caller-chosen
+// numbering) only ever contract over their site indices.  Payloads are shared, not copied.
+ChainTN sim_bonds(const ChainTN& tn) {
+    ChainTN r = tn;
+    for (int e = 0; e + 1 < (int)r.sites.size(); ++e) {
+        const Index nb = new_index(r.bonds[e].dim);
+        r.sites[e] = replaceind(r.sites[e], r.bonds[e], nb);
+        r.sites[e + 1] = replaceind(r.sites[e + 1], r.bonds[e], nb);
+        r.bonds[e] = nb;
+    }
+    return r;
+}
+
 // reference sweep_edge_full_rank (treetn/mod.rs:616-751): QR at src, absorb R into dst
 static void sweep_edge(dla::Ctx* c, ChainTN& tn, int src, int dst) {
     const int e = std::min(src, dst);
@@ -164,17 +178,15 @@ ChainTN contract_zipup(dla::Ctx* c, const ChainTN& a_in, const ChainTN& b_in, in
     T4B_REQUIRE(L == (int)b_in.length(), "contract_zipup: operands must have the same length");
     T4B_REQUIRE(center >= 0 && center < L, "contract_zipup: center out of range");
     std::vector<int> chain = zipup_chain_order(L, center);
-    // operands in exact QR form at the first sweep site (contraction.rs:457-471)
-    ChainTN a = a_in, b = b_in;   // shares buffers; canonicalize replaces tensors, never mutates
+    // operands in exact QR form at the first sweep site (contraction.rs:457-471), with fresh bond ids on both
+    // (sim_internal_inds, :470-471); shares buffers: canonicalize replaces tensors, never mutates
+    ChainTN a = sim_bonds(a_in), b = sim_bonds(b_in);
     canonicalize(c, a, chain[0]);
     canonicalize(c, b, chain[0]);
 
-    ChainTN res;
-    res.sites.resize(L);
-    res.bonds.assign(std::max(L - 1, 0), Index{});
-    res.ortho_dir.assign(std::max(L - 1, 0), 0);
     if (L == 1) {
-        res.sites[0] = contract_pair(c, a.sites[0], b.sites[0]);
+        ChainTN res;
+        res.sites = {contract_pair(c, a.sites[0], b.sites[0])};
         res.center = 0;
         return res;
     }
@@ -184,6 +196,11 @@ ChainTN contract_zipup(dla::Ctx* c, const ChainTN& a_in, const ChainTN& b_in, in
     FactorizeOptions fr = fl;
     fr.canonical = Canonical::Right;
 
+    // Result nodes in sweep order.  A site whose contraction leaves no external index is a scalar subtree: it is
+    // dropped and its tensor travels on inside the remainder (ZipupTopologyMode::PruneScalarSubtrees, the mode of
+    // the public contract_zipup, contraction.rs:540-544,636-645); the result then has fewer sites.
+    std::vector<int> kept_pos;
+    std::vector<Tensor> kept;
     auto bond_between = [&](const ChainTN& tn, int s, int t) { return tn.bonds[std::min(s, t)]; };
     Tensor remainder;
     bool have_rem = false;
@@ -195,12 +212,13 @@ ChainTN contract_zipup(dla::Ctx* c, const ChainTN& a_in, const ChainTN& b_in, in
         else contracted = contract_pair(c, a.sites[s], b.sites[s]);
         std::vector<Index> left_inds = indices_except(contracted.inds, {ra, rb});
         if (left_inds.empty()) {
-            throw Error(ST_UNSUPPORTED, "contract_zipup: sites without external indices are not supported");
+            remainder = contracted;
+            have_rem = true;
+            continue;
         }
         FactorizeResult f = factorize_auto(c, contracted, left_inds, fl);
-        res.sites[s] = f.left;
-        res.bonds[std::min(s, nx)] = f.bond;
-        res.ortho_dir[std::min(s, nx)] = nx > s ? +1 : -1;
+        kept_pos.push_back(s);
+        kept.push_back(f.left);
         remainder = f.right;
         have_rem = true;
     }
@@ -220,17 +238,74 @@ ChainTN contract_zipup(dla::Ctx* c, const ChainTN& a_in, const ChainTN& b_in, in
         last_sites.insert(last_sites.end(), lb.begin(), lb.end());
     }
     std::vector<Index> left_inds = indices_except(block.inds, last_sites);
-    T4B_REQUIRE(!left_inds.empty() && left_inds.size() < block.inds.size(),
-                "contract_zipup: final block needs indices on both sites");
-    FactorizeResult f = factorize_auto(c, block, left_inds, fr);
-    res.sites[pen] = f.left;
-    res.sites[last] = f.right;
-    res.bonds[std::min(pen, last)] = f.bond;
-    res.ortho_dir[std::min(pen, last)] = pen > last ? +1 : -1;   // last is orthogonal towards pen
-    res.center = pen;
-    if (final_truncate) truncate(c, res, center, policy, max_bond_dim);
-    else canonicalize(c, res, center);
+    const bool right_exist = left_inds.size() < block.inds.size();
+    int center_node = pen;     // numerical centre before the final reconciliation
+    if (left_inds.empty() || !right_exist) {
+        // one of the two final sites is a scalar subtree: the block stays whole on the other one
+        const int where = left_inds.empty() ? last : pen;
+        kept_pos.push_back(where);
+        kept.push_back(block);
+        center_node = where;
+    } else {
+        FactorizeResult f = factorize_auto(c, block, left_inds, fr);
+        kept_pos.push_back(pen); kept.push_back(f.left);
+        kept_pos.push_back(last); kept.push_back(f.right);
+    }
+    // assemble in ascending position order (the sweep runs either 0 -> L-1 or L-1 -> 0)
+    const int nk = (int)kept.size();
+    std::vector<int> ord(nk);
+    for (int i = 0; i < nk; ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return kept_pos[x] < kept_pos[y]; });
+    std::vector<Tensor> sites(nk);
+    std::vector<int> pos(nk);
+    for (int i = 0; i < nk; ++i) { sites[i] = kept[ord[i]]; pos[i] = kept_pos[ord[i]]; }
+    ChainTN res = make_chain(sites);
+    int cpos = -1, target = -1;
+    for (int i = 0; i < nk; ++i) {
+        if (pos[i] == center_node) cpos = i;
+        if (pos[i] == center) target = i;
+    }
+    // every node except the numerical centre is orthogonal towards it (contraction.rs:700-748)
+    for (int e = 0; e + 1 < nk; ++e) res.ortho_dir[e] = e < cpos ? +1 : -1;
+    res.center = cpos;
+    if (target < 0) return res;      // the requested centre was pruned: contraction.rs:750 skips the final pass
+    if (final_truncate) truncate(c, res, target, policy, max_bond_dim);
+    else canonicalize(c, res, target);
     return res;
+}
+
+// reference apply_linear_operator (treetn/src/operator/apply.rs:306-398), chain topology: (1) the state's true site
+// indices are renamed to the operator's internal input indices (transform_state_to_input), (2) state x MPO through
+// the `contract` dispatcher with centre = first node in sorted order, (3) the operator's internal output indices are
+// renamed to the true output indices (transform_output_to_true).  Operator sites that the mapping does not cover
+// act as the identity (the true index passes through untouched); the MPO must then still span the whole chain.
+ChainTN apply_linear_operator(dla::Ctx* c, const ChainTN& mpo, const std::vector<IndexMapping>& input,
+                              const std::vector<IndexMapping>& output, const ChainTN& state,
+                              const ContractionOptions& o) {
+    const int L = (int)state.length();
+    T4B_REQUIRE(L >= 1, "apply_linear_operator: empty state");
+    T4B_REQUIRE((int)mpo.length() == L, "apply_linear_operator: operator nodes must match the state nodes");
+    ChainTN st = state;
+    for (const IndexMapping& mp : input) {
+        T4B_REQUIRE(mp.node >= 0 && mp.node < L, "apply_linear_operator: mapping node out of range");
+        Tensor& t = st.sites[mp.node];
+        const int pos = t.find(mp.true_index);
+        T4B_REQUIRE(pos >= 0, "apply_linear_operator: state has no such true input index");
+        T4B_REQUIRE(t.inds[pos].dim == mp.internal_index.dim, "apply_linear_operator: input index dimension mismatch");
+        T4B_REQUIRE(mpo.sites[mp.node].has(mp.internal_index), "apply_linear_operator: operator has no such internal input index");
+        t = replaceind(t, t.inds[pos], mp.internal_index);
+    }
+    ChainTN out = contract(c, st, mpo, /*center=*/0, o);
+    T4B_REQUIRE((int)out.length() == L || output.empty(),
+                "apply_linear_operator: scalar sites were pruned; output mapping is positional");
+    for (const IndexMapping& mp : output) {
+        T4B_REQUIRE(mp.node >= 0 && mp.node < (int)out.length(), "apply_linear_operator: mapping node out of range");
+        Tensor& t = out.sites[mp.node];
+        const int pos = t.find(mp.internal_index);
+        T4B_REQUIRE(pos >= 0, "apply_linear_operator: result has no such internal output index");
+        t = replaceind(t, t.inds[pos], mp.true_index);
+    }
+    return out;
 }
 
 namespace {
@@ -268,8 +343,9 @@ const Tensor& get_right(dla::Ctx* c, FitEnv& env, const ChainTN& a, const ChainT
 
 }  // namespace
 
-ChainTN contract_fit(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center,
+ChainTN contract_fit(dla::Ctx* c, const ChainTN& a_in, const ChainTN& b_in, int center,
                      const ContractionOptions& o) {
+    const ChainTN a = sim_bonds(a_in), b = sim_bonds(b_in);
     const int L = (int)a.length();
     ChainTN cc = contract_zipup(c, a, b, center, o.svd_policy, o.max_bond_dim, /*final_truncate=*/false);
     if (o.nfullsweeps == 0 || L == 1) return cc;
@@ -308,6 +384,8 @@ ChainTN contract_fit(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center
         }
         if (o.convergence_tol > 0.0) {
             double n_after = norm_sqr(c, cc);
+            // a zero network has nothing left to converge (and n_after / 0 would never compare below the tolerance)
+            if (n_before == 0.0) break;
             double rel = std::fabs(std::sqrt(n_after / n_before) - 1.0);
             if (rel < o.convergence_tol) break;
         }
@@ -323,6 +401,16 @@ ChainTN contract(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center,
         case ContractMethod::Fit: return contract_fit(c, a, b, center, o);
         case ContractMethod::Naive: {
             // site-wise product with fused bonds, then truncate (reference contract_naive)
+            return contract_naive_chain(c, sim_bonds(a), sim_bonds(b), center, o);
+        }
+    }
+    throw Error(ST_INTERNAL, "contract: unknown method");
+}
+
+ChainTN contract_naive_chain(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center,
+                             const ContractionOptions& o) {
+    {
+        {
             const int L = (int)a.length();
             ChainTN r;
             r.sites.resize(L);
@@ -352,7 +440,6 @@ ChainTN contract(dla::Ctx* c, const ChainTN& a, const ChainTN& b, int center,
             return r;
         }
     }
-    throw Error(ST_INTERNAL, "contract: unknown method");
 }
 
 void inner(dla::Ctx* c, const ChainTN& a, const ChainTN& b, double* re, double* im) {

@@ -49,6 +49,21 @@ ChainTN contract_fit(dla::Ctx*, const ChainTN& a, const ChainTN& b, int center,
                      const ContractionOptions& opts);
 ChainTN contract(dla::Ctx*, const ChainTN& a, const ChainTN& b, int center,
                  const ContractionOptions& opts);
+ChainTN contract_naive_chain(dla::Ctx*, const ChainTN& a, const ChainTN& b, int center,
+                             const ContractionOptions& opts);
+// Same network with fresh bond index ids (reference sim_internal_inds); payloads shared.
+ChainTN sim_bonds(const ChainTN& tn);
+
+// reference IndexMapping / LinearOperator (treetn/src/operator/linear_operator.rs): per node, the operator's internal
+// MPO index and the true (state-facing) index it stands for
+struct IndexMapping {
+    int node = 0;
+    Index true_index, internal_index;
+};
+// reference apply_linear_operator (treetn/src/operator/apply.rs:306-398)
+ChainTN apply_linear_operator(dla::Ctx*, const ChainTN& mpo, const std::vector<IndexMapping>& input,
+                              const std::vector<IndexMapping>& output, const ChainTN& state,
+                              const ContractionOptions& opts);
 
 // Strict direct-sum addition a + b (reference TreeTN::add, treetn/addition.rs:322-...): same length, same site
 // indices on every site; every bond becomes a fresh index of dimension dim_a + dim_b, site tensors are block

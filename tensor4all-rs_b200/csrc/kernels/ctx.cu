@@ -3,6 +3,7 @@
 #include "ctx.cuh"
 
 #include <chrono>
+#include <cstdlib>
 
 namespace t4b {
 namespace dla {
@@ -56,6 +57,25 @@ Ctx* ctx_create(int device, void* cuda_stream) {
                                         std::to_string(prop.major * 10 + prop.minor));
     Ctx* c = new Ctx();
     c->device = device;
+    {
+        auto geti = [](const char* n, int dflt) { const char* v = getenv(n); return v ? atoi(v) : dflt; };
+        auto getb = [](const char* n) { return getenv(n) != nullptr; };
+        Knobs& k = c->knobs;
+        k.verbose = getenv("T4B_VERBOSE") ? (atoi(getenv("T4B_VERBOSE")) > 0 ? atoi(getenv("T4B_VERBOSE")) : 1) : 0;
+        k.jac_smemcap_kb = (size_t)geti("T4B_JAC_SMEMCAP", 0);
+        k.jac_cs = geti("T4B_JAC_CS", 0);
+        k.jac_max_sweeps = geti("T4B_JAC_MAXSWEEPS", 40);
+        k.jac_inner = geti("T4B_JAC_INNER", 1);
+        k.jac_eig_serial = getb("T4B_JAC_EIG_SERIAL");
+        k.jac_coop = geti("T4B_JAC_COOP", 1);
+        k.jac_occ2 = geti("T4B_JAC_OCC2", 0);
+        k.qr_notma = getb("T4B_QR_NOTMA"); k.qr_unfused = getb("T4B_QR_UNFUSED");
+        k.qr_nolookahead = getb("T4B_QR_NOLOOKAHEAD"); k.qr_old = getb("T4B_QR_OLD");
+        k.qr_leaf_old = getb("T4B_QR_LEAF_OLD");
+        k.gemm_nows = getb("T4B_GEMM_NOWS"); k.gemm_noskinny = getb("T4B_GEMM_NOSKINNY");
+        k.gemm_trace = getb("T4B_GEMM_TRACE"); k.gemm_nopersist = getb("T4B_GEMM_NOPERSIST");
+        k.svd_nobatch = getb("T4B_SVD_NOBATCH");
+    }
     c->num_sms = prop.multiProcessorCount;
     if (cuda_stream) {
         c->stream = (cudaStream_t)cuda_stream;
@@ -89,6 +109,20 @@ void ctx_destroy(Ctx* c) {
     delete c;
 }
 
+void make_current(Ctx* c) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != c->device) T4B_CUDA_CHECK(cudaSetDevice(c->device));
+}
+void spectra_begin(Ctx* c) { c->spectra.clear(); c->spectra_on = true; }
+void spectra_push(Ctx* c, const double* s, int64_t n) {
+    if (c->spectra_on) c->spectra.emplace_back(s, s + n);
+}
+std::vector<std::vector<double>> spectra_end(Ctx* c) {
+    c->spectra_on = false;
+    std::vector<std::vector<double>> out;
+    out.swap(c->spectra);
+    return out;
+}
 void* ctx_stream(Ctx* c) { return (void*)c->stream; }
 int ctx_device(Ctx* c) { return c->device; }
 int64_t ctx_launch_count(Ctx* c) { return c->launches; }

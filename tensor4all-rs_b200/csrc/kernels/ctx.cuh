@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../dla.h"
@@ -20,8 +21,42 @@ namespace dla {
                                                           cudaGetErrorString(_e));             \
     } while (0)
 
+// Environment knobs (debug / A-B switches), read ONCE at context creation: nothing on a launch path calls getenv().
+struct Knobs {
+    int verbose = 0;              // T4B_VERBOSE
+    size_t jac_smemcap_kb = 0;    // T4B_JAC_SMEMCAP (0 = full 227 KB)
+    int jac_cs = 0;               // T4B_JAC_CS (0 = planned)
+    int jac_max_sweeps = 40;      // T4B_JAC_MAXSWEEPS
+    int jac_inner = 1;            // T4B_JAC_INNER
+    bool jac_eig_serial = false;  // T4B_JAC_EIG_SERIAL
+    int jac_coop = 1;             // T4B_JAC_COOP (default 1: cooperative, gang-scheduled launch; 0 for Nsight Compute replay)
+    int jac_occ2 = 0;             // T4B_JAC_OCC2 (two resident CTAs per SM variant)
+    bool qr_notma = false, qr_unfused = false, qr_nolookahead = false, qr_old = false;
+    bool qr_leaf_old = false;     // T4B_QR_LEAF_OLD
+    bool gemm_nows = false, gemm_noskinny = false, gemm_trace = false, gemm_nopersist = false;
+    bool svd_nobatch = false;     // T4B_SVD_NOBATCH
+};
+
+// launch geometry of the persistent Jacobi kernel (svd.cu)
+struct JacobiPlan {
+    int cs = 1, nclusters = 1, pairs = 1, rpcx = 0, rpcv = 0, ch = 0, ldp = 0;
+    int64_t ldx = 0, ldv = 0;
+    size_t smem = 0;
+};
+
 struct Ctx {
     int device = 0;
+    Knobs knobs;
+    std::unordered_map<uint64_t, JacobiPlan> jp_plans;
+    // kernels whose function attributes (dynamic shared memory limit, non-portable cluster size) have been set
+    // through THIS context: the attributes are per device, so the registry lives in the context, not in statics
+    std::unordered_set<const void*> attr_done;
+    bool first_use(const void* kern) { return attr_done.insert(kern).second; }
+    std::unordered_map<const void*, int> cluster_ok;
+    int jac_coop_ok = -1;   // -1 undecided, 1 cooperative Jacobi launches accepted, 0 refused / disabled   // schedulability of non-portable cluster sizes (qr.cu)
+    // retained-spectrum log (parity instrumentation, see t4b_ctx_spectra_begin)
+    bool spectra_on = false;
+    std::vector<std::vector<double>> spectra;
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     int num_sms = 148;

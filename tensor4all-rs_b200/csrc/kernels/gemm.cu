@@ -703,17 +703,14 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, cons
 #define T4B_LAUNCH(AL, BL)                                                                       \
     {                                                                                            \
         auto kern = gemm_kernel<CPLX, BM, BN, WM, WN, AL, BL>;                                   \
-        static bool attr_set = false;                                                            \
-        if (!attr_set) {                                                                         \
+        if (c->first_use((const void*)kern))                                                     \
             T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                 (int)smem_bytes(AL, BL)));                       \
-            attr_set = true;                                                                     \
-        }                                                                                        \
         kern<<<g3, NT, sm, c->stream>>>(p);                                          \
     }
     bool done = false;
     if constexpr (!CPLX && BM == 128 && BN == 128) {
-        if (gops && !getenv("T4B_GEMM_NOWS")) done = launch_ws<false>(c, p, alay, blay, gops);
+        if (gops && !c->knobs.gemm_nows) done = launch_ws<false>(c, p, alay, blay, gops);
     }
     if (done) {}
     else if (alay == 0 && blay == 0) T4B_LAUNCH(0, 0)
@@ -839,12 +836,9 @@ bool launch_ws(Ctx* c, GemmParams& p, int alay, int blay, const Group* g) {
 #define T4B_LAUNCH_WS(AL, BL)                                                                    \
     {                                                                                            \
         auto kern = gemm_ws_kernel<false, AL, BL>;                                               \
-        static bool attr_set = false;                                                            \
-        if (!attr_set) {                                                                         \
+        if (c->first_use((const void*)kern))                                                     \
             T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                 (int)smem_bytes(AL, BL)));                       \
-            attr_set = true;                                                                     \
-        }                                                                                        \
         kern<<<g3, WS_THREADS, sm, c->stream>>>(wp);                                             \
     }
     if (alay == 0 && blay == 0) T4B_LAUNCH_WS(0, 0)
@@ -934,7 +928,7 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
     if (dt == F64 && K <= 32 && N <= 32 && M >= 4096 && M < (int64_t)1 << 31 && g[0].str[0] == 1 && g[4].str[0] == 1 &&
         g[0].nd <= 2 && g[4].nd <= 2 &&
         (g[0].nd == 1 || g[0].dim[0] % 8 == 0) && (g[4].nd == 1 || g[4].dim[0] % 8 == 0) &&
-        !getenv("T4B_GEMM_NOSKINNY")) {
+        !c->knobs.gemm_noskinny) {
         GemmSkinnyParams sp;
         sp.A = (const double*)A; sp.B = (const double*)B; sp.C = (double*)C;
         sp.M = M; sp.N = (int)N; sp.K = (int)K;
@@ -948,7 +942,7 @@ void gemm(Ctx* c, DType dt, int64_t M, int64_t N, int64_t K, double alpha, const
         c->launched(c->gemm_class, 2.0 * (double)M * (double)N * (double)K);
         return;
     }
-    if (getenv("T4B_GEMM_TRACE"))
+    if (c->knobs.gemm_trace)
         fprintf(stderr, "[t4b] gemm %s M=%lld N=%lld K=%lld alay=%d blay=%d nd=%d%d%d%d%d%d ksplit=%d class=%s\n",
                 dt == C64 ? "c64" : "f64", (long long)M, (long long)N, (long long)K, alay, blay, g[0].nd, g[1].nd,
                 g[2].nd, g[3].nd, g[4].nd, g[5].nd, ksplit, c->gemm_class);
@@ -981,7 +975,8 @@ void gemm_batched(Ctx* c, DType dt, int64_t batch, int64_t M, int64_t N, int64_t
     const int64_t tiles_n = (N + BNs - 1) / BNs;
     dim3 grid((unsigned)((int64_t)p.tiles_m * tiles_n), 1, (unsigned)batch);
     auto launch = [&](auto kern, size_t smem) {
-        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (c->first_use((const void*)kern))
+            T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 128, smem, c->stream>>>(p);
     };
     // A is M-fast (ALAY 0), B is K-fast (BLAY 0)

@@ -200,6 +200,47 @@ void maxabs(Ctx* c, DType dt, int64_t n, const void* x, double* out) {
     c->launched("maxabs", (double)n * (double)dtype_size(dt));
 }
 
+namespace {
+// deterministic two-pass sum (fixed grid, fixed tree): partial[2 * block + {0,1}] = (re, im)
+template <bool CPLX>
+__global__ void sum_partial_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ partial) {
+    __shared__ double shr[32], shi[32];
+    double ar = 0.0, ai = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if constexpr (CPLX) { ar += x[2 * i]; ai += x[2 * i + 1]; }
+        else ar += x[i];
+    }
+    ar = warp_sum(ar); ai = warp_sum(ai);
+    if ((threadIdx.x & 31) == 0) { shr[threadIdx.x >> 5] = ar; shi[threadIdx.x >> 5] = ai; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double vr = threadIdx.x < (blockDim.x >> 5) ? shr[threadIdx.x] : 0.0;
+        double vi = threadIdx.x < (blockDim.x >> 5) ? shi[threadIdx.x] : 0.0;
+        vr = warp_sum(vr); vi = warp_sum(vi);
+        if (threadIdx.x == 0) { partial[2 * blockIdx.x] = vr; partial[2 * blockIdx.x + 1] = vi; }
+    }
+}
+__global__ void sum_final2_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+    // one warp; lanes stride over the blocks in a fixed order
+    double ar = 0.0, ai = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) { ar += partial[2 * i]; ai += partial[2 * i + 1]; }
+    ar = warp_sum(ar); ai = warp_sum(ai);
+    if (threadIdx.x == 0) { out[0] = ar; out[1] = ai; }
+}
+}  // namespace
+
+// out[0], out[1] (device) = Re, Im of sum_i x_i   (reference sum_native_tensor, tenferro_bridge.rs)
+void sum(Ctx* c, DType dt, int64_t n, const void* x, double* out) {
+    int grid = grid_of(c, n > 0 ? n : 1);
+    if (grid > 1024) grid = 1024;
+    double* partial = (double*)c->get_scratch(sizeof(double) * 2 * grid);
+    if (dt == C64) sum_partial_kernel<true><<<grid, 256, 0, c->stream>>>((const double*)x, n, partial);
+    else sum_partial_kernel<false><<<grid, 256, 0, c->stream>>>((const double*)x, n, partial);
+    c->launched("sum_partial", (double)n * (double)dtype_size(dt));
+    sum_final2_kernel<<<1, 32, 0, c->stream>>>(partial, grid, out);
+    c->launched("sum_final");
+}
+
 void eigh(Ctx* c, DType dt, int64_t n, void* G, double* lam, void* W) {
     if (n == 0) return;
     double* shift = (double*)alloc(c, 8);

@@ -291,11 +291,9 @@ void launch_panel(Ctx* c, PanelArgs& a) {
     size_t smem = a.use_smem ? (size_t)rpc * NB * es : 0;
 
     auto kern = qr_panel_kernel<CPLX>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (c->first_use((const void*)kern)) {
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs, 1, 1);
@@ -761,11 +759,8 @@ void launch_apply(Ctx* c, const ApplyArgs& a) {
     constexpr int WPT = CPLX ? 34 : 36;
     const size_t smem = ((size_t)(NB + NT) * CP + 2 * (size_t)NT * WPT + (size_t)NB * (NB + 1)) * es;
     auto kern = tsqr_apply_kernel<CPLX, NT>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (c->first_use((const void*)kern))
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     dim3 grid((unsigned)(a.gather ? 1 : a.nblocks), (unsigned)((a.ncols + NT - 1) / NT), 1);
     kern<<<grid, AT, smem, c->stream>>>(a);
     const double rows = a.gather ? (double)a.cnt * NB : (double)a.rows;
@@ -1092,14 +1087,12 @@ bool launch_apply_fused(Ctx* c, const FusedApplyArgs& a0) {
             ok = ((uintptr_t)a.Va % 16 == 0) && ((uintptr_t)a.C % 16 == 0) && (a.lda % 2 == 0) && (a.ldc % 2 == 0) &&
                  (a.nblocks == 1 ? (a.rows % 2 == 0) : (a.h % 2 == 0 && last % 2 == 0));
         }
-        a.use_tma = (ok && !getenv("T4B_QR_NOTMA")) ? 1 : 0;
+        a.use_tma = (ok && !c->knobs.qr_notma) ? 1 : 0;
     }
     auto kern = tsqr_apply_fused_kernel<CPLX, NT>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (c->first_use((const void*)kern)) {
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.nblocks, (unsigned)((a.ncols + NT - 1) / NT), 1);
@@ -1115,14 +1108,15 @@ bool launch_apply_fused(Ctx* c, const FusedApplyArgs& a0) {
     cfg.numAttrs = 1;
     if (a.nblocks > 8) {
         // non-portable cluster sizes may not be schedulable with this much shared memory
-        static int ok16[MAXCL + 1] = {0};   // 0 unknown, 1 yes, -1 no   (per instantiation)
-        if (ok16[a.nblocks] == 0) {
+        // cached per context (device) and instantiation: key = kernel address + cluster size
+        int& ok16 = c->cluster_ok[(const char*)(const void*)kern + a.nblocks];   // 0 unknown, 1 yes, -1 no
+        if (ok16 == 0) {
             int ncl = 0;
             cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
             if (e != cudaSuccess) { cudaGetLastError(); ncl = 0; }
-            ok16[a.nblocks] = ncl > 0 ? 1 : -1;
+            ok16 = ncl > 0 ? 1 : -1;
         }
-        if (ok16[a.nblocks] < 0) return false;
+        if (ok16 < 0) return false;
     }
     T4B_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
     c->launched("qr_apply", 2.0 * (double)a.rows * (double)a.ncols * (double)es);   // bytes: C read + written once
@@ -1172,11 +1166,8 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
     block_geometry(m, hb0, nb0i);
     const int64_t nb0 = nb0i;
     auto fk = tsqr_factor_kernel<CPLX>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (c->first_use((const void*)fk))
         T4B_CUDA_CHECK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap));
-        attr_set = true;
-    }
     const int64_t npanels = (k + NB - 1) / NB;
     const size_t t_stride = (size_t)(nb0 + 1) * NB * NB;          // elements per panel
     const size_t v2_stride = (size_t)nb0 * NB * NB;
@@ -1205,7 +1196,7 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
         l2.V = (const double*)(V2all + (size_t)p * v2_stride * es); l2.ldv = (int64_t)nblocks * NB; l2.v_implicit = 0;
         l2.Tw = (const double*)(Tall + ((size_t)p * t_stride + (size_t)nblocks * NB * NB) * es);
         l2.gather = 1; l2.cnt = nblocks;
-        if (!getenv("T4B_QR_UNFUSED")) {
+        if (!c->knobs.qr_unfused) {
             FusedApplyArgs fa{};
             fa.Va = l1.V; fa.lda = m; fa.V2 = l2.V; fa.Tw = l1.Tw; fa.jb = jb;
             fa.C = (double*)Cbase; fa.ldc = m; fa.ncols = ncols;
@@ -1241,7 +1232,7 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
     // Look-ahead: as soon as panel p has been applied to the columns of panel p+1, that panel is factored
     // on a high-priority side stream while the rest of the trailing update of panel p runs on the main
     // stream (disjoint column ranges).  Disabled while profiling (per-kernel events live on one stream).
-    const bool lookahead = !c->profiling && npanels > 1 && !getenv("T4B_QR_NOLOOKAHEAD");
+    const bool lookahead = !c->profiling && npanels > 1 && !c->knobs.qr_nolookahead;
     if (lookahead) c->ensure_side();
     launch_factor(0);
     for (int64_t p = 0; p < npanels; ++p) {
@@ -1256,10 +1247,16 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
             if (lookahead) {
                 T4B_CUDA_CHECK(cudaEventRecord(c->ev_a, c->stream));
                 T4B_CUDA_CHECK(cudaStreamWaitEvent(c->side, c->ev_a, 0));
-                cudaStream_t main_stream = c->stream;
-                c->stream = c->side;
-                launch_factor(p + 1);
-                c->stream = main_stream;
+                {
+                    // the factor of panel p+1 goes to the side stream; the guard restores the context's stream even
+                    // when the launch throws (single-stream allocator invariant)
+                    struct StreamGuard {
+                        Ctx* c; cudaStream_t saved;
+                        StreamGuard(Ctx* cc, cudaStream_t s) : c(cc), saved(cc->stream) { cc->stream = s; }
+                        ~StreamGuard() { c->stream = saved; }
+                    } guard(c, c->side);
+                    launch_factor(p + 1);
+                }
                 T4B_CUDA_CHECK(cudaEventRecord(c->ev_f, c->side));
                 if (nt > jb1) apply_panel(p, At + (size_t)jb1 * (size_t)m * es, nt - jb1, true);
                 T4B_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_f, 0));
@@ -1302,7 +1299,7 @@ void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rou
     if (k == 0) return;
     const size_t es = dtype_size(dt);
     const bool cplx = dt == C64;
-    if (!getenv("T4B_QR_OLD")) {
+    if (!c->knobs.qr_old) {
         if (cplx ? qr_thin_tsqr<true>(c, m, n, A, Q, Rout) : qr_thin_tsqr<false>(c, m, n, A, Q, Rout)) return;
     }
 

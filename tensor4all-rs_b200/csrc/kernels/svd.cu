@@ -372,8 +372,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
         }                                                               \
     } while (0)
 
-template <bool CPLX>
-__global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
+// MINB = 2: register budget (<= 128) and shared memory sized for TWO resident CTAs per SM, so that the serial 32 x 32
+// eigen-solve of one pair overlaps with the DMMA passes of another pair on the same SM (the W fragments are then
+// re-read from shared memory per row fragment instead of living in registers for the whole pass).
+template <bool CPLX, int MINB>
+__global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long tprev = gtimer();
     typedef Sc<CPLX> S;
@@ -655,12 +658,16 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                     }
                     JP_STAMP(4);   // eig
                     // ---- 3. update pass: P <- P W chunk by chunk, TMA bulk write-back ------------------
-                    // W as DMMA B fragments, held in registers for the whole pass
-                    T wf[4][8];
+                    // W as DMMA B fragments: held in registers for the whole pass (MINB == 1) or fetched per row
+                    // fragment, two column fragments at a time (MINB == 2: half the register budget)
+                    constexpr int NFH = MINB == 2 ? 2 : 4;
+                    T wf[NFH][8];
+                    if constexpr (MINB == 1) {
 #pragma unroll
-                    for (int nf = 0; nf < 4; ++nf)
+                        for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) wf[nf][ks] = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
+                            for (int ks = 0; ks < 8; ++ks) wf[nf][ks] = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
+                    }
                     for (int j = 0; j < npos; ++j) {
                         const int b = (nchx - 1 + j) & 1;
                         if (j >= 2 || (j == 1 && nchx == 1)) wait_load(b);
@@ -674,10 +681,26 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                             T acc[4][2];
 #pragma unroll
                             for (int nf = 0; nf < 4; ++nf) acc[nf][0] = acc[nf][1] = S::zero();
+                            if constexpr (MINB == 1) {
 #pragma unroll
-                            for (int ks = 0; ks < 8; ++ks)
+                                for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-                                for (int nf = 0; nf < 4; ++nf) mma_frag<CPLX, false>(acc[nf], av[ks], wf[nf][ks]);
+                                    for (int nf = 0; nf < 4; ++nf) mma_frag<CPLX, false>(acc[nf], av[ks], wf[nf][ks]);
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < 4 / NFH; ++h) {
+#pragma unroll
+                                    for (int nf = 0; nf < NFH; ++nf)
+#pragma unroll
+                                        for (int ks = 0; ks < 8; ++ks)
+                                            wf[nf][ks] = Ws[((h * NFH + nf) * 8 + grp) * WP + ks * 4 + tig];
+#pragma unroll
+                                    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                                        for (int nf = 0; nf < NFH; ++nf)
+                                            mma_frag<CPLX, false>(acc[h * NFH + nf], av[ks], wf[nf][ks]);
+                                }
+                            }
                             __syncwarp();
 #pragma unroll
                             for (int nf = 0; nf < 4; ++nf)
@@ -871,11 +894,7 @@ Group gg(int64_t dim, int64_t str) {
 }
 
 // ---- persistent kernel: launch geometry ------------------------------------------------------------------
-struct JPPlan {
-    int cs = 1, nclusters = 1, pairs = 1, rpcx = 0, rpcv = 0, ch = 0, ldp = 0;
-    int64_t ldx = 0, ldv = 0;
-    size_t smem = 0;
-};
+typedef JacobiPlan JPPlan;   // declared in ctx.cuh (the context caches the plans)
 
 template <bool CPLX>
 size_t jp_smem_bytes(int ldp) {
@@ -884,9 +903,9 @@ size_t jp_smem_bytes(int ldp) {
            (size_t)(64 + JW + 2) * 8 + 2 * 8 + 2 * 256 * es + 128;
 }
 
-template <bool CPLX>
+template <bool CPLX, int MINB>
 int jp_max_clusters(int cs, size_t smem) {
-    auto kern = jacobi_persistent_kernel<CPLX>;
+    auto kern = jacobi_persistent_kernel<CPLX, MINB>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cs, 1, 1);
     cfg.blockDim = dim3(JT, 1, 1);
@@ -903,17 +922,22 @@ int jp_max_clusters(int cs, size_t smem) {
     return n;
 }
 
-template <bool CPLX>
+template <bool CPLX, int MINB>
 JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
-    static bool attr_set = false;
-    const size_t smem_max = 227 * 1024;
-    const size_t smem_cap = getenv("T4B_JAC_SMEMCAP") ? (size_t)atoi(getenv("T4B_JAC_SMEMCAP")) * 1024 : smem_max;
-    if (!attr_set) {
-        auto kern = jacobi_persistent_kernel<CPLX>;
+    // two resident CTAs per SM share the 228 KB of the SM (1 KB reserved per CTA)
+    const size_t smem_max = MINB == 2 ? 112 * 1024 : 227 * 1024;
+    size_t smem_cap = c->knobs.jac_smemcap_kb ? c->knobs.jac_smemcap_kb * 1024 : smem_max;
+    if (smem_cap > smem_max) smem_cap = smem_max;
+    auto kern = jacobi_persistent_kernel<CPLX, MINB>;
+    if (c->first_use((const void*)kern)) {
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
     }
+    // launch geometries are cached per context: the occupancy queries cost more than a small factorisation
+    const uint64_t key = ((uint64_t)nx << 40) ^ ((uint64_t)npad << 16) ^ ((uint64_t)(with_v ? 1 : 0) << 2) ^
+                         ((uint64_t)(CPLX ? 1 : 0) << 1) ^ (uint64_t)(MINB - 1);
+    auto hit = c->jp_plans.find(key);
+    if (hit != c->jp_plans.end()) return hit->second;
     auto roundup = [](int64_t v, int64_t q) { return (v + q - 1) / q * q; };
     // pitch == 4 (mod 16) real, == 2 (mod 8) complex: conflict-free fragment loads, 16-byte aligned columns
     const int chq = CPLX ? 8 : 16;
@@ -921,10 +945,11 @@ JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
     int chmax = chq;
     while (jp_smem_bytes<CPLX>(chmax + chq + pad) <= smem_cap) chmax += chq;
     const int pairs = (int)(npad / PW);
-    const int cs_force = getenv("T4B_JAC_CS") ? atoi(getenv("T4B_JAC_CS")) : 0;
+    const int cs_force = c->knobs.jac_cs;
     JPPlan best;
     long best_score = -1;
-    for (int cs = 8; cs >= 1; cs >>= 1) {
+    bool found = false;
+    for (int cs = 8; cs >= 1 && !found; cs >>= 1) {
         if (cs_force && cs != cs_force) continue;
         JPPlan pl;
         pl.cs = cs; pl.pairs = pairs;
@@ -938,27 +963,27 @@ JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
         pl.smem = jp_smem_bytes<CPLX>(pl.ldp);
         pl.ldx = (int64_t)cs * pl.rpcx;
         pl.ldv = (int64_t)cs * pl.rpcv;
-        int maxc = jp_max_clusters<CPLX>(cs, pl.smem);
+        int maxc = jp_max_clusters<CPLX, MINB>(cs, pl.smem);
         if (maxc < 1) continue;
         pl.nclusters = maxc < pairs ? maxc : pairs;
-        if (maxc >= pairs) return pl;            // every pair of a round gets its own resident cluster
+        if (maxc >= pairs) { best = pl; best_score = 1; found = true; break; }   // every pair gets its own resident cluster
         long score = (long)pl.nclusters * cs;
         if (score > best_score) { best_score = score; best = pl; }
     }
     if (best_score < 0) throw Error(ST_INTERNAL, "svd: no resident cluster configuration for the Jacobi kernel");
-    (void)c;
+    c->jp_plans[key] = best;
     return best;
 }
 
 // One-sided block Jacobi on X (ldx x npad, nx live rows); V (ldv x npad) optional.  Asynchronous: the
 // whole iteration (all sweeps, convergence decision included) is one kernel launch.
-template <bool CPLX>
+template <bool CPLX, int MINB>
 void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
     const size_t es = CPLX ? 16 : 8;
     const int p = (int)(npad / JB);
-    const int max_sweeps = getenv("T4B_JAC_MAXSWEEPS") ? atoi(getenv("T4B_JAC_MAXSWEEPS")) : 40;
+    const int max_sweeps = c->knobs.jac_max_sweeps;
     // workspace: flag[max_sweeps] (u64) | timing[8] (u64) | ready[p] | done | info[2]
-    const bool verbose = getenv("T4B_VERBOSE") != nullptr;
+    const bool verbose = c->knobs.verbose > 0;
     const size_t ws_bytes = (size_t)(max_sweeps + 8) * 8 + ((size_t)p + 4) * 4;
     double* Dblk = (double*)alloc(c, (size_t)p * 256 * es);
     unsigned char* ws = (unsigned char*)alloc(c, ws_bytes);
@@ -987,8 +1012,8 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     double* fro2 = (double*)alloc(c, 8);
     sumsq(c, CPLX ? C64 : F64, pl.ldx * npad, X, fro2);
     a.fro2 = fro2;
-    a.inner = getenv("T4B_JAC_INNER") ? atoi(getenv("T4B_JAC_INNER")) : 1;
-    a.eig_serial = getenv("T4B_JAC_EIG_SERIAL") ? 1 : 0;
+    a.inner = c->knobs.jac_inner;
+    a.eig_serial = c->knobs.jac_eig_serial ? 1 : 0;
     a.flag = (unsigned long long*)ws;
     a.timing = verbose ? (unsigned long long*)ws + max_sweeps : nullptr;
     a.ready = (unsigned*)(ws + (size_t)(max_sweeps + 8) * 8);
@@ -1005,22 +1030,22 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     // The CTAs spin on each other's progress, so the whole grid must be resident: the plan never launches more
-    // clusters than cudaOccupancyMaxActiveClusters reports.  Two such kernels from DIFFERENT contexts on one
-    // device could still be half resident at the same time; T4B_JAC_COOP=1 adds the cooperative (gang-scheduled)
-    // launch attribute for that deployment.  It is off by default because Nsight Compute cannot replay
-    // cooperative cluster launches (LaunchFailed) and the reference serialises backend calls process-wide anyway
-    // (tensorbackend/src/context.rs:318-337).
+    // clusters than cudaOccupancyMaxActiveClusters reports, and the launch is COOPERATIVE (gang-scheduled) by
+    // default so that two such kernels from different contexts / processes on one device can never be half
+    // resident at the same time.  T4B_JAC_COOP=0 drops the attribute: Nsight Compute cannot replay cooperative
+    // cluster launches (LaunchFailed), so profiling runs opt out.
     attr[1].id = cudaLaunchAttributeCooperative;
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    static int coop_ok = (getenv("T4B_JAC_COOP") && atoi(getenv("T4B_JAC_COOP")) > 0) ? 1 : 0;
-    cfg.numAttrs = coop_ok ? 2 : 1;
-    auto kern = jacobi_persistent_kernel<CPLX>;
+    if (c->jac_coop_ok < 0) c->jac_coop_ok = c->knobs.jac_coop > 0 ? 1 : 0;
+    cfg.numAttrs = c->jac_coop_ok ? 2 : 1;
+    auto kern = jacobi_persistent_kernel<CPLX, MINB>;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
-    if (le != cudaSuccess && coop_ok) {
-        // cluster + cooperative not accepted by this driver: fall back to the plain cluster launch
+    if (le != cudaSuccess && c->jac_coop_ok) {
+        // cluster + cooperative not accepted by this driver / geometry: fall back to the plain cluster launch
         cudaGetLastError();
-        coop_ok = 0;
+        if (c->knobs.verbose) fprintf(stderr, "[t4b] jacobi: cooperative cluster launch refused (%s); plain launch\n", cudaGetErrorString(le));
+        c->jac_coop_ok = 0;
         cfg.numAttrs = 1;
         le = cudaLaunchKernelEx(&cfg, kern, a);
     }
@@ -1032,16 +1057,16 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
         d2h(c, h + 64, a.timing, 64);
         d2h(c, h + 128, a.flag, 8 * max_sweeps);
         T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));   // not dla::sync: a failed iteration must still be printed
-        if (atoi(getenv("T4B_VERBOSE")) > 1) {
+        if (c->knobs.verbose > 1) {
             fprintf(stderr, "[t4b]   off per sweep:");
             for (int i = 0; i < ((const int*)h)[0]; ++i) fprintf(stderr, " %.1e", ((const double*)(h + 128))[i]);
             fprintf(stderr, "\n");
         }
         const int* hinfo = (const int*)h;
         const unsigned long long* t = (const unsigned long long*)(h + 64);
-        fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d cs=%d clusters=%d ch=%d smem=%zu sweeps=%d converged=%d | us: "
+        fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d minb=%d coop=%d cs=%d clusters=%d ch=%d smem=%zu sweeps=%d converged=%d | us: "
                 "wait %.0f gram %.0f csync %.0f reduce %.0f eig %.0f update %.0f store %.0f publish+sweepbar %.0f\n",
-                (long long)nx, (long long)npad, V ? 1 : 0, pl.cs, pl.nclusters, pl.ch, pl.smem, hinfo[0], hinfo[1],
+                (long long)nx, (long long)npad, V ? 1 : 0, MINB, c->jac_coop_ok, pl.cs, pl.nclusters, pl.ch, pl.smem, hinfo[0], hinfo[1],
                 t[0] * 1e-3, t[1] * 1e-3, t[2] * 1e-3, t[3] * 1e-3, t[4] * 1e-3, t[5] * 1e-3, t[6] * 1e-3, t[7] * 1e-3);
     }
     release(c, ws);
@@ -1063,7 +1088,8 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     qr_thin(c, dt, m, n, A, Q, Rm);
     // X = R (left vectors wanted) or R^H (only right vectors wanted)
     const bool adjoint = !want_u;
-    const JPPlan pl = plan_jp<CPLX>(c, n, npad, acc_v);
+    const bool occ2 = !CPLX && c->knobs.jac_occ2 > 0;
+    const JPPlan pl = occ2 ? plan_jp<CPLX, CPLX ? 1 : 2>(c, n, npad, acc_v) : plan_jp<CPLX, 1>(c, n, npad, acc_v);
     double* X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
     init_x_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>((const double*)Rm, n, n, pl.ldx, npad, adjoint ? 1 : 0, X);
     c->launched("svd_init_x");
@@ -1073,7 +1099,8 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         set_eye_kernel<CPLX><<<grid1d(c, pl.ldv * npad), 256, 0, c->stream>>>(V, pl.ldv, npad);
         c->launched("svd_set_eye");
     }
-    jacobi_persistent<CPLX>(c, pl, X, n, npad, V);
+    if (occ2) jacobi_persistent<CPLX, CPLX ? 1 : 2>(c, pl, X, n, npad, V);
+    else jacobi_persistent<CPLX, 1>(c, pl, X, n, npad, V);
 
     double* sig2 = (double*)alloc(c, (size_t)npad * 8);
     int64_t* rank = (int64_t*)alloc(c, (size_t)npad * 8);

@@ -116,6 +116,23 @@ class Context:
         _check(lib().t4b_ctx_launch_count(self.h, C.byref(v)))
         return v.value
 
+    # ---- retained-spectrum log (parity instrumentation) ----
+    def spectra_begin(self):
+        _check(lib().t4b_ctx_spectra_begin(self.h))
+
+    def spectra_end(self):
+        """List of float64 arrays: the singular values retained by every truncated factorisation since begin."""
+        ns, nv = C.c_int64(), C.c_int64()
+        _check(lib().t4b_ctx_spectra_end(self.h, C.byref(ns), C.byref(nv)))
+        lens = (C.c_int64 * max(ns.value, 1))()
+        vals = np.empty(max(nv.value, 1), dtype=np.float64)
+        _check(lib().t4b_ctx_spectra_get(lens, vals.ctypes.data_as(C.c_void_p)))
+        out, off = [], 0
+        for i in range(ns.value):
+            out.append(vals[off:off + lens[i]].copy())
+            off += lens[i]
+        return out
+
     # ---- memory ----
     def empty(self, shape, dt=F64) -> DeviceArray:
         return DeviceArray(self, shape, dt)
@@ -210,6 +227,42 @@ class Context:
         outl = (C.c_uint32 * max(len(out_labels), 1))(*[int(x) for x in out_labels])
         _check(lib().t4b_einsum(self.h, operands[0].dt, len(operands), ptrs, ranks, shapes, labs,
                                 len(out_labels), outl, C.c_void_p(out.ptr)))
+        return out
+
+    def scale_by_diag(self, a: DeviceArray, s: DeviceArray, side=0, invert=False):
+        """In place: side 0 rows, side 1 columns."""
+        m, n = a.shape
+        _check(lib().t4b_scale_by_diag(self.h, a.dt, side, int(invert), C.c_int64(m), C.c_int64(n), C.c_void_p(a.ptr),
+                                       C.c_int64(m), C.c_void_p(s.ptr)))
+        return a
+
+    def norm2(self, a: DeviceArray) -> float:
+        v = C.c_double()
+        _check(lib().t4b_norm2(self.h, a.dt, C.c_int64(int(np.prod(a.shape))), C.c_void_p(a.ptr), C.byref(v)))
+        return v.value
+
+    def sum(self, a: DeviceArray):
+        re, im = C.c_double(), C.c_double()
+        _check(lib().t4b_sum(self.h, a.dt, C.c_int64(int(np.prod(a.shape))), C.c_void_p(a.ptr), C.byref(re), C.byref(im)))
+        return complex(re.value, im.value) if a.dt == C64 else re.value
+
+    def maxabs(self, a: DeviceArray) -> float:
+        v = C.c_double()
+        _check(lib().t4b_maxabs(self.h, a.dt, C.c_int64(int(np.prod(a.shape))), C.c_void_p(a.ptr), C.byref(v)))
+        return v.value
+
+    def full_piv_lu(self, a: DeviceArray):
+        """Returns (p, l, u, q) as numpy arrays (n x n)."""
+        n = a.shape[0]
+        outs = [self.empty((n, n), a.dt) for _ in range(4)]
+        _check(lib().t4b_full_piv_lu(self.h, a.dt, C.c_int64(n), C.c_void_p(a.ptr), *[C.c_void_p(o.ptr) for o in outs]))
+        return tuple(o.get() for o in outs)
+
+    def solve_right_full_piv_lu(self, lhs: DeviceArray, pivot: DeviceArray) -> DeviceArray:
+        out = self.empty((lhs.shape[0], pivot.shape[1]), lhs.dt)
+        _check(lib().t4b_solve_right_full_piv_lu(self.h, lhs.dt, C.c_int64(lhs.shape[0]), C.c_int64(lhs.shape[1]),
+                                                 C.c_void_p(lhs.ptr), C.c_int64(pivot.shape[0]), C.c_int64(pivot.shape[1]),
+                                                 C.c_void_p(pivot.ptr), C.c_void_p(out.ptr)))
         return out
 
     def batched_matmul(self, a: DeviceArray, b: DeviceArray) -> DeviceArray:

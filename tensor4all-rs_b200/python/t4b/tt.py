@@ -188,6 +188,19 @@ class ChainTN:
                                      C.c_int64(max_bond_dim), nfullsweeps, C.byref(h)))
         return ChainTN(self.ctx, h, self._dt)
 
+    def apply_operator(self, op, input_mapping, output_mapping, method=0, policy: SvdPolicy | None = None,
+                       max_bond_dim=0, nfullsweeps=1):
+        """self = state.  input_mapping: [(node, true_id, internal_id)], output_mapping: [(node, internal_id, true_id)]
+        (t4b_apply_linear_operator)."""
+        h = C.c_void_p()
+        _check(lib().t4b_apply_linear_operator(
+            self.ctx.h, op.h, self.h, len(input_mapping), _i32([m[0] for m in input_mapping]),
+            _i64([m[1] for m in input_mapping]), _i64([m[2] for m in input_mapping]), len(output_mapping),
+            _i32([m[0] for m in output_mapping]), _i64([m[1] for m in output_mapping]),
+            _i64([m[2] for m in output_mapping]), method, _pol(policy), C.c_int64(max_bond_dim), nfullsweeps,
+            C.byref(h)))
+        return ChainTN(self.ctx, h, self._dt)
+
     def norm_sqr(self):
         v = C.c_double()
         _check(lib().t4b_tn_norm_sqr(self.ctx.h, self.h, C.byref(v)))

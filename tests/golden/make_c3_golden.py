@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Generates tests/golden/c3_full_oracle.npz: the ORACLE (oracle/treetn.py, LAPACK gesdd/geqrf) run of the
+BASELINE C3 sweep at FULL size on the bench inputs,
+
+    contract_zipup(make_c3(0x5EED0003, L=64, d=4, chi=512, w=8), center=0,
+                   SvdTruncationPolicy(0.0), max_bond_dim=512)
+
+and stores every retained spectrum in call order (62 zip-up steps, the final two-site block, 126 two-site
+truncation steps = 189 spectra), all bond dimensions, the final norm^2, and the wall time of the run (the
+measured full-sweep CPU time of the restatement on this container's cores).
+
+    python tests/golden/make_c3_golden.py [--L 64 --chi 512] [--out tests/golden/c3_full_oracle.npz]
+
+Takes ~10 minutes on 8 cores.  The GPU parity test (tests/test_gpu_c3_golden.py) asserts per-step spectra
+<= 1e-12 * sigma_max and norm^2 <= 1e-10 relative against this file (north_star parity gates)."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from bench import make_c3  # noqa: E402
+from oracle import treetn as otn  # noqa: E402
+from oracle.truncation import SvdTruncationPolicy  # noqa: E402
+from util import to_oracle_chain  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--L", type=int, default=64)
+    ap.add_argument("--d", type=int, default=4)
+    ap.add_argument("--chi", type=int, default=512)
+    ap.add_argument("--w", type=int, default=8)
+    ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED0003)
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "c3_full_oracle.npz"))
+    a = ap.parse_args()
+    mps, mi, mpo, oi = make_c3(a.seed, a.L, a.d, a.chi, a.w)
+    spectra = []
+    t0 = time.perf_counter()
+    ref = otn.contract_zipup(to_oracle_chain(mps, mi), to_oracle_chain(mpo, oi), 0, SvdTruncationPolicy(0.0),
+                             a.chi, spectra=spectra)
+    wall = time.perf_counter() - t0
+    n2 = float(np.linalg.norm(ref.sites[0].arr.ravel()) ** 2)    # canonical at site 0: the centre carries the norm
+    lens = np.array([len(s) for s in spectra], dtype=np.int64)
+    flat = np.concatenate(spectra).astype(np.float64)
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    np.savez_compressed(a.out, spectra=flat, lens=lens, bond_dims=np.array(ref.bond_dims(), dtype=np.int64),
+                        norm_sqr=np.float64(n2), wall_s=np.float64(wall), threads=np.int64(threads),
+                        config=np.array([a.L, a.d, a.chi, a.w, a.seed], dtype=np.int64))
+    print(f"wrote {a.out}: {len(spectra)} spectra, norm^2 = {n2!r}, oracle sweep {wall:.1f} s on {threads} threads")
+
+
+if __name__ == "__main__":
+    main()

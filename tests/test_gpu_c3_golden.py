@@ -1,0 +1,140 @@
+"""Parity of the BASELINE C3 sweep AT FULL SIZE against the oracle (north_star gates: retained spectra to 1e-12,
+TT to 1e-10).
+
+* test_c3_full_sweep_matches_oracle_golden: L=64, d=4, chi=512, w=8 on the bench inputs.  The oracle sweep
+  (oracle/treetn.py, LAPACK gesdd/geqrf, ~6.5 min on 8 cores) was run once by tests/golden/make_c3_golden.py; its 189
+  retained spectra (62 zip-up steps, final block, 126 two-site truncation steps), bond dimensions and final norm^2
+  are the committed fixture tests/golden/c3_full_oracle.npz.  Mirrors the rank-cap / zip-up assertions of the
+  reference (crates/tensor4all-treetn/src/treetn/contraction/tests/mod.rs:319-335,604-632).
+* test_c3_saturated_direct_overlap: the largest saturated size the oracle finishes in-test (L=12, chi=512): the oracle
+  runs here and the two results are compared as tensors, |<gpu|oracle>|^2 / (|gpu|^2 |oracle|^2) and
+  |gpu - oracle| / |oracle| <= 1e-10, computed from the site tensors of both chains.
+* test_c3_linearity_full_size: contract(alpha a + beta a', b) = alpha contract(a, b) + beta contract(a', b) is NOT
+  what a truncating sweep satisfies, so linearity is checked where it must hold exactly: a non-power-of-two scalar
+  (sqrt(3)), and the un-truncated regime (sum of two states at small chi against the sum of the results)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bench import make_c3  # noqa: E402
+from oracle import treetn as otn  # noqa: E402
+from oracle.truncation import SvdTruncationPolicy  # noqa: E402
+from t4b import tt as t4tt  # noqa: E402
+from util import to_oracle_chain  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden", "c3_full_oracle.npz")
+
+
+def _split(flat, lens):
+    out, off = [], 0
+    for n in lens:
+        out.append(flat[off:off + n])
+        off += n
+    return out
+
+
+def test_c3_full_sweep_matches_oracle_golden(ctx):
+    g = np.load(GOLD)
+    L, d, chi, w, seed = [int(x) for x in g["config"]]
+    assert (L, d, chi, w) == (64, 4, 512, 8)
+    mps, mi, mpo, oi = make_c3(seed, L, d, chi, w)
+    a = t4tt.chain_from_arrays(ctx, mps, mi)
+    b = t4tt.chain_from_arrays(ctx, mpo, oi)
+    ctx.spectra_begin()
+    out = a.contract(b, 0, 0, t4tt.SvdPolicy(0.0), chi)
+    got = ctx.spectra_end()
+    want = _split(g["spectra"], g["lens"])
+    assert out.bond_dims() == [int(x) for x in g["bond_dims"]]
+    assert len(got) == len(want) == 189
+    worst = 0.0
+    for k, (sg, sw) in enumerate(zip(got, want)):
+        assert len(sg) == len(sw), (k, len(sg), len(sw))
+        err = float(np.max(np.abs(sg - sw)) / sw[0])
+        worst = max(worst, err)
+        assert err <= 1e-12, (k, err)
+    n2 = out.norm_sqr()
+    assert abs(n2 - float(g["norm_sqr"])) <= 1e-10 * float(g["norm_sqr"])
+    print(f"C3 full sweep: worst spectrum deviation {worst:.2e} * sigma_max over 189 factorisations, "
+          f"norm^2 rel dev {abs(n2 - float(g['norm_sqr'])) / float(g['norm_sqr']):.2e}")
+    out.release(); a.release(); b.release()
+
+
+def _inner_arrays(sa, sb):
+    """<A|B> of two chains given as lists of (array, ids): ids >= 0 are site indices (shared), ids < 0 are bonds
+    (kept apart for bra and ket)."""
+    env = None
+    for (x, ix), (y, iy) in zip(sa, sb):
+        lx = [("s", i) if i >= 0 else ("a", i) for i in ix]
+        ly = [("s", i) if i >= 0 else ("b", i) for i in iy]
+        tx, ty = otn.LT(np.conj(x), lx), otn.LT(y, ly)
+        env = otn.contract([tx, ty]) if env is None else otn.contract([env, tx, ty])
+    return complex(env.arr)
+
+
+def test_c3_saturated_direct_overlap(ctx):
+    L, d, chi, w = 12, 4, 512, 8
+    mps, mi, mpo, oi = make_c3(0x5EED0003, L, d, chi, w)
+    pol = SvdTruncationPolicy(0.0)
+    ref = otn.contract_zipup(to_oracle_chain(mps, mi), to_oracle_chain(mpo, oi), 0, pol, chi)
+    out = t4tt.chain_from_arrays(ctx, mps, mi).contract(t4tt.chain_from_arrays(ctx, mpo, oi), 0, 0, t4tt.SvdPolicy(0.0), chi)
+    assert out.bond_dims() == ref.bond_dims()
+    assert max(out.bond_dims()) == chi
+    gs = out.sites()
+    # oracle site labels ("x", id) for externals; result bonds are fresh labels: map to ids by position
+    rs = []
+    for i, s in enumerate(ref.sites):
+        ids = [l[1] if l[0] == "x" else -(10_000 + ref.bonds.index(l)) for l in s.labels]
+        rs.append((s.arr, ids))
+    gg = _inner_arrays(gs, gs).real
+    rr = _inner_arrays(rs, rs).real
+    gr = _inner_arrays(gs, rs)
+    fidelity = abs(gr) ** 2 / (gg * rr)
+    dist2 = gg + rr - 2.0 * gr.real
+    assert abs(1.0 - fidelity) <= 1e-10, fidelity
+    assert dist2 <= (1e-10) ** 2 * rr, np.sqrt(max(dist2, 0.0) / rr)
+    assert abs(out.norm_sqr() - rr) <= 1e-10 * rr
+
+
+def test_c3_linearity_full_size(ctx):
+    L, d, chi, w = 64, 4, 512, 8
+    mps, mi, mpo, oi = make_c3(0x5EED0003, L, d, chi, w)
+    pol = t4tt.SvdPolicy(0.0)
+    a = t4tt.chain_from_arrays(ctx, mps, mi)
+    b = t4tt.chain_from_arrays(ctx, mpo, oi)
+    out1 = a.contract(b, 0, 0, pol, chi)
+    n11 = out1.norm_sqr()
+    alpha = np.sqrt(3.0)                       # not a power of two: every product rounds
+    mps2 = [x.copy() for x in mps]
+    mps2[L // 2] = alpha * mps2[L // 2]
+    a2 = t4tt.chain_from_arrays(ctx, mps2, mi)
+    out2 = a2.contract(b, 0, 0, pol, chi)
+    n22 = out2.norm_sqr()
+    n21 = out2.inner(out1)
+    assert abs(n22 - alpha ** 2 * n11) <= 1e-10 * alpha ** 2 * n11
+    assert abs(n21.real - alpha * n11) <= 1e-10 * alpha * n11 and abs(n21.imag) <= 1e-10 * n11
+    assert out2.bond_dims() == out1.bond_dims()
+    for x in (out1, out2, a, a2, b):
+        x.release()
+
+
+def test_zipup_sum_of_two_states_untruncated(ctx):
+    """Where nothing is truncated the sweep is linear: contract(a + a', b) == contract(a, b) + contract(a', b)."""
+    rng = np.random.default_rng(11)
+    from util import gpu_chain_dense, random_mpo, random_mps, relerr
+    L, d = 7, 2
+    m1, ids = random_mps(rng, L, d, 4)
+    m2, _ = random_mps(rng, L, d, 3)
+    oa, oi = random_mpo(rng, L, d, 3)
+    a1, a2 = t4tt.chain_from_arrays(ctx, m1, ids), t4tt.chain_from_arrays(ctx, m2, ids)
+    b = t4tt.chain_from_arrays(ctx, oa, oi)
+    pol = t4tt.SvdPolicy(1e-14)
+    s = a1.add(a2)
+    lhs = gpu_chain_dense(s.contract(b, 0, 0, pol, 0))
+    rhs = gpu_chain_dense(a1.contract(b, 0, 0, pol, 0)) + gpu_chain_dense(a2.contract(b, 0, 0, pol, 0))
+    assert relerr(lhs, rhs) <= 1e-10

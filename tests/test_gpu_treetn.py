@@ -149,7 +149,7 @@ def test_zipup_c3_full_size_properties(ctx):
     """BASELINE C3 at FULL size (L=64, d=4, chi=512, w=8, cap-only truncation), checked through
     size-independent properties (the oracle needs minutes per sweep at this size):
     * every bond of the result is capped at chi and the bulk reaches it;
-    * linearity: contract(2 a, b) = 2 contract(a, b)  =>  <out2|out1> = 2 <out1|out1>, <out2|out2> = 4 <out1|out1>;
+    * (linearity with a non-power-of-two scalar and the oracle comparison at this size live in test_gpu_c3_golden.py)
     * the result is already truncated: truncating it again (same cap) leaves <out|out'> = <out|out> to 1e-10
       and every bond unchanged (idempotence);
     * determinism: a second sweep on the same operands gives the identical norm."""
@@ -171,16 +171,6 @@ def test_zipup_c3_full_size_properties(ctx):
     out1b = a.contract(b, 0, 0, pol, chi)
     assert out1b.norm_sqr() == n11
     out1b.release()
-    # linearity
-    mps2 = [x.copy() for x in mps]
-    mps2[0] = 2.0 * mps2[0]
-    a2 = t4tt.chain_from_arrays(ctx, mps2, mi)
-    out2 = a2.contract(b, 0, 0, pol, chi)
-    n22 = out2.norm_sqr()
-    n21 = out2.inner(out1)
-    assert abs(n22 - 4.0 * n11) <= 1e-10 * 4.0 * n11
-    assert abs(n21.real - 2.0 * n11) <= 1e-10 * 2.0 * n11 and abs(n21.imag) <= 1e-10 * n11
-    out2.release(); a2.release()
     # idempotence of the truncation
     out3 = out1.clone()
     out3.truncate(0, pol, chi)
