@@ -7,17 +7,24 @@ on the synthetic C3 configuration (L=64, d=4, chi=512, MPO bond w=8), i.e. the r
 stack of SURVEY.md section 3.1: 2 operand canonicalisations + (L-2) zip steps + final block +
 final truncation sweep.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c1|c2|c4|c5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A single sweep is sequential over sites (replicas only): with N > 1 every rank runs an
-independent TT of the same shape (the batch-of-independent-TTs sharding of the north star, weak
-scaling), and NCCL is used only to take the max time and gather the result norms.
+A single sweep is sequential over sites (replicas only): with N > 1 every rank runs an independent TT of the
+same shape (the batch-of-independent-TTs sharding of the north star, weak scaling) - that is `value`.  What
+shards naturally is the patch set of a partitioned network: every run (all N) ALSO executes the C5 workload
+(256 patches, adaptive truncation, strong scaling over the N ranks through the C-ABI sharded driver: NCCL
+all-reduce of the patch norms, NCCL gather of the retained cores to rank 0) and reports it as the `c5`
+sub-record of the same JSON line.
 
-`value` is measured with the operands already resident in HBM; `e2e` is the same sweep through
-the C ABI from pinned HOST buffers with the H2D upload of both operands and the D2H download of
-the result inside the timed region.  `--impl reference` times the CPU restatement of the
-reference algorithm (oracle/, NumPy + LAPACK/BLAS on the host cores) on a bounded sample.
+`value` is measured with the operands already resident in HBM; `e2e` is the same sweep through the C ABI from
+pinned HOST buffers with the H2D upload of both operands and the D2H download of the result inside the timed
+region.  `--impl reference` times the CPU restatement of the reference algorithm (oracle/, NumPy + LAPACK/BLAS on
+the host cores): each step is a bounded sample - the genuine oracle calls of ONE bulk site (zip step, two two-site
+truncation steps, two QR + absorb steps at the true shapes) - and the sweep time is assembled from the measured
+boundary (a genuine oracle sweep of the 10 boundary sites, L'=10) plus (L-10) x the bulk-site sample; the JSON says
+`"extrapolated": true` and carries the one full oracle sweep measured on the build container
+(tests/golden/c3_full_oracle.npz: wall_s, threads).  `--impl reference --full` runs the genuine full sweep.
 """
 from __future__ import annotations
 
@@ -66,6 +73,79 @@ def make_c3(seed, L, d, chi, w):
             shape.append(w); ids.append(2000 + i)
         mpo.append(np.asfortranarray(rng.standard_normal(shape) / np.sqrt(w * d))); mpo_ids.append(ids)
     return mps, mps_ids, mpo, mpo_ids
+
+
+def make_c5_patch(idx, L, d, chi):
+    """Patch `idx` of the C5 partition: a QTT over the L free binary sites with bond cap chi and a
+    geometric decay along every bond so that the adaptive cutoff actually truncates."""
+    rng = np.random.default_rng(0x5EED0005 + idx)
+    bd = bond_dims(L, d, chi)
+    arrays, ids = [], []
+    for i in range(L):
+        shape, sid = [], []
+        if i > 0:
+            shape.append(bd[i - 1]); sid.append(1000 + i - 1)
+        shape.append(d); sid.append(100 + i)
+        if i < L - 1:
+            shape.append(bd[i]); sid.append(1000 + i)
+        a = rng.standard_normal(shape)
+        if i < L - 1:
+            a = a * (0.9 ** np.arange(bd[i]))[(None,) * (len(shape) - 1) + (slice(None),)]
+        arrays.append(np.asfortranarray(a / np.sqrt(max(shape)))); ids.append(sid)
+    return arrays, ids
+
+
+def c5_chis(n):
+    prng = np.random.default_rng(0x5EED0005)
+    return [int(prng.choice([64, 96, 128, 192, 256])) for _ in range(n)]
+
+
+# ---- algorithmic work of one C3 sweep (SURVEY 8d formulas on the true per-site shapes) -------------------------------
+def c3_model(L, d, chi, w):
+    """Contraction flops (2 M N K per tensordot) and LAPACK-model factorisation flops / algorithmic bytes of the
+    REFERENCE schedule (full two-site SVDs), summed over the true per-site shapes."""
+    bd = bond_dims(L, d, chi)
+    svd_fl = lambda m, n: 4.0 * max(m, n) * min(m, n) ** 2 + 22.0 * min(m, n) ** 3
+    qr_fl = lambda m, n: 2.0 * (2.0 * m * n * n - 2.0 / 3.0 * n ** 3) if m >= n else 2.0 * (2.0 * n * m * m - 2.0 / 3.0 * m ** 3)
+    svd_by = lambda m, n: 8.0 * (m * n + m * min(m, n) + min(m, n) + min(m, n) * n)
+    con = fac = byt = back = 0.0
+    nsvd = nqr = 0
+    # operand canonicalisation towards site L-1 (MPS; the MPO's are tiny) and absorb-R
+    for i in range(L - 1):
+        m, n = (bd[i - 1] if i > 0 else 1) * d, bd[i]
+        fac += qr_fl(m, n); byt += 8.0 * (m * n + m * min(m, n) + min(m, n) * n); nqr += 1
+        k = min(m, n)
+        con += 2.0 * k * n * (d * (bd[i + 1] if i + 1 < L - 1 else 1))
+    # zip-up from site L-1 down to 2, then the (1, 0) block
+    nprev = 1
+    res_b = [0] * (L - 1)
+    for s in range(L - 1, 1, -1):
+        ca = bd[s - 1]                                   # MPS bond towards the next site
+        cr = bd[s] if s < L - 1 else 1                   # MPS bond towards the processed side
+        wr = w if s < L - 1 else 1
+        con += 2.0 * (nprev * wr) * cr * (d * ca) + 2.0 * (nprev * ca) * (wr * d) * (d * w)
+        m, n = nprev * d, ca * w
+        fac += svd_fl(m, n); byt += svd_by(m, n); nsvd += 1
+        nprev = min(min(m, n), chi)
+        back += 2.0 * nprev * m * n                      # S Vh = U^H M (a diagonal scaling in the reference)
+        res_b[s - 1] = nprev
+    m, n = nprev * d, d
+    fac += svd_fl(m, n); byt += svd_by(m, n); nsvd += 1
+    res_b[0] = min(m, n, chi)
+    # final truncation sweep on the result: canonicalise towards 0, then 2 (L-1) two-site steps
+    for i in range(L - 1, 0, -1):
+        m, n = (res_b[i] if i < L - 1 else 1) * d, res_b[i - 1]
+        fac += qr_fl(m, n); nqr += 1
+        con += 2.0 * min(m, n) * n * (d * (res_b[i - 2] if i >= 2 else 1))
+    for rep in range(2):
+        for e in range(L - 1):
+            m = (res_b[e - 1] if e > 0 else 1) * d
+            n = d * (res_b[e + 1] if e + 1 < L - 1 else 1)
+            con += 2.0 * m * res_b[e] * n
+            fac += svd_fl(m, n); byt += svd_by(m, n); nsvd += 1
+            back += 2.0 * min(m, n, chi) * m * n
+    return {"contraction_flops": con, "backmultiply_flops": back, "factorization_model_flops": fac, "factorization_algorithmic_bytes": byt,
+            "n_svd": nsvd, "n_qr": nqr}
 
 
 # ---- clocks ---------------------------------------------------------------------------------------
@@ -117,38 +197,6 @@ class ClockSampler:
 
 
 # ---- reference arm / cpu baseline (oracle on host cores) -----------------------------------------
-def cpu_sample(L, d, chi, w, seed=0x5EED0003):
-    """Bounded sample of the CPU restatement: one bulk zip-up step, one bulk two-site truncation
-    step and one bulk canonicalisation step at full chi, scaled by the step counts of one sweep."""
-    import scipy.linalg as sla
-    rng = np.random.default_rng(seed)
-    n = chi
-    R = rng.standard_normal((n, chi, w))
-    A = rng.standard_normal((chi, d, chi))
-    B = rng.standard_normal((w, d, d, w))
-    t0 = time.perf_counter()
-    RA = np.tensordot(R, A, axes=([1], [0]))                      # [n, w, d, chi']
-    M = np.tensordot(RA, B, axes=([1, 2], [0, 2]))                # [n, chi', d_out, w']
-    M = np.transpose(M, (0, 2, 1, 3)).reshape(n * d, chi * w, order="F")
-    u, s, vh = sla.svd(M, full_matrices=False, lapack_driver="gesdd")
-    left, right = u[:, :chi], s[:chi, None] * vh[:chi]
-    t_zip = time.perf_counter() - t0
-    A2 = rng.standard_normal((chi, d, chi))
-    t0 = time.perf_counter()
-    AB = np.tensordot(A, A2, axes=([2], [0])).reshape(chi * d, d * chi, order="F")
-    u, s, vh = sla.svd(AB, full_matrices=False, lapack_driver="gesdd")
-    left, right = u[:, :chi], s[:chi, None] * vh[:chi]
-    t_two = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    q, r = sla.qr(A.reshape(chi * d, chi, order="F"), mode="economic")
-    nxt = np.tensordot(r, A2, axes=([1], [0]))
-    t_qr = time.perf_counter() - t0
-    # one sweep: (L-2) zip steps + final block (~ one zip step), 2(L-1) two-site steps,
-    # (L-1) QR+absorb for the MPS operand, (L-1) for the result's centre move (MPO QRs are tiny)
-    sweep = (L - 1) * t_zip + 2 * (L - 1) * t_two + 2 * (L - 1) * t_qr
-    return {"sweep_s": sweep, "t_zip": t_zip, "t_two_site": t_two, "t_qr": t_qr}
-
-
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
     try:
@@ -168,25 +216,104 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def _to_oracle_chain(arrays, ids):
+    from oracle import treetn as otn
+    return otn.Chain([otn.LT(a, [("x", i) for i in sid]) for a, sid in zip(arrays, ids)])
+
+
+def oracle_full_sweep(L, d, chi, w, seed=0x5EED0003):
+    """The genuine thing: oracle.treetn.contract_zipup on the bench inputs.  Returns seconds."""
+    from oracle import treetn as otn
+    from oracle.truncation import SvdTruncationPolicy
+    mps, mi, mpo, oi = make_c3(seed, L, d, chi, w)
+    t0 = time.perf_counter()
+    otn.contract_zipup(_to_oracle_chain(mps, mi), _to_oracle_chain(mpo, oi), 0, SvdTruncationPolicy(0.0), chi)
+    return time.perf_counter() - t0
+
+
+def oracle_bulk_site(d, chi, w, seed):
+    """The oracle calls one BULK site of the sweep costs, at the true shapes, through the oracle's own functions
+    (same code path as the full sweep): one zip-up step (3-tensor contract + truncated SVD of (chi d) x (chi w)),
+    two two-site truncation steps (contract + SVD of (chi d) x (d chi), the reference takes no isometry shortcut),
+    the QR + absorb of the operand canonicalisation and of the result canonicalisation.  Returns seconds."""
+    from oracle import treetn as otn
+    from oracle.truncation import SvdTruncationPolicy
+    rng = np.random.default_rng(seed)
+    pol = SvdTruncationPolicy(0.0)
+    rem = otn.LT(rng.standard_normal((chi, chi, w)), ["n", "ra", "rb"])
+    a = otn.LT(rng.standard_normal((chi, d, chi)), ["la", "s", "ra"])
+    b = otn.LT(rng.standard_normal((w, d, d, w)), ["lb", "t", "s", "rb"])
+    au = otn.LT(rng.standard_normal((chi, d, chi)), ["l", "su", "m"])
+    av = otn.LT(rng.standard_normal((chi, d, chi)), ["m", "sv", "r"])
+    t0 = time.perf_counter()
+    contracted = otn.contract([rem, a, b])
+    otn.factorize_svd(contracted, ["n", "t"], "left", pol, chi)
+    for _ in range(2):
+        ab = otn.contract([au, av])
+        otn.factorize_svd(ab, ["l", "su"], "left", pol, chi)
+    for _ in range(2):
+        q, r, nb = otn.factorize_qr(au, ["l", "su"], truncate=False)
+        otn.contract([av, r])
+    return time.perf_counter() - t0
+
+
+_BOUNDARY_CACHE = {}
+
+
+def oracle_boundary(d, chi, w):
+    """Genuine oracle sweep of the boundary: the L' = 2 ceil(log_d chi) + ... sites whose bonds are below chi.  For
+    d=4, chi=512 that is L'=10, whose 10 sites have exactly the shapes of sites 0-4 and 59-63 of the L=64 chain."""
+    lb = 2
+    while bond_dims(lb, d, chi)[lb // 2 - 1] < chi:
+        lb += 2
+    key = (lb, d, chi, w)
+    if key not in _BOUNDARY_CACHE:
+        _BOUNDARY_CACHE[key] = oracle_full_sweep(lb, d, chi, w)
+    return lb, _BOUNDARY_CACHE[key]
+
+
+def golden_full_sweep_record():
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "c3_full_oracle.npz"))
+        return {"seconds": float(g["wall_s"]), "threads": int(g["threads"]),
+                "where": "build container (no GPU), tests/golden/make_c3_golden.py, L=64 d=4 chi=512 w=8"}
+    except Exception:
+        return None
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     L, d, chi, w = args.L, args.d, args.chi, args.w
     use_all_host_threads()
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(L, d, min(chi, 64), w)
-    samples = [cpu_sample(L, d, chi, w, seed=0x5EED0003 + i) for i in range(max(1, min(args.steps, 2)))]
-    sweep_s = statistics.median([s["sweep_s"] for s in samples])
+    cores = host_threads()
+    if args.full:
+        for _ in range(args.warmup):
+            oracle_full_sweep(min(L, 8), d, min(chi, 64), w)
+        times = [oracle_full_sweep(L, d, chi, w) for _ in range(args.steps)]
+        sweep_s = statistics.median(times)
+        extrap = False
+        sample = f"{args.steps} genuine full oracle sweep(s) (oracle.treetn.contract_zipup on the bench inputs)"
+        detail = {"sweep_seconds": times}
+    else:
+        lb, t_boundary = oracle_boundary(d, chi, w)      # measured once (cached): part of the warm-up
+        for i in range(args.warmup):
+            oracle_bulk_site(d, min(chi, 64), w, 7 + i)
+        bulk = [oracle_bulk_site(d, chi, w, 0x5EED0003 + i) for i in range(args.steps)]
+        t_bulk = statistics.median(bulk)
+        sweep_s = t_boundary + (L - lb) * t_bulk if L > lb else oracle_full_sweep(L, d, chi, w)
+        extrap = True
+        sample = (f"per step: the genuine oracle calls of ONE bulk site at the true shapes (zip step gesdd {chi*d}x{chi*w}, "
+                  f"2 two-site steps gesdd {chi*d}x{chi*d}, 2 QR+absorb {chi*d}x{chi}); boundary = genuine oracle sweep of the "
+                  f"{lb} boundary sites (L'={lb}, {t_boundary:.2f} s, measured once); sweep = boundary + {L - lb} x median bulk site")
+        detail = {"bulk_site_seconds": bulk, "boundary_seconds": t_boundary, "boundary_sites": lb}
     val = 1.0 / sweep_s
-    sample = (f"1 bulk zip step (contract + gesdd {chi*d}x{chi*w}), 1 bulk two-site step (gesdd {chi*d}x{chi*d}), "
-              f"1 QR+absorb step ({chi*d}x{chi}) at full chi, scaled by the per-sweep step counts "
-              f"({args.L-1} / {2*(args.L-1)} / {2*(args.L-1)})")
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sweep_s, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                             "sample": sample},
+            "extrapolated": extrap, "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "extrapolated": extrap, "full_sweep_measured": golden_full_sweep_record(), **detail},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -197,7 +324,238 @@ def workload_config(args):
                         f"f64, center=0, max_bond_dim={args.chi}, SvdTruncationPolicy(0.0) (cap-only)",
             "L": args.L, "d": args.d, "chi": args.chi, "w": args.w,
             "l2_policy": "operands (MPS 0.5 GB at chi=512) and SVD work buffers exceed the 126 MB L2",
-            "parallelism": "independent TT replica per GPU (a single sweep is sequential)"}
+            "parallelism": "independent TT replica per GPU (a single sweep is sequential); the c5 sub-record is the "
+                           "patch-sharded strong-scaling workload"}
+
+
+# ---- helpers of our arm -----------------------------------------------------------------------------
+class Env:
+    pass
+
+
+def profile(ctx, fn):
+    """Per-kernel-class CUDA-event profile of fn() (t4b_ctx_profile_*): {class: {launches, ms, work}}."""
+    import ctypes as C
+    import t4b
+    t4b._check(t4b.lib().t4b_ctx_profile_begin(ctx.h))
+    fn()
+    need = C.c_size_t()
+    t4b._check(t4b.lib().t4b_ctx_profile_end(ctx.h, None, C.c_size_t(0), C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    t4b._check(t4b.lib().t4b_ctx_profile_end(ctx.h, buf, need, None))
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        nm, n, tms, work = ln.split()
+        prof[nm] = {"launches": int(n), "ms": float(tms), "work": float(work)}
+    return prof
+
+
+def peaks():
+    pk = {}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(pk.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in pk else "fallback 6650 GB/s (B200_PROFILING.md)"
+    f64, f64_src = 37.04, ("DMMA.8x8x4 issue peak measured on this pool by tools/peak_f64.cu (profiles/peak_f64_r01.json); "
+                           "MEASURED_PEAKS.json carries no FP64 figure")
+    try:
+        f64 = float(json.load(open(os.path.join(ROOT, "profiles", "peak_f64_r01.json")))["dmma_tflops_w8"])
+    except Exception:
+        f64_src = "fallback 37.04 TFLOP/s (DMMA issue peak measured in round 1)"
+    return hbm, hbm_src, f64, f64_src
+
+
+def ncu_capture(name):
+    """Per-launch DRAM bytes / DMMA % of the committed ncu --set full capture of a kernel (profiles/ncu_summary_*.json)."""
+    try:
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("ncu_summary_"))
+        for f in reversed(cands):
+            d = json.load(open(os.path.join(ROOT, "profiles", f)))
+            if name in d and d[name]:
+                return d[name][0], f
+    except Exception:
+        pass
+    return None, None
+
+
+# ---- C5: patch-sharded adaptive truncation (strong scaling) ------------------------------------------
+def run_c5(env, n=256, L=24, d=2, reps=2, cutoff=1e-10, max_bond=64):
+    import torch
+    from t4b import patches as tp
+    from t4b import tt as t4tt
+    ctx, rank, world, stream = env.ctx, env.rank, env.world, env.stream
+    chis = c5_chis(n)
+    bd = np.array([bond_dims(L, d, chis[k]) for k in range(n)], dtype=np.int64)
+    owner, costs = tp.lpt_assign_cabi(bd, d, world)
+    volumes = [d ** L] * n
+    mine_raw = {k: make_c5_patch(k, L, d, chis[k]) for k in range(n) if owner[k] == rank}
+    comm = tp.NcclComm(ctx, rank, world, env.dist) if world > 1 else None
+    times, phase, res = [], None, None
+    for rep in range(reps + 1):
+        mine = {k: t4tt.chain_from_arrays(ctx, a, ids) for k, (a, ids) in mine_raw.items()}
+        env.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = tp.truncate_adaptive_sharded(ctx, comm, rank, world, owner, mine, volumes, 0, cutoff, max_bond,
+                                           gather_root=0, nbonds=L - 1)
+        e1.record(stream)
+        env.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1), *res["timing_ms"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            env.dist.all_reduce(ms, op=env.dist.ReduceOp.MAX)
+        if rep > 0:
+            times.append(float(ms[0]))
+            phase = [float(x) for x in ms[1:]]
+        gathered_norm = 0.0
+        if rank == 0:
+            for k in range(n):
+                if res["keep"][k]:
+                    t = mine[k] if k in mine else res["gathered"][k]
+                    gathered_norm += t.norm_sqr()
+        for t in res["gathered"].values():
+            t.release()
+        for t in mine.values():
+            t.release()
+    if comm is not None:
+        comm.close()
+    gb = torch.tensor([float(res["gather_bytes"])], device="cuda", dtype=torch.float64)
+    if world > 1:
+        env.dist.all_reduce(gb, op=env.dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    best = min(times)
+    loads = [float(sum(c for c, o in zip(costs, owner) if o == r)) for r in range(world)]
+    return {"metric": "C5: adaptive truncation of a 256-patch partitioned 2-D QTT, patches/s", "value": n / (best * 1e-3),
+            "unit": "patches/s", "n_gpus": world, "ms": best, "scaling": "strong", "patches": n, "free_sites": L,
+            "cutoff": cutoff, "max_bond_dim": max_bond,
+            "phase_ms": {"stats_allreduce_and_tables": phase[0], "truncate": phase[1], "gather_to_rank0": phase[2]},
+            "gather_bytes_rank0": float(gb[0]), "kept": int(np.sum(res["keep"])),
+            "max_bond_after": int(res["bond_dims"].max()),
+            "checksum_norm": float(np.sum(res["norm_after"])), "checksum_gathered_norm": gathered_norm,
+            "load_imbalance": max(loads) / (sum(loads) / world),
+            "collectives": "ncclAllReduce(n norms) + ncclAllReduce(result table) + grouped ncclSend/ncclRecv of the retained "
+                           "cores to rank 0, issued by t4b_patches_truncate_adaptive_sharded (C ABI)"}
+
+
+# ---- C4: prrLU on the TCI2 candidate matrix ------------------------------------------------------------
+def c4_pi(m, n, seed=1):
+    """Pi(i, j) of an oscillatory 3-D integrand sampled on random multi-indices: smooth oscillatory kernel whose
+    numerical rank decays slowly enough that 300 pivots are taken."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((m, 3)); y = rng.random((n, 3))
+    r2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    return np.asfortranarray(np.cos(40.0 * np.sqrt(r2)) * np.exp(-r2) + 1e-6 * rng.standard_normal((m, n)))
+
+
+def run_c4(env, steps, warmup):
+    import torch
+    from t4b import tt as t4tt
+    ctx, stream = env.ctx, env.stream
+    hbm, hbm_src, _, _ = peaks()
+    out = []
+    for (m, n, cap) in [(600, 600, 300), (2400, 2400, 300)]:
+        a = ctx.upload(c4_pi(m, n))
+        for _ in range(warmup):
+            t4tt.LU(ctx, a, cap, 1e-8, 0.0, True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            lu = t4tt.LU(ctx, a, cap, 1e-8, 0.0, True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        r = lu.rank
+        byt = sum(16.0 * (m - k) * (n - k) for k in range(r))
+        flo = sum(3.0 * (m - k) * (n - k) for k in range(r))
+        out.append({"shape": [m, n], "rank": r, "ms": ms, "algorithmic_bytes": byt, "algorithmic_flops": flo,
+                    "roofline": {"bound": "hbm", "achieved": byt / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                 "frac": byt / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": hbm_src,
+                                 "note": "HBM-equivalent rate of the trailing-block read+write model; the working set "
+                                         f"({8 * m * n / 1e6:.1f} MB) is L2 resident"},
+                    "gflops": flo / (ms * 1e-3) / 1e9})
+    return out
+
+
+# ---- C1: simplett compress -------------------------------------------------------------------------------
+def run_c1(env, steps, warmup, batch=64):
+    import torch
+    from t4b import tt as t4tt
+    ctx, stream = env.ctx, env.stream
+    L, d, chi = 20, 2, 64
+    rng = np.random.default_rng(0x5EED0001)
+    bd = bond_dims(L, d, chi)
+    arrays = [np.asfortranarray(rng.standard_normal(((bd[i - 1] if i else 1), d, (bd[i] if i < L - 1 else 1)))) for i in range(L)]
+
+    def one():
+        tt = t4tt.Train.from_arrays(ctx, arrays)
+        tt.compress(2, 1e-12, 32, True)
+        tt.release()
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps * batch):
+        one()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (steps * batch)
+    return {"workload": "C1: SimpleTensorTrain L=20 d=2 chi=64 -> SVD compress, max_bond_dim=32, tol 1e-12",
+            "ms_per_compress": ms, "compress_per_s": 1e3 / ms, "independent_tts_timed": steps * batch,
+            "note": "38 factorisations of <= 128x64 per compress, issued one after the other (latency bound)"}
+
+
+# ---- C2: Fourier MPO applied to a complex QTT ----------------------------------------------------------------
+def run_c2(env, steps, warmup):
+    import torch
+    from t4b import tt as t4tt
+    ctx, stream = env.ctx, env.stream
+    R, chi = 40, 256
+    op = t4tt.Train.fourier_mpo(ctx, R)                 # built on the device side (t4b_fourier_mpo)
+    sites = op.arrays()
+    arrays, ids = [], []
+    for i, s in enumerate(sites):
+        l, _, r = s.shape
+        t = np.transpose(s.reshape(l, 2, 2, r, order="F"), (0, 2, 1, 3))   # [l, tau(out), sigma(in), r] -> [l, out, in, r]
+        sid = [2000 + i - 1, 200 + i, 100 + i, 2000 + i]
+        if i == 0:
+            t, sid = t[0], sid[1:]
+        if i == R - 1:
+            t, sid = t[..., 0], sid[:-1]
+        arrays.append(np.asfortranarray(t)); ids.append(sid)
+    rng = np.random.default_rng(0x5EED0002)
+    bd = bond_dims(R, 2, chi)
+    mps, mids = [], []
+    for i in range(R):
+        shape, sid = [], []
+        if i > 0:
+            shape.append(bd[i - 1]); sid.append(1000 + i - 1)
+        shape.append(2); sid.append(100 + i)
+        if i < R - 1:
+            shape.append(bd[i]); sid.append(1000 + i)
+        mps.append(np.asfortranarray((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2 * max(shape))))
+        mids.append(sid)
+    a = t4tt.chain_from_arrays(ctx, mps, mids)
+    b = t4tt.chain_from_arrays(ctx, arrays, ids)
+    pol = t4tt.SvdPolicy(1e-12)
+    for _ in range(warmup):
+        a.contract(b, 0, 0, pol, chi).release()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        out = a.contract(b, 0, 0, pol, chi)
+        nb = max(out.bond_dims())
+        out.release()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "C2: quantics Fourier MPO (R=40, bond <= 12) applied to a Complex64 QTT (chi <= 256) by zip-up, "
+                        "max_bond_dim 256, SvdTruncationPolicy(1e-12)", "ms_per_apply": ms, "applies_per_s": 1e3 / ms,
+            "max_bond_out": nb, "mpo_bonds": [int(s.shape[2]) for s in sites[:-1]][:6]}
 
 
 # ---- our arm ------------------------------------------------------------------------------------------
@@ -207,11 +565,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4", "c5"])
+    ap.add_argument("--full", action="store_true", help="reference arm: genuine full oracle sweeps instead of the sample")
     ap.add_argument("--L", type=int, default=64)
     ap.add_argument("--d", type=int, default=4)
     ap.add_argument("--chi", type=int, default=512)
     ap.add_argument("--w", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -238,6 +599,25 @@ def main():
     stream = torch.cuda.Stream()
     ctx = t4b.Context(local_rank, stream.cuda_stream)
 
+    env = Env()
+    env.ctx, env.rank, env.world, env.stream, env.dist, env.local_rank = ctx, rank, world, stream, dist, local_rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    env.barrier = barrier
+
+    if args.workload != "c3":
+        rec = {"c1": lambda: run_c1(env, args.steps, args.warmup), "c2": lambda: run_c2(env, args.steps, args.warmup),
+               "c4": lambda: run_c4(env, args.steps, args.warmup), "c5": lambda: run_c5(env)}[args.workload]()
+        if rank == 0:
+            print(json.dumps({"workload": args.workload, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                              "data": "synthetic", "record": rec}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     L, d, chi, w = args.L, args.d, args.chi, args.w
     mps, mps_ids, mpo, mpo_ids = make_c3(0x5EED0003 + rank, L, d, chi, w)
     policy = t4tt.SvdPolicy(0.0)
@@ -258,13 +638,7 @@ def main():
     b_dev = t4tt.chain_from_arrays(ctx, mpo, mpo_ids)
 
     def sweep_resident():
-        out = a_dev.contract(b_dev, 0, 0, policy, chi)
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        return a_dev.contract(b_dev, 0, 0, policy, chi)
 
     for _ in range(args.warmup):
         sweep_resident().release()
@@ -289,7 +663,6 @@ def main():
     bonds = last.bond_dims()
 
     # ---- e2e: host buffers in, host buffers out ----------------------------------------------------
-    # pinned result buffers (the shapes of the result are fixed by the cap-only truncation)
     out_pin = []
     for i in range(L):
         shp, _ = last.site_shape(i)
@@ -320,18 +693,17 @@ def main():
     ms_e2e = e2.elapsed_time(e3)
 
     # ---- per-kernel profile of one extra sweep (roofline) ------------------------------------------
-    t4b._check(t4b.lib().t4b_ctx_profile_begin(ctx.h))
-    sweep_resident().release()
-    import ctypes as C
-    need = C.c_size_t()
-    t4b._check(t4b.lib().t4b_ctx_profile_end(ctx.h, None, C.c_size_t(0), C.byref(need)))
-    buf = C.create_string_buffer(need.value)
-    t4b._check(t4b.lib().t4b_ctx_profile_end(ctx.h, buf, need, None))
-    prof = {}
-    for ln in buf.value.decode().splitlines():
-        nm, n, tms, work = ln.split()
-        prof[nm] = {"launches": int(n), "ms": float(tms), "work": float(work)}
+    prof = profile(ctx, lambda: sweep_resident().release())
+    l2b = prof.pop("jacobi_l2_bytes", None)
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+
+    # ---- C5 sub-record (strong scaling over the same ranks) ----------------------------------------
+    c5 = None
+    if not args.no_c5:
+        try:
+            c5 = run_c5(env)
+        except Exception as e:   # a failure here must not void the headline line, but it must be visible
+            c5 = {"error": repr(e)}
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
@@ -347,44 +719,47 @@ def main():
         norm_list = [norm2]
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        f64_peak, f64_src = 37.04, "measured DMMA.8x8x4 issue peak on this pool (profiles/peak_f64_r01.json)"
-        try:
-            pk = json.load(open(os.path.join(ROOT, "profiles", "peak_f64_r01.json")))
-            f64_peak = float(pk["dmma_tflops_w8"])
-        except Exception:
-            f64_src = "fallback 37.04 TFLOP/s (DMMA issue peak measured round 1)"
+        hbm_peak, hbm_src, f64_peak, f64_src = peaks()
+        model = c3_model(L, d, chi, w)
         dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
         roof = None
         if dom:
             p = prof[dom]
-            if dom == "gemm":
-                ach = p["work"] / (p["ms"] * 1e-3) / 1e12
-                roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
-                        "frac": ach / f64_peak, "traffic": None, "peak_source": f64_src}
+            per_launch_s = p["ms"] * 1e-3 / max(p["launches"], 1)
+            if dom in ("jacobi", "gemm", "gemm_factor"):
+                # tensor bound: executed FP64 tensor-pipe flops per launch / average launch duration
+                ach = p["work"] / max(p["launches"], 1) / per_launch_s / 1e12
+                roof = {"kernel": "jacobi_persistent_kernel" if dom == "jacobi" else dom, "bound": "tensor",
+                        "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach / f64_peak, "traffic": None,
+                        "peak_source": f64_src,
+                        "flops_definition": "DMMA flops EXECUTED by the launch, counted on the device (sweep count and skipped "
+                                            "updates are data dependent): per visited pair 2*rows*16*16 cross-Gram (32*32 in "
+                                            "round 0) + 2*rows*32*32 update when the pair is rotated"}
             else:
-                ach = p["work"] / (p["ms"] * 1e-3) / 1e9
+                ach = p["work"] / max(p["launches"], 1) / per_launch_s / 1e9
                 roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                         "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src}
-            # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
-            try:
-                cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("ncu_summary_"))
-                ncu = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
-                if dom == "jacobi":
-                    cap = ncu["jacobi_2048"][0]
+            if dom == "jacobi":
+                cap, capfile = ncu_capture("jacobi_2048")
+                if cap:
                     roof["traffic"] = cap["dram_bytes"]
-                    roof["traffic_note"] = ("dram__bytes_read+write of one jacobi_persistent_kernel launch on the 2048x2048 "
-                                            "zip-up factor (profiles/ncu_jacobi_2048_*.csv): the panel is L2-resident, "
-                                            "DRAM sees the matrix once while the algorithmic (L2) traffic of that launch is "
-                                            "~100 GB; DMMA pipe %.1f%% busy" % cap["fp64_tensor_pct"])
-            except Exception:
-                pass
+                    roof["traffic_note"] = (f"dram__bytes_read+write of one launch on the 2048x2048 zip-up factor ({capfile}); the "
+                                            "SVD's algorithmic bytes 8(mn+mk+k+kn) for the 2048x4096 zip-up matrix are 134 MB, the "
+                                            "Jacobi launch itself touches the 33.5 MB factor once in DRAM (ratio 1.1) and "
+                                            "re-reads it from L2 every round")
+                    roof["ncu_fp64_tensor_pipe_pct"] = cap.get("fp64_tensor_pct")
+                if l2b:
+                    roof["l2_panel_bytes_per_launch"] = l2b["work"] / max(p["launches"], 1)
+                # whole-factorisation view: LAPACK-model flops of the reference schedule / time spent factorising
+                fac_ms = sum(prof[k]["ms"] for k in prof if k.startswith(("jacobi", "qr_", "svd_", "gemm_factor")))
+                roof["factorization_model"] = {"model_flops_per_sweep": model["factorization_model_flops"],
+                                               "algorithmic_bytes_per_sweep": model["factorization_algorithmic_bytes"],
+                                               "ms_per_sweep": fac_ms,
+                                               "model_tflops": model["factorization_model_flops"] / (fac_ms * 1e-3) / 1e12,
+                                               "hbm_equiv_gbs": model["factorization_algorithmic_bytes"] / (fac_ms * 1e-3) / 1e9,
+                                               "hbm_frac": model["factorization_algorithmic_bytes"] / (fac_ms * 1e-3) / 1e9 / hbm_peak,
+                                               "note": "gesdd-class model (4 max k^2 + 22 k^3 per SVD, 2(2mn^2 - 2n^3/3) per QR with Q) on the "
+                                                       "reference's shapes; the factorisations are compute/latency bound, not HBM bound"}
             roof["share_of_step"] = p["ms"] / tot_ms
             roof["launches_per_step"] = p["launches"]
             roof["avg_launch_us"] = 1e3 * p["ms"] / max(p["launches"], 1)
@@ -395,6 +770,7 @@ def main():
             roof_gemm = {"kernel": "gemm (DMMA tensordot, all contractions of the sweep)", "bound": "tensor",
                          "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach / f64_peak,
                          "share_of_step": g["ms"] / tot_ms, "launches_per_step": g["launches"],
+                         "algorithmic_flops_per_sweep": g["work"], "model_flops_per_sweep": model["contraction_flops"],
                          "peak_source": f64_src}
         value = world * args.steps / (ms * 1e-3)
         e2e_val = world * args.steps / (ms_e2e * 1e-3)
@@ -409,14 +785,19 @@ def main():
                 "kernel_profile_note": "per-kernel CUDA-event times of one extra sweep; the QR look-ahead (factor of panel "
                                        "p+1 on a side stream) is serialised while profiling, so qr_* sum to more than they "
                                        "cost in the timed region",
-                "result": {"norm_sqr": norm_list, "max_bond": max(bonds) if bonds else 1}}
+                "result": {"norm_sqr": norm_list, "max_bond": max(bonds) if bonds else 1},
+                "c5": c5}
         if not args.no_cpu_baseline:
             use_all_host_threads()
-            cs = cpu_sample(L, d, chi, w)
-            line["cpu_baseline"] = {"value": 1.0 / cs["sweep_s"], "unit": UNIT, "cores": host_threads(),
-                                    "kind": "port",
-                                    "sample": f"1 bulk zip step ({cs['t_zip']:.2f} s), 1 two-site step ({cs['t_two_site']:.2f} s), "
-                                              f"1 QR+absorb step ({cs['t_qr']:.2f} s) at full chi, scaled to one sweep"}
+            lb, t_boundary = oracle_boundary(d, chi, w)
+            t_bulk = oracle_bulk_site(d, chi, w, 0x5EED0003)
+            sweep_s = t_boundary + (L - lb) * t_bulk if L > lb else t_boundary
+            line["cpu_baseline"] = {"value": 1.0 / sweep_s, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                                    "extrapolated": True,
+                                    "sample": f"genuine oracle sweep of the {lb} boundary sites ({t_boundary:.2f} s) + {L - lb} x one "
+                                              f"bulk site through the oracle's own functions at the true shapes ({t_bulk:.2f} s: zip step, "
+                                              "2 full two-site SVDs, 2 QR+absorb)",
+                                    "full_sweep_measured": golden_full_sweep_record()}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -275,6 +275,31 @@ int t4b_patches_truncate_adaptive(t4b_ctx* ctx, int64_t n, t4b_tn* const* patche
                                   const uint64_t* volume, int center, double cutoff,
                                   int64_t max_bond_dim, int32_t* keep_out);
 
+/* Sharded form (one process per GPU; the north star's multi-GPU unit).  `nccl_comm` is an ncclComm_t of `nranks` ranks
+ * whose rank `rank` runs on this context's device; libt4b resolves NCCL with dlopen (the copy already loaded into the
+ * process wins), so it can be created either by the host (ncclCommInitRank) or with the two helpers below (rank 0 calls
+ * t4b_nccl_unique_id and ships the 128 bytes to the other ranks out of band).  owner[i] is the rank that holds patch i
+ * (patches[i] may be NULL elsewhere); every array argument is identical on all ranks.  Collectives: one ncclAllReduce
+ * of the per-patch norm^2 vector (exactly one non-zero contributor per entry: exact, so t4b_adaptive_cutoffs yields
+ * bit-identical cutoffs everywhere - the reference's sequential sum, patching.rs:883-897,930), one ncclAllReduce of
+ * the result table, and - when gather_root >= 0 - grouped ncclSend/ncclRecv of the retained cores to that rank
+ * (patching.rs:697-712 collects them into one PartitionedTreeTN).  gathered_out[i] (root only) receives a NEW handle
+ * for every retained patch the root did not own.  timing_ms_out[3] = host wall time of (statistics + tables,
+ * truncation, gather); bond_dims_out is n x nbonds (row-major, zero padded). */
+int t4b_nccl_unique_id(void* id_out_128);
+int t4b_nccl_comm_create(t4b_ctx* ctx, const void* id_128, int rank, int nranks, void** comm_out);
+int t4b_nccl_comm_destroy(void* comm);
+/* Longest-processing-time assignment on the SVD-cost estimate sum_bonds (chi_l d) chi_r min(chi_l d, chi_r); host
+ * only, deterministic.  bond_dims is n x nbonds (row-major). */
+int t4b_patches_lpt_assign(int64_t n, const int64_t* bond_dims, int64_t nbonds, int64_t site_dim, int nranks,
+                           int32_t* owner_out, double* cost_out);
+int t4b_patches_truncate_adaptive_sharded(t4b_ctx* ctx, void* nccl_comm, int rank, int nranks, int64_t n,
+                                          const int32_t* owner, t4b_tn* const* patches, const uint64_t* volume,
+                                          int center, double cutoff, int64_t max_bond_dim, int gather_root,
+                                          int32_t* keep_out, double* norm_sqr_before_out, double* norm_sqr_after_out,
+                                          int64_t* bond_dims_out, int64_t nbonds, t4b_tn** gathered_out,
+                                          double* timing_ms_out, int64_t* gather_bytes_out);
+
 /* ---- positional tensor trains / MPOs (tensor4all-simplett) ----------------------------------
  * rank 3: sites [left, site, right]; rank 4: MPO sites [left, s1, s2, right]. */
 typedef struct t4b_train t4b_train;
@@ -293,6 +318,12 @@ int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int a
                      double tolerance, int64_t max_bond_dim, t4b_train** out);
 int t4b_train_inner_product(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, double* re,
                             double* im);
+/* Quantics Fourier MPO as a Complex64 train with sites [left, 4, right], site index s = tau*2 + sigma (out, in):
+ * quantics_fourier_mpo (quanticstransform/src/fourier.rs:291-404) with FourierOptions {k = 25, sign = -1,
+ * tolerance = 1e-14, max_bond_dim = 12, normalize} as defaults (fourier.rs:99-109).  The closed-form core is host
+ * arithmetic, the LU compression runs on the device. */
+int t4b_fourier_mpo(t4b_ctx* ctx, int r, int k, double sign, double tolerance, int64_t max_bond_dim, int normalize,
+                    t4b_train** out);
 
 #ifdef __cplusplus
 }

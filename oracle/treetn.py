@@ -27,6 +27,10 @@ import scipy.linalg as sla
 from .truncation import SvdTruncationPolicy, compute_retained_rank_qr, svd_rank
 
 _counter = itertools.count(1)
+# LAPACK driver of every dense SVD.  gesdd is the default; tests/golden/make_c3_golden.py re-runs the full C3 sweep with
+# gesvd to measure how far two backward-stable SVDs drift apart over the 189 dependent truncations (the noise floor
+# against which the device spectra are judged).
+SVD_DRIVER = "gesdd"
 
 
 def new_label(prefix="b"):
@@ -79,7 +83,7 @@ def _unfold(t, left):
 
 def factorize_svd(t, left, canonical="left", policy=None, max_bond_dim=None, truncate=True):
     mat, left, right, shape = _unfold(t, left)
-    u, s, vh = sla.svd(mat, full_matrices=False, lapack_driver="gesdd")
+    u, s, vh = sla.svd(mat, full_matrices=False, lapack_driver=SVD_DRIVER)
     r = svd_rank(s, policy, max_bond_dim, truncate)
     u, s_r, vh = u[:, :r], s[:r], vh[:r, :]
     bond = new_label()

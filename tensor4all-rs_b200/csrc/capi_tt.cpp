@@ -6,6 +6,7 @@
 
 #include "../../include/t4b.h"
 #include "capi_common.h"
+#include "host/nccl_shim.h"
 #include "host/factorize.h"
 #include "host/luci.h"
 #include "host/simplett.h"
@@ -538,6 +539,90 @@ int t4b_patches_truncate_adaptive(t4b_ctx* ctx, int64_t n, t4b_tn* const* patche
     }
     auto keep = truncate_adaptive(ctx->c, ps, std::vector<uint64_t>(volume, volume + n), center, cutoff, opt_bond(max_bond_dim));
     for (int64_t i = 0; i < n; ++i) keep_out[i] = keep[i];
+    T4B_CATCH
+}
+
+int t4b_fourier_mpo(t4b_ctx* ctx, int r, int k, double sign, double tolerance, int64_t max_bond_dim, int normalize,
+                    t4b_train** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(out, "null out pointer");
+    auto* h = new t4b_train();
+    try {
+        h->tt = stt::fourier_mpo(ctx->c, r, k, sign, tolerance, opt_bond(max_bond_dim), normalize != 0);
+    } catch (...) { delete h; throw; }
+    *out = h;
+    T4B_CATCH
+}
+
+// ---- sharded patches (NCCL) ---------------------------------------------------------------------------------
+int t4b_nccl_unique_id(void* id_out_128) {
+    T4B_TRY
+    T4B_REQUIRE(id_out_128, "nccl_unique_id: null output");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    nccl::check(nccl::api().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id_out_128, &id, sizeof(id));
+    T4B_CATCH
+}
+int t4b_nccl_comm_create(t4b_ctx* ctx, const void* id_128, int rank, int nranks, void** comm_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(id_128 && comm_out && nranks >= 1 && rank >= 0 && rank < nranks, "nccl_comm_create: bad arguments");
+    ncclUniqueId id;
+    std::memcpy(&id, id_128, sizeof(id));
+    ncclComm_t comm = nullptr;
+    nccl::check(nccl::api().CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank");
+    *comm_out = (void*)comm;
+    T4B_CATCH
+}
+int t4b_nccl_comm_destroy(void* comm) {
+    T4B_TRY
+    if (comm) nccl::check(nccl::api().CommDestroy((ncclComm_t)comm), "ncclCommDestroy");
+    T4B_CATCH
+}
+int t4b_patches_lpt_assign(int64_t n, const int64_t* bond_dims, int64_t nbonds, int64_t site_dim, int nranks,
+                           int32_t* owner_out, double* cost_out) {
+    T4B_TRY
+    T4B_REQUIRE(n >= 0 && nbonds >= 0 && nranks >= 1 && (n == 0 || (bond_dims && owner_out)), "patches_lpt_assign: bad arguments");
+    std::vector<double> costs(n);
+    for (int64_t i = 0; i < n; ++i)
+        costs[i] = patch_cost(std::vector<int64_t>(bond_dims + i * nbonds, bond_dims + (i + 1) * nbonds), site_dim);
+    std::vector<int> owner = lpt_assign(costs, nranks);
+    for (int64_t i = 0; i < n; ++i) { owner_out[i] = owner[i]; if (cost_out) cost_out[i] = costs[i]; }
+    T4B_CATCH
+}
+int t4b_patches_truncate_adaptive_sharded(t4b_ctx* ctx, void* nccl_comm, int rank, int nranks, int64_t n,
+                                          const int32_t* owner, t4b_tn* const* patches, const uint64_t* volume,
+                                          int center, double cutoff, int64_t max_bond_dim, int gather_root,
+                                          int32_t* keep_out, double* norm_sqr_before_out, double* norm_sqr_after_out,
+                                          int64_t* bond_dims_out, int64_t nbonds, t4b_tn** gathered_out,
+                                          double* timing_ms_out, int64_t* gather_bytes_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && (n == 0 || (owner && patches && volume && keep_out)), "patches_truncate_adaptive_sharded: bad arguments");
+    std::vector<ChainTN*> ps(n, nullptr);
+    std::vector<int> own(owner, owner + n);
+    for (int64_t i = 0; i < n; ++i)
+        if (patches[i]) ps[i] = &patches[i]->tn;
+    ShardedResult r = truncate_adaptive_sharded(ctx->c, nccl_comm, rank, nranks, own, ps,
+                                                std::vector<uint64_t>(volume, volume + n), center, cutoff,
+                                                opt_bond(max_bond_dim), gather_root);
+    for (int64_t i = 0; i < n; ++i) {
+        keep_out[i] = r.keep[i];
+        if (norm_sqr_before_out) norm_sqr_before_out[i] = r.norm_sqr_before[i];
+        if (norm_sqr_after_out) norm_sqr_after_out[i] = r.norm_sqr_after[i];
+        if (bond_dims_out)
+            for (int64_t e = 0; e < nbonds; ++e)
+                bond_dims_out[i * nbonds + e] = e < (int64_t)r.bond_dims[i].size() ? r.bond_dims[i][e] : 0;
+        if (gathered_out) {
+            gathered_out[i] = nullptr;
+            // handles for the patches this rank did not own (owned ones are the caller's own handles)
+            if (rank == gather_root && r.keep[i] && own[i] != rank) gathered_out[i] = new t4b_tn{r.gathered[i]};
+        }
+    }
+    if (timing_ms_out) { timing_ms_out[0] = r.ms_stats; timing_ms_out[1] = r.ms_truncate; timing_ms_out[2] = r.ms_gather; }
+    if (gather_bytes_out) *gather_bytes_out = r.gather_bytes;
     T4B_CATCH
 }
 }

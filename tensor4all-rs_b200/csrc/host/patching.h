@@ -30,3 +30,36 @@ std::vector<char> truncate_adaptive(dla::Ctx*, std::vector<ChainTN*>& patches,
                                     std::optional<int64_t> max_bond_dim);
 
 }  // namespace t4b
+
+namespace t4b {
+
+// ---- sharded truncate_adaptive (one process per GPU, NCCL over NVLink) ------------------------------------------------
+// The reference loop (patching.rs:665-718) has exactly two cross-patch steps: the totals of (norm^2, volume) before
+// the per-patch truncation (:688, patch_stats_and_totals :883-897) and the collection of the retained patches
+// (:697-712).  Here rank r owns the patches with owner[i] == r:
+//   1. local norm^2 of the owned patches; ONE ncclAllReduce(sum) of the n-vector - every entry has exactly one
+//      non-zero contributor, so the reduced vector is exact and adaptive_cutoffs() (sequential sum in patch order,
+//      the reference's checked_finite_sum :930) gives bit-identical cutoffs on every rank;
+//   2. local truncation of the owned, kept patches;
+//   3. ONE ncclAllReduce of the per-patch result table (norm^2 after, site ranks / dims / ids);
+//   4. optional gather of the retained cores to `root`: grouped ncclSend / ncclRecv, one message per site tensor.
+struct ShardedResult {
+    std::vector<char> keep;                 // n
+    std::vector<double> norm_sqr_before;    // n
+    std::vector<double> norm_sqr_after;     // n (0 for dropped patches)
+    std::vector<std::vector<int64_t>> bond_dims;   // n, after truncation
+    std::vector<ChainTN> gathered;          // on root: n entries (empty chain for dropped patches); else empty
+    double ms_stats = 0.0, ms_truncate = 0.0, ms_gather = 0.0;   // host wall time of the three phases (synchronised)
+    int64_t gather_bytes = 0;               // bytes this rank sent or received in phase 4
+};
+ShardedResult truncate_adaptive_sharded(dla::Ctx*, void* nccl_comm, int rank, int nranks,
+                                        const std::vector<int>& owner, std::vector<ChainTN*>& patches,
+                                        const std::vector<uint64_t>& volume, int center, double cutoff,
+                                        std::optional<int64_t> max_bond_dim, int root /* -1: no gather */);
+
+// Longest-processing-time-first assignment of patches to ranks on the SVD-cost estimate
+// sum over bonds of (chi_l d)(chi_r) min(chi_l d, chi_r) (deterministic: ties by patch index, then by rank).
+double patch_cost(const std::vector<int64_t>& bond_dims, int64_t site_dim);
+std::vector<int> lpt_assign(const std::vector<double>& costs, int nranks);
+
+}  // namespace t4b

@@ -47,6 +47,11 @@ void right_canonicalize(dla::Ctx*, Train& mpo);
 // bilinear <a,b> (no conjugation, like the reference); returns (re, im)
 void inner_product(dla::Ctx*, const Train& a, const Train& b, double* re, double* im);
 
+// quantics_fourier_mpo (reference crates/tensor4all-quanticstransform/src/fourier.rs:291-404): Tensor3 sites
+// [left, 4, right] with s = tau*2 + sigma, LU-compressed (FourierOptions: k, sign, tolerance, max_bond_dim, normalize)
+Train fourier_mpo(dla::Ctx*, int r, int k, double sign, double tolerance, std::optional<int64_t> max_bond_dim,
+                  bool normalize);
+
 // rank rule shared by compression.rs:286-306 and mpo/factorize.rs:206-250
 int64_t simplett_rank(const std::vector<double>& s, double tolerance, bool normalize_error,
                       std::optional<int64_t> max_bond_dim);

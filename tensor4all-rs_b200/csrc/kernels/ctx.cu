@@ -68,7 +68,6 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.jac_inner = geti("T4B_JAC_INNER", 1);
         k.jac_eig_serial = getb("T4B_JAC_EIG_SERIAL");
         k.jac_coop = geti("T4B_JAC_COOP", 1);
-        k.jac_occ2 = geti("T4B_JAC_OCC2", 0);
         k.qr_notma = getb("T4B_QR_NOTMA"); k.qr_unfused = getb("T4B_QR_UNFUSED");
         k.qr_nolookahead = getb("T4B_QR_NOLOOKAHEAD"); k.qr_old = getb("T4B_QR_OLD");
         k.qr_leaf_old = getb("T4B_QR_LEAF_OLD");
@@ -455,10 +454,15 @@ std::string profile_end(Ctx* c) {
     if (c->dev_stats) cudaMemcpy(hstats, c->dev_stats, sizeof(hstats), cudaMemcpyDeviceToHost);
     std::string out;
     for (auto& a : aggs) {
-        if (a.name == "jacobi") a.work = hstats[0];   // measured on the device (actual sweep counts)
+        if (a.name == "jacobi") a.work = hstats[0];   // executed DMMA flops, counted on the device (data-dependent sweeps)
         char line[256];
         snprintf(line, sizeof(line), "%s %lld %.6f %.6e\n", a.name.c_str(), (long long)a.n, a.ms, a.work);
         out += line;
+        if (a.name == "jacobi") {
+            // second line: the panel bytes the same launches moved through L2 (reads + writes of every round)
+            snprintf(line, sizeof(line), "jacobi_l2_bytes %lld %.6f %.6e\n", (long long)a.n, 0.0, hstats[1]);
+            out += line;
+        }
     }
     for (auto& r : c->prof) cudaEventDestroy(r.ev);
     c->prof.clear();

@@ -30,7 +30,6 @@ struct Knobs {
     int jac_inner = 1;            // T4B_JAC_INNER
     bool jac_eig_serial = false;  // T4B_JAC_EIG_SERIAL
     int jac_coop = 1;             // T4B_JAC_COOP (default 1: cooperative, gang-scheduled launch; 0 for Nsight Compute replay)
-    int jac_occ2 = 0;             // T4B_JAC_OCC2 (two resident CTAs per SM variant)
     bool qr_notma = false, qr_unfused = false, qr_nolookahead = false, qr_old = false;
     bool qr_leaf_old = false;     // T4B_QR_LEAF_OLD
     bool gemm_nows = false, gemm_noskinny = false, gemm_trace = false, gemm_nopersist = false;

@@ -334,7 +334,7 @@ struct JPArgs {
     double* D;             // [p][16*16] diagonal Gram block carried with every column block
     double tol_early;      // a sweep that starts below this ends converged (quadratic convergence)
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
-    double* stats;         // optional device work counter (bytes), else null
+    double* stats;         // optional device work counters ([0] executed flops, [1] panel bytes through L2), else null
     unsigned* fail;        // sticky failure counter of the context (sweep limit reached)
     const double* fro2;    // ||X||_F^2 (device scalar): columns below (16 eps)^2 ||X||_F^2 are numerically zero
     double bytes_per_sweep;
@@ -372,11 +372,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
         }                                                               \
     } while (0)
 
-// MINB = 2: register budget (<= 128) and shared memory sized for TWO resident CTAs per SM, so that the serial 32 x 32
-// eigen-solve of one pair overlaps with the DMMA passes of another pair on the same SM (the W fragments are then
-// re-read from shared memory per row fragment instead of living in registers for the whole pass).
-template <bool CPLX, int MINB>
-__global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
+// (A variant with two resident CTAs per SM - 121 registers, 107 KB of shared memory, W fragments re-read per row
+// fragment - was measured in round 2: every phase got slower, 58 ms instead of 45 ms at n = 2048; see
+// profiles/jacobi_analysis_r02.md.  One CTA per SM it stays.)
+template <bool CPLX>
+__global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long tprev = gtimer();
     typedef Sc<CPLX> S;
@@ -430,6 +430,9 @@ __global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
     int sweep = 0;
     int converged = 0;
     double prev_off = 1.0;
+    // executed DMMA flops of this CTA (thread 0): Gram pass of every item, update pass of the rotated ones
+    double fl_exec = 0.0;
+    constexpr double FLOPS_PER_MAC = CPLX ? 8.0 : 2.0;
 
     for (; sweep < a.max_sweeps; ++sweep) {
         for (int r = 0; r < rounds; ++r) {
@@ -561,6 +564,7 @@ __global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
                     }
                 }
                 JP_STAMP(1);   // load + partial Gram
+                if (tid == 0) fl_exec += FLOPS_PER_MAC * (double)a.rpcx * (full_inner ? (double)(PW * PW) : (double)(JB * JB));
                 cluster.sync();   // every CTA's partial Gram is visible cluster-wide
                 JP_STAMP(2);   // cluster barrier
                 // every CTA reduces the partial Grams in the same fixed order (bitwise identical G on
@@ -658,16 +662,12 @@ __global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
                     }
                     JP_STAMP(4);   // eig
                     // ---- 3. update pass: P <- P W chunk by chunk, TMA bulk write-back ------------------
-                    // W as DMMA B fragments: held in registers for the whole pass (MINB == 1) or fetched per row
-                    // fragment, two column fragments at a time (MINB == 2: half the register budget)
-                    constexpr int NFH = MINB == 2 ? 2 : 4;
-                    T wf[NFH][8];
-                    if constexpr (MINB == 1) {
+                    // W as DMMA B fragments, held in registers for the whole pass
+                    T wf[4][8];
 #pragma unroll
-                        for (int nf = 0; nf < 4; ++nf)
+                    for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) wf[nf][ks] = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
-                    }
+                        for (int ks = 0; ks < 8; ++ks) wf[nf][ks] = Ws[(nf * 8 + grp) * WP + ks * 4 + tig];
                     for (int j = 0; j < npos; ++j) {
                         const int b = (nchx - 1 + j) & 1;
                         if (j >= 2 || (j == 1 && nchx == 1)) wait_load(b);
@@ -681,26 +681,10 @@ __global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
                             T acc[4][2];
 #pragma unroll
                             for (int nf = 0; nf < 4; ++nf) acc[nf][0] = acc[nf][1] = S::zero();
-                            if constexpr (MINB == 1) {
 #pragma unroll
-                                for (int ks = 0; ks < 8; ++ks)
+                            for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-                                    for (int nf = 0; nf < 4; ++nf) mma_frag<CPLX, false>(acc[nf], av[ks], wf[nf][ks]);
-                            } else {
-#pragma unroll
-                                for (int h = 0; h < 4 / NFH; ++h) {
-#pragma unroll
-                                    for (int nf = 0; nf < NFH; ++nf)
-#pragma unroll
-                                        for (int ks = 0; ks < 8; ++ks)
-                                            wf[nf][ks] = Ws[((h * NFH + nf) * 8 + grp) * WP + ks * 4 + tig];
-#pragma unroll
-                                    for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                                        for (int nf = 0; nf < NFH; ++nf)
-                                            mma_frag<CPLX, false>(acc[h * NFH + nf], av[ks], wf[nf][ks]);
-                                }
-                            }
+                                for (int nf = 0; nf < 4; ++nf) mma_frag<CPLX, false>(acc[nf], av[ks], wf[nf][ks]);
                             __syncwarp();
 #pragma unroll
                             for (int nf = 0; nf < 4; ++nf)
@@ -721,6 +705,7 @@ __global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
                             }
                         }
                     }
+                    if (tid == 0) fl_exec += FLOPS_PER_MAC * (double)(a.rpcx + a.rpcv) * (double)(PW * PW);
                     JP_STAMP(5);   // update + store issue
                     if (warp == 0) {
                         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -779,11 +764,12 @@ __global__ void __launch_bounds__(JT, MINB) jacobi_persistent_kernel(JPArgs a) {
     }
     if (blockIdx.x == 0 && tid == 0) {
         a.info[0] = sweep; a.info[1] = converged;
-        if (a.stats) atomicAdd(a.stats, (double)sweep * a.bytes_per_sweep);
+        if (a.stats) atomicAdd(a.stats + 1, (double)sweep * a.bytes_per_sweep);
         if (!converged && a.fail) atomicAdd(a.fail, 1u);
         if (a.timing)
             for (int k = 0; k < 8; ++k) a.timing[k] = tacc[k];
     }
+    if (tid == 0 && a.stats) atomicAdd(a.stats, fl_exec);
     cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 }
 
@@ -903,9 +889,9 @@ size_t jp_smem_bytes(int ldp) {
            (size_t)(64 + JW + 2) * 8 + 2 * 8 + 2 * 256 * es + 128;
 }
 
-template <bool CPLX, int MINB>
+template <bool CPLX>
 int jp_max_clusters(int cs, size_t smem) {
-    auto kern = jacobi_persistent_kernel<CPLX, MINB>;
+    auto kern = jacobi_persistent_kernel<CPLX>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cs, 1, 1);
     cfg.blockDim = dim3(JT, 1, 1);
@@ -922,20 +908,19 @@ int jp_max_clusters(int cs, size_t smem) {
     return n;
 }
 
-template <bool CPLX, int MINB>
+template <bool CPLX>
 JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
-    // two resident CTAs per SM share the 228 KB of the SM (1 KB reserved per CTA)
-    const size_t smem_max = MINB == 2 ? 112 * 1024 : 227 * 1024;
+    const size_t smem_max = 227 * 1024;
     size_t smem_cap = c->knobs.jac_smemcap_kb ? c->knobs.jac_smemcap_kb * 1024 : smem_max;
     if (smem_cap > smem_max) smem_cap = smem_max;
-    auto kern = jacobi_persistent_kernel<CPLX, MINB>;
+    auto kern = jacobi_persistent_kernel<CPLX>;
     if (c->first_use((const void*)kern)) {
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
     // launch geometries are cached per context: the occupancy queries cost more than a small factorisation
     const uint64_t key = ((uint64_t)nx << 40) ^ ((uint64_t)npad << 16) ^ ((uint64_t)(with_v ? 1 : 0) << 2) ^
-                         ((uint64_t)(CPLX ? 1 : 0) << 1) ^ (uint64_t)(MINB - 1);
+                         ((uint64_t)(CPLX ? 1 : 0) << 1);
     auto hit = c->jp_plans.find(key);
     if (hit != c->jp_plans.end()) return hit->second;
     auto roundup = [](int64_t v, int64_t q) { return (v + q - 1) / q * q; };
@@ -963,7 +948,7 @@ JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
         pl.smem = jp_smem_bytes<CPLX>(pl.ldp);
         pl.ldx = (int64_t)cs * pl.rpcx;
         pl.ldv = (int64_t)cs * pl.rpcv;
-        int maxc = jp_max_clusters<CPLX, MINB>(cs, pl.smem);
+        int maxc = jp_max_clusters<CPLX>(cs, pl.smem);
         if (maxc < 1) continue;
         pl.nclusters = maxc < pairs ? maxc : pairs;
         if (maxc >= pairs) { best = pl; best_score = 1; found = true; break; }   // every pair gets its own resident cluster
@@ -977,7 +962,7 @@ JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
 
 // One-sided block Jacobi on X (ldx x npad, nx live rows); V (ldv x npad) optional.  Asynchronous: the
 // whole iteration (all sweeps, convergence decision included) is one kernel launch.
-template <bool CPLX, int MINB>
+template <bool CPLX>
 void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
     const size_t es = CPLX ? 16 : 8;
     const int p = (int)(npad / JB);
@@ -1039,7 +1024,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     cfg.attrs = attr;
     if (c->jac_coop_ok < 0) c->jac_coop_ok = c->knobs.jac_coop > 0 ? 1 : 0;
     cfg.numAttrs = c->jac_coop_ok ? 2 : 1;
-    auto kern = jacobi_persistent_kernel<CPLX, MINB>;
+    auto kern = jacobi_persistent_kernel<CPLX>;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
     if (le != cudaSuccess && c->jac_coop_ok) {
         // cluster + cooperative not accepted by this driver / geometry: fall back to the plain cluster launch
@@ -1064,9 +1049,9 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
         }
         const int* hinfo = (const int*)h;
         const unsigned long long* t = (const unsigned long long*)(h + 64);
-        fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d minb=%d coop=%d cs=%d clusters=%d ch=%d smem=%zu sweeps=%d converged=%d | us: "
+        fprintf(stderr, "[t4b] jacobi nx=%lld npad=%lld V=%d coop=%d cs=%d clusters=%d ch=%d smem=%zu sweeps=%d converged=%d | us: "
                 "wait %.0f gram %.0f csync %.0f reduce %.0f eig %.0f update %.0f store %.0f publish+sweepbar %.0f\n",
-                (long long)nx, (long long)npad, V ? 1 : 0, MINB, c->jac_coop_ok, pl.cs, pl.nclusters, pl.ch, pl.smem, hinfo[0], hinfo[1],
+                (long long)nx, (long long)npad, V ? 1 : 0, c->jac_coop_ok, pl.cs, pl.nclusters, pl.ch, pl.smem, hinfo[0], hinfo[1],
                 t[0] * 1e-3, t[1] * 1e-3, t[2] * 1e-3, t[3] * 1e-3, t[4] * 1e-3, t[5] * 1e-3, t[6] * 1e-3, t[7] * 1e-3);
     }
     release(c, ws);
@@ -1088,8 +1073,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     qr_thin(c, dt, m, n, A, Q, Rm);
     // X = R (left vectors wanted) or R^H (only right vectors wanted)
     const bool adjoint = !want_u;
-    const bool occ2 = !CPLX && c->knobs.jac_occ2 > 0;
-    const JPPlan pl = occ2 ? plan_jp<CPLX, CPLX ? 1 : 2>(c, n, npad, acc_v) : plan_jp<CPLX, 1>(c, n, npad, acc_v);
+    const JPPlan pl = plan_jp<CPLX>(c, n, npad, acc_v);
     double* X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
     init_x_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>((const double*)Rm, n, n, pl.ldx, npad, adjoint ? 1 : 0, X);
     c->launched("svd_init_x");
@@ -1099,8 +1083,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         set_eye_kernel<CPLX><<<grid1d(c, pl.ldv * npad), 256, 0, c->stream>>>(V, pl.ldv, npad);
         c->launched("svd_set_eye");
     }
-    if (occ2) jacobi_persistent<CPLX, CPLX ? 1 : 2>(c, pl, X, n, npad, V);
-    else jacobi_persistent<CPLX, 1>(c, pl, X, n, npad, V);
+    jacobi_persistent<CPLX>(c, pl, X, n, npad, V);
 
     double* sig2 = (double*)alloc(c, (size_t)npad * 8);
     int64_t* rank = (int64_t*)alloc(c, (size_t)npad * 8);

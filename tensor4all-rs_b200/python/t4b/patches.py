@@ -51,6 +51,66 @@ def lpt_assign(costs, world):
     return owner
 
 
+def lpt_assign_cabi(bond_dims, site_dim, world):
+    """t4b_patches_lpt_assign: (owner[n], cost[n]) from an n x nbonds table of bond dimensions."""
+    bd = np.ascontiguousarray(bond_dims, dtype=np.int64)
+    n, nb = bd.shape
+    owner = np.zeros(n, np.int32)
+    cost = np.zeros(n)
+    _check(lib().t4b_patches_lpt_assign(C.c_int64(n), bd.ctypes.data_as(C.c_void_p), C.c_int64(nb), C.c_int64(site_dim),
+                                        int(world), owner.ctypes.data_as(C.c_void_p), cost.ctypes.data_as(C.c_void_p)))
+    return owner, cost
+
+
+class NcclComm:
+    """ncclComm_t created through the C ABI; the 128-byte unique id travels over torch.distributed (plumbing)."""
+
+    def __init__(self, ctx, rank, world, dist=None):
+        import torch
+        self.h = C.c_void_p()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _check(lib().t4b_nccl_unique_id(buf))
+        if world > 1:
+            t = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            buf = (C.c_uint8 * 128)(*t.cpu().tolist())
+        _check(lib().t4b_nccl_comm_create(ctx.h, buf, rank, world, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().t4b_nccl_comm_destroy(self.h)
+            self.h = None
+
+
+def truncate_adaptive_sharded(ctx, comm, rank, world, owner, my_patches, volumes, center, cutoff, max_bond_dim,
+                              gather_root=-1, nbonds=None):
+    """t4b_patches_truncate_adaptive_sharded.  my_patches: {index: ChainTN} owned by this rank.  Returns a dict with
+    keep, norm_before, norm_after, bond_dims (n x nbonds), gathered ({index: ChainTN}, root only), timing_ms, gather_bytes."""
+    from .tt import ChainTN
+    n = len(owner)
+    if nbonds is None:
+        nbonds = max([p.length() - 1 for p in my_patches.values()] or [1])
+    own = np.ascontiguousarray(owner, dtype=np.int32)
+    vol = np.ascontiguousarray(volumes, dtype=np.uint64)
+    handles = (C.c_void_p * max(n, 1))(*[(my_patches[i].h if i in my_patches else None) for i in range(n)])
+    keep = np.zeros(n, np.int32)
+    nb, na = np.zeros(n), np.zeros(n)
+    bd = np.zeros((n, nbonds), np.int64)
+    gathered = (C.c_void_p * max(n, 1))()
+    timing = np.zeros(3)
+    gbytes = C.c_int64()
+    _check(lib().t4b_patches_truncate_adaptive_sharded(
+        ctx.h, comm.h if comm is not None else None, rank, world, C.c_int64(n), own.ctypes.data_as(C.c_void_p), handles,
+        vol.ctypes.data_as(C.c_void_p), center, C.c_double(cutoff), C.c_int64(max_bond_dim or 0), gather_root,
+        keep.ctypes.data_as(C.c_void_p), nb.ctypes.data_as(C.c_void_p), na.ctypes.data_as(C.c_void_p),
+        bd.ctypes.data_as(C.c_void_p), C.c_int64(nbonds), gathered, timing.ctypes.data_as(C.c_void_p), C.byref(gbytes)))
+    dt = next(iter(my_patches.values()))._dt if my_patches else 0
+    got = {i: ChainTN(ctx, C.c_void_p(gathered[i]), dt) for i in range(n) if gathered[i]}
+    return {"keep": keep.astype(bool), "norm_before": nb, "norm_after": na, "bond_dims": bd, "gathered": got,
+            "timing_ms": timing, "gather_bytes": gbytes.value}
+
+
 class CAbiBackend:
     """Production backend: patches live on this rank's GPU as t4b ChainTN handles."""
 

@@ -243,6 +243,13 @@ class Train:
         _check(lib().t4b_train_create(ctx.h, dt, r, len(arrs), dims, ptrs, C.byref(h)))
         return cls(ctx, h, dt, r)
 
+    @classmethod
+    def fourier_mpo(cls, ctx: Context, r, k=25, sign=-1.0, tolerance=1e-14, max_bond_dim=12, normalize=True):
+        h = C.c_void_p()
+        _check(lib().t4b_fourier_mpo(ctx.h, int(r), int(k), C.c_double(sign), C.c_double(tolerance),
+                                     C.c_int64(max_bond_dim or 0), int(normalize), C.byref(h)))
+        return cls(ctx, h, C64, 3)
+
     def length(self):
         n = C.c_int()
         _check(lib().t4b_train_length(self.h, C.byref(n)))

@@ -38,7 +38,26 @@ def main():
     ap.add_argument("--w", type=int, default=8)
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED0003)
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "c3_full_oracle.npz"))
+    ap.add_argument("--driver", default="gesdd", choices=["gesdd", "gesvd"],
+                    help="LAPACK SVD driver of the oracle; a gesvd run next to the gesdd golden measures the noise floor")
+    ap.add_argument("--merge-floor", default=None,
+                    help="path of a second run (other driver): stores per-step max |s - s'| / s_max into --out as `noise_floor`")
     a = ap.parse_args()
+    if a.merge_floor:
+        g = dict(np.load(a.out))
+        h = np.load(a.merge_floor)
+        assert np.array_equal(g["lens"], h["lens"])
+        floor, off = [], 0
+        for n in g["lens"]:
+            x, y = g["spectra"][off:off + n], h["spectra"][off:off + n]
+            floor.append(float(np.max(np.abs(x - y)) / x[0]))
+            off += n
+        g["noise_floor"] = np.array(floor)
+        g["noise_floor_norm_sqr"] = np.float64(abs(float(g["norm_sqr"]) - float(h["norm_sqr"])) / float(g["norm_sqr"]))
+        np.savez_compressed(a.out, **g)
+        print(f"noise floor (gesdd vs gesvd): max {max(floor):.2e}, median {np.median(floor):.2e}; norm^2 {float(g['noise_floor_norm_sqr']):.2e}")
+        return
+    otn.SVD_DRIVER = a.driver
     mps, mi, mpo, oi = make_c3(a.seed, a.L, a.d, a.chi, a.w)
     spectra = []
     t0 = time.perf_counter()

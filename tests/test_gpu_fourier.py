@@ -91,3 +91,16 @@ def test_fourier_r40_chi256_properties(ctx):
     again.truncate(0, t4tt.SvdPolicy(1e-12), chi)       # idempotence of the truncation
     ov = out.inner(again)
     assert abs(ov - n_out) <= 1e-10 * n_out
+
+
+def test_fourier_mpo_product_builder_matches_oracle(ctx):
+    """t4b_fourier_mpo (host/fourier.cpp: closed-form core on the host, LU compression on the device) against the
+    oracle's restatement of quantics_fourier_mpo (fourier.rs:291-404)."""
+    for r in (2, 5, 9):
+        got = t4tt.Train.fourier_mpo(ctx, r).arrays()
+        ref = ofo.fourier_mpo(r)
+        assert [a.shape for a in got] == [a.shape for a in ref]
+        assert relerr(ostt.tt_dense(got), ostt.tt_dense(ref)) <= 1e-10
+    un = t4tt.Train.fourier_mpo(ctx, 4, k=10, sign=1.0, tolerance=1e-12, max_bond_dim=8, normalize=False).arrays()
+    rf = ofo.fourier_mpo(4, k=10, sign=1.0, tolerance=1e-12, max_bond_dim=8, normalize=False)
+    assert relerr(ostt.tt_dense(un), ostt.tt_dense(rf)) <= 1e-10

@@ -60,3 +60,28 @@ def test_sharded_driver_single_rank_equals_fused_call(ctx):
         if keep_ref[i]:
             assert bonds[i] == ref[i].bond_dims()
             assert abs(norms[i] - opatch.norm_sqr(ref[i])) <= 1e-10 * norms[i]
+
+
+def test_sharded_cabi_single_rank_matches_oracle(ctx):
+    """t4b_patches_truncate_adaptive_sharded with one rank (no communicator needed): same keep flags, bond dimensions
+    and norms as oracle/patching.py; LPT assignment of the ABI equals the Python plumbing's."""
+    rng = np.random.default_rng(23)
+    L, d, n = 6, 2, 9
+    raw = _patches(rng, n, L, d)
+    volumes = [int(d ** (L - int(rng.integers(0, 3)))) for _ in range(n)]
+    ref, keep_ref = opatch.truncate_adaptive([to_oracle_chain(a, i) for a, i in raw], volumes, 0, 1e-6, 5)
+    tns = {i: t4tt.chain_from_arrays(ctx, a, ids) for i, (a, ids) in enumerate(raw)}
+    res = tpatch.truncate_adaptive_sharded(ctx, None, 0, 1, [0] * n, tns, volumes, 0, 1e-6, 5, gather_root=0, nbonds=L - 1)
+    assert list(res["keep"]) == keep_ref
+    assert res["gathered"] == {}                      # the root owns everything: nothing to receive
+    for i in range(n):
+        if keep_ref[i]:
+            assert [int(x) for x in res["bond_dims"][i] if x > 0] == ref[i].bond_dims()
+            assert abs(res["norm_after"][i] - opatch.norm_sqr(ref[i])) <= 1e-10 * res["norm_after"][i]
+            assert relerr(gpu_chain_dense(tns[i]), oracle_chain_dense(ref[i])) <= 1e-10
+        else:
+            assert res["norm_after"][i] == 0.0
+    bd = np.array([[4, 8, 8, 4, 2], [2, 4, 4, 4, 2], [2, 4, 8, 4, 2], [2, 2, 2, 2, 2]])
+    owner, cost = tpatch.lpt_assign_cabi(bd, 2, 3)
+    want = tpatch.lpt_assign([tpatch.patch_cost(list(r), 2) for r in bd], 3)
+    assert list(owner) == want
