@@ -468,6 +468,7 @@ def run_c4(env, steps, warmup):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         r = lu.rank
+        prof = profile(ctx, lambda: t4tt.LU(ctx, a, cap, 1e-8, 0.0, True))
         byt = sum(16.0 * (m - k) * (n - k) for k in range(r))
         flo = sum(3.0 * (m - k) * (n - k) for k in range(r))
         out.append({"shape": [m, n], "rank": r, "ms": ms, "algorithmic_bytes": byt, "algorithmic_flops": flo,
@@ -475,7 +476,8 @@ def run_c4(env, steps, warmup):
                                  "frac": byt / (ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": hbm_src,
                                  "note": "HBM-equivalent rate of the trailing-block read+write model; the working set "
                                          f"({8 * m * n / 1e6:.1f} MB) is L2 resident"},
-                    "gflops": flo / (ms * 1e-3) / 1e9})
+                    "gflops": flo / (ms * 1e-3) / 1e9,
+                    "kernel_profile_ms": {k: round(v["ms"], 3) for k, v in prof.items()}})
     return out
 
 

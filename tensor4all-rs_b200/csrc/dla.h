@@ -85,6 +85,17 @@ void qr_thin(Ctx*, DType dt, int64_t m, int64_t n, void* A, void* Q, void* R);
 // (reference crates/tensor4all-core/src/defaults/svd.rs:265-267, backend.rs:715-734).
 void svd_thin(Ctx*, DType dt, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh);
 
+// Small / batched SVD: every problem is factored by ONE CTA with the matrix resident in shared memory (one launch for
+// the whole batch).  A (m x n, ld = lda) is PRESERVED; U (m x k, ld = ldu) / Vh (k x n, ld = ldvh) may be null.
+struct SvdProblem {
+    const void* A; int64_t m, n, lda;
+    void* U; int64_t ldu;
+    double* S;
+    void* Vh; int64_t ldvh;
+};
+bool svd_small_fits(DType dt, int64_t m, int64_t n, bool want_u, bool want_vh);
+void svd_small_batched(Ctx*, DType dt, int64_t batch, const SvdProblem* problems);
+
 // Hermitian eigendecomposition G = W diag(lam) W^H of an n x n matrix (ld = n);
 // lam ascending is NOT guaranteed (Jacobi order) - callers sort.  G destroyed.
 // Replaces tenferro eigh (reference crates/tensor4all-tensorbackend/src/matrix.rs:660-900).

@@ -5,8 +5,21 @@
 #include <chrono>
 #include <cstdlib>
 
+#include <mutex>
+#include <unordered_set>
+
 namespace t4b {
 namespace dla {
+
+// Live contexts.  Handles created through a context (networks, trains, LU factors) own device buffers that point back
+// at it; a handle released AFTER its context was destroyed must not touch freed state: ctx_destroy frees every
+// outstanding allocation itself, and a late release() of such a buffer is a no-op.
+static std::mutex g_ctx_mutex;
+static std::unordered_set<const Ctx*> g_live_ctx;
+static bool ctx_alive(const Ctx* c) {
+    std::lock_guard<std::mutex> lk(g_ctx_mutex);
+    return g_live_ctx.count(c) != 0;
+}
 
 void* Ctx::get_scratch(size_t bytes) {
     if (bytes > scratch_bytes) {
@@ -70,7 +83,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.jac_coop = geti("T4B_JAC_COOP", 1);
         k.qr_notma = getb("T4B_QR_NOTMA"); k.qr_unfused = getb("T4B_QR_UNFUSED");
         k.qr_nolookahead = getb("T4B_QR_NOLOOKAHEAD"); k.qr_old = getb("T4B_QR_OLD");
-        k.qr_leaf_old = getb("T4B_QR_LEAF_OLD");
+        k.qr_leaf_old = !getb("T4B_QR_LEAF_NEW");   // blocked single-warp leaf measured 2x slower (r02d): opt-in only
         k.gemm_nows = getb("T4B_GEMM_NOWS"); k.gemm_noskinny = getb("T4B_GEMM_NOSKINNY");
         k.gemm_trace = getb("T4B_GEMM_TRACE"); k.gemm_nopersist = getb("T4B_GEMM_NOPERSIST");
         k.svd_nobatch = getb("T4B_SVD_NOBATCH");
@@ -89,15 +102,25 @@ Ctx* ctx_create(int device, void* cuda_stream) {
     T4B_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = UINT64_MAX;
     T4B_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        g_live_ctx.insert(c);
+    }
     return c;
 }
 
 void ctx_destroy(Ctx* c) {
     if (!c) return;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mutex);
+        if (!g_live_ctx.erase(c)) return;   // already destroyed
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_f); }
     if (c->dev_stats) cudaFree(c->dev_stats);
+    if (c->sk_ws) cudaFree(c->sk_ws);
+    if (c->sk_flags) cudaFree(c->sk_flags);
     if (c->fail_dev) cudaFree(c->fail_dev);
     if (c->scratch) cudaFreeAsync(c->scratch, c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -172,8 +195,8 @@ void* alloc(Ctx* c, size_t bytes) {
     return p;
 }
 void release(Ctx* c, void* p) {
+    if (!p || !ctx_alive(c)) return;   // the context is gone: ctx_destroy already freed the block
     HostTimer t(c->host_free_s);
-    if (!p) return;
     auto it = c->live.find(p);
     if (it == c->live.end()) throw Error(ST_INTERNAL, "release of a pointer not owned by this context");
     const size_t sz = it->second;

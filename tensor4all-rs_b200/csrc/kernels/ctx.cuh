@@ -31,7 +31,7 @@ struct Knobs {
     bool jac_eig_serial = false;  // T4B_JAC_EIG_SERIAL
     int jac_coop = 1;             // T4B_JAC_COOP (default 1: cooperative, gang-scheduled launch; 0 for Nsight Compute replay)
     bool qr_notma = false, qr_unfused = false, qr_nolookahead = false, qr_old = false;
-    bool qr_leaf_old = false;     // T4B_QR_LEAF_OLD
+    bool qr_leaf_old = true;      // cleared by T4B_QR_LEAF_NEW (blocked single-warp TSQR leaf, slower: A/B only)
     bool gemm_nows = false, gemm_noskinny = false, gemm_trace = false, gemm_nopersist = false;
     bool svd_nobatch = false;     // T4B_SVD_NOBATCH
 };
@@ -52,6 +52,10 @@ struct Ctx {
     std::unordered_set<const void*> attr_done;
     bool first_use(const void* kern) { return attr_done.insert(kern).second; }
     std::unordered_map<const void*, int> cluster_ok;
+    // stream-K workspace of the warp-specialised GEMM (gemm.cu): one 128 x 128 slot + flag per SM, epoch per launch
+    double* sk_ws = nullptr;
+    unsigned* sk_flags = nullptr;
+    unsigned sk_epoch = 0;
     int jac_coop_ok = -1;   // -1 undecided, 1 cooperative Jacobi launches accepted, 0 refused / disabled   // schedulability of non-portable cluster sizes (qr.cu)
     // retained-spectrum log (parity instrumentation, see t4b_ctx_spectra_begin)
     bool spectra_on = false;

@@ -295,6 +295,15 @@ struct GemmWsParams {
     Group am, ak, bk, bn;      // simplified operand groups (producer-side address generation)
     CUtensorMap tmA, tmB;      // valid for K-fast operands only
     TmapCoord tcA, tcB;
+    // stream-K (persistent) mode: the (tile, k-tile) units are dealt out in contiguous ranges to gridDim.x CTAs; a
+    // tile that is split between CTAs is finished by the CTA holding its FIRST k-range (that CTA's last segment),
+    // which adds the partial sums of the higher-numbered CTAs (their first segments) in ascending order
+    // (deterministic), read from sk_ws after their sk_flags turn.
+    int streamk;
+    int64_t sk_tiles;          // output tiles
+    double* sk_ws;             // gridDim.x slots of 128 x 128 doubles (fragment order)
+    unsigned* sk_flags;        // gridDim.x flags, == sk_epoch once the slot is valid
+    unsigned sk_epoch;
 };
 
 __device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -353,6 +362,15 @@ __device__ __forceinline__ void g_tensor_g2s(void* sdst, const CUtensorMap* tm, 
 // element index inside a K-fast tile: 128-byte rows (16 doubles), 16-byte chunks XOR-swizzled by the row
 __device__ __forceinline__ int kfast_idx(int m, int k) { return m * 16 + ((((k >> 1) ^ (m & 7)) << 1) | (k & 1)); }
 
+__device__ __forceinline__ unsigned g_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void g_st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <bool CPLX, int ALAY, int BLAY>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_constant__ GemmWsParams wp) {
     constexpr int BM = WS_BM, BN = WS_BN, WM = WS_WM, WN = WS_WN;
@@ -374,13 +392,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_con
     double* smem = reinterpret_cast<double*>(ws_smem_raw + ((1024u - (g_smem_u32(ws_smem_raw) & 1023u)) & 1023u));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
-    const int64_t m0 = (tile % p.tiles_m) * BM;
-    const int64_t n0 = (tile / p.tiles_m) * BN;
     const int64_t KT_all = p.K / BK;
-    const int64_t kt_begin = (int64_t)blockIdx.y * p.kt_per_split;
-    const int64_t kt_stop = (kt_begin + p.kt_per_split < KT_all) ? kt_begin + p.kt_per_split : KT_all;
-    const int64_t KT = kt_stop > kt_begin ? kt_stop - kt_begin : 0;
+    // unit range of this CTA: units are (tile, k-tile) pairs, tile-major
+    int64_t u0, u1;
+    if (wp.streamk) {
+        const int64_t U = wp.sk_tiles * KT_all;
+        u0 = U * (int64_t)blockIdx.x / (int64_t)gridDim.x;
+        u1 = U * ((int64_t)blockIdx.x + 1) / (int64_t)gridDim.x;
+    } else {
+        const int64_t kt_begin = (int64_t)blockIdx.y * p.kt_per_split;
+        const int64_t kt_stop = (kt_begin + p.kt_per_split < KT_all) ? kt_begin + p.kt_per_split : KT_all;
+        u0 = (int64_t)blockIdx.x * KT_all + kt_begin;
+        u1 = (int64_t)blockIdx.x * KT_all + (kt_stop > kt_begin ? kt_stop : kt_begin);
+    }
 
     if (tid == 0) {
 #pragma unroll
@@ -391,35 +415,44 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_con
 
     if (warp == WS_CONSUMERS) {
         // ================= producer warp =================
-        const int vm = (int)((p.M - m0) < BM ? (p.M - m0) : BM);     // valid rows / columns of this tile
-        const int vn = (int)((p.N - n0) < BN ? (p.N - n0) : BN);
-        // K-fast tiles are full boxes (out-of-range rows are zero-filled by the TMA unit)
-        const unsigned bytes = (unsigned)(((ALAY == 0 ? vm : BM) + (BLAY == 1 ? vn : BN)) * BK) * 8u;
-        const int64_t a_m0 = ALAY == 0 ? group_offset(wp.am, m0) : 0;
-        const int64_t b_n0 = BLAY == 1 ? group_offset(wp.bn, n0) : 0;
-        for (int64_t kt = 0; kt < KT; ++kt) {
-            const int stage = (int)(kt % WS_STAGES);
-            const int64_t round = kt / WS_STAGES;
-            if (round > 0) g_mbar_wait(&empty_bar[stage], (unsigned)((round - 1) & 1));
-            if (lane == 0) g_mbar_expect_tx(&full_bar[stage], bytes);
-            __syncwarp();
-            double* sA = smem + (size_t)stage * STAGE_DOUBLES;
-            double* sB = sA + B_OFF;
-            const int64_t k0 = (kt_begin + kt) * BK;
-            if (ALAY == 0) {
-                if (lane < BK)
-                    g_bulk_g2s(sA + (size_t)lane * PITCH_A, p.A + (a_m0 + group_offset(wp.ak, k0 + lane)),
-                               (unsigned)vm * 8u, &full_bar[stage]);
-            } else if (lane == 0) {
-                g_tensor_g2s(sA, &wp.tmA, wp.tcA, k0, m0, &full_bar[stage]);
+        int64_t it = 0;                                   // k-tiles staged so far (ring position)
+        for (int64_t u = u0; u < u1;) {
+            const int64_t tile = u / KT_all;
+            const int64_t kb = u - tile * KT_all;
+            const int64_t ke = (kb + (u1 - u) < KT_all) ? kb + (u1 - u) : KT_all;
+            const int64_t m0 = (tile % p.tiles_m) * BM;
+            const int64_t n0 = (tile / p.tiles_m) * BN;
+            const int vm = (int)((p.M - m0) < BM ? (p.M - m0) : BM);     // valid rows / columns of this tile
+            const int vn = (int)((p.N - n0) < BN ? (p.N - n0) : BN);
+            // K-fast tiles are full boxes (out-of-range rows are zero-filled by the TMA unit)
+            const unsigned bytes = (unsigned)(((ALAY == 0 ? vm : BM) + (BLAY == 1 ? vn : BN)) * BK) * 8u;
+            const int64_t a_m0 = ALAY == 0 ? group_offset(wp.am, m0) : 0;
+            const int64_t b_n0 = BLAY == 1 ? group_offset(wp.bn, n0) : 0;
+            for (int64_t kt = kb; kt < ke; ++kt, ++it) {
+                const int stage = (int)(it % WS_STAGES);
+                const int64_t round = it / WS_STAGES;
+                if (round > 0) g_mbar_wait(&empty_bar[stage], (unsigned)((round - 1) & 1));
+                if (lane == 0) g_mbar_expect_tx(&full_bar[stage], bytes);
+                __syncwarp();
+                double* sA = smem + (size_t)stage * STAGE_DOUBLES;
+                double* sB = sA + B_OFF;
+                const int64_t k0 = kt * BK;
+                if (ALAY == 0) {
+                    if (lane < BK)
+                        g_bulk_g2s(sA + (size_t)lane * PITCH_A, p.A + (a_m0 + group_offset(wp.ak, k0 + lane)),
+                                   (unsigned)vm * 8u, &full_bar[stage]);
+                } else if (lane == 0) {
+                    g_tensor_g2s(sA, &wp.tmA, wp.tcA, k0, m0, &full_bar[stage]);
+                }
+                if (BLAY == 1) {
+                    if (lane < BK)
+                        g_bulk_g2s(sB + (size_t)lane * PITCH_B, p.B + (b_n0 + group_offset(wp.bk, k0 + lane)),
+                                   (unsigned)vn * 8u, &full_bar[stage]);
+                } else if (lane == 0) {
+                    g_tensor_g2s(sB, &wp.tmB, wp.tcB, k0, n0, &full_bar[stage]);
+                }
             }
-            if (BLAY == 1) {
-                if (lane < BK)
-                    g_bulk_g2s(sB + (size_t)lane * PITCH_B, p.B + (b_n0 + group_offset(wp.bk, k0 + lane)),
-                               (unsigned)vn * 8u, &full_bar[stage]);
-            } else if (lane == 0) {
-                g_tensor_g2s(sB, &wp.tmB, wp.tcB, k0, n0, &full_bar[stage]);
-            }
+            u += ke - kb;
         }
         return;
     }
@@ -428,91 +461,126 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_kernel(const __grid_con
     const int wm0 = (warp % (BM / WM)) * WM;
     const int wn0 = (warp / (BM / WM)) * WN;
     const int grp = lane >> 2, tig = lane & 3;
-    double acc[MF][NF][2 * ES];
+    int64_t it = 0;
+    for (int64_t u = u0; u < u1;) {
+        const int64_t tile = u / KT_all;
+        const int64_t kb = u - tile * KT_all;
+        const int64_t ke = (kb + (u1 - u) < KT_all) ? kb + (u1 - u) : KT_all;
+        const int64_t m0 = (tile % p.tiles_m) * BM;
+        const int64_t n0 = (tile / p.tiles_m) * BN;
+        double acc[MF][NF][2 * ES];
 #pragma unroll
-    for (int i = 0; i < MF; ++i)
+        for (int i = 0; i < MF; ++i)
 #pragma unroll
-        for (int j = 0; j < NF; ++j)
+            for (int j = 0; j < NF; ++j)
 #pragma unroll
-            for (int e = 0; e < 2 * ES; ++e) acc[i][j][e] = 0.0;
-    for (int64_t kt = 0; kt < KT; ++kt) {
-        const int stage = (int)(kt % WS_STAGES);
-        g_mbar_wait(&full_bar[stage], (unsigned)((kt / WS_STAGES) & 1));
-        const double* sA = smem + (size_t)stage * STAGE_DOUBLES;
-        const double* sB = sA + B_OFF;
+                for (int e = 0; e < 2 * ES; ++e) acc[i][j][e] = 0.0;
+        for (int64_t kt = kb; kt < ke; ++kt, ++it) {
+            const int stage = (int)(it % WS_STAGES);
+            g_mbar_wait(&full_bar[stage], (unsigned)((it / WS_STAGES) & 1));
+            const double* sA = smem + (size_t)stage * STAGE_DOUBLES;
+            const double* sB = sA + B_OFF;
 #pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
-            const int k = ks * 4 + tig;
-            double af[MF], bf[NF];
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                const int k = ks * 4 + tig;
+                double af[MF], bf[NF];
+#pragma unroll
+                for (int i = 0; i < MF; ++i) {
+                    const int m = wm0 + i * 8 + grp;
+                    af[i] = sA[ALAY == 0 ? k * PITCH_A + m : kfast_idx(m, k)];
+                }
+#pragma unroll
+                for (int j = 0; j < NF; ++j) {
+                    const int n = wn0 + j * 8 + grp;
+                    bf[j] = sB[BLAY == 1 ? k * PITCH_B + n : kfast_idx(n, k)];
+                }
+#pragma unroll
+                for (int i = 0; i < MF; ++i)
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) g_mbar_arrive(&empty_bar[stage]);
+        }
+        u += ke - kb;
+
+        if (wp.streamk) {
+            // fragment-order slot layout: ((warp * MF + i) * NF + j) * 2 + c) * 32 + lane  (coalesced 256-byte rows)
+            if (kb > 0) {
+                // tail (or interior) k-range of a tile whose head belongs to a lower-numbered CTA: this is always the
+                // FIRST segment of this CTA, so the partial sums are published before anything else is computed and
+                // nobody ever waits on a CTA that is itself waiting (no serial chain, no residency requirement).
+                double* slot = wp.sk_ws + (size_t)blockIdx.x * (size_t)(BM * BN);
+#pragma unroll
+                for (int i = 0; i < MF; ++i)
+#pragma unroll
+                    for (int j = 0; j < NF; ++j)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            slot[((((size_t)warp * MF + i) * NF + j) * 2 + c) * 32 + lane] = acc[i][j][c];
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(WS_CONSUMERS * 32) : "memory");   // consumer warps only
+                if (tid == 0) g_st_release(wp.sk_flags + blockIdx.x, wp.sk_epoch);
+                continue;
+            }
+            if (ke < KT_all) {
+                // finisher = the CTA holding the HEAD of the tile (its LAST segment): add the partial sums of the
+                // higher-numbered CTAs that hold the later k-ranges, in ascending CTA order (deterministic).  Units are
+                // contiguous, so those CTAs are blockIdx.x + 1 .. last, last = the CTA whose range contains the
+                // tile's final unit.
+                const int64_t U = wp.sk_tiles * KT_all;
+                const int64_t G = (int64_t)gridDim.x;
+                const int64_t ulast = (tile + 1) * KT_all - 1;
+                int64_t last = (ulast * G) / U;
+                if (last >= G) last = G - 1;
+                while (last > 0 && U * last / G > ulast) --last;
+                while (last + 1 < G && U * (last + 1) / G <= ulast) ++last;
+                for (int64_t cta = (int64_t)blockIdx.x + 1; cta <= last; ++cta) {
+                    if (lane == 0) while (g_ld_acquire(wp.sk_flags + cta) != wp.sk_epoch) {}
+                    __syncwarp();
+                    const double* slot = wp.sk_ws + (size_t)cta * (size_t)(BM * BN);
+#pragma unroll
+                    for (int i = 0; i < MF; ++i)
+#pragma unroll
+                        for (int j = 0; j < NF; ++j)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                acc[i][j][c] += __ldcg(slot + ((((size_t)warp * MF + i) * NF + j) * 2 + c) * 32 + lane);
+                }
+            }
+        } else if (p.ksplit > 1) {
+            // split-K: raw partial sums, reduced by splitk_reduce_kernel
+            double* part = p.partial + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N * ES;
 #pragma unroll
             for (int i = 0; i < MF; ++i) {
-                const int m = wm0 + i * 8 + grp;
-                af[i] = sA[ALAY == 0 ? k * PITCH_A + m : kfast_idx(m, k)];
+                int64_t gm = m0 + wm0 + i * 8 + grp;
+                if (gm >= p.M) continue;
+#pragma unroll
+                for (int j = 0; j < NF; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        int64_t gn = n0 + wn0 + j * 8 + 2 * tig + c;
+                        if (gn >= p.N) continue;
+                        part[(size_t)gm + (size_t)gn * (size_t)p.M] = acc[i][j][c];
+                    }
+                }
             }
-#pragma unroll
-            for (int j = 0; j < NF; ++j) {
-                const int n = wn0 + j * 8 + grp;
-                bf[j] = sB[BLAY == 1 ? k * PITCH_B + n : kfast_idx(n, k)];
-            }
-#pragma unroll
-            for (int i = 0; i < MF; ++i)
-#pragma unroll
-                for (int j = 0; j < NF; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            continue;
         }
-        __syncwarp();
-        if (lane == 0) g_mbar_arrive(&empty_bar[stage]);
-    }
 
-    // epilogue (same as gemm_kernel): thread holds rows (grp) and columns (2*tig, 2*tig+1) of each fragment
-    if (p.ksplit > 1) {
-        double* part = p.partial + (size_t)blockIdx.y * (size_t)p.M * (size_t)p.N * ES;
+        // epilogue: thread holds rows (grp) and columns (2*tig, 2*tig+1) of each 8 x 8 fragment
 #pragma unroll
         for (int i = 0; i < MF; ++i) {
             int64_t gm = m0 + wm0 + i * 8 + grp;
             if (gm >= p.M) continue;
+            int64_t om = off_of(p.tcm, p.scm, gm);
 #pragma unroll
             for (int j = 0; j < NF; ++j) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     int64_t gn = n0 + wn0 + j * 8 + 2 * tig + c;
                     if (gn >= p.N) continue;
-                    size_t o = (size_t)gm + (size_t)gn * (size_t)p.M;
-                    if constexpr (CPLX) {
-                        double2 r;
-                        r.x = acc[i][j][c];
-                        r.y = acc[i][j][2 * ES - 2 + c];
-                        reinterpret_cast<double2*>(part)[o] = r;
-                    } else {
-                        part[o] = acc[i][j][c];
-                    }
-                }
-            }
-        }
-        return;
-    }
-#pragma unroll
-    for (int i = 0; i < MF; ++i) {
-        int64_t gm = m0 + wm0 + i * 8 + grp;
-        if (gm >= p.M) continue;
-        int64_t om = off_of(p.tcm, p.scm, gm);
-#pragma unroll
-        for (int j = 0; j < NF; ++j) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                int64_t gn = n0 + wn0 + j * 8 + 2 * tig + c;
-                if (gn >= p.N) continue;
-                int64_t o = om + off_of(p.tcn, p.scn, gn);
-                if constexpr (CPLX) {
-                    double2 r;
-                    r.x = p.alpha * acc[i][j][c];
-                    r.y = p.alpha * acc[i][j][2 * ES - 2 + c];
-                    double2* dst = reinterpret_cast<double2*>(p.C) + o;
-                    if (p.beta != 0.0) {
-                        double2 old = *dst;
-                        r.x += p.beta * old.x; r.y += p.beta * old.y;
-                    }
-                    *dst = r;
-                } else {
+                    int64_t o = om + off_of(p.tcn, p.scn, gn);
                     double r = p.alpha * acc[i][j][c];
                     if (p.beta != 0.0) r += p.beta * p.C[o];
                     p.C[o] = r;
@@ -698,7 +766,7 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, cons
     int64_t tiles_n = (p.N + BN - 1) / BN;
     int64_t grid = (int64_t)p.tiles_m * tiles_n;
     size_t sm = smem_bytes(alay, blay);
-    const int ksplit = p.ksplit;  // planned by gemm() (scratch already sized)
+    int ksplit = p.ksplit;  // planned by gemm() (scratch already sized); the stream-K kernel resets it to 1
     dim3 g3((unsigned)grid, (unsigned)ksplit, 1);
 #define T4B_LAUNCH(AL, BL)                                                                       \
     {                                                                                            \
@@ -712,7 +780,7 @@ void launch_cfg(Ctx* c, GemmParams& p, int alay, int blay, const Group& cm, cons
     if constexpr (!CPLX && BM == 128 && BN == 128) {
         if (gops && !c->knobs.gemm_nows) done = launch_ws<false>(c, p, alay, blay, gops);
     }
-    if (done) {}
+    if (done) { ksplit = p.ksplit; }
     else if (alay == 0 && blay == 0) T4B_LAUNCH(0, 0)
     else if (alay == 0 && blay == 1) T4B_LAUNCH(0, 1)
     else if (alay == 1 && blay == 0) T4B_LAUNCH(1, 0)
@@ -830,8 +898,42 @@ bool launch_ws(Ctx* c, GemmParams& p, int alay, int blay, const Group* g) {
     };
     p.tiles_m = (int)((p.M + WS_BM - 1) / WS_BM);
     int64_t tiles_n = (p.N + WS_BN - 1) / WS_BN;
+    // Stream-K: one persistent CTA per SM walks a contiguous range of (tile, k-tile) units, so tile-count
+    // quantisation (256 tiles on 148 SMs = 1.73 waves) and few-tile / long-K shapes cost nothing; it replaces the
+    // two-pass split-K for this kernel.  Not used on the look-ahead side stream (one workspace per context).
+    const int64_t tiles = (int64_t)p.tiles_m * tiles_n;
+    const int64_t units = tiles * (p.K / BK);
+    wp.streamk = 0;
+    // Few-tile / long-K shapes keep the two-pass split-K: with more than ~4 CTAs per tile the finisher's serial
+    // fix-up (one 128 KB slot per contributing CTA) costs more than the quantisation it removes (measured: 16 tiles x
+    // 128 k-tiles 54 us split-K vs 99 us stream-K; 256 tiles x 32 k-tiles 171 us -> 159 us with stream-K).
+    if (!c->knobs.gemm_nopersist && c->stream != c->side && units >= 8 && tiles * 4 >= c->num_sms) {
+        int64_t G = units / 4;                      // at least four k-tiles per CTA
+        if (G > c->num_sms) G = c->num_sms;
+        if (G < 1) G = 1;
+        if (!c->sk_ws) {
+            T4B_CUDA_CHECK(cudaMalloc((void**)&c->sk_ws, (size_t)c->num_sms * WS_BM * WS_BN * sizeof(double)));
+            T4B_CUDA_CHECK(cudaMalloc((void**)&c->sk_flags, (size_t)c->num_sms * sizeof(unsigned)));
+            T4B_CUDA_CHECK(cudaMemsetAsync(c->sk_flags, 0, (size_t)c->num_sms * sizeof(unsigned), c->stream));
+            c->sk_epoch = 0;
+        }
+        wp.streamk = 1;
+        wp.sk_tiles = tiles;
+        wp.sk_ws = c->sk_ws;
+        wp.sk_flags = c->sk_flags;
+        wp.sk_epoch = ++c->sk_epoch;
+        if (c->sk_epoch == 0) wp.sk_epoch = ++c->sk_epoch;      // 0 is the "never written" value
+        p.ksplit = 1;                                            // no reduction pass
+        p.kt_per_split = p.K / BK;
+    }
     wp.p = p; wp.am = g[0]; wp.ak = g[1]; wp.bk = g[2]; wp.bn = g[3];
-    dim3 g3((unsigned)((int64_t)p.tiles_m * tiles_n), (unsigned)p.ksplit, 1);
+    dim3 g3((unsigned)tiles, (unsigned)p.ksplit, 1);
+    if (wp.streamk) {
+        int64_t G = units / 4;
+        if (G > c->num_sms) G = c->num_sms;
+        if (G < 1) G = 1;
+        g3 = dim3((unsigned)G, 1, 1);
+    }
     size_t sm = smem_bytes(alay, blay);
 #define T4B_LAUNCH_WS(AL, BL)                                                                    \
     {                                                                                            \

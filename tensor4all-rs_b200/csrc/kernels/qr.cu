@@ -598,6 +598,325 @@ __global__ void __launch_bounds__(FT, 1) tsqr_factor_kernel(FactorArgs a) {
     }
 }
 
+// =====================================================================================================
+// Blocked TSQR leaf (f64, blocks of <= 512 rows): the Householder factorisation of an r x 32 block is cut into
+// sub-panels of SB columns.  ONE warp factors a sub-panel entirely in registers (lane owns rows lane, lane + 32, ...
+// of all SB columns: norms and dot products are warp shuffles, there is no block barrier inside a sub-panel), builds
+// the sub-panel's compact-WY factor T_jj, and the whole CTA then applies the sub-panel to the remaining panel columns
+// as two small DMMA products (W = V^H C split over the warps' row ranges, C -= V (T_jj^H W)).  The old leaf needed one
+// 1024-thread barrier per column and ran at ~1.8 us per column; this one has 4 (r <= 256) or 8 barrier phases per
+// level.  The panel's 32 x 32 T is assembled at the end from the T_jj and the Gram matrix V^H V (DMMA).
+// While a block is being factored P holds the EXPLICIT reflectors (unit diagonal, zeros above) of the finished
+// columns and the R entries live in Rs; LAPACK storage is restored on the way out.
+// =====================================================================================================
+constexpr int F2T = 256;
+constexpr int F2W = F2T / 32;
+constexpr int RP = NB + 1;
+
+struct Leaf2Smem {
+    double* Rs;      // [32][RP]  R[i][c] at Rs[c * RP + i]
+    double* Ts;      // [32][RP]  T[k][c] at Ts[k * RP + c]
+    double* Gs;      // [32][RP]  G[l][c] = v_l^H v_c at Gs[l * RP + c]
+    double* Wp;      // [F2W][8][32] per-warp partial W
+    double* Wf;      // [8][32]
+    double* W2;      // [8][32]
+    double* tau_s;   // [32]
+};
+__host__ __device__ constexpr int leaf2_extra_doubles() { return 3 * NB * RP + F2W * 8 * 32 + 2 * 8 * 32 + NB; }
+
+template <int RPL, int SB>
+__device__ void house_factor_blocked(double* P, int pitch, int r, int jb, const Leaf2Smem& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane >> 2, tig = lane & 3;
+    double* Rs = sm.Rs; double* Ts = sm.Ts; double* Gs = sm.Gs; double* tau_s = sm.tau_s;
+    for (int e = tid; e < NB * RP; e += F2T) { Rs[e] = 0.0; Ts[e] = 0.0; Gs[e] = 0.0; }
+    if (tid < NB) tau_s[tid] = 0.0;
+    __syncthreads();
+    const int r4 = (r + 3) & ~3, r8 = (r + 7) & ~7;      // rows r .. r8-1 of P hold zeros (caller)
+
+    for (int c0 = 0; c0 < jb; c0 += SB) {
+        const int sb = (jb - c0) < SB ? (jb - c0) : SB;
+        if (warp == 0) {
+            double x[SB][RPL];
+#pragma unroll
+            for (int cc = 0; cc < SB; ++cc)
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    const int row = lane + 32 * t;
+                    x[cc][t] = (cc < sb && row < r) ? P[(size_t)(c0 + cc) * pitch + row] : 0.0;
+                }
+            // rows above the sub-panel: R entries finished by the earlier sub-panels' updates
+#pragma unroll
+            for (int cc = 0; cc < SB; ++cc)
+                if (cc < sb && lane < c0) Rs[(c0 + cc) * RP + lane] = x[cc][0];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                if (c < sb) {
+                    const int gc = c0 + c;                    // column == diagonal row (< 32: lane gc, t = 0)
+                    double nacc = 0.0;
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t)
+                        if (lane + 32 * t > gc) nacc = fma(x[c][t], x[c][t], nacc);
+                    nacc = warp_sum(nacc);
+                    const double alpha = __shfl_sync(0xffffffffu, x[c][0], gc);
+                    double beta, tau, scale;
+                    larfg_fast<false>(alpha, nacc, beta, tau, scale);
+                    const bool triv = tau == 0.0;
+                    if (lane == 0) { tau_s[gc] = tau; Rs[gc * RP + gc] = beta; }
+                    if (lane >= c0 && lane < gc) Rs[gc * RP + lane] = x[c][0];   // R entries made inside the sub-panel
+                    if (!triv) {
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t)
+                            if (lane + 32 * t > gc) x[c][t] *= scale;
+#pragma unroll
+                        for (int k = c + 1; k < SB; ++k) {
+                            if (k < sb) {
+                                double d = (lane == gc) ? x[k][0] : 0.0;      // unit diagonal of v
+#pragma unroll
+                                for (int t = 0; t < RPL; ++t)
+                                    if (lane + 32 * t > gc) d = fma(x[c][t], x[k][t], d);
+                                d = warp_sum(d);
+                                const double f = tau * d;
+#pragma unroll
+                                for (int t = 0; t < RPL; ++t)
+                                    if (lane + 32 * t > gc) x[k][t] = fma(-f, x[c][t], x[k][t]);
+                                if (lane == gc) x[k][0] -= f;
+                            }
+                        }
+                    }
+                }
+            }
+            // Gram of the sub-panel's reflectors (l < c): v_l^H v_c = v_l[row gc] + sum_{row > gc} v_l v_c
+#pragma unroll
+            for (int c = 1; c < SB; ++c) {
+                if (c < sb) {
+                    const int gc = c0 + c;
+#pragma unroll
+                    for (int l = 0; l < c; ++l) {
+                        double d = (lane == gc) ? x[l][0] : 0.0;
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t)
+                            if (lane + 32 * t > gc) d = fma(x[l][t], x[c][t], d);
+                        d = warp_sum(d);
+                        if (lane == 0) Gs[(c0 + l) * RP + gc] = d;
+                    }
+                }
+            }
+            // explicit reflectors replace the columns in P
+#pragma unroll
+            for (int cc = 0; cc < SB; ++cc) {
+                if (cc < sb) {
+                    const int gc = c0 + cc;
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        const int row = lane + 32 * t;
+                        if (row < r8) P[(size_t)gc * pitch + row] = row > gc ? x[cc][t] : (row == gc ? 1.0 : 0.0);
+                    }
+                }
+            }
+            __syncwarp();
+            // T_jj: T[c][c] = tau_c, T[0:c, c] = -tau_c T[0:c, 0:c] G[0:c, c]   (indices inside the sub-panel)
+            for (int c = 0; c < sb; ++c) {
+                const int gc = c0 + c;
+                const double tc = tau_s[gc];
+                if (lane < c) {
+                    double t = 0.0;
+                    for (int q = lane; q < c; ++q) t = fma(Ts[(c0 + lane) * RP + c0 + q], Gs[(c0 + q) * RP + gc], t);
+                    Ts[(c0 + lane) * RP + gc] = -tc * t;
+                } else if (lane == c) {
+                    Ts[gc * RP + gc] = tc;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const int ct0 = c0 + sb;               // first trailing column of the panel
+        const int ncols = jb - ct0;
+        if (ncols > 0) {
+            const int nfr = (ncols + 7) >> 3;  // <= 4
+            // pass 1: W = V_sub^H C, the rows split over the warps
+            {
+                double acc[4][2];
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf) acc[nf][0] = acc[nf][1] = 0.0;
+                for (int k0 = (c0 & ~3) + 4 * warp; k0 < r4; k0 += 4 * F2W) {
+                    const double av = (grp < sb) ? P[(size_t)(c0 + grp) * pitch + k0 + tig] : 0.0;
+#pragma unroll
+                    for (int nf = 0; nf < 4; ++nf) {
+                        if (nf < nfr) {
+                            const int col = ct0 + nf * 8 + grp;
+                            const double bv = col < jb ? P[(size_t)col * pitch + k0 + tig] : 0.0;
+                            dmma884(acc[nf][0], acc[nf][1], av, bv);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) sm.Wp[(warp * 8 + grp) * 32 + nf * 8 + 2 * tig + c2] = acc[nf][c2];
+            }
+            __syncthreads();
+            {   // fixed-order reduction over the warps (one entry per thread)
+                const int i = tid >> 5, col = tid & 31;
+                double sacc = 0.0;
+#pragma unroll
+                for (int w = 0; w < F2W; ++w) sacc += sm.Wp[(w * 8 + i) * 32 + col];
+                sm.Wf[i * 32 + col] = sacc;
+            }
+            __syncthreads();
+            {   // W2 = T_jj^H W
+                const int i = tid >> 5, col = tid & 31;
+                double t = 0.0;
+                if (i < sb)
+                    for (int l = 0; l <= i; ++l) t = fma(Ts[(c0 + l) * RP + c0 + i], sm.Wf[l * 32 + col], t);
+                sm.W2[i * 32 + col] = t;
+            }
+            __syncthreads();
+            // pass 2: C -= V_sub W2
+            for (int mf = (c0 >> 3) + warp; mf < (r8 >> 3); mf += F2W) {
+                double av[SB / 4];
+#pragma unroll
+                for (int ks = 0; ks < SB / 4; ++ks) {
+                    const int kk = ks * 4 + tig;
+                    av[ks] = kk < sb ? P[(size_t)(c0 + kk) * pitch + mf * 8 + grp] : 0.0;
+                }
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf) {
+                    if (nf < nfr) {
+                        double a2[2] = {0.0, 0.0};
+#pragma unroll
+                        for (int ks = 0; ks < SB / 4; ++ks) dmma884(a2[0], a2[1], av[ks], sm.W2[(ks * 4 + tig) * 32 + nf * 8 + grp]);
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2) {
+                            const int col = ct0 + nf * 8 + 2 * tig + c2;
+                            if (col < jb) P[(size_t)col * pitch + mf * 8 + grp] -= a2[c2];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- the panel's T: Gram of all reflectors on DMMA (8 x 8 tiles fi <= fj), then the block recurrence ----------
+    for (int t = warp; t < 10; t += F2W) {
+        int fj = 0, rem = t;
+        while (rem > fj) { rem -= fj + 1; ++fj; }
+        const int fi = rem;
+        if (fi == fj && SB == 8) continue;             // diagonal tiles are intra-sub-panel for SB = 8 (already in Gs)
+        double acc[2] = {0.0, 0.0};
+        const int ca = fi * 8 + grp, cb = fj * 8 + grp;
+        for (int k0 = (fi * 8) & ~3; k0 < r4; k0 += 4) {
+            const double av = ca < jb ? P[(size_t)ca * pitch + k0 + tig] : 0.0;
+            const double bv = cb < jb ? P[(size_t)cb * pitch + k0 + tig] : 0.0;
+            dmma884(acc[0], acc[1], av, bv);
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int row = fi * 8 + grp, col = fj * 8 + 2 * tig + c2;
+            // keep the intra-sub-panel entries computed above; fill the others
+            if (row < col && (row / SB) != (col / SB)) Gs[row * RP + col] = acc[c2];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // T[0:c0, sub-panel j] = -T[0:c0, 0:c0] (G[0:c0, sub-panel j] T_jj)
+        for (int c0 = SB; c0 < jb; c0 += SB) {
+            const int sb = (jb - c0) < SB ? (jb - c0) : SB;
+            double* X = sm.Wf;                          // [c0][SB] scratch (<= 28 x 4 or 24 x 8 entries)
+            for (int e = lane; e < c0 * sb; e += 32) {
+                const int q = e / sb, c = e - q * sb;
+                double t = 0.0;
+                for (int pp = 0; pp <= c; ++pp) t = fma(Gs[q * RP + c0 + pp], Ts[(c0 + pp) * RP + c0 + c], t);
+                X[q * SB + c] = t;
+            }
+            __syncwarp();
+            for (int e = lane; e < c0 * sb; e += 32) {
+                const int l = e / sb, c = e - l * sb;
+                double t = 0.0;
+                for (int q = l; q < c0; ++q) t = fma(Ts[l * RP + q], X[q * SB + c], t);
+                Ts[l * RP + c0 + c] = -t;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void leaf2_dispatch(double* P, int pitch, int r, int jb, const Leaf2Smem& sm) {
+    if (r <= 256) house_factor_blocked<8, 8>(P, pitch, r, jb, sm);
+    else house_factor_blocked<16, 4>(P, pitch, r, jb, sm);
+}
+
+// Same contract as tsqr_factor_kernel (f64 only, every block <= 512 rows, nblocks * 32 <= 512).
+__global__ void __launch_bounds__(F2T, 1) tsqr_factor2_kernel(FactorArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int is_last;
+    const int pitch = a.pitch;
+    double* P = reinterpret_cast<double*>(smem_raw);
+    Leaf2Smem sm;
+    sm.Rs = P + (size_t)NB * pitch;
+    sm.Ts = sm.Rs + NB * RP;
+    sm.Gs = sm.Ts + NB * RP;
+    sm.Wp = sm.Gs + NB * RP;
+    sm.Wf = sm.Wp + F2W * 8 * 32;
+    sm.W2 = sm.Wf + 8 * 32;
+    sm.tau_s = sm.W2 + 8 * 32;
+    const int jb = a.jb;
+    const int b = blockIdx.x;
+    const int64_t blk0 = (int64_t)b * a.h;
+    const int r = (int)((b == a.nblocks - 1) ? (a.rows - blk0) : a.h);
+    const int r8 = (r + 7) & ~7;
+    double* Ag = a.A + (a.row0 + blk0) + a.col0 * a.lda;
+
+    // ---- level 1: this CTA's row block --------------------------------------------------------------
+    for (int c = warp; c < NB; c += F2W)
+        for (int i = lane; i < r8; i += 32) P[(size_t)c * pitch + i] = (c < jb && i < r) ? Ag[i + (int64_t)c * a.lda] : 0.0;
+    __syncthreads();
+    leaf2_dispatch(P, pitch, r, jb, sm);
+    for (int c = warp; c < jb; c += F2W)
+        for (int i = lane; i < r; i += 32) Ag[i + (int64_t)c * a.lda] = (i <= c) ? sm.Rs[c * RP + i] : P[(size_t)c * pitch + i];
+    {
+        double* Tg = a.Tw + (size_t)b * NB * NB;
+        for (int e = tid; e < NB * NB; e += F2T) Tg[e] = sm.Ts[(e & 31) * RP + (e >> 5)];
+    }
+    if (a.nblocks == 1) return;
+
+    // ---- level 2: the last block to arrive factors the stacked triangles -----------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned old = atomicAdd(a.counter, 1u);
+        is_last = (old == (unsigned)a.nblocks - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int r2 = a.nblocks * NB;
+    const double* Atop = a.A + a.row0 + a.col0 * a.lda;
+    for (int c = warp; c < NB; c += F2W)
+        for (int i = lane; i < r2; i += 32) {
+            const int s = i >> 5, q = i & 31;
+            double v = 0.0;
+            if (c < jb && q <= c) v = __ldcg(Atop + (int64_t)s * a.h + q + (int64_t)c * a.lda);
+            P[(size_t)c * pitch + i] = v;
+        }
+    __syncthreads();
+    leaf2_dispatch(P, pitch, r2, jb, sm);
+    double* Aw = a.A + a.row0 + a.col0 * a.lda;
+    for (int e = tid; e < NB * NB; e += F2T) {
+        const int q = e & 31, c = e >> 5;
+        if (c < jb && q <= c) Aw[q + (int64_t)c * a.lda] = sm.Rs[c * RP + q];
+    }
+    // explicit V' (P already holds unit diagonal / zeros above; zero columns beyond jb)
+    for (int c = warp; c < NB; c += F2W)
+        for (int i = lane; i < r2; i += 32) a.V2[i + (size_t)c * r2] = c < jb ? P[(size_t)c * pitch + i] : 0.0;
+    {
+        double* Tg = a.Tw + (size_t)a.nblocks * NB * NB;
+        for (int e = tid; e < NB * NB; e += F2T) Tg[e] = sm.Ts[(e & 31) * RP + (e >> 5)];
+    }
+}
+
 struct ApplyArgs {
     const double* V; int64_t ldv;   // contiguous: panel origin inside A (LAPACK storage); gather: explicit V'
     int v_implicit;                 // 1: unit diagonal / zeros above are implied
@@ -1225,6 +1544,21 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
         fa.Tw = (double*)(Tall + (size_t)p * t_stride * es);
         fa.V2 = (double*)(V2all + (size_t)p * v2_stride * es);
         fa.counter = counters + p;
+        if constexpr (!CPLX) {
+            // blocked leaf: every level-1 block and the level-2 stack fit in 512 rows
+            const int64_t r1 = nblocks == 1 ? rows : h;
+            const int64_t r2 = nblocks > 1 ? (int64_t)nblocks * NB : 0;
+            if (!c->knobs.qr_leaf_old && r1 <= 512 && r2 <= 512) {
+                const int64_t rm = ((r1 > r2 ? r1 : r2) + 7) & ~(int64_t)7;
+                fa.pitch = factor_pitch(false, (int)rm);
+                const size_t smem2 = ((size_t)NB * fa.pitch + leaf2_extra_doubles()) * sizeof(double);
+                if (c->first_use((const void*)tsqr_factor2_kernel))
+                    T4B_CUDA_CHECK(cudaFuncSetAttribute(tsqr_factor2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                tsqr_factor2_kernel<<<nblocks, F2T, smem2, c->stream>>>(fa);
+                c->launched("qr_factor", 2.0 * (double)rows * (double)jb * (double)es);
+                return;
+            }
+        }
         const size_t smem = ((size_t)NB * fa.pitch + NB * (NB + 1)) * es;
         fk<<<nblocks, FT, smem, c->stream>>>(fa);
         c->launched("qr_factor", 2.0 * (double)rows * (double)jb * (double)es);   // bytes: panel read + write

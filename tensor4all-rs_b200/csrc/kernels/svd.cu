@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "scalar.cuh"
@@ -1119,12 +1120,242 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     if (Q) release(c, Q);
 }
 
+
+// =====================================================================================================
+// Small / batched SVD: ONE CTA per problem, the whole matrix resident in shared memory.
+//
+// One-sided (Hestenes) Jacobi straight on the columns of X = A (m >= n) or X = A^H (m < n): every warp owns one
+// column pair of the round-robin round (norms, inner product and the rotation by warp shuffles over the rows, one
+// __syncthreads per round), right vectors accumulated in a second shared-memory panel when they are wanted.
+// Convergence, descending sort, normalisation and the write-out of U / S / Vh happen in the same launch, so a
+// factorisation is one launch and a batch of independent factorisations (sites of many tensor trains, patches) is
+// ONE launch with gridDim.x = batch.  This is the small-chi regime of the north star (C1: <= 128 x 64 matrices,
+// boundary sites of every sweep, truncated patches), where the QR-preconditioned cluster pipeline above is pure
+// launch latency.  Replaces the same tenferro `.svd()` (core/src/defaults/svd.rs:265-267).
+// =====================================================================================================
+struct SmallSvdDesc {
+    const double* A; int m, n; long long lda;     // input (preserved)
+    double* U; long long ldu;                     // m x k or null
+    double* S;                                    // k
+    double* Vh; long long ldvh;                   // k x n or null
+};
+
+template <bool CPLX>
+__global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* __restrict__ descs, SmallSvdDesc single,
+                                                            int max_sweeps, unsigned* fail) {
+    typedef Sc<CPLX> S_;
+    typedef typename S_::T T;
+    const SmallSvdDesc d = descs ? descs[blockIdx.x] : single;     // a single problem travels in the launch parameters
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const bool tall = d.m >= d.n;
+    const int mx = tall ? d.m : d.n, nx = tall ? d.n : d.m;
+    const int np = (nx + 1) & ~1;                          // even number of columns (a zero column pads odd nx)
+    const bool need_v = tall ? (d.Vh != nullptr) : (d.U != nullptr);
+    const int ldx = mx | 1, ldv = np | 1;                  // odd pitches: conflict-free column walks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* X = reinterpret_cast<T*>(smem_raw);                 // [np][ldx]
+    T* V = X + (size_t)np * ldx;                           // [np][ldv] (only when need_v)
+    double* sig2 = reinterpret_cast<double*>(V + (need_v ? (size_t)np * ldv : 0));   // [np]
+    int* rank = reinterpret_cast<int*>(sig2 + np);         // [np]
+    __shared__ double red[32];
+    __shared__ double fro2_s;
+
+    const T* Ag = reinterpret_cast<const T*>(d.A);
+    for (int e = tid; e < mx * np; e += blockDim.x) {
+        const int j = e / mx, i = e - j * mx;
+        T v = S_::zero();
+        if (j < nx) v = tall ? Ag[i + (long long)j * d.lda] : S_::conj(Ag[j + (long long)i * d.lda]);
+        X[(size_t)j * ldx + i] = v;
+    }
+    if (need_v)
+        for (int e = tid; e < np * np; e += blockDim.x) {
+            const int j = e / np, i = e - j * np;
+            V[(size_t)j * ldv + i] = i == j ? S_::one() : S_::zero();
+        }
+    __syncthreads();
+    // ||X||_F^2: columns below (16 eps)^2 ||X||_F^2 are numerically zero (same rule as the cluster kernel)
+    {
+        double acc = 0.0;
+        for (int e = tid; e < mx * np; e += blockDim.x) { const int j = e / mx; acc += S_::abs2(X[(size_t)j * ldx + (e - j * mx)]); }
+        acc = warp_sum(acc);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double v = lane < nwarps ? red[lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) fro2_s = v;
+        }
+        __syncthreads();
+    }
+    const double eps = 2.220446049250313e-16;
+    const double zthr = 1.2621774483536189e-29 * fro2_s;
+    const double tol = 4.0 * eps * sqrt((double)(mx > 4 ? mx : 4));
+    const double tol2 = tol * tol;
+    const int pairs = np >> 1, p1 = np - 1;
+    int converged = 0, sweep = 0;
+    for (; sweep < max_sweeps && !converged; ++sweep) {
+        double mxcos2 = 0.0;
+        for (int r = 0; r < p1; ++r) {
+            for (int k = warp; k < pairs; k += nwarps) {
+                int pi, qi;
+                if (k == 0) { pi = r % p1; qi = np - 1; }
+                else { pi = (r + k) % p1; qi = (r - k + 2 * p1) % p1; }
+                if (pi > qi) { const int t = pi; pi = qi; qi = t; }
+                T* xp = X + (size_t)pi * ldx;
+                T* xq = X + (size_t)qi * ldx;
+                double app = 0.0, aqq = 0.0;
+                T g = S_::zero();
+                for (int i = lane; i < mx; i += 32) {
+                    const T a = xp[i], b = xq[i];
+                    app += S_::abs2(a); aqq += S_::abs2(b);
+                    g = S_::add(g, S_::mul(S_::conj(a), b));
+                }
+                app = warp_sum(app); aqq = warp_sum(aqq);
+                g = warp_sum_t<CPLX>(g);
+                const double g2 = S_::abs2(g);
+                if (app > zthr && aqq > zthr) {
+                    const double c2 = g2 / (app * aqq);
+                    if (c2 > mxcos2) mxcos2 = c2;
+                }
+                double c, sn, tg;
+                T ph;
+                jacobi_rotation<CPLX>(app, aqq, g, tol2 * 0.00390625, c, sn, ph, tg, zthr);
+                if (sn != 0.0) {
+                    // columns <- columns J, J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]] (ph = e^{-i phi})
+                    for (int i = lane; i < mx; i += 32) {
+                        const T a = xp[i], fq = S_::mul(xq[i], ph);
+                        xp[i] = S_::sub(S_::scale(a, c), S_::scale(fq, sn));
+                        xq[i] = S_::add(S_::scale(a, sn), S_::scale(fq, c));
+                    }
+                    if (need_v) {
+                        T* vp = V + (size_t)pi * ldv;
+                        T* vq = V + (size_t)qi * ldv;
+                        for (int i = lane; i < np; i += 32) {
+                            const T a = vp[i], fq = S_::mul(vq[i], ph);
+                            vp[i] = S_::sub(S_::scale(a, c), S_::scale(fq, sn));
+                            vq[i] = S_::add(S_::scale(a, sn), S_::scale(fq, c));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // convergence: largest cosine seen in this sweep
+        if (lane == 0) red[warp] = mxcos2;
+        __syncthreads();
+        double m2 = 0.0;
+        for (int w = 0; w < nwarps; ++w) m2 = red[w] > m2 ? red[w] : m2;
+        __syncthreads();
+        if (m2 <= tol2) converged = 1;
+    }
+    if (!converged && tid == 0 && fail) atomicAdd(fail, 1u);
+
+    // sigma, descending order (ties by column index)
+    for (int j = warp; j < np; j += nwarps) {
+        double acc = 0.0;
+        for (int i = lane; i < mx; i += 32) acc += S_::abs2(X[(size_t)j * ldx + i]);
+        acc = warp_sum(acc);
+        if (lane == 0) sig2[j] = j < nx ? acc : -1.0;      // the padding column sorts last
+    }
+    __syncthreads();
+    for (int j = tid; j < np; j += blockDim.x) {
+        const double sj = sig2[j];
+        int rk = 0;
+        for (int i = 0; i < np; ++i) { const double si = sig2[i]; rk += (si > sj) || (si == sj && i < j); }
+        rank[j] = rk;
+    }
+    __syncthreads();
+    double smax2 = 0.0;
+    for (int j = 0; j < nx; ++j) smax2 = sig2[j] > smax2 ? sig2[j] : smax2;
+    const double floor2 = (eps * (double)nx) * (eps * (double)nx) * smax2;   // directions below the noise floor: zero vector
+    const int k = nx;
+    T* Ug = reinterpret_cast<T*>(d.U);
+    T* Vg = reinterpret_cast<T*>(d.Vh);
+    for (int j = warp; j < nx; j += nwarps) {
+        const int rk = rank[j];
+        if (rk >= k) continue;
+        const double s2 = sig2[j];
+        const double sg = sqrt(s2 > 0.0 ? s2 : 0.0);
+        const double inv = (s2 > floor2 && s2 > 0.0) ? 1.0 / sg : 0.0;
+        if (lane == 0) d.S[rk] = sg;
+        const T* xj = X + (size_t)j * ldx;
+        const T* vj = V + (size_t)j * ldv;
+        if (tall) {
+            if (Ug) for (int i = lane; i < mx; i += 32) Ug[i + (long long)rk * d.ldu] = S_::scale(xj[i], inv);
+            if (Vg) for (int i = lane; i < nx; i += 32) Vg[rk + (long long)i * d.ldvh] = S_::conj(vj[i]);
+        } else {
+            // X = A^H = U_X S V_X^H  =>  A = V_X S U_X^H
+            if (Ug) for (int i = lane; i < nx; i += 32) Ug[i + (long long)rk * d.ldu] = vj[i];
+            if (Vg) for (int i = lane; i < mx; i += 32) Vg[rk + (long long)i * d.ldvh] = S_::conj(S_::scale(xj[i], inv));
+        }
+    }
+}
+
+// shared memory the kernel needs for one problem
+size_t svd_small_smem(bool cplx, int64_t m, int64_t n, bool want_u, bool want_vh) {
+    const size_t es = cplx ? 16 : 8;
+    const bool tall = m >= n;
+    const int64_t mx = tall ? m : n, nx = tall ? n : m;
+    const int64_t np = (nx + 1) & ~(int64_t)1;
+    const bool need_v = tall ? want_vh : want_u;
+    return (size_t)np * (mx | 1) * es + (need_v ? (size_t)np * (np | 1) * es : 0) + (size_t)np * 12 + 64;
+}
+constexpr size_t kSmallSvdSmemCap = 200 * 1024;
+
 }  // namespace
+
+bool svd_small_fits(DType dt, int64_t m, int64_t n, bool want_u, bool want_vh) {
+    const int64_t nx = m < n ? m : n, mx = m < n ? n : m;
+    return nx >= 1 && nx <= 128 && mx <= 4096 && svd_small_smem(dt == C64, m, n, want_u, want_vh) <= kSmallSvdSmemCap;
+}
+
+void svd_small_batched(Ctx* c, DType dt, int64_t batch, const SvdProblem* probs) {
+    if (batch <= 0) return;
+    std::vector<SmallSvdDesc> h((size_t)batch);
+    size_t smem = 0;
+    int64_t maxpairs = 1;
+    for (int64_t b = 0; b < batch; ++b) {
+        const SvdProblem& p = probs[b];
+        T4B_REQUIRE(p.m >= 1 && p.n >= 1, "svd_small_batched: empty matrix");
+        T4B_REQUIRE(svd_small_fits(dt, p.m, p.n, p.U != nullptr, p.Vh != nullptr), "svd_small_batched: problem does not fit one CTA");
+        h[b] = SmallSvdDesc{(const double*)p.A, (int)p.m, (int)p.n, (long long)p.lda, (double*)p.U, (long long)p.ldu,
+                            p.S, (double*)p.Vh, (long long)p.ldvh};
+        const size_t sm = svd_small_smem(dt == C64, p.m, p.n, p.U != nullptr, p.Vh != nullptr);
+        if (sm > smem) smem = sm;
+        const int64_t nx = p.m < p.n ? p.m : p.n;
+        if ((nx + 1) / 2 > maxpairs) maxpairs = (nx + 1) / 2;
+    }
+    int warps = (int)(maxpairs < 32 ? maxpairs : 32);
+    if (warps < 2) warps = 2;
+    SmallSvdDesc* dev = nullptr;
+    if (batch > 1) {
+        dev = (SmallSvdDesc*)alloc(c, (size_t)batch * sizeof(SmallSvdDesc));
+        // pageable source: cudaMemcpyAsync stages it before returning, so `h` may go out of scope
+        h2d(c, dev, h.data(), (size_t)batch * sizeof(SmallSvdDesc));
+    }
+    const int max_sweeps = c->knobs.jac_max_sweeps;
+    if (dt == C64) {
+        auto kern = svd_small_kernel<true>;
+        if (c->first_use((const void*)kern)) T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSvdSmemCap));
+        kern<<<(unsigned)batch, warps * 32, smem, c->stream>>>(dev, h[0], max_sweeps, c->fail_dev);
+    } else {
+        auto kern = svd_small_kernel<false>;
+        if (c->first_use((const void*)kern)) T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSvdSmemCap));
+        kern<<<(unsigned)batch, warps * 32, smem, c->stream>>>(dev, h[0], max_sweeps, c->fail_dev);
+    }
+    c->launched("svd_small", 0.0);
+    if (dev) release(c, dev);
+}
 
 void svd_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh) {
     struct ClassGuard { Ctx* c; const char* prev; ClassGuard(Ctx* cc) : c(cc), prev(cc->gemm_class) { cc->gemm_class = "gemm_factor"; } ~ClassGuard() { c->gemm_class = prev; } } class_guard(c);
     if (m == 0 || n == 0) return;
     const size_t es = dtype_size(dt);
+    if (!c->knobs.svd_nobatch && svd_small_fits(dt, m, n, U != nullptr, Vh != nullptr)) {
+        SvdProblem p{A, m, n, m, U, m, S, Vh, m < n ? m : n};
+        svd_small_batched(c, dt, 1, &p);
+        return;
+    }
     if (m >= n) {
         if (dt == C64) svd_tall<true>(c, m, n, A, U, S, Vh);
         else svd_tall<false>(c, m, n, A, U, S, Vh);

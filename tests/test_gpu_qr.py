@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [(1, 1), (5, 3), (3, 5), (32, 32), (33, 31), (64, 40), (100, 100), (128, 64), (257, 70),
           (600, 130), (2048, 96), (70, 257), (4100, 64), (9000, 40), (2048, 512), (1000, 1000),
-          (3072, 512), (777, 300)]
+          (3072, 512), (777, 300), (300, 33), (512, 129), (4096, 160), (1500, 260)]
 
 
 def _rand(rng, shape, cplx):
@@ -53,3 +53,19 @@ def test_qr_r_only(ctx):
     _, r = ctx.qr_thin(ctx.upload(a), want_q=False)
     r = r.get()
     assert np.allclose(r.T @ r, a.T @ a, rtol=0, atol=1e-11 * np.linalg.norm(a) ** 2)
+
+
+def test_qr_c3_zipup_shape_r_only(ctx):
+    """The R-only QR of the zip-up SVD preconditioner at the BASELINE C3 shape (4096 x 2048, f64): blocked TSQR leaf on
+    16 row blocks of 256 + a 512-row second level per panel."""
+    rng = np.random.default_rng(13)
+    a = _rand(rng, (4096, 2048), False)
+    _, r = ctx.qr_thin(ctx.upload(a), want_q=False)
+    r = r.get()
+    assert np.all(np.tril(r, -1) == 0)
+    r_ref = np.linalg.qr(a, mode="r")
+    d, d_ref = np.abs(np.diag(r)), np.abs(np.diag(r_ref))
+    assert np.allclose(d, d_ref, rtol=1e-11)
+    # R is unique up to row signs: compare after fixing them
+    sg = np.sign(np.diag(r)) * np.sign(np.diag(r_ref))
+    assert np.linalg.norm(sg[:, None] * r - r_ref) <= 1e-12 * np.linalg.norm(r_ref)

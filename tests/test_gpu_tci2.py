@@ -101,3 +101,66 @@ def test_fill_site_tensor_last_site(ctx):
     pi1 = np.asfortranarray(rng.standard_normal((6 * 2, 1)))
     out = ttci.site_tensor(ctx, ctx.upload(pi1), None, 6, 2).get()
     assert np.array_equal(out, otci.site_tensor_from_pi1(pi1, None, 6, 2))
+
+
+def quantics_f_batch(R, k):
+    """Same integrand with a vectorised candidate-matrix evaluation (the batch callback of tensorci2.rs:1862-1893)."""
+    w = 2.0 ** -(np.arange(R) + 1.0)
+    full_w = np.zeros((3, 3 * R))
+    for s in range(3 * R):
+        full_w[s % 3, s] = w[s // 3]
+
+    def f(idx):
+        idx = np.asarray(idx, dtype=np.float64)
+        c = full_w @ idx
+        r = np.sqrt(np.sum(c * c))
+        return np.cos(k * r) * np.exp(-r * r)
+
+    def batch(I, J):
+        p = I.shape[1]
+        c = (I @ full_w[:, :p].T)[:, None, :] + (J @ full_w[:, p:].T)[None, :, :]
+        r = np.sqrt((c ** 2).sum(-1))
+        return np.cos(k * r) * np.exp(-r * r)
+    f.batch = batch
+    return f
+
+
+def test_c4_full_size_sweeps_bit_exact(ctx):
+    """BASELINE C4 at FULL size: R = 20 bits per dimension (60 binary sites), max bond 300, tolerance 1e-8, Full pivot
+    search.  Ten alternating two-site sweeps take the bonds from 1 to the 300 cap (Pi reaches 600 x 600); after EVERY
+    bond update the selected row / column candidates and the bond error are bit-identical to the oracle's."""
+    R = 20
+    f = quantics_f_batch(R, 3000.0)
+    rng = np.random.default_rng(0)
+    I, J = rng.integers(0, 2, (3, 7)), rng.integers(0, 2, (2, 3 * R - 7))
+    assert abs(f.batch(I, J)[2, 1] - f(tuple(I[2]) + tuple(J[1]))) <= 1e-15
+    dims = [2] * (3 * R)
+    first = tuple([1, 0, 1] * R)
+    ref = otci.TCI2(f, dims, first)
+    gpu = otci.TCI2(f, dims, first)
+    ref.sweep2site(otci.update_from_pi, 10, max_bond_dim=300, tolerance=1e-8)
+    gpu.sweep2site(gpu_backend(ctx), 10, max_bond_dim=300, tolerance=1e-8)
+    assert max(len(s) for s in ref.i_set) == 300                 # the cap is reached: 600 x 600 candidate matrices
+    assert len(ref.pivot_log) == len(gpu.pivot_log) == 10 * (3 * R - 1)
+    for a, b in zip(ref.pivot_log, gpu.pivot_log):
+        assert a == b
+    assert ref.i_set == gpu.i_set and ref.j_set == gpu.j_set
+    assert ref.bond_errors == gpu.bond_errors
+    for ta, tb in zip(ref.site_tensors, gpu.site_tensors):
+        assert ta.shape == tb.shape
+        assert np.abs(ta - tb).max() <= 1e-9 * max(1.0, np.abs(ta).max())
+
+
+def test_c4_fused_d8_shape_update(ctx):
+    """The fused-quantics variant of C4 (20 sites, d = 8): one update on the 2400 x 2400 candidate matrix, cap 300."""
+    rng = np.random.default_rng(6)
+    x = rng.random((2400, 3)); y = rng.random((2400, 3))
+    r2 = ((x[:, None, :] + y[None, :, :]) ** 2).sum(-1)
+    pi = np.asfortranarray(np.cos(300.0 * np.sqrt(r2)) * np.exp(-r2))
+    got = TciUpdate(ctx, pi, 300, 8, 8, 300, 300, 1e-8, True)
+    rank, rows, cols, tb, tp, err = otci.update_from_pi(pi, 300, 8, 8, 300, 300, 1e-8, True)
+    assert rank == 300
+    assert got.rank == rank and list(got.row_indices) == rows and list(got.col_indices) == cols
+    assert got.bond_error == err
+    assert np.abs(got.tensor_b - tb).max() <= 1e-9 * np.abs(tb).max()
+    assert np.abs(got.tensor_bp1 - tp).max() <= 1e-9 * np.abs(tp).max()

@@ -136,3 +136,48 @@ def test_tensordot_odd_alignment_falls_back(ctx):
     a, b = _rand(rng, (129, 80), False), _rand(rng, (80, 131), False)
     out = ctx.tensordot(ctx.upload(a), ctx.upload(b), [1], [0]).get()
     assert _relerr(out, a @ b) <= TOL
+
+
+STREAMK_CASES = [
+    # (M, N, K, transpose_a, transpose_b): shapes whose 128 x 128 tiles are SPLIT between the persistent CTAs of the
+    # stream-K scheduler (few tiles / long K, tile counts that are no multiple of the SM count, ragged edges)
+    (256, 256, 2048, False, False),     # 4 tiles x 128 k-tiles: every tile spans ~32 CTAs
+    (384, 640, 512, False, False),      # 15 tiles
+    (512, 512, 2048, True, False),      # U^H M of the two-site step (K-fast A: tensor-map path)
+    (512, 2048, 512, False, False),     # absorb-R
+    (2048, 2048, 512, False, True),     # two-site A.B, 256 tiles = 1.73 waves
+    (4096, 2048, 512, False, False),    # zip-up R.A
+    (200, 300, 1024, False, False),     # ragged tiles
+    (128, 128, 64, False, False),       # a single tile, 4 k-tiles
+    (1000, 136, 4096, True, True),
+]
+
+
+@pytest.mark.parametrize("case", STREAMK_CASES)
+def test_streamk_gemm_matches_numpy_and_is_deterministic(ctx, case):
+    m, n, k, ta, tb = case
+    rng = np.random.default_rng(m * 31 + n * 7 + k)
+    a = _rand(rng, (k, m) if ta else (m, k), False)
+    b = _rand(rng, (n, k) if tb else (k, n), False)
+    ref = (a.T if ta else a) @ (b.T if tb else b)
+    da, db = ctx.upload(a), ctx.upload(b)
+    xa, xb = [0 if ta else 1], [1 if tb else 0]
+    out1 = ctx.tensordot(da, db, xa, xb).get()
+    out2 = ctx.tensordot(da, db, xa, xb).get()
+    assert _relerr(out1, ref) <= TOL
+    assert np.array_equal(out1, out2)           # fixed reduction order: bit-identical run to run
+
+
+def test_streamk_many_launches_back_to_back(ctx):
+    """The flag epoch protocol: different shapes alternate on the same workspace without a host synchronisation."""
+    rng = np.random.default_rng(99)
+    a1, b1 = _rand(rng, (256, 1024), False), _rand(rng, (1024, 384), False)
+    a2, b2 = _rand(rng, (640, 512), False), _rand(rng, (512, 256), False)
+    d = [ctx.upload(x) for x in (a1, b1, a2, b2)]
+    outs = []
+    for _ in range(20):
+        outs.append(ctx.tensordot(d[0], d[1], [1], [0]))
+        outs.append(ctx.tensordot(d[2], d[3], [1], [0]))
+    r1, r2 = a1 @ b1, a2 @ b2
+    for i, o in enumerate(outs):
+        assert _relerr(o.get(), r1 if i % 2 == 0 else r2) <= TOL
