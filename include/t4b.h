@@ -207,6 +207,17 @@ int t4b_tci_update_rank(const t4b_tci_update* u, int64_t* rank, int64_t* new_bon
 int t4b_tci_update_indices(const t4b_tci_update* u, int64_t* rows_host, int64_t* cols_host, int64_t* n);
 int t4b_tci_update_tensors(t4b_ctx* ctx, const t4b_tci_update* u, void* tensor_b_host, void* tensor_bp1_host);
 int t4b_tci_update_release(t4b_tci_update* u);
+/* pivot_errors of the selection (|pivot| per step + final residual), query-then-fill */
+int t4b_tci_update_pivot_errors(const t4b_tci_update* u, double* errors_host, int64_t* n);
+/* TreeTCI2 update_edge, numeric part (treetci/src/update.rs:22-112): `values` is the candidate matrix, column-major
+ * with the n_left left candidates as rows (:55-57,216-230).  Kernel options of the optimizer (optimize.rs:317-331):
+ * rel_tol 1e-14, abs_tol = tolerance * error_scale (the caller passes the product), left_orthogonal; an empty
+ * selection keeps index 0 (:66-76); t4b_tci_update_rank's bond_error is the last pivot error (:106-108).
+ * max_sample_value_out = max(max_sample_value_in, max |values|) (:49-51).  The MatrixLuciFactors come back through
+ * t4b_tci_update_tensors as [n_left, 1, r] and [r, 1, n_right]. */
+int t4b_treetci_update_edge(t4b_ctx* ctx, int dtype, const void* values, int values_on_device, int64_t n_left,
+                            int64_t n_right, int64_t max_bond_dim /* 0 = none */, double abs_tol,
+                            double max_sample_value_in, t4b_tci_update** out, double* max_sample_value_out);
 /* One-site tensor of fill_site_tensors (tensorci/src/tensorci2.rs:1065-1199): out[l, s, r] = (Pi1 P^-1)[l*d + s, r],
  * Pi1 ((left_dim*site_dim) x nj device matrix, rows l*d + s), P (nj x nj pivot matrix); a numerically zero P gives
  * a zero tensor.  p_dev == NULL: last site (nj == 1), Pi1 is stored directly.  out: [left_dim, site_dim, nj]. */
@@ -260,6 +271,34 @@ int t4b_tn_add(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, t4b_tn** out);
 int t4b_tn_norm_sqr(t4b_ctx* ctx, const t4b_tn* tn, double* out);
 int t4b_tn_inner(t4b_ctx* ctx, const t4b_tn* a, const t4b_tn* b, double* re, double* im);
 
+/* ---- tree tensor networks (tensor4all-treetn, any loop-free topology) -----------------------
+ * Same conventions as t4b_tn_create; the edges are the node pairs that share exactly one index id (the reference's
+ * TreeTN::from_tensors auto-connection).  Node names are the positions 0..n-1.  canonicalize: post-order leaves ->
+ * centre, or the path from the current centre (treetn/canonicalize.rs:134-165, node_name_network.rs:430-521);
+ * truncate: canonicalize + two-site sweep over the DFS Euler tour (treetn/truncate.rs:129-198,
+ * localupdate.rs:103-160,526-645; named_graph.rs:307-345) - t4b_tree_sweep_plan returns that step list;
+ * contract: the tree-general zip-up (contract_zipup_impl, treetn/contraction.rs:768-1124: leaves -> centre, SVD
+ * factorisation at every node, the right factors meet at the parent; scalar subtrees are pruned).  Result nodes
+ * keep the order of the input nodes (pruned nodes removed). */
+typedef struct t4b_tree t4b_tree;
+int t4b_tree_create(t4b_ctx* ctx, int dtype, int n_nodes, const int32_t* ranks, const int64_t* shapes,
+                    const int64_t* index_ids, const void* const* node_data, int data_on_device, t4b_tree** out);
+int t4b_tree_clone(t4b_ctx* ctx, const t4b_tree* tn, t4b_tree** out);
+int t4b_tree_release(t4b_tree* tn);
+int t4b_tree_num_nodes(const t4b_tree* tn, int* out);
+/* edges_out: (n_nodes - 1) x 2 node ids, bond_dims_out: n_nodes - 1 (either may be NULL) */
+int t4b_tree_edges(const t4b_tree* tn, int32_t* edges_out, int64_t* bond_dims_out);
+int t4b_tree_node_rank(const t4b_tree* tn, int node, int* out);
+int t4b_tree_node_shape(const t4b_tree* tn, int node, int64_t* shape_out, int64_t* index_ids_out);
+int t4b_tree_download_node(t4b_ctx* ctx, const t4b_tree* tn, int node, void* host_out);
+int t4b_tree_sweep_plan(const t4b_tree* tn, int center, int32_t* steps_out /* nsteps x 2 or NULL */, int* nsteps);
+int t4b_tree_canonicalize(t4b_ctx* ctx, t4b_tree* tn, int center);
+int t4b_tree_truncate(t4b_ctx* ctx, t4b_tree* tn, int center, const t4b_svd_policy* policy, int64_t max_bond_dim);
+int t4b_tree_contract_zipup(t4b_ctx* ctx, const t4b_tree* a, const t4b_tree* b, int center,
+                            const t4b_svd_policy* policy, int64_t max_bond_dim, t4b_tree** out);
+int t4b_tree_norm_sqr(t4b_ctx* ctx, const t4b_tree* tn, double* out);
+int t4b_tree_inner(t4b_ctx* ctx, const t4b_tree* a, const t4b_tree* b, double* re, double* im);
+
 /* ---- partitioned adaptive truncation (tensor4all-partitionedtreetn; the multi-GPU unit) -----
  * truncate_adaptive (partitionedtreetn/src/patching.rs:665-718).  A patch is a chain network plus
  * its volume.  t4b_adaptive_cutoffs is pure host arithmetic in the reference's order of
@@ -300,6 +339,29 @@ int t4b_patches_truncate_adaptive_sharded(t4b_ctx* ctx, void* nccl_comm, int ran
                                           int64_t* bond_dims_out, int64_t nbonds, t4b_tn** gathered_out,
                                           double* timing_ms_out, int64_t* gather_bytes_out);
 
+/* PartitionedTreeTN::contract (partitionedtreetn/src/partitioned_tree_tn.rs:407-483; per pair SubDomainTreeTN::contract,
+ * subdomain_tree_tn.rs:459-487).  Patch i of an operand is a chain network with already masked data plus its projector:
+ * nproj[i] pairs (site index id, fixed value), flattened in proj_ids / proj_vals.  Patches are visited in canonical
+ * projector order, every compatible (left, right) pair goes through the contract dispatcher (method / policy /
+ * max_bond_dim / nfullsweeps as in t4b_tn_contract), contributions are grouped by output projector (the merged
+ * projector restricted to the surviving site indices), summed with the strict direct-sum addition and truncated once
+ * per multi-contribution group.  Sharding: the grouping follows from the projectors alone, so rank r of nranks
+ * computes exactly the groups g with g % nranks == r and no tensor crosses ranks (pass 0, 1 for one device).
+ * The result handle owns the local output patches until t4b_partition_result_take moves one out. */
+typedef struct t4b_partition_result t4b_partition_result;
+int t4b_partitioned_contract(t4b_ctx* ctx, int64_t n_left, const t4b_tn* const* left, const int32_t* left_nproj,
+                             const int64_t* left_proj_ids, const int64_t* left_proj_vals, int64_t n_right,
+                             const t4b_tn* const* right, const int32_t* right_nproj, const int64_t* right_proj_ids,
+                             const int64_t* right_proj_vals, int center, int method, const t4b_svd_policy* policy,
+                             int64_t max_bond_dim, int nfullsweeps, int rank, int nranks, t4b_partition_result** out);
+int t4b_partition_result_count(const t4b_partition_result* r, int64_t* n_groups_total, int64_t* n_local);
+/* i-th local output: position in canonical projector order, number of summed contributions, projector (query-then-
+ * fill: proj_ids / proj_vals may be NULL) */
+int t4b_partition_result_info(const t4b_partition_result* r, int64_t i, int64_t* group_index, int32_t* n_contributions,
+                              int32_t* nproj, int64_t* proj_ids, int64_t* proj_vals);
+int t4b_partition_result_take(t4b_partition_result* r, int64_t i, t4b_tn** out);   /* ownership moves to the caller */
+int t4b_partition_result_release(t4b_partition_result* r);
+
 /* ---- positional tensor trains / MPOs (tensor4all-simplett) ----------------------------------
  * rank 3: sites [left, site, right]; rank 4: MPO sites [left, s1, s2, right]. */
 typedef struct t4b_train t4b_train;
@@ -312,6 +374,12 @@ int t4b_train_download_site(t4b_ctx* ctx, const t4b_train* tt, int site, void* h
 /* SimpleTensorTrain::compress (simplett/src/compression.rs:375-501); method 0 LU, 1 CI, 2 SVD */
 int t4b_train_compress(t4b_ctx* ctx, t4b_train* tt, int method, double tolerance,
                        int64_t max_bond_dim, int normalize_error);
+/* The same compress for a batch of independent trains of equal length (C1 "batch 1 and 1024"): every sweep position
+ * is ONE launch of the single-CTA SVD kernel plus ONE ragged batched GEMM launch for the whole batch, one host read of
+ * all spectra per truncating step.  Per train the result equals t4b_train_compress up to rounding.  Pivoted methods
+ * and matrices that do not fit one CTA (min dim > 128) fall back to the per-train loop. */
+int t4b_train_compress_batched(t4b_ctx* ctx, int64_t n, t4b_train* const* tts, int method, double tolerance,
+                               int64_t max_bond_dim, int normalize_error);
 /* mpo::contract (simplett/src/mpo/dispatch.rs:67): algorithm 0 ZipUp, 1 Naive (+compress), 2 Naive
  * without compression */
 int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int algorithm,

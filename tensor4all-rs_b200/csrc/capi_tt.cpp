@@ -408,6 +408,24 @@ int t4b_train_compress(t4b_ctx* ctx, t4b_train* tt, int method, double tolerance
     stt::compress(ctx->c, tt->tt, o);
     T4B_CATCH
 }
+int t4b_train_compress_batched(t4b_ctx* ctx, int64_t n, t4b_train* const* tts, int method, double tolerance,
+                               int64_t max_bond_dim, int normalize_error) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n >= 0 && (n == 0 || tts) && method >= 0 && method <= 2, "bad arguments");
+    stt::CompressionOptions o;
+    o.method = method == 0 ? stt::CompressionMethod::LU : method == 1 ? stt::CompressionMethod::CI : stt::CompressionMethod::SVD;
+    o.tolerance = tolerance;
+    o.max_bond_dim = opt_bond(max_bond_dim);
+    o.normalize_error = normalize_error != 0;
+    std::vector<stt::Train*> v;
+    for (int64_t i = 0; i < n; ++i) {
+        T4B_REQUIRE(tts[i], "train_compress_batched: null train");
+        v.push_back(&tts[i]->tt);
+    }
+    stt::compress_batched(ctx->c, v, o);
+    T4B_CATCH
+}
 int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int algorithm,
                      double tolerance, int64_t max_bond_dim, t4b_train** out) {
     T4B_TRY
@@ -460,6 +478,35 @@ int t4b_tci2_update_pivots(t4b_ctx* ctx, int dtype, const void* pi, int pi_on_de
                                                     right_dim, opt_bond(max_bond_dim), tolerance,
                                                     left_orthogonal != 0)};
     *out = h;
+    T4B_CATCH
+}
+int t4b_treetci_update_edge(t4b_ctx* ctx, int dtype, const void* values, int values_on_device, int64_t n_left,
+                            int64_t n_right, int64_t max_bond_dim, double abs_tol, double max_sample_value_in,
+                            t4b_tci_update** out, double* max_sample_value_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(values && out, "treetci_update_edge: null argument");
+    T4B_REQUIRE(n_left >= 1 && n_right >= 1, "treetci_update_edge: proposer returned an empty candidate list");
+    DType dt = to_dtype(dtype);
+    const size_t bytes = (size_t)n_left * (size_t)n_right * dtype_size(dt);
+    std::shared_ptr<Buffer> staged;
+    const void* dev = values;
+    if (!values_on_device) {
+        staged = std::make_shared<Buffer>(ctx->c, bytes);
+        dla::h2d(ctx->c, staged->p, values, bytes);
+        dev = staged->p;
+    }
+    TreeTciEdgeUpdate r = treetci_update_edge(ctx->c, dt, dev, n_left, n_right, opt_bond(max_bond_dim), abs_tol,
+                                              max_sample_value_in);
+    if (max_sample_value_out) *max_sample_value_out = r.max_sample_value;
+    *out = new t4b_tci_update{std::move(r.update)};
+    T4B_CATCH
+}
+int t4b_tci_update_pivot_errors(const t4b_tci_update* u, double* errors_host, int64_t* n) {
+    T4B_TRY
+    T4B_REQUIRE(u, "null argument");
+    if (n) *n = (int64_t)u->u.pivot_errors.size();
+    if (errors_host) std::memcpy(errors_host, u->u.pivot_errors.data(), sizeof(double) * u->u.pivot_errors.size());
     T4B_CATCH
 }
 int t4b_tci_update_rank(const t4b_tci_update* u, int64_t* rank, int64_t* new_bond_dim, double* bond_error) {
@@ -626,3 +673,85 @@ int t4b_patches_truncate_adaptive_sharded(t4b_ctx* ctx, void* nccl_comm, int ran
     T4B_CATCH
 }
 }
+
+// ---- PartitionedTreeTN::contract ---------------------------------------------------------------------------------------
+struct t4b_partition_result {
+    PartitionedContractResult r;
+    std::vector<char> taken;
+};
+extern "C" {
+int t4b_partitioned_contract(t4b_ctx* ctx, int64_t n_left, const t4b_tn* const* left, const int32_t* left_nproj,
+                             const int64_t* left_proj_ids, const int64_t* left_proj_vals, int64_t n_right,
+                             const t4b_tn* const* right, const int32_t* right_nproj, const int64_t* right_proj_ids,
+                             const int64_t* right_proj_vals, int center, int method, const t4b_svd_policy* policy,
+                             int64_t max_bond_dim, int nfullsweeps, int rank, int nranks, t4b_partition_result** out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(n_left >= 1 && n_right >= 1 && left && right && left_nproj && right_nproj && out,
+                "partitioned_contract: bad arguments");
+    T4B_REQUIRE(method >= 0 && method <= 2, "method must be 0 (zipup), 1 (fit) or 2 (naive)");
+    auto gather = [](int64_t n, const t4b_tn* const* tns, const int32_t* np, const int64_t* ids, const int64_t* vals) {
+        std::vector<ProjectedChain> v;
+        size_t off = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            T4B_REQUIRE(tns[i], "partitioned_contract: null patch handle");
+            ProjectedChain pc;
+            pc.tn = &tns[i]->tn;
+            for (int32_t k = 0; k < np[i]; ++k) {
+                T4B_REQUIRE(ids && vals && ids[off + k] >= 0 && vals[off + k] >= 0, "partitioned_contract: bad projector");
+                T4B_REQUIRE(pc.projector.emplace(ids[off + k], vals[off + k]).second, "partitioned_contract: projector fixes an index twice");
+            }
+            off += np[i];
+            v.push_back(std::move(pc));
+        }
+        return v;
+    };
+    ContractionOptions o;
+    o.method = method == 0 ? ContractMethod::Zipup : method == 1 ? ContractMethod::Fit : ContractMethod::Naive;
+    o.svd_policy = opt_policy(policy);
+    o.max_bond_dim = opt_bond(max_bond_dim);
+    o.nfullsweeps = nfullsweeps;
+    auto* h = new t4b_partition_result{partitioned_contract(ctx->c, gather(n_left, left, left_nproj, left_proj_ids, left_proj_vals),
+                                                            gather(n_right, right, right_nproj, right_proj_ids, right_proj_vals),
+                                                            center, o, rank, nranks), {}};
+    h->taken.assign(h->r.patches.size(), 0);
+    *out = h;
+    T4B_CATCH
+}
+int t4b_partition_result_count(const t4b_partition_result* r, int64_t* n_groups_total, int64_t* n_local) {
+    T4B_TRY
+    T4B_REQUIRE(r, "null argument");
+    if (n_groups_total) *n_groups_total = r->r.n_groups;
+    if (n_local) *n_local = (int64_t)r->r.patches.size();
+    T4B_CATCH
+}
+int t4b_partition_result_info(const t4b_partition_result* r, int64_t i, int64_t* group_index, int32_t* n_contributions,
+                              int32_t* nproj, int64_t* proj_ids, int64_t* proj_vals) {
+    T4B_TRY
+    T4B_REQUIRE(r && i >= 0 && i < (int64_t)r->r.patches.size(), "partition_result_info: bad arguments");
+    if (group_index) *group_index = r->r.group_index[i];
+    if (n_contributions) *n_contributions = r->r.n_contributions[i];
+    if (nproj) *nproj = (int32_t)r->r.projectors[i].size();
+    size_t k = 0;
+    for (auto& kv : r->r.projectors[i]) {
+        if (proj_ids) proj_ids[k] = kv.first;
+        if (proj_vals) proj_vals[k] = kv.second;
+        ++k;
+    }
+    T4B_CATCH
+}
+int t4b_partition_result_take(t4b_partition_result* r, int64_t i, t4b_tn** out) {
+    T4B_TRY
+    T4B_REQUIRE(r && out && i >= 0 && i < (int64_t)r->r.patches.size(), "partition_result_take: bad arguments");
+    T4B_REQUIRE(!r->taken[i], "partition_result_take: patch already taken");
+    *out = new t4b_tn{std::move(r->r.patches[i])};
+    r->taken[i] = 1;
+    T4B_CATCH
+}
+int t4b_partition_result_release(t4b_partition_result* r) {
+    T4B_TRY
+    delete r;
+    T4B_CATCH
+}
+}
+

@@ -93,6 +93,18 @@ struct SvdProblem {
     double* S;
     void* Vh; int64_t ldvh;
 };
+// Small / batched GEMM with ragged shapes (one CTA per 64 x 64 output tile of one problem, one launch for the batch):
+// C (m x n, ldc) = diag(row_scale) * A (m x k, lda) * B (k x n, ldb) * diag(col_scale); scales may be null.
+// The companion of svd_small_batched in the batched sweeps (S Vh X, X U S of many tensor trains in one launch).
+struct SmallGemmProblem {
+    const void* A; int64_t lda;
+    const void* B; int64_t ldb;
+    void* C; int64_t ldc;
+    int64_t m, n, k;
+    const double* row_scale;
+    const double* col_scale;
+};
+void gemm_small_batched(Ctx*, DType dt, int64_t batch, const SmallGemmProblem* problems);
 bool svd_small_fits(DType dt, int64_t m, int64_t n, bool want_u, bool want_vh);
 void svd_small_batched(Ctx*, DType dt, int64_t batch, const SvdProblem* problems);
 

@@ -1,6 +1,8 @@
 #include "patching.h"
 
+#include <algorithm>
 #include <cmath>
+#include <iterator>
 
 namespace t4b {
 
@@ -53,6 +55,79 @@ std::vector<char> truncate_adaptive(dla::Ctx* c, std::vector<ChainTN*>& patches,
     for (size_t i = 0; i < patches.size(); ++i)
         if (plan.keep[i]) truncate_patch_with_cutoff(c, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
     return plan.keep;
+}
+
+
+// ---- PartitionedTreeTN::contract ---------------------------------------------------------------------------------------
+static int64_t ext_id(const Index& ix) { return ix.id < 0 ? -(ix.id + 1) : -ix.id; }   // caller ids are stored as -(id+1)
+
+static std::vector<int64_t> external_site_ids(const ChainTN& tn) {
+    std::vector<int64_t> ids;
+    for (int i = 0; i < (int)tn.length(); ++i)
+        for (auto& ix : tn.site_inds(i)) ids.push_back(ext_id(ix));
+    std::sort(ids.begin(), ids.end());
+    return ids;
+}
+
+// Projector::is_compatible_with: no index fixed to two different values
+static bool projectors_compatible(const Projector& p, const Projector& q) {
+    for (auto& kv : p) {
+        auto it = q.find(kv.first);
+        if (it != q.end() && it->second != kv.second) return false;
+    }
+    return true;
+}
+
+PartitionedContractResult partitioned_contract(dla::Ctx* c, std::vector<ProjectedChain> left,
+                                               std::vector<ProjectedChain> right, int center,
+                                               const ContractionOptions& opts, int rank, int nranks) {
+    T4B_REQUIRE(!left.empty() && !right.empty(), "partitioned contract: empty operand");
+    T4B_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "partitioned contract: bad rank / nranks");
+    validate_svd_truncation_options(opts.max_bond_dim, opts.svd_policy);
+    auto by_projector = [](const ProjectedChain& a, const ProjectedChain& b) { return a.projector < b.projector; };
+    std::stable_sort(left.begin(), left.end(), by_projector);
+    std::stable_sort(right.begin(), right.end(), by_projector);
+    std::vector<std::vector<int64_t>> ext_l, ext_r;
+    for (auto& p : left) { T4B_REQUIRE(p.tn, "partitioned contract: null patch"); ext_l.push_back(external_site_ids(*p.tn)); }
+    for (auto& p : right) { T4B_REQUIRE(p.tn, "partitioned contract: null patch"); ext_r.push_back(external_site_ids(*p.tn)); }
+
+    // host-side plan: which pairs feed which output projector (first-appearance order inside a group = the
+    // reference's visiting order, left-major)
+    std::map<Projector, std::vector<std::pair<int, int>>> plan;
+    for (size_t il = 0; il < left.size(); ++il)
+        for (size_t ir = 0; ir < right.size(); ++ir) {
+            if (!projectors_compatible(left[il].projector, right[ir].projector)) continue;
+            // site indices that survive the contraction: the symmetric difference of the two external sets
+            std::vector<int64_t> surviving;
+            std::set_symmetric_difference(ext_l[il].begin(), ext_l[il].end(), ext_r[ir].begin(), ext_r[ir].end(),
+                                          std::back_inserter(surviving));
+            Projector merged = left[il].projector;
+            for (auto& kv : right[ir].projector) merged[kv.first] = kv.second;
+            Projector out;
+            for (auto& kv : merged)
+                if (std::binary_search(surviving.begin(), surviving.end(), kv.first)) out.insert(kv);
+            plan[out].push_back({(int)il, (int)ir});
+        }
+    PartitionedContractResult res;
+    res.n_groups = (int64_t)plan.size();
+    int64_t g = 0;
+    for (auto& kv : plan) {
+        const int64_t gi = g++;
+        if (gi % nranks != rank) continue;
+        ChainTN combined;
+        bool have = false;
+        for (auto& pr : kv.second) {
+            ChainTN out = contract(c, *left[pr.first].tn, *right[pr.second].tn, center, opts);
+            if (!have) { combined = std::move(out); have = true; }
+            else combined = add(c, combined, out);
+        }
+        if (kv.second.size() > 1) truncate(c, combined, std::min<int>(center, (int)combined.length() - 1), opts.svd_policy, opts.max_bond_dim);
+        res.group_index.push_back(gi);
+        res.n_contributions.push_back((int)kv.second.size());
+        res.projectors.push_back(kv.first);
+        res.patches.push_back(std::move(combined));
+    }
+    return res;
 }
 
 }  // namespace t4b

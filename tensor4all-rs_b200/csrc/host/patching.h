@@ -63,3 +63,33 @@ double patch_cost(const std::vector<int64_t>& bond_dims, int64_t site_dim);
 std::vector<int> lpt_assign(const std::vector<double>& costs, int nranks);
 
 }  // namespace t4b
+
+#include <map>
+namespace t4b {
+
+// ---- PartitionedTreeTN::contract (reference partitionedtreetn/src/partitioned_tree_tn.rs:407-483,
+//      SubDomainTreeTN::contract subdomain_tree_tn.rs:459-487) ------------------------------------------------------
+// A projector fixes site indices to values: {external site index id -> value}; std::map's order on (id, value) is
+// the canonical projector order (Projector::canonical_cmp).  Patches carry already masked data.
+using Projector = std::map<int64_t, int64_t>;
+struct ProjectedChain {
+    Projector projector;
+    const ChainTN* tn = nullptr;
+};
+struct PartitionedContractResult {
+    int64_t n_groups = 0;                    // output projectors of the whole (unsharded) result
+    std::vector<int64_t> group_index;        // position of every local result in canonical projector order
+    std::vector<int> n_contributions;        // compatible (left, right) pairs summed into it
+    std::vector<Projector> projectors;
+    std::vector<ChainTN> patches;
+};
+// All compatible pairs are contracted through the contract dispatcher, grouped by output projector (merged
+// projector filtered to the surviving site indices), summed with the strict direct-sum TreeTN::add in canonical
+// order and truncated ONCE per multi-contribution group.  The grouping is decided from the projectors alone, so in a
+// sharded run rank r computes exactly the groups g with g % nranks == r and no tensor crosses ranks.
+PartitionedContractResult partitioned_contract(dla::Ctx*, std::vector<ProjectedChain> left,
+                                               std::vector<ProjectedChain> right, int center,
+                                               const ContractionOptions& opts, int rank, int nranks);
+
+}  // namespace t4b
+

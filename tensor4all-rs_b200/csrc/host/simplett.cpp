@@ -129,6 +129,110 @@ void compress(dla::Ctx* c, Train& tt, const CompressionOptions& o) {
     }
 }
 
+void compress_batched(dla::Ctx* c, const std::vector<Train*>& tts, const CompressionOptions& o) {
+    const int64_t B = (int64_t)tts.size();
+    if (B == 0) return;
+    bool batched = o.method == CompressionMethod::SVD;
+    const int n = (int)tts[0]->sites.size();
+    const DType dt = tts[0]->dt;
+    for (auto* t : tts) {
+        T4B_REQUIRE(t && t->rank == 3, "compress expects tensor trains of rank-3 sites");
+        if ((int)t->sites.size() != n || t->dt != dt) batched = false;
+    }
+    if (batched)
+        for (auto* t : tts)
+            for (int ell = 0; ell < n && batched; ++ell) {
+                const Site& s = t->sites[ell];
+                // bonds only shrink during the sweeps, so the input shapes bound every problem
+                if (!dla::svd_small_fits(dt, s.d[0] * s.d[1], s.d[2], true, true) ||
+                    !dla::svd_small_fits(dt, s.d[0], s.d[1] * s.d[2], true, true))
+                    batched = false;
+            }
+    if (!batched || n <= 1) {
+        for (auto* t : tts) compress(c, *t, o);
+        return;
+    }
+    const size_t es = dtype_size(dt);
+    std::vector<dla::SvdProblem> sp((size_t)B);
+    std::vector<dla::SmallGemmProblem> gp((size_t)B);
+    std::vector<std::shared_ptr<Buffer>> ub((size_t)B), vb((size_t)B), nb((size_t)B);
+    std::vector<int64_t> kk((size_t)B), soff((size_t)B);
+    // all spectra of one step live in one buffer (one download per truncating step)
+    auto run_step = [&](int ell, bool left_to_right) {
+        int64_t stot = 0;
+        for (int64_t b = 0; b < B; ++b) {
+            const Site& s = tts[b]->sites[ell];
+            const int64_t m = left_to_right ? s.d[0] * s.d[1] : s.d[0], nn = left_to_right ? s.d[2] : s.d[1] * s.d[2];
+            kk[b] = std::min(m, nn);
+            soff[b] = stot;
+            stot += kk[b];
+        }
+        auto sbuf = std::make_shared<Buffer>(c, (size_t)stot * sizeof(double));
+        for (int64_t b = 0; b < B; ++b) {
+            const Site& s = tts[b]->sites[ell];
+            const int64_t m = left_to_right ? s.d[0] * s.d[1] : s.d[0], nn = left_to_right ? s.d[2] : s.d[1] * s.d[2];
+            ub[b] = std::make_shared<Buffer>(c, (size_t)m * kk[b] * es);
+            vb[b] = std::make_shared<Buffer>(c, (size_t)kk[b] * nn * es);
+            sp[b] = dla::SvdProblem{s.buf->p, m, nn, m, ub[b]->p, m, (double*)sbuf->p + soff[b], vb[b]->p, kk[b]};
+        }
+        dla::svd_small_batched(c, dt, B, sp.data());
+        std::vector<int64_t> rank((size_t)B);
+        if (left_to_right) {
+            // tolerance 0, normalised, no cap: every singular value is kept (compression.rs:388-443)
+            for (int64_t b = 0; b < B; ++b) rank[b] = kk[b];
+        } else {
+            std::vector<double> sh((size_t)stot);
+            dla::d2h(c, sh.data(), sbuf->p, (size_t)stot * sizeof(double));
+            dla::sync(c);
+            for (int64_t b = 0; b < B; ++b)
+                rank[b] = simplett_rank(std::vector<double>(sh.begin() + soff[b], sh.begin() + soff[b] + kk[b]),
+                                        o.tolerance, o.normalize_error, o.max_bond_dim);
+        }
+        for (int64_t b = 0; b < B; ++b) {
+            Site& s = tts[b]->sites[ell];
+            const double* sv = (const double*)sbuf->p + soff[b];
+            if (left_to_right) {
+                // site <- U [l*d, k]; next <- (S Vh) next
+                Site& nx = tts[b]->sites[ell + 1];
+                const int64_t r = s.d[2], cols = nx.d[1] * nx.d[2];
+                nb[b] = std::make_shared<Buffer>(c, (size_t)rank[b] * cols * es);
+                gp[b] = dla::SmallGemmProblem{vb[b]->p, kk[b], nx.buf->p, r, nb[b]->p, rank[b], rank[b], cols, r, sv, nullptr};
+            } else {
+                // site <- Vh [k, d*r] (first `rank` rows); prev <- prev (U S)
+                Site& pv = tts[b]->sites[ell - 1];
+                const int64_t l = s.d[0], rows = pv.d[0] * pv.d[1];
+                nb[b] = std::make_shared<Buffer>(c, (size_t)rows * rank[b] * es);
+                gp[b] = dla::SmallGemmProblem{pv.buf->p, rows, ub[b]->p, l, nb[b]->p, rows, rows, rank[b], l, nullptr, sv};
+            }
+        }
+        dla::gemm_small_batched(c, dt, B, gp.data());
+        for (int64_t b = 0; b < B; ++b) {
+            Site& s = tts[b]->sites[ell];
+            if (left_to_right) {
+                Site& nx = tts[b]->sites[ell + 1];
+                s.buf = ub[b]; s.d[2] = rank[b];
+                nx.buf = nb[b]; nx.d[0] = rank[b];
+            } else {
+                Site& pv = tts[b]->sites[ell - 1];
+                const int64_t cols = s.d[1] * s.d[2];
+                if (rank[b] == kk[b]) {
+                    s.buf = vb[b];
+                } else {
+                    // keep the first `rank` rows of Vh (ld = k): strided copy into a compact buffer
+                    auto vr = std::make_shared<Buffer>(c, (size_t)rank[b] * cols * es);
+                    dla::permute(c, dt, vr->p, vb[b]->p, g2(rank[b], 1, cols, kk[b]), false);
+                    s.buf = vr;
+                }
+                s.d[0] = rank[b];
+                pv.buf = nb[b]; pv.d[2] = rank[b];
+            }
+        }
+        // sbuf is released here; the queued kernels that read it are stream-ordered before any reuse
+    };
+    for (int ell = 0; ell + 1 < n; ++ell) run_step(ell, true);
+    for (int ell = n - 1; ell >= 1; --ell) run_step(ell, false);
+}
+
 Train contract_zipup(dla::Ctx* c, const Train& a, const Train& b, const MpoContractionOptions& o) {
     T4B_REQUIRE(a.rank == 4 && b.rank == 4, "contract_zipup expects MPOs");
     T4B_REQUIRE(a.sites.size() == b.sites.size(), "MPO length mismatch");

@@ -35,6 +35,13 @@ struct CompressionOptions {   // reference compression.rs:88-124
     bool normalize_error = true;
 };
 void compress(dla::Ctx*, Train& tt, const CompressionOptions& opts);
+// The same two-pass compress for a BATCH of independent tensor trains of equal length (the small-chi regime of the
+// north star: C1 "batch 1 and 1024"): at every sweep position the factorisations of all trains are ONE launch of the
+// single-CTA SVD kernel and the absorb products ONE ragged batched GEMM launch; the only host synchronisation is one
+// read of all spectra per truncating step (the rank rule stays on the host, compression.rs:286-306).  Per train the
+// result equals compress() up to rounding.  Falls back to the per-train loop for pivoted methods or matrices that do
+// not fit one CTA.
+void compress_batched(dla::Ctx*, const std::vector<Train*>& tts, const CompressionOptions& opts);
 
 struct MpoContractionOptions {   // reference mpo/types.rs ContractionOptions
     double tolerance = 1e-12;

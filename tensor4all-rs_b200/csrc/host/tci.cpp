@@ -4,18 +4,12 @@
 
 namespace t4b {
 
-TciUpdate tci2_update_pivots(dla::Ctx* c, DType dt, const void* pi_dev, int64_t left_dim,
-                             int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
-                             std::optional<int64_t> max_bond_dim, double tolerance,
-                             bool left_orthogonal) {
+static TciUpdate update_with_options(dla::Ctx* c, DType dt, const void* pi_dev, int64_t left_dim,
+                                     int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
+                                     const RrLUOptions& o) {
     const int64_t nrows = left_dim * site_dim_b, ncols = site_dim_bp1 * right_dim;
-    T4B_REQUIRE(nrows > 0 && ncols > 0, "tci2_update_pivots: empty candidate matrix");
+    T4B_REQUIRE(nrows > 0 && ncols > 0, "pivot update: empty candidate matrix");
     const size_t es = dtype_size(dt);
-    RrLUOptions o;   // tensorci2.rs:1895-1903
-    o.max_bond_dim = max_bond_dim.value_or(INT64_MAX);
-    o.rel_tol = tolerance;
-    o.abs_tol = 0.0;
-    o.left_orthogonal = left_orthogonal;
     LuFactors f = luci_factor_matrix(c, dt, nrows, ncols, pi_dev, o);
 
     TciUpdate u;
@@ -50,6 +44,39 @@ TciUpdate tci2_update_pivots(dla::Ctx* c, DType dt, const void* pi_dev, int64_t 
     gp.dim[2] = right_dim; gp.str[2] = r;
     dla::permute(c, dt, u.tensor_bp1->p, f.right->p, gp, false);
     return u;
+}
+
+TciUpdate tci2_update_pivots(dla::Ctx* c, DType dt, const void* pi_dev, int64_t left_dim,
+                             int64_t site_dim_b, int64_t site_dim_bp1, int64_t right_dim,
+                             std::optional<int64_t> max_bond_dim, double tolerance,
+                             bool left_orthogonal) {
+    RrLUOptions o;   // tensorci2.rs:1895-1903
+    o.max_bond_dim = max_bond_dim.value_or(INT64_MAX);
+    o.rel_tol = tolerance;
+    o.abs_tol = 0.0;
+    o.left_orthogonal = left_orthogonal;
+    return update_with_options(c, dt, pi_dev, left_dim, site_dim_b, site_dim_bp1, right_dim, o);
+}
+
+TreeTciEdgeUpdate treetci_update_edge(dla::Ctx* c, DType dt, const void* values_dev, int64_t n_left, int64_t n_right,
+                                      std::optional<int64_t> max_bond_dim, double abs_tol, double max_sample_value_in) {
+    T4B_REQUIRE(n_left > 0 && n_right > 0, "treetci_update_edge: proposer returned an empty candidate list");
+    TreeTciEdgeUpdate r;
+    // state.max_sample_value = max(state.max_sample_value, |value|) over the candidate matrix (update.rs:49-51)
+    double* dmax = (double*)dla::alloc(c, 8);
+    dla::maxabs(c, dt, n_left * n_right, values_dev, dmax);
+    double hmax = 0.0;
+    dla::d2h(c, &hmax, dmax, 8);
+    RrLUOptions o;   // optimize.rs:317-331
+    o.max_bond_dim = max_bond_dim.value_or(INT64_MAX);
+    o.rel_tol = 1e-14;
+    o.abs_tol = abs_tol;
+    o.left_orthogonal = true;
+    r.update = update_with_options(c, dt, values_dev, n_left, 1, 1, n_right, o);
+    dla::sync(c);
+    dla::release(c, dmax);
+    r.max_sample_value = std::max(max_sample_value_in, hmax);
+    return r;
 }
 
 void tci2_site_tensor(dla::Ctx* c, DType dt, int64_t left_dim, int64_t site_dim, int64_t nj, const void* pi1_dev,

@@ -29,6 +29,18 @@ TciUpdate tci2_update_pivots(dla::Ctx*, DType dt, const void* pi_dev, int64_t le
                              std::optional<int64_t> max_bond_dim, double tolerance,
                              bool left_orthogonal);
 
+// TreeTCI2 edge update, device part (reference crates/tensor4all-treetci/src/update.rs:22-112): the candidate matrix
+// (column-major, left candidates as rows, :55-57,216-230) goes through matrix_luci_factors_from_matrix with the kernel
+// options of the optimizer (optimize.rs:317-331: rel_tol 1e-14, abs_tol = tolerance * error_scale, left_orthogonal),
+// empty selections keep index 0 (:66-76), last pivot error = bond error (:106-108); max_sample_value is raised to the
+// largest |value| of the matrix (:49-51).  The factors come back as tensor_b [n_left, 1, r] / tensor_bp1 [r, 1, n_right].
+struct TreeTciEdgeUpdate {
+    TciUpdate update;
+    double max_sample_value = 0.0;
+};
+TreeTciEdgeUpdate treetci_update_edge(dla::Ctx*, DType dt, const void* values_dev, int64_t n_left, int64_t n_right,
+                                      std::optional<int64_t> max_bond_dim, double abs_tol, double max_sample_value_in);
+
 // One-site tensor of fill_site_tensors (reference tensorci2.rs:1065-1199): out[l, s, r] = (Pi1 P^-1)[l*d + s, r]
 // with Pi1 ((left_dim*site_dim) x nj, rows l*d + s) and the pivot matrix P (nj x nj); a numerically zero P
 // (every |P_ij| < eps) gives a zero tensor.  p_dev == null: last site (nj == 1), Pi1 is stored directly.

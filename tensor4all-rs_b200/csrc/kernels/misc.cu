@@ -1,5 +1,8 @@
 // misc.cu — small triangular solves and index-array permutations used by the LU/CI factor
 // assembly (reference crates/tensor4all-core/src/matrix_luci.rs:176-279).
+#include <algorithm>
+#include <vector>
+
 #include "scalar.cuh"
 
 namespace t4b {
@@ -255,6 +258,105 @@ void eigh(Ctx* c, DType dt, int64_t n, void* G, double* lam, void* W) {
     unshift_kernel<<<grid, 256, 0, c->stream>>>(lam, n, shift);
     c->launched("eigh_shift");
     release(c, shift);
+}
+
+
+// =====================================================================================================
+// Ragged batched small GEMM: blockIdx.y = problem, blockIdx.x = 64 x 64 output tile (tiles beyond the problem's
+// own count exit at once).  16 x 16 threads, 4 x 4 outputs per thread, K staged through shared memory in slices of 16.
+// =====================================================================================================
+struct SmallGemmDesc {
+    const double* A; long long lda;
+    const double* B; long long ldb;
+    double* C; long long ldc;
+    int m, n, k;
+    const double* rs;
+    const double* cs;
+};
+template <bool CPLX>
+__global__ void __launch_bounds__(256) gemm_small_batched_kernel(const SmallGemmDesc* __restrict__ descs) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const SmallGemmDesc d = descs[blockIdx.y];
+    const int tm = (d.m + 63) >> 6, tn = (d.n + 63) >> 6;
+    if ((int)blockIdx.x >= tm * tn) return;
+    const int m0 = ((int)blockIdx.x % tm) * 64, n0 = ((int)blockIdx.x / tm) * 64;
+    __shared__ T As[16][65];
+    __shared__ T Bs[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const T* A = reinterpret_cast<const T*>(d.A);
+    const T* B = reinterpret_cast<const T*>(d.B);
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = S::zero();
+    for (int k0 = 0; k0 < d.k; k0 += 16) {
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int i = e & 63, kk = e >> 6;       // A: rows fastest in memory
+            const int gi = m0 + i, gk = k0 + kk;
+            As[kk][i] = (gi < d.m && gk < d.k) ? A[gi + (long long)gk * d.lda] : S::zero();
+        }
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e & 15, j = e >> 4;       // B: k fastest in memory
+            const int gk = k0 + kk, gj = n0 + j;
+            Bs[kk][j] = (gk < d.k && gj < d.n) ? B[gk + (long long)gj * d.ldb] : S::zero();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = S::add(acc[i][j], S::mul(a[i], b[j]));
+        }
+        __syncthreads();
+    }
+    T* Cg = reinterpret_cast<T*>(d.C);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = m0 + tx + 16 * i;
+        if (gi >= d.m) continue;
+        const double r = d.rs ? d.rs[gi] : 1.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = n0 + ty + 16 * j;
+            if (gj >= d.n) continue;
+            const double sc = d.cs ? r * d.cs[gj] : r;
+            Cg[gi + (long long)gj * d.ldc] = (d.rs || d.cs) ? S::scale(acc[i][j], sc) : acc[i][j];
+        }
+    }
+}
+
+void gemm_small_batched(Ctx* c, DType dt, int64_t batch, const SmallGemmProblem* probs) {
+    if (batch <= 0) return;
+    std::vector<SmallGemmDesc> h((size_t)batch);
+    int64_t maxtiles = 1;
+    double flops = 0.0;
+    for (int64_t b = 0; b < batch; ++b) {
+        const SmallGemmProblem& p = probs[b];
+        T4B_REQUIRE(p.m >= 0 && p.n >= 0 && p.k >= 0 && p.m < (1 << 30) && p.n < (1 << 30) && p.k < (1 << 30), "gemm_small_batched: bad shape");
+        h[b] = SmallGemmDesc{(const double*)p.A, (long long)p.lda, (const double*)p.B, (long long)p.ldb, (double*)p.C,
+                             (long long)p.ldc, (int)p.m, (int)p.n, (int)p.k, p.row_scale, p.col_scale};
+        const int64_t t = ((p.m + 63) / 64) * ((p.n + 63) / 64);
+        if (t > maxtiles) maxtiles = t;
+        flops += (dt == C64 ? 8.0 : 2.0) * (double)p.m * (double)p.n * (double)p.k;
+    }
+    SmallGemmDesc* dev = (SmallGemmDesc*)alloc(c, (size_t)batch * sizeof(SmallGemmDesc));
+    h2d(c, dev, h.data(), (size_t)batch * sizeof(SmallGemmDesc));
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const unsigned nb = (unsigned)std::min<int64_t>(65535, batch - b0);
+        dim3 grid((unsigned)maxtiles, nb, 1);
+        if (dt == C64) gemm_small_batched_kernel<true><<<grid, 256, 0, c->stream>>>(dev + b0);
+        else gemm_small_batched_kernel<false><<<grid, 256, 0, c->stream>>>(dev + b0);
+    }
+    c->launched("gemm_small_batched", flops);
+    release(c, dev);
 }
 
 }  // namespace dla

@@ -1140,13 +1140,19 @@ struct SmallSvdDesc {
     double* Vh; long long ldvh;                   // k x n or null
 };
 
-template <bool CPLX>
+// LPP lanes own one column pair (a power of two <= 32): short columns are handled by narrow lane groups, so that the
+// reductions are log2(LPP) shuffle levels and one warp instruction serves 32 / LPP pairs.  The squared column norms
+// are MAINTAINED across a sweep (app' = app - t|g|, aqq' = aqq + t|g|: de Rijk) and recomputed from the data at the
+// start of every sweep, or at once when a rotation shrinks a column by more than 16x (cancellation): a pair costs one
+// inner product instead of three.
+template <bool CPLX, int LPP>
 __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* __restrict__ descs, SmallSvdDesc single,
                                                             int max_sweeps, unsigned* fail) {
     typedef Sc<CPLX> S_;
     typedef typename S_::T T;
     const SmallSvdDesc d = descs ? descs[blockIdx.x] : single;     // a single problem travels in the launch parameters
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int gl = tid & (LPP - 1), grp = tid / LPP, ngroups = blockDim.x / LPP;
     const bool tall = d.m >= d.n;
     const int mx = tall ? d.m : d.n, nx = tall ? d.n : d.m;
     const int np = (nx + 1) & ~1;                          // even number of columns (a zero column pads odd nx)
@@ -1155,10 +1161,27 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* X = reinterpret_cast<T*>(smem_raw);                 // [np][ldx]
     T* V = X + (size_t)np * ldx;                           // [np][ldv] (only when need_v)
-    double* sig2 = reinterpret_cast<double*>(V + (need_v ? (size_t)np * ldv : 0));   // [np]
+    double* sig2 = reinterpret_cast<double*>(V + (need_v ? (size_t)np * ldv : 0));   // [np] squared column norms
     int* rank = reinterpret_cast<int*>(sig2 + np);         // [np]
     __shared__ double red[32];
     __shared__ double fro2_s;
+
+    // Control flow is uniform inside a lane group but not across the groups of a warp (different trip counts, rotated
+    // or skipped pairs): every shuffle names exactly the lanes of its own group.
+    const unsigned gmask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (lane & ~(LPP - 1)));
+    auto group_sum = [&](double v) -> double {
+#pragma unroll
+        for (int o = LPP >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    };
+    auto group_sum_t = [&](T v) -> T {
+#pragma unroll
+        for (int o = LPP >> 1; o > 0; o >>= 1) {
+            if constexpr (CPLX) v = make_double2(v.x + __shfl_xor_sync(gmask, v.x, o), v.y + __shfl_xor_sync(gmask, v.y, o));
+            else v += __shfl_xor_sync(gmask, v, o);
+        }
+        return v;
+    };
 
     const T* Ag = reinterpret_cast<const T*>(d.A);
     for (int e = tid; e < mx * np; e += blockDim.x) {
@@ -1173,10 +1196,21 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
             V[(size_t)j * ldv + i] = i == j ? S_::one() : S_::zero();
         }
     __syncthreads();
-    // ||X||_F^2: columns below (16 eps)^2 ||X||_F^2 are numerically zero (same rule as the cluster kernel)
+    // exact squared norms of all columns (one lane group per column); also ||X||_F^2
+    auto refresh_norms = [&]() {
+        for (int j = grp; j < np; j += ngroups) {
+            const T* xj = X + (size_t)j * ldx;
+            double acc = 0.0;
+            for (int i = gl; i < mx; i += LPP) acc += S_::abs2(xj[i]);
+            acc = group_sum(acc);
+            if (gl == 0) sig2[j] = acc;
+        }
+        __syncthreads();
+    };
+    refresh_norms();
     {
         double acc = 0.0;
-        for (int e = tid; e < mx * np; e += blockDim.x) { const int j = e / mx; acc += S_::abs2(X[(size_t)j * ldx + (e - j * mx)]); }
+        for (int j = tid; j < np; j += blockDim.x) acc += sig2[j];
         acc = warp_sum(acc);
         if (lane == 0) red[warp] = acc;
         __syncthreads();
@@ -1188,30 +1222,29 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
         __syncthreads();
     }
     const double eps = 2.220446049250313e-16;
+    // columns below (16 eps)^2 ||X||_F^2 are numerically zero (same rule as the cluster kernel)
     const double zthr = 1.2621774483536189e-29 * fro2_s;
     const double tol = 4.0 * eps * sqrt((double)(mx > 4 ? mx : 4));
     const double tol2 = tol * tol;
     const int pairs = np >> 1, p1 = np - 1;
     int converged = 0, sweep = 0;
     for (; sweep < max_sweeps && !converged; ++sweep) {
+        if (sweep > 0) refresh_norms();
         double mxcos2 = 0.0;
         for (int r = 0; r < p1; ++r) {
-            for (int k = warp; k < pairs; k += nwarps) {
+            for (int k = grp; k < pairs; k += ngroups) {
                 int pi, qi;
                 if (k == 0) { pi = r % p1; qi = np - 1; }
                 else { pi = (r + k) % p1; qi = (r - k + 2 * p1) % p1; }
                 if (pi > qi) { const int t = pi; pi = qi; qi = t; }
                 T* xp = X + (size_t)pi * ldx;
                 T* xq = X + (size_t)qi * ldx;
-                double app = 0.0, aqq = 0.0;
+                // norms are read BEFORE the reduction: its shuffles order these reads of every lane of the group before
+                // lane 0's update of sig2 further down
+                const double app = sig2[pi], aqq = sig2[qi];
                 T g = S_::zero();
-                for (int i = lane; i < mx; i += 32) {
-                    const T a = xp[i], b = xq[i];
-                    app += S_::abs2(a); aqq += S_::abs2(b);
-                    g = S_::add(g, S_::mul(S_::conj(a), b));
-                }
-                app = warp_sum(app); aqq = warp_sum(aqq);
-                g = warp_sum_t<CPLX>(g);
+                for (int i = gl; i < mx; i += LPP) g = S_::add(g, S_::mul(S_::conj(xp[i]), xq[i]));
+                g = group_sum_t(g);
                 const double g2 = S_::abs2(g);
                 if (app > zthr && aqq > zthr) {
                     const double c2 = g2 / (app * aqq);
@@ -1222,15 +1255,22 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
                 jacobi_rotation<CPLX>(app, aqq, g, tol2 * 0.00390625, c, sn, ph, tg, zthr);
                 if (sn != 0.0) {
                     // columns <- columns J, J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]] (ph = e^{-i phi})
-                    for (int i = lane; i < mx; i += 32) {
+                    const double napp = app - tg, naqq = aqq + tg;
+                    const bool recompute = napp < 0.0625 * app || naqq < 0.0625 * aqq;
+                    double sp = 0.0, sq = 0.0;
+                    for (int i = gl; i < mx; i += LPP) {
                         const T a = xp[i], fq = S_::mul(xq[i], ph);
-                        xp[i] = S_::sub(S_::scale(a, c), S_::scale(fq, sn));
-                        xq[i] = S_::add(S_::scale(a, sn), S_::scale(fq, c));
+                        const T na = S_::sub(S_::scale(a, c), S_::scale(fq, sn));
+                        const T nq = S_::add(S_::scale(a, sn), S_::scale(fq, c));
+                        xp[i] = na; xq[i] = nq;
+                        if (recompute) { sp += S_::abs2(na); sq += S_::abs2(nq); }
                     }
+                    if (recompute) { sp = group_sum(sp); sq = group_sum(sq); }
+                    if (gl == 0) { sig2[pi] = recompute ? sp : napp; sig2[qi] = recompute ? sq : naqq; }
                     if (need_v) {
                         T* vp = V + (size_t)pi * ldv;
                         T* vq = V + (size_t)qi * ldv;
-                        for (int i = lane; i < np; i += 32) {
+                        for (int i = gl; i < np; i += LPP) {
                             const T a = vp[i], fq = S_::mul(vq[i], ph);
                             vp[i] = S_::sub(S_::scale(a, c), S_::scale(fq, sn));
                             vq[i] = S_::add(S_::scale(a, sn), S_::scale(fq, c));
@@ -1241,6 +1281,13 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
             __syncthreads();
         }
         // convergence: largest cosine seen in this sweep
+        {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double other = __shfl_xor_sync(0xffffffffu, mxcos2, o);
+                mxcos2 = other > mxcos2 ? other : mxcos2;
+            }
+        }
         if (lane == 0) red[warp] = mxcos2;
         __syncthreads();
         double m2 = 0.0;
@@ -1250,12 +1297,12 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
     }
     if (!converged && tid == 0 && fail) atomicAdd(fail, 1u);
 
-    // sigma, descending order (ties by column index)
-    for (int j = warp; j < np; j += nwarps) {
+    // sigma from the data, descending order (ties by column index)
+    for (int j = grp; j < np; j += ngroups) {
         double acc = 0.0;
-        for (int i = lane; i < mx; i += 32) acc += S_::abs2(X[(size_t)j * ldx + i]);
-        acc = warp_sum(acc);
-        if (lane == 0) sig2[j] = j < nx ? acc : -1.0;      // the padding column sorts last
+        for (int i = gl; i < mx; i += LPP) acc += S_::abs2(X[(size_t)j * ldx + i]);
+        acc = group_sum(acc);
+        if (gl == 0) sig2[j] = j < nx ? acc : -1.0;      // the padding column sorts last
     }
     __syncthreads();
     for (int j = tid; j < np; j += blockDim.x) {
@@ -1325,8 +1372,19 @@ void svd_small_batched(Ctx* c, DType dt, int64_t batch, const SvdProblem* probs)
         const int64_t nx = p.m < p.n ? p.m : p.n;
         if ((nx + 1) / 2 > maxpairs) maxpairs = (nx + 1) / 2;
     }
-    int warps = (int)(maxpairs < 32 ? maxpairs : 32);
-    if (warps < 2) warps = 2;
+    // lanes per pair: ~16 rows per lane, 4 <= LPP <= 32; the CTA holds min(1024, pairs * LPP) threads
+    int64_t maxmx = 1;
+    for (int64_t b = 0; b < batch; ++b) {
+        const int64_t mxb = probs[b].m > probs[b].n ? probs[b].m : probs[b].n;
+        if (mxb > maxmx) maxmx = mxb;
+    }
+    int lpp = 4;
+    while (lpp < 32 && (int64_t)lpp * 16 < maxmx) lpp <<= 1;
+    if (c->knobs.svd_lpp > 0) lpp = c->knobs.svd_lpp;
+    int64_t threads = maxpairs * lpp;
+    threads = (threads + 31) & ~(int64_t)31;
+    if (threads > 1024) threads = 1024;
+    if (threads < 64) threads = 64;
     SmallSvdDesc* dev = nullptr;
     if (batch > 1) {
         dev = (SmallSvdDesc*)alloc(c, (size_t)batch * sizeof(SmallSvdDesc));
@@ -1334,15 +1392,26 @@ void svd_small_batched(Ctx* c, DType dt, int64_t batch, const SvdProblem* probs)
         h2d(c, dev, h.data(), (size_t)batch * sizeof(SmallSvdDesc));
     }
     const int max_sweeps = c->knobs.jac_max_sweeps;
-    if (dt == C64) {
-        auto kern = svd_small_kernel<true>;
-        if (c->first_use((const void*)kern)) T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSvdSmemCap));
-        kern<<<(unsigned)batch, warps * 32, smem, c->stream>>>(dev, h[0], max_sweeps, c->fail_dev);
-    } else {
-        auto kern = svd_small_kernel<false>;
-        if (c->first_use((const void*)kern)) T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSvdSmemCap));
-        kern<<<(unsigned)batch, warps * 32, smem, c->stream>>>(dev, h[0], max_sweeps, c->fail_dev);
+#define T4B_SVD_SMALL_LAUNCH(CP, LP)                                                                                     \
+    {                                                                                                                    \
+        auto kern = svd_small_kernel<CP, LP>;                                                                            \
+        if (c->first_use((const void*)kern))                                                                             \
+            T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSvdSmemCap)); \
+        kern<<<(unsigned)batch, (unsigned)threads, smem, c->stream>>>(dev, h[0], max_sweeps, c->fail_dev);               \
     }
+    if (dt == C64) {
+        if (lpp == 4) T4B_SVD_SMALL_LAUNCH(true, 4)
+        else if (lpp == 8) T4B_SVD_SMALL_LAUNCH(true, 8)
+        else if (lpp == 16) T4B_SVD_SMALL_LAUNCH(true, 16)
+        else T4B_SVD_SMALL_LAUNCH(true, 32)
+    } else {
+        if (lpp == 4) T4B_SVD_SMALL_LAUNCH(false, 4)
+        else if (lpp == 8) T4B_SVD_SMALL_LAUNCH(false, 8)
+        else if (lpp == 16) T4B_SVD_SMALL_LAUNCH(false, 16)
+        else T4B_SVD_SMALL_LAUNCH(false, 32)
+    }
+#undef T4B_SVD_SMALL_LAUNCH
+    T4B_CUDA_CHECK(cudaGetLastError());
     c->launched("svd_small", 0.0);
     if (dev) release(c, dev);
 }

@@ -202,3 +202,43 @@ def contract_partitioned(left, right, center, policy=None, max_bond_dim=0, rank=
             combined.truncate(center, policy, max_bond_dim)
         result.append((proj, combined))
     return result
+
+
+def contract_partitioned_cabi(ctx, left, right, center, method=0, policy=None, max_bond_dim=0, nfullsweeps=1, rank=0,
+                              world=1):
+    """t4b_partitioned_contract: the whole driver (pair plan, zip-up / fit / naive per pair, direct-sum add, one
+    truncation per group, rank sharding) behind the C ABI.  left / right: [(projector dict, ChainTN)].
+    Returns (n_groups_total, [(group_index, n_contributions, projector, ChainTN)])."""
+    from .tt import ChainTN, _pol
+
+    def flat(side):
+        n = len(side)
+        hs = (C.c_void_p * n)(*[c.h for _, c in side])
+        npj = np.ascontiguousarray([len(p) for p, _ in side], dtype=np.int32)
+        ids = np.ascontiguousarray([k for p, _ in side for k in p], dtype=np.int64)
+        vals = np.ascontiguousarray([p[k] for p, _ in side for k in p], dtype=np.int64)
+        return n, hs, npj, ids, vals
+
+    nl, hl, pl, il, vl = flat(left)
+    nr, hr, pr, ir, vr = flat(right)
+    h = C.c_void_p()
+    _check(lib().t4b_partitioned_contract(
+        ctx.h, C.c_int64(nl), hl, pl.ctypes.data_as(C.c_void_p), il.ctypes.data_as(C.c_void_p),
+        vl.ctypes.data_as(C.c_void_p), C.c_int64(nr), hr, pr.ctypes.data_as(C.c_void_p),
+        ir.ctypes.data_as(C.c_void_p), vr.ctypes.data_as(C.c_void_p), center, method, _pol(policy),
+        C.c_int64(max_bond_dim or 0), nfullsweeps, rank, world, C.byref(h)))
+    ng, nloc = C.c_int64(), C.c_int64()
+    _check(lib().t4b_partition_result_count(h, C.byref(ng), C.byref(nloc)))
+    out = []
+    dt = left[0][1]._dt
+    for i in range(nloc.value):
+        gi, nc, npj = C.c_int64(), C.c_int32(), C.c_int32()
+        _check(lib().t4b_partition_result_info(h, C.c_int64(i), C.byref(gi), C.byref(nc), C.byref(npj), None, None))
+        ids = (C.c_int64 * max(npj.value, 1))()
+        vals = (C.c_int64 * max(npj.value, 1))()
+        _check(lib().t4b_partition_result_info(h, C.c_int64(i), None, None, None, ids, vals))
+        th = C.c_void_p()
+        _check(lib().t4b_partition_result_take(h, C.c_int64(i), C.byref(th)))
+        out.append((gi.value, nc.value, {ids[k]: vals[k] for k in range(npj.value)}, ChainTN(ctx, th, dt)))
+    _check(lib().t4b_partition_result_release(h))
+    return ng.value, out

@@ -227,6 +227,97 @@ def chain_from_arrays(ctx, arrays, ids):
     return ChainTN.from_arrays(ctx, arrays, ids)
 
 
+# ---- tree tensor networks ----------------------------------------------------------------------------
+class TreeTN:
+    """t4b_tree handle (any loop-free topology).  nodes: list of (ndarray, [index ids]); edges = shared ids."""
+
+    def __init__(self, ctx: Context, handle, dt=F64):
+        self.ctx, self.h, self._dt = ctx, handle, dt
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, arrays, ids):
+        n = len(arrays)
+        arrs = [np.asfortranarray(a) for a in arrays]
+        dt = dtype_of(arrs[0])
+        ranks = _i32([a.ndim for a in arrs])
+        shapes = _i64([s for a in arrs for s in a.shape])
+        idl = _i64([i for node in ids for i in node])
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data_as(C.c_void_p).value for a in arrs])
+        h = C.c_void_p()
+        _check(lib().t4b_tree_create(ctx.h, dt, n, ranks, shapes, idl, ptrs, 0, C.byref(h)))
+        return cls(ctx, h, dt)
+
+    def clone(self):
+        h = C.c_void_p()
+        _check(lib().t4b_tree_clone(self.ctx.h, self.h, C.byref(h)))
+        return TreeTN(self.ctx, h, self._dt)
+
+    def num_nodes(self):
+        n = C.c_int()
+        _check(lib().t4b_tree_num_nodes(self.h, C.byref(n)))
+        return n.value
+
+    def edges(self):
+        n = self.num_nodes()
+        e = (C.c_int32 * (2 * max(n - 1, 1)))()
+        d = (C.c_int64 * max(n - 1, 1))()
+        _check(lib().t4b_tree_edges(self.h, e, d))
+        return [(e[2 * i], e[2 * i + 1]) for i in range(n - 1)], list(d)[: n - 1]
+
+    def node(self, i):
+        r = C.c_int()
+        _check(lib().t4b_tree_node_rank(self.h, i, C.byref(r)))
+        shape = (C.c_int64 * max(r.value, 1))()
+        ids = (C.c_int64 * max(r.value, 1))()
+        _check(lib().t4b_tree_node_shape(self.h, i, shape, ids))
+        out = np.empty(tuple(shape)[: r.value], dtype=np_dtype(self._dt), order="F")
+        _check(lib().t4b_tree_download_node(self.ctx.h, self.h, i, out.ctypes.data_as(C.c_void_p)))
+        return out, list(ids)[: r.value]
+
+    def nodes(self):
+        return [self.node(i) for i in range(self.num_nodes())]
+
+    def sweep_plan(self, center):
+        n = C.c_int()
+        _check(lib().t4b_tree_sweep_plan(self.h, center, None, C.byref(n)))
+        buf = (C.c_int32 * (2 * max(n.value, 1)))()
+        _check(lib().t4b_tree_sweep_plan(self.h, center, buf, C.byref(n)))
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(n.value)]
+
+    def canonicalize(self, center):
+        _check(lib().t4b_tree_canonicalize(self.ctx.h, self.h, center))
+
+    def truncate(self, center, policy: SvdPolicy | None = None, max_bond_dim=0):
+        _check(lib().t4b_tree_truncate(self.ctx.h, self.h, center, _pol(policy), C.c_int64(max_bond_dim)))
+
+    def contract_zipup(self, other, center, policy: SvdPolicy | None = None, max_bond_dim=0):
+        h = C.c_void_p()
+        _check(lib().t4b_tree_contract_zipup(self.ctx.h, self.h, other.h, center, _pol(policy),
+                                             C.c_int64(max_bond_dim), C.byref(h)))
+        return TreeTN(self.ctx, h, self._dt)
+
+    def norm_sqr(self):
+        v = C.c_double()
+        _check(lib().t4b_tree_norm_sqr(self.ctx.h, self.h, C.byref(v)))
+        return v.value
+
+    def inner(self, other):
+        re, im = C.c_double(), C.c_double()
+        _check(lib().t4b_tree_inner(self.ctx.h, self.h, other.h, C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
+
+    def release(self):
+        if self.h:
+            lib().t4b_tree_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 # ---- positional trains -------------------------------------------------------------------------------
 class Train:
     def __init__(self, ctx: Context, handle, dt, site_rank):
@@ -268,6 +359,14 @@ class Train:
     def compress(self, method=2, tolerance=1e-12, max_bond_dim=0, normalize_error=True):
         _check(lib().t4b_train_compress(self.ctx.h, self.h, method, C.c_double(tolerance),
                                         C.c_int64(max_bond_dim), int(normalize_error)))
+
+    @staticmethod
+    def compress_batched(ctx, trains, method=2, tolerance=1e-12, max_bond_dim=0, normalize_error=True):
+        """t4b_train_compress_batched: one launch chain for the whole batch of independent trains."""
+        n = len(trains)
+        hs = (C.c_void_p * max(n, 1))(*[t.h for t in trains])
+        _check(lib().t4b_train_compress_batched(ctx.h, C.c_int64(n), hs, method, C.c_double(tolerance),
+                                                C.c_int64(max_bond_dim), int(normalize_error)))
 
     def mpo_contract(self, other, algorithm=0, tolerance=1e-12, max_bond_dim=0):
         h = C.c_void_p()

@@ -98,3 +98,36 @@ def test_inner_product(ctx):
         got = t4tt.Train.from_arrays(ctx, a).inner_product(t4tt.Train.from_arrays(ctx, b))
         ref = ostt.inner_product(a, b)
         assert abs(got - ref) <= 1e-12 * abs(ref)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_compress_batched_matches_per_train_and_oracle(ctx, cplx):
+    """t4b_train_compress_batched (one launch chain for the whole batch) against the per-train entry point and the
+    oracle: same bond dimensions, same tensor to 1e-10; ragged batch (different bond dimensions per train)."""
+    rng = np.random.default_rng(21)
+    L, d = 8, 2
+    batch = []
+    for b in range(5):
+        chi = [6, 9, 12, 16, 3][b]
+        bd = [min(d ** (i + 1), d ** (L - 1 - i), chi) for i in range(L - 1)]
+        arrs = []
+        for i in range(L):
+            sh = ((bd[i - 1] if i else 1), d, (bd[i] if i < L - 1 else 1))
+            a = rng.standard_normal(sh)
+            if cplx:
+                a = a + 1j * rng.standard_normal(sh)
+            arrs.append(np.asfortranarray(a))
+        batch.append(arrs)
+    for tol, maxdim in [(1e-12, 0), (1e-2, 0), (1e-12, 4)]:
+        tts = [t4tt.Train.from_arrays(ctx, a) for a in batch]
+        t4tt.Train.compress_batched(ctx, tts, 2, tol, maxdim, True)
+        for a, tt in zip(batch, tts):
+            one = t4tt.Train.from_arrays(ctx, a)
+            one.compress(2, tol, maxdim, True)
+            got, single = tt.arrays(), one.arrays()
+            assert [x.shape for x in got] == [x.shape for x in single]
+            ref = ostt.compress([x.copy() for x in a], "SVD", tol, maxdim or None, True)
+            assert [x.shape for x in got] == [x.shape for x in ref]
+            dg, dr = ostt.tt_dense(got), ostt.tt_dense(ref)
+            assert np.linalg.norm(dg - dr) <= 1e-10 * np.linalg.norm(dr)
+            assert np.linalg.norm(dg - ostt.tt_dense(single)) <= 1e-10 * np.linalg.norm(dr)

@@ -117,6 +117,48 @@ def test_gpu_partitioned_contract_matches_oracle(ctx, cplx):
         sorted(tpatch.projector_key(p) for p, _ in ref)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cplx", [False, True])
+def test_gpu_partitioned_contract_cabi_driver_matches_oracle(ctx, cplx):
+    """The all-pairs driver behind the C ABI (t4b_partitioned_contract): same groups, projectors, bond dimensions and
+    tensors as the oracle; sharded over 2 and 3 ranks the union of the ranks' groups is the single-rank result."""
+    from t4b import patches as tpatch
+    from t4b import tt as t4tt
+    from util import gpu_chain_dense
+    (ma, mi), (oa, oi), left, right = _problem(cplx)
+    pol = SvdTruncationPolicy(1e-12)
+    ref = opatch.contract_partitioned([(_olab(p), to_oracle_chain(a, mi)) for p, a in left],
+                                      [(_olab(p), to_oracle_chain(a, oi)) for p, a in right], 0, pol, 6)
+    # the ABI sorts the patches itself: feed them in reversed order
+    gl = [(p, t4tt.chain_from_arrays(ctx, a, mi)) for p, a in reversed(left)]
+    gr = [(p, t4tt.chain_from_arrays(ctx, a, oi)) for p, a in reversed(right)]
+    ng, got = tpatch.contract_partitioned_cabi(ctx, gl, gr, 0, 0, t4tt.SvdPolicy(1e-12), 6)
+    assert ng == len(ref) == len(got)
+    assert [g[0] for g in got] == list(range(ng))
+    assert [_olab(g[2]) for g in got] == [p for p, _ in ref]
+    assert all(g[1] == 2 for g in got)          # two compatible pairs feed every output projector here
+    dense = {}
+    for (gi, nc, p, g), (_, r) in zip(got, ref):
+        assert g.bond_dims() == r.bond_dims()
+        dense[gi] = gpu_chain_dense(g)
+        assert relerr(dense[gi], oracle_chain_dense(r)) <= 1e-10
+    for world in (2, 3):
+        seen = {}
+        for r in range(world):
+            n2, part = tpatch.contract_partitioned_cabi(ctx, gl, gr, 0, 0, t4tt.SvdPolicy(1e-12), 6, rank=r, world=world)
+            assert n2 == ng
+            for gi, nc, p, g in part:
+                assert gi % world == r and gi not in seen
+                seen[gi] = gpu_chain_dense(g)
+        assert sorted(seen) == list(range(ng))
+        for gi in seen:
+            assert np.array_equal(seen[gi], dense[gi])      # sharding does not change a single bit
+    # the sum over the output patches is O psi
+    full = sum(dense.values())
+    want = oracle_chain_dense(otn.contract_zipup(to_oracle_chain(ma, mi), to_oracle_chain(oa, oi), 0, SvdTruncationPolicy(1e-14), None))
+    assert relerr(full, want) <= 1e-9
+
+
 class _FakeChain:
     """Host-only stand-in with the ChainTN methods the partitioned driver touches: records what was asked."""
 
