@@ -140,6 +140,11 @@ int t4b_solve_right_full_piv_lu(t4b_ctx* ctx, int dtype, int64_t lhs_rows, int64
  * product of the dims of the union of the two label sets (multiply-adds). */
 int t4b_contraction_order(int n_ops, const int32_t* ranks, const int64_t* shapes, const uint32_t* labels,
                           int32_t* pairs_out, double* cost_out);
+/* The planner behind t4b_einsum / the sweep drivers caches its plans per network signature (operand label patterns
+ * relabelled by first appearance + dims; the reference caches compiled einsum programs the same way,
+ * tensorbackend/src/tenferro_bridge.rs:619-749): a sweep plans its bulk site once.  Host only. */
+int t4b_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
+int t4b_plan_cache_clear(void);
 
 /* Batched matrix product c[:, :, b] = a[:, :, b] * b[:, :, b]: a (m x k x batch), b (k x n x batch), c (m x n x batch),
  * dense column-major, one launch.  Replaces batched_mat_mul_same_shape (tensorbackend/src/matrix.rs:1538-1584). */
@@ -380,6 +385,16 @@ int t4b_train_compress(t4b_ctx* ctx, t4b_train* tt, int method, double tolerance
  * and matrices that do not fit one CTA (min dim > 128) fall back to the per-train loop. */
 int t4b_train_compress_batched(t4b_ctx* ctx, int64_t n, t4b_train* const* tts, int method, double tolerance,
                                int64_t max_bond_dim, int normalize_error);
+/* Batched evaluation of a tensor train at npts full multi-indices (indices_host: npts x length, point-major):
+ * TTCache::evaluate_many (simplett/src/cache.rs:594-690) on the device; values_host receives npts scalars. */
+int t4b_train_evaluate(t4b_ctx* ctx, const t4b_train* tt, int64_t npts, const int64_t* indices_host,
+                       void* values_host);
+/* Candidate matrix Pi of the TCI2 two-site update at bond b for a TT-valued integrand, built on the device (the batch
+ * callback of tensorci/src/tensorci2.rs:1862-1893 with f = this train): i_multi_host ni x b, j_multi_host
+ * nj x (length - b - 2), point-major.  pi_dev_out: (ni * d_b) x (d_{b+1} * nj) device matrix, rows i*d_b + s,
+ * columns s'*nj + j (kronecker_i / kronecker_j, :1224-1246) - feed it to t4b_tci2_update_pivots(pi_on_device = 1). */
+int t4b_train_tci2_pi(t4b_ctx* ctx, const t4b_train* tt, int b, int64_t ni, const int64_t* i_multi_host, int64_t nj,
+                      const int64_t* j_multi_host, void* pi_dev_out);
 /* mpo::contract (simplett/src/mpo/dispatch.rs:67): algorithm 0 ZipUp, 1 Naive (+compress), 2 Naive
  * without compression */
 int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int algorithm,

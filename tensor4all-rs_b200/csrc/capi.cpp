@@ -200,6 +200,16 @@ int t4b_solve(t4b_ctx* ctx, int dtype, int64_t n, int64_t nrhs, const void* a_de
     T4B_CATCH
 }
 
+int t4b_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries) {
+    T4B_TRY
+    plan_cache_stats(hits, misses, entries);
+    T4B_CATCH
+}
+int t4b_plan_cache_clear(void) {
+    T4B_TRY
+    plan_cache_clear();
+    T4B_CATCH
+}
 int t4b_contraction_order(int n_ops, const int32_t* ranks, const int64_t* shapes, const uint32_t* labels,
                           int32_t* pairs_out, double* cost_out) {
     T4B_TRY

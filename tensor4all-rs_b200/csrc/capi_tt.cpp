@@ -426,6 +426,30 @@ int t4b_train_compress_batched(t4b_ctx* ctx, int64_t n, t4b_train* const* tts, i
     stt::compress_batched(ctx->c, v, o);
     T4B_CATCH
 }
+int t4b_train_evaluate(t4b_ctx* ctx, const t4b_train* tt, int64_t npts, const int64_t* indices_host,
+                       void* values_host) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tt && npts >= 0 && (npts == 0 || (indices_host && values_host)), "train_evaluate: bad arguments");
+    if (npts == 0) return T4B_OK;
+    const size_t es = dtype_size(tt->tt.dt);
+    auto out = std::make_shared<Buffer>(ctx->c, (size_t)npts * es);
+    stt::evaluate_many(ctx->c, tt->tt, npts, indices_host, out->p);
+    dla::d2h(ctx->c, values_host, out->p, (size_t)npts * es);
+    dla::sync(ctx->c);
+    T4B_CATCH
+}
+int t4b_train_tci2_pi(t4b_ctx* ctx, const t4b_train* tt, int b, int64_t ni, const int64_t* i_multi_host, int64_t nj,
+                      const int64_t* j_multi_host, void* pi_dev_out) {
+    T4B_TRY
+    require_ctx(ctx);
+    T4B_REQUIRE(tt && pi_dev_out, "train_tci2_pi: null argument");
+    const int n = (int)tt->tt.sites.size();
+    T4B_REQUIRE(b >= 0 && b + 1 < n, "train_tci2_pi: bond out of range");
+    T4B_REQUIRE((b == 0 || i_multi_host) && (b + 2 == n || j_multi_host), "train_tci2_pi: null multi-index array");
+    stt::tci2_pi_from_train(ctx->c, tt->tt, b, ni, i_multi_host, nj, j_multi_host, pi_dev_out);
+    T4B_CATCH
+}
 int t4b_mpo_contract(t4b_ctx* ctx, const t4b_train* a, const t4b_train* b, int algorithm,
                      double tolerance, int64_t max_bond_dim, t4b_train** out) {
     T4B_TRY

@@ -105,6 +105,21 @@ struct SmallGemmProblem {
     const double* col_scale;
 };
 void gemm_small_batched(Ctx*, DType dt, int64_t batch, const SmallGemmProblem* problems);
+// Batched strided 2-D copies dst[0:rows, 0:cols] (ld = ldd) = src[0:rows, 0:cols] (ld = lds), one launch.
+struct Copy2dProblem {
+    const void* src; int64_t lds;
+    void* dst; int64_t ldd;
+    int64_t rows, cols;
+};
+void copy2d_batched(Ctx*, DType dt, int64_t batch, const Copy2dProblem* problems);
+// Batched partial evaluation of a tensor train (device side of TTCache::evaluate_left / evaluate_right, reference
+// crates/tensor4all-simplett/src/cache.rs:439-535): for every point p the product of the site slices
+//   left : e_0^T T_0[:, i_0, :] ... T_{ns-1}[:, i_{ns-1}, :]        -> out[p + npts * c], c < right dim of the last site
+//   right: T_0[:, i_0, :] ... T_{ns-1}[:, i_{ns-1}, :] e_0          -> out[p + npts * a], a < left dim of the first site
+// sites[k] are column-major [l_k, d_k, r_k] device tensors (dims[3k..3k+2], host), idx is a DEVICE int64 array,
+// point-major (idx[p * ns + k]).  One CTA per point, the running vector lives in shared memory.
+void tt_env(Ctx*, DType dt, bool left, int ns, const void* const* sites, const int64_t* dims, int64_t npts,
+            const int64_t* idx_dev, void* out_dev);
 bool svd_small_fits(DType dt, int64_t m, int64_t n, bool want_u, bool want_vh);
 void svd_small_batched(Ctx*, DType dt, int64_t batch, const SvdProblem* problems);
 

@@ -206,6 +206,7 @@ void compress_batched(dla::Ctx* c, const std::vector<Train*>& tts, const Compres
             }
         }
         dla::gemm_small_batched(c, dt, B, gp.data());
+        std::vector<dla::Copy2dProblem> cp;
         for (int64_t b = 0; b < B; ++b) {
             Site& s = tts[b]->sites[ell];
             if (left_to_right) {
@@ -218,19 +219,85 @@ void compress_batched(dla::Ctx* c, const std::vector<Train*>& tts, const Compres
                 if (rank[b] == kk[b]) {
                     s.buf = vb[b];
                 } else {
-                    // keep the first `rank` rows of Vh (ld = k): strided copy into a compact buffer
+                    // keep the first `rank` rows of Vh (ld = k): strided copy into a compact buffer (one launch for
+                    // all trains below)
                     auto vr = std::make_shared<Buffer>(c, (size_t)rank[b] * cols * es);
-                    dla::permute(c, dt, vr->p, vb[b]->p, g2(rank[b], 1, cols, kk[b]), false);
+                    cp.push_back(dla::Copy2dProblem{vb[b]->p, kk[b], vr->p, rank[b], rank[b], cols});
                     s.buf = vr;
                 }
                 s.d[0] = rank[b];
                 pv.buf = nb[b]; pv.d[2] = rank[b];
             }
         }
+        if (!cp.empty()) dla::copy2d_batched(c, dt, (int64_t)cp.size(), cp.data());
         // sbuf is released here; the queued kernels that read it are stream-ordered before any reuse
     };
     for (int ell = 0; ell + 1 < n; ++ell) run_step(ell, true);
     for (int ell = n - 1; ell >= 1; --ell) run_step(ell, false);
+}
+
+// environments of `npts` partial multi-indices over sites [k0, k0 + ns): returns an npts x chi device matrix
+static std::shared_ptr<Buffer> env_batch(dla::Ctx* c, const Train& tt, bool left, int k0, int ns, int64_t npts,
+                                         const int64_t* idx_host) {
+    const size_t es = dtype_size(tt.dt);
+    const int64_t chi = ns == 0 ? 1 : (left ? tt.sites[k0 + ns - 1].d[2] : tt.sites[k0].d[0]);
+    auto out = std::make_shared<Buffer>(c, (size_t)npts * chi * es);
+    if (ns == 0) {
+        std::vector<double> ones((size_t)npts * (tt.dt == C64 ? 2 : 1), 0.0);
+        for (int64_t p = 0; p < npts; ++p) ones[p * (tt.dt == C64 ? 2 : 1)] = 1.0;
+        dla::h2d(c, out->p, ones.data(), (size_t)npts * es);
+        dla::sync(c);
+        return out;
+    }
+    std::vector<const void*> ptrs;
+    std::vector<int64_t> dims;
+    for (int k = k0; k < k0 + ns; ++k) {
+        ptrs.push_back(tt.sites[k].buf->p);
+        dims.push_back(tt.sites[k].d[0]); dims.push_back(tt.sites[k].d[1]); dims.push_back(tt.sites[k].d[2]);
+        for (int64_t p = 0; p < npts; ++p)
+            T4B_REQUIRE(idx_host[p * ns + (k - k0)] >= 0 && idx_host[p * ns + (k - k0)] < tt.sites[k].d[1], "local index out of range for its site");
+    }
+    auto didx = std::make_shared<Buffer>(c, (size_t)npts * ns * sizeof(int64_t));
+    dla::h2d(c, didx->p, idx_host, (size_t)npts * ns * sizeof(int64_t));
+    dla::tt_env(c, tt.dt, left, ns, ptrs.data(), dims.data(), npts, (const int64_t*)didx->p, out->p);
+    dla::sync(c);   // idx_host may be pageable: the staged copy has completed, and the caller may free it
+    return out;
+}
+
+void evaluate_many(dla::Ctx* c, const Train& tt, int64_t npts, const int64_t* indices, void* out_dev) {
+    T4B_REQUIRE(tt.rank == 3 && !tt.sites.empty(), "evaluate_many expects a non-empty tensor train of rank-3 sites");
+    if (npts <= 0) return;
+    const int n = (int)tt.sites.size();
+    T4B_REQUIRE(tt.sites[0].d[0] == 1 && tt.sites[n - 1].d[2] == 1, "evaluate_many: boundary bonds must have dimension 1");
+    // the left environment through ALL sites is the value itself (a 1-vector per point)
+    auto v = env_batch(c, tt, true, 0, n, npts, indices);
+    dla::d2d(c, out_dev, v->p, (size_t)npts * dtype_size(tt.dt));
+    dla::sync(c);
+}
+
+void tci2_pi_from_train(dla::Ctx* c, const Train& tt, int b, int64_t ni, const int64_t* i_multi, int64_t nj,
+                        const int64_t* j_multi, void* pi_dev) {
+    const int n = (int)tt.sites.size();
+    T4B_REQUIRE(tt.rank == 3 && b >= 0 && b + 1 < n && ni >= 1 && nj >= 1 && pi_dev, "tci2_pi_from_train: bad arguments");
+    T4B_REQUIRE(tt.sites[0].d[0] == 1 && tt.sites[n - 1].d[2] == 1, "tci2_pi_from_train: boundary bonds must have dimension 1");
+    const DType dt = tt.dt;
+    const size_t es = dtype_size(dt);
+    const Site& sb = tt.sites[b];
+    const Site& sp = tt.sites[b + 1];
+    const int64_t l = sb.d[0], d1 = sb.d[1], chi = sb.d[2], d2 = sp.d[1], r = sp.d[2];
+    auto lenv = env_batch(c, tt, true, 0, b, ni, i_multi);                    // ni x l
+    auto renv = env_batch(c, tt, false, b + 2, n - b - 2, nj, j_multi);       // nj x r
+    // A[i, s, c] = sum_a Lenv[i, a] T_b[a, s, c]                                  (ni x l) . (l x d1 chi)
+    auto A = std::make_shared<Buffer>(c, (size_t)ni * d1 * chi * es);
+    dla::gemm(c, dt, ni, d1 * chi, l, 1.0, lenv->p, g1(ni, 1), g1(l, ni), false, sb.buf->p, g1(l, 1), g1(d1 * chi, l),
+              false, 0.0, A->p, g1(ni, 1), g1(d1 * chi, ni));
+    // Bm[c, s', j] = sum_e T_{b+1}[c, s', e] Renv[j, e]                          (chi d2 x r) . (r x nj)
+    auto Bm = std::make_shared<Buffer>(c, (size_t)chi * d2 * nj * es);
+    dla::gemm(c, dt, chi * d2, nj, r, 1.0, sp.buf->p, g1(chi * d2, 1), g1(r, chi * d2), false, renv->p, g1(r, nj),
+              g1(nj, 1), false, 0.0, Bm->p, g1(chi * d2, 1), g1(nj, chi * d2));
+    // Pi[(i, s), (s', j)] = sum_c A[i, s, c] Bm[c, s', j]; rows i*d1 + s (s fastest), columns s'*nj + j (j fastest)
+    dla::gemm(c, dt, ni * d1, d2 * nj, chi, 1.0, A->p, g2(d1, ni, ni, 1), g1(chi, ni * d1), false, Bm->p, g1(chi, 1),
+              g2(nj, chi * d2, d2, chi), false, 0.0, pi_dev, g1(ni * d1, 1), g1(d2 * nj, ni * d1));
 }
 
 Train contract_zipup(dla::Ctx* c, const Train& a, const Train& b, const MpoContractionOptions& o) {

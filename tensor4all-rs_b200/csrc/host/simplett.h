@@ -59,6 +59,18 @@ void inner_product(dla::Ctx*, const Train& a, const Train& b, double* re, double
 Train fourier_mpo(dla::Ctx*, int r, int k, double sign, double tolerance, std::optional<int64_t> max_bond_dim,
                   bool normalize);
 
+// Batched evaluation of a tensor train on the device (TTCache::evaluate_many, reference simplett/src/cache.rs:594-690:
+// values = <left environment | right environment>): indices is npts x L point-major on the HOST; out: npts values on
+// the device.
+void evaluate_many(dla::Ctx*, const Train& tt, int64_t npts, const int64_t* indices, void* out_dev);
+// Candidate matrix Pi of the TCI2 two-site update for a TT-valued integrand, built entirely on the device (the batch
+// callback of reference tensorci/src/tensorci2.rs:1862-1893 with f = the tensor train): rows i*d_b + s over the ni
+// left multi-indices (ni x b, host, point-major), columns s'*nj + j over the nj right multi-indices (nj x (L-b-2));
+// Pi[(i,s),(s',j)] = Lenv_i T_b[:, s, :] T_{b+1}[:, s', :] Renv_j as two environment launches and three GEMMs.
+// out: (ni*d_b) x (d_{b+1}*nj) device matrix.
+void tci2_pi_from_train(dla::Ctx*, const Train& tt, int b, int64_t ni, const int64_t* i_multi, int64_t nj,
+                        const int64_t* j_multi, void* pi_dev);
+
 // rank rule shared by compression.rs:286-306 and mpo/factorize.rs:206-250
 int64_t simplett_rank(const std::vector<double>& s, double tolerance, bool normalize_error,
                       std::optional<int64_t> max_bond_dim);

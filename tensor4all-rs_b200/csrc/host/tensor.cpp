@@ -1,5 +1,9 @@
 #include "tensor.h"
 
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include <algorithm>
 #include <functional>
 #include <atomic>
@@ -140,6 +144,19 @@ Tensor contract_pair(dla::Ctx* c, const Tensor& a, const Tensor& b, bool conj_a,
 // a step (i, j) (positions in the CURRENT operand list, i < j) replaces operand i by the contraction of i and j
 // (indices = those of i not in j, then those of j not in i) and removes operand j.  Cost of a step = product
 // of the dims of the union of the two index lists.  Outer products are only taken once nothing is connected.
+namespace {
+struct PlanCache {
+    struct Entry { std::vector<std::pair<int, int>> plan; double cost; };
+    std::mutex mu;
+    std::unordered_map<std::string, Entry> map;
+    int64_t hits = 0, misses = 0;
+};
+PlanCache& plan_cache() {
+    static PlanCache pc;
+    return pc;
+}
+}  // namespace
+
 std::vector<std::pair<int, int>> plan_contraction_order(const std::vector<std::vector<Index>>& sets_in,
                                                         double* total_cost) {
     typedef std::vector<std::vector<Index>> Sets;
@@ -179,9 +196,59 @@ std::vector<std::pair<int, int>> plan_contraction_order(const std::vector<std::v
             }
     };
     if (sets.size() <= 1) { if (total_cost) *total_cost = 0.0; return {}; }
+    // Plan cache (reference run_cached_native_einsum / compile_native_einsum_program,
+    // tensorbackend/src/tenferro_bridge.rs:619-749): the order depends only on the SIGNATURE of the network - which
+    // operands share which indices, and the dims - not on the index ids, which are fresh at every sweep step.
+    // Indices are relabelled by first appearance; a sweep re-plans nothing after its first bulk site.
+    std::string key;
+    {
+        std::vector<int64_t> seen;
+        key.reserve(sets.size() * 24);
+        for (auto& st : sets) {
+            for (auto& ix : st) {
+                size_t pos = std::find(seen.begin(), seen.end(), ix.id) - seen.begin();
+                if (pos == seen.size()) seen.push_back(ix.id);
+                key += std::to_string(pos);
+                key += ':';
+                key += std::to_string(ix.dim);
+                key += ',';
+            }
+            key += ';';
+        }
+    }
+    PlanCache& pc = plan_cache();
+    {
+        std::lock_guard<std::mutex> lk(pc.mu);
+        auto it = pc.map.find(key);
+        if (it != pc.map.end()) {
+            ++pc.hits;
+            if (total_cost) *total_cost = it->second.cost;
+            return it->second.plan;
+        }
+    }
     dfs(sets, 0.0);
     if (total_cost) *total_cost = best_cost;
+    {
+        std::lock_guard<std::mutex> lk(pc.mu);
+        ++pc.misses;
+        if (pc.map.size() >= 4096) pc.map.clear();      // bounded: signatures of one workload are a handful
+        pc.map.emplace(std::move(key), PlanCache::Entry{best_plan, best_cost});
+    }
     return best_plan;
+}
+
+void plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries) {
+    PlanCache& pc = plan_cache();
+    std::lock_guard<std::mutex> lk(pc.mu);
+    if (hits) *hits = pc.hits;
+    if (misses) *misses = pc.misses;
+    if (entries) *entries = (int64_t)pc.map.size();
+}
+void plan_cache_clear() {
+    PlanCache& pc = plan_cache();
+    std::lock_guard<std::mutex> lk(pc.mu);
+    pc.map.clear();
+    pc.hits = pc.misses = 0;
 }
 
 Tensor contract(dla::Ctx* c, const std::vector<const Tensor*>& ts,

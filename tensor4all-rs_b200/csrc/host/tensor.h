@@ -82,6 +82,10 @@ Tensor contract(dla::Ctx*, const std::vector<const Tensor*>& ts,
 // positions in the current operand list: operand i <- contract(i, j), operand j removed.
 std::vector<std::pair<int, int>> plan_contraction_order(const std::vector<std::vector<Index>>& sets,
                                                         double* total_cost);
+// The planner caches its result per network signature (operand index patterns relabelled by first appearance + dims):
+// counters and reset of that process-wide cache (reference tenferro_bridge.rs:619-749 program cache).
+void plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
+void plan_cache_clear();
 // Materialised axis permutation (reference permute_indices, idx_tensor.rs:3389).
 Tensor permute(dla::Ctx*, const Tensor& t, const std::vector<Index>& new_order, bool conj = false);
 // sum |t|^2 (synchronises)

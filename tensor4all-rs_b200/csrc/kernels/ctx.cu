@@ -87,6 +87,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.gemm_nows = getb("T4B_GEMM_NOWS"); k.gemm_noskinny = getb("T4B_GEMM_NOSKINNY");
         k.gemm_trace = getb("T4B_GEMM_TRACE"); k.gemm_nopersist = getb("T4B_GEMM_NOPERSIST");
         k.svd_nobatch = getb("T4B_SVD_NOBATCH");
+        k.svd_small_single_max = geti("T4B_SVD_SMALL_MAX", 32);
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;
     }

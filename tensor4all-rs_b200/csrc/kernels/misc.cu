@@ -359,5 +359,120 @@ void gemm_small_batched(Ctx* c, DType dt, int64_t batch, const SmallGemmProblem*
     release(c, dev);
 }
 
+
+// =====================================================================================================
+// Batched TT environment vectors (see dla.h tt_env): blockIdx.x = point.
+// =====================================================================================================
+struct TtEnvSite {
+    const double* T;
+    int l, d, r;
+};
+template <bool CPLX>
+__global__ void __launch_bounds__(128) tt_env_kernel(const TtEnvSite* __restrict__ sites, int ns, int left,
+                                                     const long long* __restrict__ idx, long long npts,
+                                                     double* __restrict__ out, int maxdim) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    extern __shared__ __align__(16) unsigned char tt_env_smem[];
+    T* v0 = reinterpret_cast<T*>(tt_env_smem);
+    T* v1 = v0 + maxdim;
+    const long long p = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) v0[0] = S::one();
+    __syncthreads();
+    T* cur = v0;
+    T* nxt = v1;
+    int curdim = 1;
+    for (int kk = 0; kk < ns; ++kk) {
+        const int k = left ? kk : ns - 1 - kk;
+        const TtEnvSite st = sites[k];
+        const long long sidx = idx[p * ns + k];
+        const T* Tk = reinterpret_cast<const T*>(st.T) + (long long)st.l * sidx;   // slice [:, s, :], column c at + l*d*c
+        const long long cstride = (long long)st.l * st.d;
+        if (left) {
+            // nxt[c] = sum_a cur[a] T[a, s, c]: a is contiguous -> one warp per output, lanes over a
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int c = warp; c < st.r; c += 4) {
+                T acc = S::zero();
+                const T* col = Tk + cstride * c;
+                for (int a = lane; a < st.l; a += 32) acc = S::add(acc, S::mul(cur[a], col[a]));
+                acc = warp_sum_t<CPLX>(acc);
+                if (lane == 0) nxt[c] = acc;
+            }
+            curdim = st.r;
+        } else {
+            // nxt[a] = sum_c T[a, s, c] cur[c]: threads over a (coalesced), serial over c
+            for (int a = tid; a < st.l; a += 128) {
+                T acc = S::zero();
+                for (int c = 0; c < st.r; ++c) acc = S::add(acc, S::mul(Tk[a + cstride * c], cur[c]));
+                nxt[a] = acc;
+            }
+            curdim = st.l;
+        }
+        __syncthreads();
+        T* t = cur; cur = nxt; nxt = t;
+    }
+    T* o = reinterpret_cast<T*>(out);
+    for (int c = tid; c < curdim; c += 128) o[p + npts * c] = cur[c];
+}
+
+void tt_env(Ctx* c, DType dt, bool left, int ns, const void* const* sites, const int64_t* dims, int64_t npts,
+            const int64_t* idx_dev, void* out_dev) {
+    if (npts <= 0) return;
+    T4B_REQUIRE(ns >= 1 && sites && dims && idx_dev && out_dev, "tt_env: bad arguments");
+    std::vector<TtEnvSite> h((size_t)ns);
+    int maxdim = 1;
+    for (int k = 0; k < ns; ++k) {
+        h[k] = TtEnvSite{(const double*)sites[k], (int)dims[3 * k], (int)dims[3 * k + 1], (int)dims[3 * k + 2]};
+        maxdim = std::max(maxdim, std::max(h[k].l, h[k].r));
+        if (k > 0) T4B_REQUIRE(dims[3 * k] == dims[3 * k - 1], "tt_env: bond dimensions of neighbouring sites differ");
+    }
+    T4B_REQUIRE(left ? dims[0] == 1 : dims[3 * ns - 1] == 1, "tt_env: the chain must start from a boundary bond of dimension 1");
+    TtEnvSite* dev = (TtEnvSite*)alloc(c, (size_t)ns * sizeof(TtEnvSite));
+    h2d(c, dev, h.data(), (size_t)ns * sizeof(TtEnvSite));
+    const size_t smem = 2 * (size_t)maxdim * dtype_size(dt);
+    T4B_REQUIRE(smem <= 48 * 1024, "tt_env: bond dimension too large for the shared-memory vectors");
+    for (int64_t p0 = 0; p0 < npts; p0 += 1 << 30) {
+        const unsigned nb = (unsigned)std::min<int64_t>(1 << 30, npts - p0);
+        T4B_REQUIRE(p0 == 0, "tt_env: more than 2^30 points per call");
+        if (dt == C64) tt_env_kernel<true><<<nb, 128, smem, c->stream>>>(dev, ns, left ? 1 : 0, (const long long*)idx_dev, (long long)npts, (double*)out_dev, maxdim);
+        else tt_env_kernel<false><<<nb, 128, smem, c->stream>>>(dev, ns, left ? 1 : 0, (const long long*)idx_dev, (long long)npts, (double*)out_dev, maxdim);
+    }
+    c->launched("tt_env", 0.0);
+    release(c, dev);
+}
+
+
+struct Copy2dDesc {
+    const double* src; long long lds;
+    double* dst; long long ldd;
+    int rows, cols;
+};
+template <bool CPLX>
+__global__ void copy2d_batched_kernel(const Copy2dDesc* __restrict__ descs) {
+    typedef typename Sc<CPLX>::T T;
+    const Copy2dDesc d = descs[blockIdx.x];
+    const T* s = reinterpret_cast<const T*>(d.src);
+    T* o = reinterpret_cast<T*>(d.dst);
+    const long long total = (long long)d.rows * d.cols;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+        const long long j = e / d.rows, i = e - j * d.rows;
+        o[i + j * d.ldd] = s[i + j * d.lds];
+    }
+}
+void copy2d_batched(Ctx* c, DType dt, int64_t batch, const Copy2dProblem* probs) {
+    if (batch <= 0) return;
+    std::vector<Copy2dDesc> h((size_t)batch);
+    for (int64_t b = 0; b < batch; ++b)
+        h[b] = Copy2dDesc{(const double*)probs[b].src, (long long)probs[b].lds, (double*)probs[b].dst, (long long)probs[b].ldd,
+                          (int)probs[b].rows, (int)probs[b].cols};
+    Copy2dDesc* dev = (Copy2dDesc*)alloc(c, (size_t)batch * sizeof(Copy2dDesc));
+    h2d(c, dev, h.data(), (size_t)batch * sizeof(Copy2dDesc));
+    if (dt == C64) copy2d_batched_kernel<true><<<(unsigned)batch, 256, 0, c->stream>>>(dev);
+    else copy2d_batched_kernel<false><<<(unsigned)batch, 256, 0, c->stream>>>(dev);
+    c->launched("copy2d_batched", 0.0);
+    release(c, dev);
+}
+
 }  // namespace dla
 }  // namespace t4b

@@ -1246,10 +1246,8 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
                 for (int i = gl; i < mx; i += LPP) g = S_::add(g, S_::mul(S_::conj(xp[i]), xq[i]));
                 g = group_sum_t(g);
                 const double g2 = S_::abs2(g);
-                if (app > zthr && aqq > zthr) {
-                    const double c2 = g2 / (app * aqq);
-                    if (c2 > mxcos2) mxcos2 = c2;
-                }
+                // convergence test |x_p^H x_q|^2 <= tol^2 |x_p|^2 |x_q|^2 without the division
+                if (app > zthr && aqq > zthr && g2 > tol2 * app * aqq) mxcos2 = 1.0;
                 double c, sn, tg;
                 T ph;
                 jacobi_rotation<CPLX>(app, aqq, g, tol2 * 0.00390625, c, sn, ph, tg, zthr);
@@ -1293,7 +1291,7 @@ __global__ void __launch_bounds__(1024, 1) svd_small_kernel(const SmallSvdDesc* 
         double m2 = 0.0;
         for (int w = 0; w < nwarps; ++w) m2 = red[w] > m2 ? red[w] : m2;
         __syncthreads();
-        if (m2 <= tol2) converged = 1;
+        if (m2 == 0.0) converged = 1;     // no pair of this sweep violated the orthogonality test
     }
     if (!converged && tid == 0 && fail) atomicAdd(fail, 1u);
 
@@ -1372,14 +1370,14 @@ void svd_small_batched(Ctx* c, DType dt, int64_t batch, const SvdProblem* probs)
         const int64_t nx = p.m < p.n ? p.m : p.n;
         if ((nx + 1) / 2 > maxpairs) maxpairs = (nx + 1) / 2;
     }
-    // lanes per pair: ~16 rows per lane, 4 <= LPP <= 32; the CTA holds min(1024, pairs * LPP) threads
+    // lanes per pair (LPP); the CTA holds min(1024, pairs * LPP) threads
     int64_t maxmx = 1;
     for (int64_t b = 0; b < batch; ++b) {
         const int64_t mxb = probs[b].m > probs[b].n ? probs[b].m : probs[b].n;
         if (mxb > maxmx) maxmx = mxb;
     }
-    int lpp = 4;
-    while (lpp < 32 && (int64_t)lpp * 16 < maxmx) lpp <<= 1;
+    // measured (tools/probe_svd_small.py): 16 lanes per pair are the fastest from 16 x 16 up to 128 x 128
+    int lpp = maxmx > 256 ? 32 : 16;
     if (c->knobs.svd_lpp > 0) lpp = c->knobs.svd_lpp;
     int64_t threads = maxpairs * lpp;
     threads = (threads + 31) & ~(int64_t)31;
@@ -1420,7 +1418,11 @@ void svd_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* U, double* 
     struct ClassGuard { Ctx* c; const char* prev; ClassGuard(Ctx* cc) : c(cc), prev(cc->gemm_class) { cc->gemm_class = "gemm_factor"; } ~ClassGuard() { c->gemm_class = prev; } } class_guard(c);
     if (m == 0 || n == 0) return;
     const size_t es = dtype_size(dt);
-    if (!c->knobs.svd_nobatch && svd_small_fits(dt, m, n, U != nullptr, Vh != nullptr)) {
+    // One problem at a time the single-CTA kernel only wins for tiny matrices (measured, profiles/svd_small_r02.md:
+    // 16 x 16 130 us vs 310 us for the cluster pipeline, but 64 x 64 880 us vs 740 us): its place is the BATCHED
+    // entry point, where hundreds of CTAs run side by side.
+    if (!c->knobs.svd_nobatch && (m < n ? m : n) <= c->knobs.svd_small_single_max &&
+        svd_small_fits(dt, m, n, U != nullptr, Vh != nullptr)) {
         SvdProblem p{A, m, n, m, U, m, S, Vh, m < n ? m : n};
         svd_small_batched(c, dt, 1, &p);
         return;

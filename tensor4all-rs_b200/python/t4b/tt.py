@@ -368,6 +368,26 @@ class Train:
         _check(lib().t4b_train_compress_batched(ctx.h, C.c_int64(n), hs, method, C.c_double(tolerance),
                                                 C.c_int64(max_bond_dim), int(normalize_error)))
 
+    def evaluate(self, indices):
+        """t4b_train_evaluate: values of the train at the rows of `indices` (npts x length)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        out = np.zeros(idx.shape[0], dtype=np_dtype(self.dt))
+        _check(lib().t4b_train_evaluate(self.ctx.h, self.h, C.c_int64(idx.shape[0]), idx.ctypes.data_as(C.c_void_p),
+                                        out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def tci2_pi(self, b, i_multi, j_multi):
+        """t4b_train_tci2_pi: candidate matrix of the two-site update at bond b as a DeviceArray."""
+        dims = [self.site(k).shape for k in (b, b + 1)]
+        L = self.length()
+        im = np.ascontiguousarray(i_multi, dtype=np.int64).reshape(-1, b) if b > 0 else np.zeros((1, 0), np.int64)
+        jm = np.ascontiguousarray(j_multi, dtype=np.int64).reshape(-1, L - b - 2) if L - b - 2 > 0 else np.zeros((1, 0), np.int64)
+        ni, nj = im.shape[0], jm.shape[0]
+        out = self.ctx.empty((ni * dims[0][1], dims[1][1] * nj), self.dt)
+        _check(lib().t4b_train_tci2_pi(self.ctx.h, self.h, b, C.c_int64(ni), im.ctypes.data_as(C.c_void_p),
+                                       C.c_int64(nj), jm.ctypes.data_as(C.c_void_p), C.c_void_p(out.ptr)))
+        return out
+
     def mpo_contract(self, other, algorithm=0, tolerance=1e-12, max_bond_dim=0):
         h = C.c_void_p()
         _check(lib().t4b_mpo_contract(self.ctx.h, self.h, other.h, algorithm, C.c_double(tolerance),

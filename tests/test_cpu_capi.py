@@ -150,3 +150,26 @@ def test_contraction_order_chain_is_optimal():
         return best
     assert cost == brute([tuple(l) for l in labels])
     assert len(plan) == 3
+
+
+def test_plan_cache_hits_on_relabelled_signature():
+    """The planner caches per SIGNATURE (label pattern by first appearance + dims), not per label value: the same
+    zip-up site with fresh bond labels is a cache hit and returns the same plan and cost (reference program cache,
+    tensorbackend/src/tenferro_bridge.rs:619-749)."""
+    import ctypes as C
+    import t4b
+    lib = t4b.lib()
+    assert lib.t4b_plan_cache_clear() == 0
+    shapes = [(64, 64, 8), (64, 4, 64), (8, 4, 4, 8)]
+    p1, c1 = _order(shapes, [(0, 1, 2), (1, 3, 4), (2, 3, 5, 6)])
+    h, m, e = C.c_int64(), C.c_int64(), C.c_int64()
+    assert lib.t4b_plan_cache_stats(C.byref(h), C.byref(m), C.byref(e)) == 0
+    assert (h.value, m.value, e.value) == (0, 1, 1)
+    p2, c2 = _order(shapes, [(70, 11, 42), (11, 33, 54), (42, 33, 95, 6)])      # same pattern, other labels
+    lib.t4b_plan_cache_stats(C.byref(h), C.byref(m), C.byref(e))
+    assert (h.value, m.value, e.value) == (1, 1, 1)
+    assert p1 == p2 and c1 == c2
+    p3, c3 = _order([(64, 64, 8), (64, 4, 32), (8, 4, 4, 8)], [(0, 1, 2), (1, 3, 4), (2, 3, 5, 6)])   # other dims
+    lib.t4b_plan_cache_stats(C.byref(h), C.byref(m), C.byref(e))
+    assert (h.value, m.value, e.value) == (1, 2, 2)
+    assert c3 != c1

@@ -164,3 +164,72 @@ def test_c4_fused_d8_shape_update(ctx):
     assert got.bond_error == err
     assert np.abs(got.tensor_b - tb).max() <= 1e-9 * np.abs(tb).max()
     assert np.abs(got.tensor_bp1 - tp).max() <= 1e-9 * np.abs(tp).max()
+
+
+# ---- TT-valued integrands: Pi built on the device ------------------------------------------------------
+def _tt_eval_np(sites, idx):
+    v = np.ones((1,), dtype=sites[0].dtype)
+    for t, s in zip(sites, idx):
+        v = v @ t[:, s, :]
+    return v[0]
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_train_evaluate_matches_numpy(ctx, cplx):
+    """t4b_train_evaluate == TTCache::evaluate_many (simplett/src/cache.rs:594-690): product of the site slices."""
+    from t4b import tt as t4tt
+    rng = np.random.default_rng(31)
+    L, d, chi = 9, 3, 7
+    bd = [1] + [min(d ** (i + 1), d ** (L - 1 - i), chi) for i in range(L - 1)] + [1]
+    sites = []
+    for i in range(L):
+        a = rng.standard_normal((bd[i], d, bd[i + 1]))
+        if cplx:
+            a = a + 1j * rng.standard_normal(a.shape)
+        sites.append(np.asfortranarray(a))
+    tt = t4tt.Train.from_arrays(ctx, sites)
+    pts = rng.integers(0, d, size=(200, L))
+    got = tt.evaluate(pts)
+    want = np.array([_tt_eval_np(sites, p) for p in pts])
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("b", [0, 2, 5, 6])
+def test_tci2_pi_from_train_matches_pointwise_evaluation(ctx, cplx, b):
+    """t4b_train_tci2_pi builds the candidate matrix of update_pivots on the device with the reference's candidate
+    ordering (rows i*d + s, columns s'*#J + j: kronecker_i / kronecker_j, tensorci2.rs:1224-1246) - entry by entry equal
+    to evaluating the train at i ++ s ++ s' ++ j (the batch callback of tensorci2.rs:1862-1893); the prrLU of the
+    device-built Pi selects the same pivots as the prrLU of the host-evaluated one."""
+    from oracle import rrlu as orrlu
+    from t4b import tt as t4tt
+    from t4b.tci import TciUpdate
+    rng = np.random.default_rng(32 + b)
+    L, d, chi = 8, 2, 6
+    bd = [1] + [min(d ** (i + 1), d ** (L - 1 - i), chi) for i in range(L - 1)] + [1]
+    sites = []
+    for i in range(L):
+        a = rng.standard_normal((bd[i], d, bd[i + 1]))
+        if cplx:
+            a = a + 1j * rng.standard_normal(a.shape)
+        sites.append(np.asfortranarray(a))
+    tt = t4tt.Train.from_arrays(ctx, sites)
+    ni, nj = (1 if b == 0 else 5), (1 if b + 2 == L else 4)
+    I = rng.integers(0, d, size=(ni, b))
+    J = rng.integers(0, d, size=(nj, L - b - 2))
+    pi = tt.tci2_pi(b, I, J).get()
+    assert pi.shape == (ni * d, d * nj)
+    want = np.zeros_like(pi)
+    for i in range(ni):
+        for s in range(d):
+            for s2 in range(d):
+                for j in range(nj):
+                    want[i * d + s, s2 * nj + j] = _tt_eval_np(sites, list(I[i]) + [s, s2] + list(J[j]))
+    assert np.max(np.abs(pi - want)) <= 1e-12 * np.max(np.abs(want))
+    if not cplx:
+        # same pivots from the device-built and the host-evaluated matrix (well separated pivots on random data)
+        u = TciUpdate(ctx, np.asfortranarray(pi), ni, d, d, nj, 0, 1e-8, True)
+        lu = orrlu.rrlu(want, None, 1e-8, 0.0, True)
+        assert u.rank == lu.n_pivot
+        assert list(u.row_indices[:u.rank]) == [int(x) for x in lu.row_perm[:lu.n_pivot]]
+        assert list(u.col_indices[:u.rank]) == [int(x) for x in lu.col_perm[:lu.n_pivot]]
