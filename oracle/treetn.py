@@ -378,7 +378,12 @@ def contract_fit(a, b, center, policy=None, max_bond_dim=None, nfullsweeps=1):
 
 def inner(a, b):
     a2 = a.sim_bonds()
-    return complex(contract([s.conj() for s in a2.sites] + list(b.sites)).arr)
+    if len(a2.sites) * 2 <= 16:
+        return complex(contract([s.conj() for s in a2.sites] + list(b.sites)).arr)
+    env = None      # long chains: site by site (einsum runs out of letters beyond ~25 sites)
+    for x, y in zip(a2.sites, b.sites):
+        env = contract([x.conj(), y]) if env is None else contract([env, x.conj(), y])
+    return complex(env.arr)
 
 
 def add(a, b):

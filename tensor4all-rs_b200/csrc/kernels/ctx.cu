@@ -86,7 +86,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.qr_leaf_old = !getb("T4B_QR_LEAF_NEW");   // blocked single-warp leaf measured 2x slower (r02d): opt-in only
         k.gemm_nows = getb("T4B_GEMM_NOWS"); k.gemm_noskinny = getb("T4B_GEMM_NOSKINNY");
         k.gemm_trace = getb("T4B_GEMM_TRACE"); k.gemm_nopersist = getb("T4B_GEMM_NOPERSIST");
-        k.svd_nobatch = getb("T4B_SVD_NOBATCH");
+        k.svd_nobatch = getb("T4B_SVD_NOBATCH"); k.svd_nogram = getb("T4B_SVD_NOGRAM");
         k.svd_small_single_max = geti("T4B_SVD_SMALL_MAX", 32);
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;

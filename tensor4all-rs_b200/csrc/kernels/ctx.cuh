@@ -34,6 +34,7 @@ struct Knobs {
     bool qr_leaf_old = true;      // cleared by T4B_QR_LEAF_NEW (blocked single-warp TSQR leaf, slower: A/B only)
     bool gemm_nows = false, gemm_noskinny = false, gemm_trace = false, gemm_nopersist = false;
     bool svd_nobatch = false;     // T4B_SVD_NOBATCH
+    bool svd_nogram = false;      // T4B_SVD_NOGRAM: never take the Gram + Cholesky preconditioner
     int svd_small_single_max = 32;   // T4B_SVD_SMALL_MAX: largest min(m, n) a SINGLE svd_thin sends to the one-CTA kernel
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
 };

@@ -150,3 +150,38 @@ def test_svd_reports_non_convergence(monkeypatch):
     u, s, vh = ctx.svd_thin(b)
     assert np.allclose(s.get(), np.arange(48.0, 0.0, -1.0))
     ctx.close()
+
+
+@pytest.mark.parametrize("kind", ["flat", "graded", "rank_deficient", "tall_vh_only"])
+def test_svd_gram_cholesky_preconditioner_and_fallback(ctx, kind):
+    """The R-only preconditioner of wide f64 matrices (U only) is the Cholesky factor of the Gram matrix when the
+    pivots certify a small condition number, and the Householder TSQR otherwise: a flat spectrum takes the fast path,
+    a graded (kappa = 1e10) or rank-deficient matrix must be REJECTED and still come out to LAPACK accuracy."""
+    rng = np.random.default_rng(77)
+    m, n = 384, 900
+    if kind == "tall_vh_only":
+        a = np.asfortranarray(rng.standard_normal((n, m)))
+        _, s, vh = ctx.svd_thin(ctx.upload(a), want_u=False)
+        _check(a, None, s.get(), vh.get())
+        return
+    u0, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    v0, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    if kind == "flat":
+        sv = np.linspace(1.0, 0.2, m)
+    elif kind == "graded":
+        sv = np.logspace(0, -10, m)
+    else:
+        sv = np.concatenate([np.linspace(1.0, 0.5, m // 2), np.zeros(m - m // 2)])
+    a = np.asfortranarray((u0 * sv) @ v0.T)
+    u, s, _ = ctx.svd_thin(ctx.upload(a), want_vh=False)
+    u, s = u.get(), s.get()
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
+    if kind == "graded":
+        # relative accuracy of the SMALL singular values: only the Householder path delivers it
+        big = s_ref > 1e-9 * s_ref[0]
+        assert np.max(np.abs(s[big] - s_ref[big]) / s_ref[big]) <= 1e-6
+    r = int(np.sum(sv > 0))
+    # the retained left vectors span the column space: || U_r^H A ||_F^2 == sum sigma^2
+    assert abs(np.linalg.norm(u[:, :r].conj().T @ a) ** 2 - np.sum(s_ref ** 2)) <= 1e-11 * np.sum(s_ref ** 2)
+    assert np.linalg.norm(u[:, :r].conj().T @ u[:, :r] - np.eye(r)) <= 1e-11 * r
