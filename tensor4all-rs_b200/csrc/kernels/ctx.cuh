@@ -147,5 +147,10 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Blocked Cholesky of a Hermitian positive definite f64 matrix with a condition certificate (svd.cu): shared by the
+// Gram preconditioners of the SVD and of the QR.
+constexpr int kCholBlock = 128;
+bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out, double* linv_all);
+
 }  // namespace dla
 }  // namespace t4b

@@ -14,6 +14,8 @@
 
 #include <cstdlib>
 
+#include <cstdio>
+
 #include "scalar.cuh"
 
 namespace cg = cooperative_groups;
@@ -1627,12 +1629,64 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
 
 }  // namespace
 
+// R (n x n, ld = n) = L^H: upper triangle from the lower triangle of L (ld = ldl), zeros below
+__global__ void lower_to_upper_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double* __restrict__ R) {
+    const int64_t total = n * n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t j = e / n, i = e - j * n;
+        R[e] = i <= j ? L[j + i * ldl] : 0.0;
+    }
+}
+
+// A (m x n, destroyed) = Q R through the Cholesky factor of the Gram matrix; false = rejected (A untouched).
+static bool qr_thin_cholesky(Ctx* c, int64_t m, int64_t n, double* A, double* Q, double* R) {
+    auto gq = [](int64_t dim, int64_t str) { Group g; g.nd = 1; g.dim[0] = dim; g.str[0] = str; return g; };
+    const int64_t nblk = (n + kCholBlock - 1) / kCholBlock;
+    double* G = (double*)alloc(c, (size_t)n * n * 8);
+    double* Linv = (double*)alloc(c, (size_t)nblk * kCholBlock * kCholBlock * 8);
+    gemm(c, F64, n, n, m, 1.0, A, gq(n, m), gq(m, 1), true, A, gq(m, 1), gq(n, m), false, 0.0, G, gq(n, 1), gq(n, n));
+    double ratio = 0.0;
+    const bool ok = cholesky_blocked(c, n, G, &ratio, Linv);
+    if (c->knobs.verbose) fprintf(stderr, "[t4b] qr %lld x %lld: Cholesky QR %s (diag ratio %.3e)\n", (long long)m, (long long)n, ok ? "taken" : "rejected", ratio);
+    if (ok) {
+        int64_t g1d = (n * n + 255) / 256;
+        if (g1d > (int64_t)c->num_sms * 8) g1d = (int64_t)c->num_sms * 8;
+        lower_to_upper_kernel<<<(unsigned)g1d, 256, 0, c->stream>>>(G, n, n, R);
+        c->launched("qr_extract_r");
+        for (int64_t b = 0; b < nblk; ++b) {
+            const int64_t j0 = b * kCholBlock;
+            const int64_t nb = std::min<int64_t>(kCholBlock, n - j0);
+            double* Ab = A + j0 * m;
+            if (b > 0) {
+                // A_b -= Q[:, 0:j0] L[j0:j0+nb, 0:j0]^H
+                gemm(c, F64, m, nb, j0, -1.0, Q, gq(m, 1), gq(j0, m), false, G + j0, gq(j0, n), gq(nb, 1), true, 1.0, Ab,
+                     gq(m, 1), gq(nb, m));
+            }
+            // Q_b = A_b Linv_bb^H
+            const double* Lb = Linv + b * (size_t)kCholBlock * kCholBlock;
+            gemm(c, F64, m, nb, nb, 1.0, Ab, gq(m, 1), gq(nb, m), false, Lb, gq(nb, nb), gq(nb, 1), true, 0.0, Q + j0 * m,
+                 gq(m, 1), gq(nb, m));
+        }
+    }
+    release(c, Linv);
+    release(c, G);
+    return ok;
+}
+
 void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
     struct ClassGuard { Ctx* c; const char* prev; ClassGuard(Ctx* cc) : c(cc), prev(cc->gemm_class) { cc->gemm_class = "gemm_factor"; } ~ClassGuard() { c->gemm_class = prev; } } class_guard(c);
     const int64_t k = m < n ? m : n;
     if (k == 0) return;
     const size_t es = dtype_size(dt);
     const bool cplx = dt == C64;
+    if (!cplx && Q && Rout && !c->knobs.svd_nogram && n >= 2 * kCholBlock && m >= 2 * n) {
+        // Cholesky QR for tall f64 matrices whose Gram pivots certify a small condition number (the isometry sweeps of
+        // a canonical tensor train): A^H A = L L^H (one DMMA GEMM + the blocked Cholesky), R = L^H, Q = A R^-1 by block
+        // forward substitution with the inverted diagonal blocks - GEMMs only, no chain of dependent panel
+        // factorisations.  ||Q^H Q - I|| ~ eps kappa^2; rejected matrices take the Householder TSQR below.
+        if (qr_thin_cholesky(c, m, n, (double*)A, (double*)Q, (double*)Rout)) return;
+    }
     if (!c->knobs.qr_old) {
         if (cplx ? qr_thin_tsqr<true>(c, m, n, A, Q, Rout) : qr_thin_tsqr<false>(c, m, n, A, Q, Rout)) return;
     }

@@ -825,7 +825,7 @@ __global__ void gather_cols_kernel(const double* __restrict__ src, int64_t ld_sr
         double s2 = sig2[col];
         double smax = S[0];
         // directions below the noise floor of the Jacobi iteration are not trustworthy: zero them
-        scale = (s2 > sig2_floor_rel * smax * smax && s2 > 0.0) ? 1.0 / sqrt(s2) : 0.0;
+        scale = (s2 > sig2_floor_rel * smax * smax && s2 > 0.0) ? (normalize == 2 ? 1.0 / s2 : 1.0 / sqrt(s2)) : 0.0;
     }
     const T* s = reinterpret_cast<const T*>(src) + col * ld_src;
     T* d = reinterpret_cast<T*>(dst);
@@ -1074,61 +1074,135 @@ constexpr int CHB = 128;     // Cholesky block
 
 // Diagonal block (nb <= 128, lower triangle of G at ld) -> L (in place, lower) and its inverse Linv (nb x nb, ld = nb,
 // zeros above the diagonal).  info[0] != 0: a pivot was not positive.  stat[0] / stat[1]: running min / max of diag(L).
+//
+// Right-looking and register blocked: the 16 x 16 threads own the entries (ty + 16 a, tx + 16 b), a, b < 8, of the
+// 128 x 128 block in registers (cyclic, so the shrinking trailing block stays balanced).  Per column: the owners
+// publish the column through shared memory, ONE barrier, and every thread applies the rank-1 update to its 64 entries
+// (independent FMAs) - against a left-looking column loop whose j-th step is a serial chain of j FMAs.  The inverse is
+// the same scheme on the identity (forward substitution, right-looking): row j of L^-1 is final after j updates.
 __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ G, int64_t ld, int nb,
                                                            double* __restrict__ Linv, int* __restrict__ info,
                                                            double* __restrict__ stat) {
-    // One nb x (nb + 1) array holds both triangles: L in the lower one (A[i + j * lp], i >= j) and the strictly
-    // lower part of L^-1 TRANSPOSED into the strictly upper one (X[i][c], i > c, at A[c + i * lp]); diag(L^-1) apart.
+    constexpr int LP = CHB + 1;
     extern __shared__ __align__(16) unsigned char chol_smem[];
-    double* A = reinterpret_cast<double*>(chol_smem);
-    const int lp = nb + 1;
-    double* xd = A + (size_t)nb * lp;                          // [nb] diagonal of the inverse
-    const int tid = threadIdx.x;
+    double* Ls = reinterpret_cast<double*>(chol_smem);          // [CHB][LP] column-major: L[i + j * LP]
+    double* vec = Ls + (size_t)CHB * LP;                        // [2][CHB] published column / row (double buffered)
+    double* dinv = vec + 2 * CHB;                               // [CHB] 1 / L[j][j]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     __shared__ int bad;
     if (tid == 0) bad = info[0];
-    for (int e = tid; e < nb * nb; e += 256) {
-        const int j = e / nb, i = e - j * nb;
-        A[i + j * lp] = i >= j ? G[i + (int64_t)j * ld] : 0.0;
-    }
+    double a[8][8];
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) {
+            const int i = ty + 16 * ia, j = tx + 16 * ib;
+            a[ia][ib] = (i < nb && j < nb && i >= j) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);   // identity padding
+        }
     __syncthreads();
     if (bad) return;
     double dmin = stat[0], dmax = stat[1];
-    // left-looking: column j minus the contributions of columns < j, then scale
-    for (int j = 0; j < nb; ++j) {
-        for (int i = j + tid; i < nb; i += 256) {
-            double acc = A[i + j * lp];
-            for (int k = 0; k < j; ++k) acc = fma(-A[i + k * lp], A[j + k * lp], acc);
-            A[i + j * lp] = acc;
+    // ---- Cholesky, right-looking ----
+    // (rsqrt instead of sqrt + division: the pivot step is on the critical path of every column; slices of the register
+    // block that lie entirely at or above the pivot are skipped - the bound 16 ia + 15 > j is uniform over the CTA)
+    for (int j = 0; j < CHB; ++j) {
+        double* col = vec + (j & 1) * CHB;
+        if (tx == (j & 15)) {
+            const int jb = j >> 4;      // (register arrays are only ever indexed by unrolled constants)
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (ib == jb) col[ty + 16 * ia] = a[ia][ib];
         }
         __syncthreads();
-        const double d = A[j + j * lp];
+        const double d = col[j];
         if (!(d > 0.0) || !isfinite(d)) {
             if (tid == 0) info[0] = 1;
             return;
         }
-        const double sd = sqrt(d), inv = 1.0 / sd;
-        __syncthreads();
-        for (int i = j + tid; i < nb; i += 256) A[i + j * lp] = i == j ? sd : A[i + j * lp] * inv;
-        dmin = sd < dmin ? sd : dmin;
-        dmax = sd > dmax ? sd : dmax;
-        __syncthreads();
-    }
-    // inverse by forward substitution, one thread per column c of the inverse: x = L^-1 e_c (x[i] for i >= c)
-    for (int c = tid; c < nb; c += 256) {
-        const double xc = 1.0 / A[c + c * lp];
-        xd[c] = xc;
-        for (int i = c + 1; i < nb; ++i) {
-            double acc = -A[i + c * lp] * xc;
-            for (int k = c + 1; k < i; ++k) acc = fma(-A[i + k * lp], A[c + k * lp], acc);   // X[k][c] at (c, k)
-            A[c + i * lp] = acc / A[i + i * lp];
+        const double inv = rsqrt(d), sd = d * inv;
+        if (tid == 0) dinv[j] = inv;
+        if (j < nb) { dmin = sd < dmin ? sd : dmin; dmax = sd > dmax ? sd : dmax; }
+        double li[8], lc[8];
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) { const int i = ty + 16 * ia; li[ia] = i > j ? col[i] * inv : 0.0; }
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) { const int c = tx + 16 * ib; lc[ib] = c > j ? col[c] * inv : 0.0; }
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) {
+            if (16 * ia + 15 > j) {
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (16 * ib + 15 > j) a[ia][ib] = fma(-li[ia], lc[ib], a[ia][ib]);
+            }
+        }
+        if (tx == (j & 15)) {
+            // the finished column of L: registers and shared memory
+            const int jb = j >> 4;
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia) {
+                const int i = ty + 16 * ia;
+                const double v = i > j ? li[ia] : (i == j ? sd : 0.0);
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (ib == jb) a[ia][ib] = v;
+                Ls[i + j * LP] = v;
+            }
         }
     }
     __syncthreads();
-    for (int e = tid; e < nb * nb; e += 256) {
-        const int j = e / nb, i = e - j * nb;
-        if (i >= j) G[i + (int64_t)j * ld] = A[i + j * lp];
-        Linv[e] = i > j ? A[j + i * lp] : (i == j ? xd[i] : 0.0);
+    // L back to global memory (lower triangle only)
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) {
+            const int i = ty + 16 * ia, j = tx + 16 * ib;
+            if (i < nb && j < nb && i >= j) G[i + (int64_t)j * ld] = a[ia][ib];
+        }
+    // ---- inverse: forward substitution on the identity, right-looking.  a <- residual R (starts as I) ----
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) a[ia][ib] = (ty + 16 * ia) == (tx + 16 * ib) ? 1.0 : 0.0;
+    for (int j = 0; j < CHB; ++j) {
+        double* row = vec + (j & 1) * CHB;
+        const double inv = dinv[j];
+        if (ty == (j & 15)) {
+            const int ja = j >> 4;
+#pragma unroll
+            for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (ia == ja) {
+                        const double y = a[ia][ib] * inv;        // row j of L^-1 is final
+                        a[ia][ib] = y;
+                        row[tx + 16 * ib] = y;
+                    }
+        }
+        __syncthreads();
+        double lj[8], yr[8];
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) { const int i = ty + 16 * ia; lj[ia] = i > j ? Ls[i + j * LP] : 0.0; }
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) yr[ib] = row[tx + 16 * ib];
+        // row j of the inverse is zero beyond column j, and only rows below j are updated
+#pragma unroll
+        for (int ia = 0; ia < 8; ++ia) {
+            if (16 * ia + 15 > j) {
+#pragma unroll
+                for (int ib = 0; ib < 8; ++ib)
+                    if (16 * ib <= j) a[ia][ib] = fma(-lj[ia], yr[ib], a[ia][ib]);
+            }
+        }
     }
+#pragma unroll
+    for (int ia = 0; ia < 8; ++ia)
+#pragma unroll
+        for (int ib = 0; ib < 8; ++ib) {
+            const int i = ty + 16 * ia, j = tx + 16 * ib;
+            if (i < nb && j < nb) Linv[i + (size_t)j * nb] = i >= j ? a[ia][ib] : 0.0;
+        }
     if (tid == 0) { stat[0] = dmin; stat[1] = dmax; }
 }
 
@@ -1143,24 +1217,28 @@ __global__ void init_x_lower_kernel(const double* __restrict__ L, int64_t ldl, i
     }
 }
 
+}  // namespace
+
 // G (n x n, ld = n, full Hermitian on entry) -> lower Cholesky factor in its lower triangle.  Returns false when a
-// pivot was not positive or the diagonal ratio certifies nothing (see above); G is garbage then.
-bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out) {
+// pivot was not positive or the diagonal ratio certifies nothing (see above); G is garbage then.  linv_all (optional):
+// the inverses of the diagonal blocks, block b (nb x nb, ld = nb) at linv_all + b * CHB * CHB.
+bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out, double* linv_all) {
     int* info = (int*)alloc(c, sizeof(int) + 2 * sizeof(double) + 8);
     double* stat = reinterpret_cast<double*>(reinterpret_cast<char*>(info) + 8);
     {
         struct { int info, pad; double dmin, dmax; } init = {0, 0, 1e308, 0.0};
         h2d(c, info, &init, sizeof(init));
     }
-    double* Linv = (double*)alloc(c, (size_t)CHB * CHB * 8);
+    double* Linv1 = linv_all ? nullptr : (double*)alloc(c, (size_t)CHB * CHB * 8);
     double* Pc = n > CHB ? (double*)alloc(c, (size_t)(n - CHB) * CHB * 8) : nullptr;
-    const size_t smem = (size_t)CHB * (CHB + 1) * 8 + (size_t)CHB * 8;
+    const size_t smem = (size_t)CHB * (CHB + 1) * 8 + (size_t)3 * CHB * 8;
     if (c->first_use((const void*)potrf_inv_kernel))
         T4B_CUDA_CHECK(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t k = 0; k < n; k += CHB) {
         const int nb = (int)std::min<int64_t>(CHB, n - k);
         double* Gkk = G + k + k * n;
-        potrf_inv_kernel<<<1, 256, (size_t)nb * (nb + 1) * 8 + (size_t)nb * 8, c->stream>>>(Gkk, n, nb, Linv, info, stat);
+        double* Linv = linv_all ? linv_all + (k / CHB) * (size_t)CHB * CHB : Linv1;
+        potrf_inv_kernel<<<1, 256, smem, c->stream>>>(Gkk, n, nb, Linv, info, stat);
         c->launched("chol_potrf");
         const int64_t r = n - k - nb;
         if (r <= 0) break;
@@ -1181,7 +1259,7 @@ bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out) {
     struct { int info, pad; double dmin, dmax; } res;
     d2h(c, &res, info, sizeof(res));
     sync(c);
-    release(c, Linv);
+    if (Linv1) release(c, Linv1);
     if (Pc) release(c, Pc);
     release(c, info);
     const double ratio = (res.info == 0 && res.dmax > 0.0) ? res.dmin / res.dmax : 0.0;
@@ -1189,7 +1267,8 @@ bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out) {
     return res.info == 0 && ratio >= 1.0 / 32.0;
 }
 
-// m >= n.  A destroyed.  U (m x n) / Vh (n x n) optional.
+namespace {
+
 // `Ah` (n x m, ld = n), when given, is the adjoint of the matrix to factor (the caller's wide original): the Gram
 // path reads it directly and the m x n copy `A` is only materialised (by the caller-supplied buffer rule below) when
 // the Householder path has to run.  A may be null then.
@@ -1206,14 +1285,35 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     void* Rm = nullptr;
     void* Aown = nullptr;
     bool gram_done = false;
+    bool gram_tried = false;
+    bool gram_u = false;          // left vectors through U = A V Sigma^-1 (V = left vectors of the Cholesky factor)
     if constexpr (!CPLX) {
+        if (want_u && !want_v && !Ah && !c->knobs.svd_nogram && n >= 2 * CHB && m >= 2 * n) {
+            // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
+            // L = U_X Sigma J^H, i.e. the RIGHT singular vectors of A are U_X and U = A U_X Sigma^-1 - no Q is ever
+            // formed.  Orthogonality of U is eps kappa^2, so the same pivot certificate gates the path.
+            double* G = (double*)alloc(c, (size_t)n * n * 8);
+            gemm(c, F64, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
+            double ratio = 0.0;
+            gram_tried = true;
+            gram_u = cholesky_blocked(c, n, G, &ratio, nullptr);
+            if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld (U): Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_u ? "taken" : "rejected", ratio);
+            if (gram_u) {
+                gram_done = true;
+                X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
+                init_x_lower_kernel<<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>(G, n, n, pl.ldx, npad, X);
+                c->launched("svd_init_x");
+            }
+            release(c, G);
+        }
         if (!want_u && want_v && !c->knobs.svd_nogram && n >= 2 * CHB) {
             // Gram + Cholesky preconditioner: X = L with L L^H = A^H A (= R^H up to column signs)
             double* G = (double*)alloc(c, (size_t)n * n * 8);
             if (Ah) gemm(c, F64, n, n, m, 1.0, Ah, gg(n, 1), gg(m, n), false, Ah, gg(m, n), gg(n, 1), true, 0.0, G, gg(n, 1), gg(n, n));
             else gemm(c, F64, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
             double ratio = 0.0;
-            gram_done = cholesky_blocked(c, n, G, &ratio);
+            gram_tried = true;
+            gram_done = cholesky_blocked(c, n, G, &ratio, nullptr);
             if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld: Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_done ? "taken" : "rejected", ratio);
             if (gram_done) {
                 X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
@@ -1236,7 +1336,12 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         // QR preconditioner
         Q = want_u ? alloc(c, (size_t)m * n * es) : nullptr;
         Rm = alloc(c, (size_t)n * n * es);
-        qr_thin(c, dt, m, n, A, Q, Rm);
+        {
+            // a Gram matrix that was just rejected above would be rejected again by the Cholesky QR: go straight to
+            // the Householder factorisation (when no Gram was tried, e.g. both vector sets wanted, qr_thin decides)
+            struct NoGram { Ctx* c; bool saved; NoGram(Ctx* cc, bool on) : c(cc), saved(cc->knobs.svd_nogram) { if (on) cc->knobs.svd_nogram = true; } ~NoGram() { c->knobs.svd_nogram = saved; } } guard(c, gram_tried);
+            qr_thin(c, dt, m, n, A, Q, Rm);
+        }
         // X = R (left vectors wanted) or R^H (only right vectors wanted)
         const bool adjoint = !want_u;
         X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
@@ -1263,9 +1368,10 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         // U_X = sorted, normalised columns of X (n x n); U = Q U_X
         double* UX = (double*)alloc(c, (size_t)n * n * es);
         zero(c, UX, (size_t)n * n * es);
-        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, 1, 0, UX, n, n, S);
+        // Householder path: U = Q U_X.  Gram path: U = A U_X Sigma^-1 = A (x_j / sigma_j^2)
+        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, gram_u ? 2 : 1, 0, UX, n, n, S);
         c->launched("svd_gather_u");
-        gemm(c, dt, m, n, n, 1.0, Q, gg(m, 1), gg(n, m), false, UX, gg(n, 1), gg(n, n), false, 0.0, U,
+        gemm(c, dt, m, n, n, 1.0, gram_u ? A : Q, gg(m, 1), gg(n, m), false, UX, gg(n, 1), gg(n, n), false, 0.0, U,
              gg(m, 1), gg(n, m));
         release(c, UX);
         if (want_v) {

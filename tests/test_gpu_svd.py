@@ -185,3 +185,24 @@ def test_svd_gram_cholesky_preconditioner_and_fallback(ctx, kind):
     # the retained left vectors span the column space: || U_r^H A ||_F^2 == sum sigma^2
     assert abs(np.linalg.norm(u[:, :r].conj().T @ a) ** 2 - np.sum(s_ref ** 2)) <= 1e-11 * np.sum(s_ref ** 2)
     assert np.linalg.norm(u[:, :r].conj().T @ u[:, :r] - np.eye(r)) <= 1e-11 * r
+
+
+@pytest.mark.parametrize("kind", ["flat", "graded"])
+def test_svd_tall_left_vectors_gram_path(ctx, kind):
+    """Tall f64, left vectors only (the two-site truncation step): U = A V Sigma^-1 from the Cholesky factor of the Gram
+    matrix when certified, Householder otherwise; U must be an isometry spanning the column space."""
+    rng = np.random.default_rng(78)
+    m, n = 1280, 320
+    u0, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    v0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sv = np.linspace(1.0, 0.25, n) if kind == "flat" else np.logspace(0, -9, n)
+    a = np.asfortranarray((u0 * sv) @ v0.T)
+    u, s, _ = ctx.svd_thin(ctx.upload(a), want_vh=False)
+    u, s = u.get(), s.get()
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
+    assert np.linalg.norm(u.T @ u - np.eye(n)) <= 1e-11 * n
+    assert np.linalg.norm(u @ (u.T @ a) - a) <= 1e-11 * np.linalg.norm(a)
+    # S Vh = U^H A reproduces the singular values as row norms
+    rn = np.linalg.norm(u.T @ a, axis=1)
+    assert np.max(np.abs(rn - s_ref)) <= 1e-11 * s_ref[0]
