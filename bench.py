@@ -603,9 +603,13 @@ def run_c2(env, steps, warmup):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    prof = profile(ctx, lambda: a.contract(b, 0, 0, pol, chi).release())
+    prof.pop("jacobi_l2_bytes", None)
     return {"workload": "C2: quantics Fourier MPO (R=40, bond <= 12) applied to a Complex64 QTT (chi <= 256) by zip-up, "
                         "max_bond_dim 256, SvdTruncationPolicy(1e-12)", "ms_per_apply": ms, "applies_per_s": 1e3 / ms,
-            "max_bond_out": nb, "mpo_bonds": [int(s.shape[2]) for s in sites[:-1]][:6]}
+            "max_bond_out": nb, "mpo_bonds": [int(s.shape[2]) for s in sites[:-1]][:6],
+            "kernel_profile_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+            "kernel_launches": {k: int(v["launches"]) for k, v in prof.items()}}
 
 
 # ---- our arm ------------------------------------------------------------------------------------------

@@ -93,7 +93,7 @@ def build_product(verbose=True):
     if (not os.path.exists(lib)) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
         # static cudart: the library carries its own runtime and shares the primary context
         # with torch, so device pointers / streams from torch are directly usable.
-        _run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-o", lib] + objs)
+        _run([NVCC] + ARCH + ["-shared", "-cudart", "static", "-o", lib] + objs + ["-lpthread"])
         if verbose:
             print("linked", os.path.relpath(lib, ROOT))
     return lib

@@ -44,6 +44,12 @@ std::string host_stats(Ctx*);
 // Stream-ordered memory.
 void* alloc(Ctx*, size_t bytes);
 void release(Ctx*, void* p);
+// Child contexts on the same device (own stream, own allocator), created on first use and owned by `parent`: the
+// executors of parallel_for_independent() (host/parallel.h).  set_foreign_owner / flush_deferred: see ctx.cu.
+std::vector<Ctx*> ctx_workers(Ctx* parent, int k);
+int ctx_patch_workers(Ctx*);   // T4B_PATCH_WORKERS (default 4)
+void set_foreign_owner(Ctx* parent);
+void flush_deferred(Ctx* parent);
 void h2d(Ctx*, void* dst, const void* src, size_t bytes);
 void d2h(Ctx*, void* dst, const void* src, size_t bytes);  // asynchronous; call sync() before reading dst
 void d2d(Ctx*, void* dst, const void* src, size_t bytes);

@@ -1,4 +1,5 @@
 #include "patching.h"
+#include "parallel.h"
 
 #include <algorithm>
 #include <cmath>
@@ -52,8 +53,13 @@ std::vector<char> truncate_adaptive(dla::Ctx* c, std::vector<ChainTN*>& patches,
     std::vector<double> norms(patches.size());
     for (size_t i = 0; i < patches.size(); ++i) norms[i] = norm_sqr(c, *patches[i]);
     AdaptivePlan plan = adaptive_cutoffs(norms, volume, cutoff);
+    std::vector<size_t> kept;
     for (size_t i = 0; i < patches.size(); ++i)
-        if (plan.keep[i]) truncate_patch_with_cutoff(c, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
+        if (plan.keep[i]) kept.push_back(i);
+    parallel_for_independent(c, kept.size(), [&](dla::Ctx* wc, size_t k) {
+        const size_t i = kept[k];
+        truncate_patch_with_cutoff(wc, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
+    });
     return plan.keep;
 }
 
@@ -110,23 +116,29 @@ PartitionedContractResult partitioned_contract(dla::Ctx* c, std::vector<Projecte
         }
     PartitionedContractResult res;
     res.n_groups = (int64_t)plan.size();
+    std::vector<const std::vector<std::pair<int, int>>*> my_pairs;
     int64_t g = 0;
     for (auto& kv : plan) {
         const int64_t gi = g++;
         if (gi % nranks != rank) continue;
-        ChainTN combined;
-        bool have = false;
-        for (auto& pr : kv.second) {
-            ChainTN out = contract(c, *left[pr.first].tn, *right[pr.second].tn, center, opts);
-            if (!have) { combined = std::move(out); have = true; }
-            else combined = add(c, combined, out);
-        }
-        if (kv.second.size() > 1) truncate(c, combined, std::min<int>(center, (int)combined.length() - 1), opts.svd_policy, opts.max_bond_dim);
         res.group_index.push_back(gi);
         res.n_contributions.push_back((int)kv.second.size());
         res.projectors.push_back(kv.first);
-        res.patches.push_back(std::move(combined));
+        my_pairs.push_back(&kv.second);
     }
+    res.patches.resize(my_pairs.size());
+    // the groups are independent of each other: one host thread / child context per group in flight
+    parallel_for_independent(c, my_pairs.size(), [&](dla::Ctx* wc, size_t k) {
+        ChainTN combined;
+        bool have = false;
+        for (auto& pr : *my_pairs[k]) {
+            ChainTN out = contract(wc, *left[pr.first].tn, *right[pr.second].tn, center, opts);
+            if (!have) { combined = std::move(out); have = true; }
+            else combined = add(wc, combined, out);
+        }
+        if (my_pairs[k]->size() > 1) truncate(wc, combined, std::min<int>(center, (int)combined.length() - 1), opts.svd_policy, opts.max_bond_dim);
+        res.patches[k] = std::move(combined);
+    });
     return res;
 }
 

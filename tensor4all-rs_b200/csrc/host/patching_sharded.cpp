@@ -5,6 +5,7 @@
 
 #include "nccl_shim.h"
 #include "patching.h"
+#include "parallel.h"
 
 namespace t4b {
 
@@ -106,9 +107,16 @@ ShardedResult truncate_adaptive_sharded(dla::Ctx* c, void* comm_v, int rank, int
 
     // ---- 2. local truncation -------------------------------------------------------------------------------------
     t0 = now_ms();
-    for (size_t i = 0; i < n; ++i)
-        if (owner[i] == rank && plan.keep[i])
-            truncate_patch_with_cutoff(c, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
+    {
+        // the owned, kept patches are independent: several host threads / child contexts keep the GPU busy
+        std::vector<size_t> mine;
+        for (size_t i = 0; i < n; ++i)
+            if (owner[i] == rank && plan.keep[i]) mine.push_back(i);
+        parallel_for_independent(c, mine.size(), [&](dla::Ctx* wc, size_t k) {
+            const size_t i = mine[k];
+            truncate_patch_with_cutoff(wc, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
+        });
+    }
     dla::sync(c);
     res.ms_truncate = now_ms() - t0;
 

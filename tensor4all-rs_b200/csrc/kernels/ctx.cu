@@ -88,6 +88,9 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.gemm_trace = getb("T4B_GEMM_TRACE"); k.gemm_nopersist = getb("T4B_GEMM_NOPERSIST");
         k.svd_nobatch = getb("T4B_SVD_NOBATCH"); k.svd_nogram = getb("T4B_SVD_NOGRAM");
         k.svd_small_single_max = geti("T4B_SVD_SMALL_MAX", 32);
+        k.patch_workers = geti("T4B_PATCH_WORKERS", 4);
+        if (k.patch_workers < 1) k.patch_workers = 1;
+        if (k.patch_workers > 16) k.patch_workers = 16;
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;
     }
@@ -112,8 +115,20 @@ Ctx* ctx_create(int device, void* cuda_stream) {
     return c;
 }
 
+int ctx_patch_workers(Ctx* c) { return c->knobs.patch_workers; }
+
+std::vector<Ctx*> ctx_workers(Ctx* c, int k) {
+    while ((int)c->workers.size() < k) {
+        Ctx* w = ctx_create(c->device, nullptr);
+        c->workers.push_back(w);
+    }
+    return std::vector<Ctx*>(c->workers.begin(), c->workers.begin() + k);
+}
+
 void ctx_destroy(Ctx* c) {
     if (!c) return;
+    for (Ctx* w : c->workers) ctx_destroy(w);
+    c->workers.clear();
     {
         std::lock_guard<std::mutex> lk(g_ctx_mutex);
         if (!g_live_ctx.erase(c)) return;   // already destroyed
@@ -170,7 +185,23 @@ static size_t round_size(size_t bytes) {
     if (bytes < 256) return 256;
     return (bytes + 255) / 256 * 256;
 }
+// While a worker thread of parallel_for_independent() runs, blocks of the PARENT context that it releases (the old site
+// tensors of the patch it is rewriting) may still be read by kernels queued on the worker's stream; the parent's
+// allocator would hand them out again in the parent's stream order.  Such releases are parked and returned to the
+// cache by flush_deferred() once every worker stream has been synchronised.
+static thread_local Ctx* tl_foreign_owner = nullptr;
+void set_foreign_owner(Ctx* parent) { tl_foreign_owner = parent; }
+void flush_deferred(Ctx* c) {
+    std::vector<void*> d;
+    {
+        std::lock_guard<std::mutex> lk(c->mem_mu);
+        d.swap(c->deferred);
+    }
+    for (void* p : d) release(c, p);
+}
+
 void* alloc(Ctx* c, size_t bytes) {
+    std::lock_guard<std::mutex> mem_lock(c->mem_mu);
     HostTimer t(c->host_alloc_s);
     ++c->host_alloc_n;
     const size_t sz = round_size(bytes);
@@ -199,6 +230,8 @@ void* alloc(Ctx* c, size_t bytes) {
 }
 void release(Ctx* c, void* p) {
     if (!p || !ctx_alive(c)) return;   // the context is gone: ctx_destroy already freed the block
+    std::lock_guard<std::mutex> mem_lock(c->mem_mu);
+    if (c == tl_foreign_owner) { c->deferred.push_back(p); return; }
     HostTimer t(c->host_free_s);
     auto it = c->live.find(p);
     if (it == c->live.end()) throw Error(ST_INTERNAL, "release of a pointer not owned by this context");

@@ -4,6 +4,7 @@
 
 #include <cstdio>
 #include <string>
+#include <mutex>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -36,6 +37,7 @@ struct Knobs {
     bool svd_nobatch = false;     // T4B_SVD_NOBATCH
     bool svd_nogram = false;      // T4B_SVD_NOGRAM: never take the Gram + Cholesky preconditioner
     int svd_small_single_max = 32;   // T4B_SVD_SMALL_MAX: largest min(m, n) a SINGLE svd_thin sends to the one-CTA kernel
+    int patch_workers = 4;        // T4B_PATCH_WORKERS: host threads (child contexts) for independent patches / groups
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
 };
 
@@ -87,7 +89,11 @@ struct Ctx {
     // host-side overhead counters (seconds / counts), see host_stats()
     double host_alloc_s = 0.0, host_free_s = 0.0, host_sync_s = 0.0;
     int64_t host_alloc_n = 0, host_sync_n = 0;
-    // exact-size caching allocator (see alloc()/release() in ctx.cu)
+    // exact-size caching allocator (see alloc()/release() in ctx.cu); mem_mu guards it because a worker thread of
+    // parallel_for_independent() may drop the last reference to a block of ANOTHER context (deferred, see release())
+    std::mutex mem_mu;
+    std::vector<void*> deferred;            // blocks released by a foreign thread: returned to the cache by flush_deferred()
+    std::vector<Ctx*> workers;              // child contexts on the same device (own stream + allocator), owned by this one
     std::unordered_map<size_t, std::vector<void*>> free_lists;
     std::unordered_map<void*, size_t> live;
     size_t cached_bytes = 0;
@@ -149,7 +155,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Blocked Cholesky of a Hermitian positive definite f64 matrix with a condition certificate (svd.cu): shared by the
 // Gram preconditioners of the SVD and of the QR.
-constexpr int kCholBlock = 128;
+// 64: the diagonal-block kernel is a single CTA whose cost grows with the cube of the block (measured 197 us per 128
+// block against ~15 us per 64 block), the GEMM-rich rest does not care
+constexpr int kCholBlock = 64;
 bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out, double* linv_all);
 
 }  // namespace dla

@@ -818,18 +818,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // initialised exactly once, also when several host threads (child contexts) hit it together
+    static const EncodeTiledFn fn = [] {
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-        else
-            cudaGetLastError();
-    }
+            return (EncodeTiledFn)ptr;
+        cudaGetLastError();
+        return (EncodeTiledFn) nullptr;
+    }();
     return fn;
 }
 

@@ -1070,13 +1070,13 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
 // is only taken when the diagonal of the factor certifies a small condition number (dmin / dmax >= 1/32 over all
 // pivots; any non-positive pivot aborts); everything else falls back to the Householder path.
 // =====================================================================================================
-constexpr int CHB = 128;     // Cholesky block
+constexpr int CHB = kCholBlock;     // Cholesky block (ctx.cuh)
 
-// Diagonal block (nb <= 128, lower triangle of G at ld) -> L (in place, lower) and its inverse Linv (nb x nb, ld = nb,
+// Diagonal block (nb <= CHB, lower triangle of G at ld) -> L (in place, lower) and its inverse Linv (nb x nb, ld = nb,
 // zeros above the diagonal).  info[0] != 0: a pivot was not positive.  stat[0] / stat[1]: running min / max of diag(L).
 //
-// Right-looking and register blocked: the 16 x 16 threads own the entries (ty + 16 a, tx + 16 b), a, b < 8, of the
-// 128 x 128 block in registers (cyclic, so the shrinking trailing block stays balanced).  Per column: the owners
+// Right-looking and register blocked: the 16 x 16 threads own the entries (ty + 16 a, tx + 16 b), a, b < CHB / 16, of
+// the CHB x CHB block in registers (cyclic, so the shrinking trailing block stays balanced).  Per column: the owners
 // publish the column through shared memory, ONE barrier, and every thread applies the rank-1 update to its 64 entries
 // (independent FMAs) - against a left-looking column loop whose j-th step is a serial chain of j FMAs.  The inverse is
 // the same scheme on the identity (forward substitution, right-looking): row j of L^-1 is final after j updates.
@@ -1091,11 +1091,12 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     __shared__ int bad;
     if (tid == 0) bad = info[0];
-    double a[8][8];
+    constexpr int TB = CHB / 16;     // register tile edge
+    double a[TB][TB];
 #pragma unroll
-    for (int ia = 0; ia < 8; ++ia)
+    for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) {
+        for (int ib = 0; ib < TB; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
             a[ia][ib] = (i < nb && j < nb && i >= j) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);   // identity padding
         }
@@ -1110,9 +1111,9 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
         if (tx == (j & 15)) {
             const int jb = j >> 4;      // (register arrays are only ever indexed by unrolled constants)
 #pragma unroll
-            for (int ia = 0; ia < 8; ++ia)
+            for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
+                for (int ib = 0; ib < TB; ++ib)
                     if (ib == jb) col[ty + 16 * ia] = a[ia][ib];
         }
         __syncthreads();
@@ -1124,16 +1125,16 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
         const double inv = rsqrt(d), sd = d * inv;
         if (tid == 0) dinv[j] = inv;
         if (j < nb) { dmin = sd < dmin ? sd : dmin; dmax = sd > dmax ? sd : dmax; }
-        double li[8], lc[8];
+        double li[TB], lc[TB];
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) { const int i = ty + 16 * ia; li[ia] = i > j ? col[i] * inv : 0.0; }
+        for (int ia = 0; ia < TB; ++ia) { const int i = ty + 16 * ia; li[ia] = i > j ? col[i] * inv : 0.0; }
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) { const int c = tx + 16 * ib; lc[ib] = c > j ? col[c] * inv : 0.0; }
+        for (int ib = 0; ib < TB; ++ib) { const int c = tx + 16 * ib; lc[ib] = c > j ? col[c] * inv : 0.0; }
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) {
+        for (int ia = 0; ia < TB; ++ia) {
             if (16 * ia + 15 > j) {
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
+                for (int ib = 0; ib < TB; ++ib)
                     if (16 * ib + 15 > j) a[ia][ib] = fma(-li[ia], lc[ib], a[ia][ib]);
             }
         }
@@ -1141,11 +1142,11 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
             // the finished column of L: registers and shared memory
             const int jb = j >> 4;
 #pragma unroll
-            for (int ia = 0; ia < 8; ++ia) {
+            for (int ia = 0; ia < TB; ++ia) {
                 const int i = ty + 16 * ia;
                 const double v = i > j ? li[ia] : (i == j ? sd : 0.0);
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
+                for (int ib = 0; ib < TB; ++ib)
                     if (ib == jb) a[ia][ib] = v;
                 Ls[i + j * LP] = v;
             }
@@ -1154,26 +1155,26 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
     __syncthreads();
     // L back to global memory (lower triangle only)
 #pragma unroll
-    for (int ia = 0; ia < 8; ++ia)
+    for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) {
+        for (int ib = 0; ib < TB; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
             if (i < nb && j < nb && i >= j) G[i + (int64_t)j * ld] = a[ia][ib];
         }
     // ---- inverse: forward substitution on the identity, right-looking.  a <- residual R (starts as I) ----
 #pragma unroll
-    for (int ia = 0; ia < 8; ++ia)
+    for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) a[ia][ib] = (ty + 16 * ia) == (tx + 16 * ib) ? 1.0 : 0.0;
+        for (int ib = 0; ib < TB; ++ib) a[ia][ib] = (ty + 16 * ia) == (tx + 16 * ib) ? 1.0 : 0.0;
     for (int j = 0; j < CHB; ++j) {
         double* row = vec + (j & 1) * CHB;
         const double inv = dinv[j];
         if (ty == (j & 15)) {
             const int ja = j >> 4;
 #pragma unroll
-            for (int ia = 0; ia < 8; ++ia)
+            for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
+                for (int ib = 0; ib < TB; ++ib)
                     if (ia == ja) {
                         const double y = a[ia][ib] * inv;        // row j of L^-1 is final
                         a[ia][ib] = y;
@@ -1181,25 +1182,25 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
                     }
         }
         __syncthreads();
-        double lj[8], yr[8];
+        double lj[TB], yr[TB];
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) { const int i = ty + 16 * ia; lj[ia] = i > j ? Ls[i + j * LP] : 0.0; }
+        for (int ia = 0; ia < TB; ++ia) { const int i = ty + 16 * ia; lj[ia] = i > j ? Ls[i + j * LP] : 0.0; }
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) yr[ib] = row[tx + 16 * ib];
+        for (int ib = 0; ib < TB; ++ib) yr[ib] = row[tx + 16 * ib];
         // row j of the inverse is zero beyond column j, and only rows below j are updated
 #pragma unroll
-        for (int ia = 0; ia < 8; ++ia) {
+        for (int ia = 0; ia < TB; ++ia) {
             if (16 * ia + 15 > j) {
 #pragma unroll
-                for (int ib = 0; ib < 8; ++ib)
+                for (int ib = 0; ib < TB; ++ib)
                     if (16 * ib <= j) a[ia][ib] = fma(-lj[ia], yr[ib], a[ia][ib]);
             }
         }
     }
 #pragma unroll
-    for (int ia = 0; ia < 8; ++ia)
+    for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-        for (int ib = 0; ib < 8; ++ib) {
+        for (int ib = 0; ib < TB; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
             if (i < nb && j < nb) Linv[i + (size_t)j * nb] = i >= j ? a[ia][ib] : 0.0;
         }

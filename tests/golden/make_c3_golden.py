@@ -40,6 +40,10 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "c3_full_oracle.npz"))
     ap.add_argument("--driver", default="gesdd", choices=["gesdd", "gesvd"],
                     help="LAPACK SVD driver of the oracle; a gesvd run next to the gesdd golden measures the noise floor")
+    ap.add_argument("--perturb", type=float, default=0.0,
+                    help="relative size of an i.i.d. perturbation of every input entry (2.2e-16 = one ulp): a second run "
+                         "with it measures how far the spectra of the DEPENDENT factorisations move under rounding-level "
+                         "changes of the input, i.e. the reproducibility floor of the reference algorithm itself")
     ap.add_argument("--merge-floor", default=None,
                     help="path of a second run (other driver): stores per-step max |s - s'| / s_max into --out as `noise_floor`")
     a = ap.parse_args()
@@ -55,10 +59,14 @@ def main():
         g["noise_floor"] = np.array(floor)
         g["noise_floor_norm_sqr"] = np.float64(abs(float(g["norm_sqr"]) - float(h["norm_sqr"])) / float(g["norm_sqr"]))
         np.savez_compressed(a.out, **g)
-        print(f"noise floor (gesdd vs gesvd): max {max(floor):.2e}, median {np.median(floor):.2e}; norm^2 {float(g['noise_floor_norm_sqr']):.2e}")
+        print(f"noise floor (second run vs golden): max {max(floor):.2e}, median {np.median(floor):.2e}; norm^2 {float(g['noise_floor_norm_sqr']):.2e}")
         return
     otn.SVD_DRIVER = a.driver
     mps, mi, mpo, oi = make_c3(a.seed, a.L, a.d, a.chi, a.w)
+    if a.perturb > 0.0:
+        prng = np.random.default_rng(0xF100D)
+        mps = [np.asfortranarray(x * (1.0 + a.perturb * prng.standard_normal(x.shape))) for x in mps]
+        mpo = [np.asfortranarray(x * (1.0 + a.perturb * prng.standard_normal(x.shape))) for x in mpo]
     spectra = []
     t0 = time.perf_counter()
     ref = otn.contract_zipup(to_oracle_chain(mps, mi), to_oracle_chain(mpo, oi), 0, SvdTruncationPolicy(0.0),
