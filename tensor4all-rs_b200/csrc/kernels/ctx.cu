@@ -91,6 +91,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.patch_workers = geti("T4B_PATCH_WORKERS", 4);
         if (k.patch_workers < 1) k.patch_workers = 1;
         if (k.patch_workers > 16) k.patch_workers = 16;
+        k.rrlu_bps = geti("T4B_RRLU_BPS", 0);
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;
     }

@@ -38,6 +38,7 @@ struct Knobs {
     bool svd_nogram = false;      // T4B_SVD_NOGRAM: never take the Gram + Cholesky preconditioner
     int svd_small_single_max = 32;   // T4B_SVD_SMALL_MAX: largest min(m, n) a SINGLE svd_thin sends to the one-CTA kernel
     int patch_workers = 4;        // T4B_PATCH_WORKERS: host threads (child contexts) for independent patches / groups
+    int rrlu_bps = 0;             // T4B_RRLU_BPS: resident prrLU blocks per SM (0 = planned from the matrix size)
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
 };
 
@@ -153,12 +154,12 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Blocked Cholesky of a Hermitian positive definite f64 matrix with a condition certificate (svd.cu): shared by the
+// Blocked Cholesky of a Hermitian positive definite matrix (f64 / Complex64) with a condition certificate (svd.cu): shared by the
 // Gram preconditioners of the SVD and of the QR.
 // 64: the diagonal-block kernel is a single CTA whose cost grows with the cube of the block (measured 197 us per 128
 // block against ~15 us per 64 block), the GEMM-rich rest does not care
 constexpr int kCholBlock = 64;
-bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out, double* linv_all);
+bool cholesky_blocked(Ctx* c, DType dt, int64_t n, void* G, double* ratio_out, void* linv_all, double min_ratio);
 
 }  // namespace dla
 }  // namespace t4b

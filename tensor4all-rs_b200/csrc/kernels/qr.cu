@@ -1630,47 +1630,122 @@ bool qr_thin_tsqr(Ctx* c, int64_t m, int64_t n, void* A, void* Q, void* Rout) {
 }  // namespace
 
 // R (n x n, ld = n) = L^H: upper triangle from the lower triangle of L (ld = ldl), zeros below
-__global__ void lower_to_upper_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, double* __restrict__ R) {
+template <bool CPLX>
+__global__ void lower_to_upper_kernel(const double* __restrict__ Ld, int64_t ldl, int64_t n, double* __restrict__ Rd) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const T* L = reinterpret_cast<const T*>(Ld);
+    T* R = reinterpret_cast<T*>(Rd);
     const int64_t total = n * n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int64_t j = e / n, i = e - j * n;
-        R[e] = i <= j ? L[j + i * ldl] : 0.0;
+        R[e] = i <= j ? S::conj(L[j + i * ldl]) : S::zero();
     }
 }
 
-// A (m x n, destroyed) = Q R through the Cholesky factor of the Gram matrix; false = rejected (A untouched).
-static bool qr_thin_cholesky(Ctx* c, int64_t m, int64_t n, double* A, double* Q, double* R) {
+// One Cholesky-QR pass: In (m x n, overwritten) -> Out = In R^-1 with R = L^H, L L^H = In^H In; R (n x n, upper) written
+// to Rout.  false = the pivot gate rejected the Gram matrix (In untouched).
+static bool cholqr_pass(Ctx* c, DType dt, int64_t m, int64_t n, char* In, char* Out, void* Rout, double min_ratio,
+                        double* ratio_out) {
     auto gq = [](int64_t dim, int64_t str) { Group g; g.nd = 1; g.dim[0] = dim; g.str[0] = str; return g; };
+    const size_t es = dtype_size(dt);
     const int64_t nblk = (n + kCholBlock - 1) / kCholBlock;
-    double* G = (double*)alloc(c, (size_t)n * n * 8);
-    double* Linv = (double*)alloc(c, (size_t)nblk * kCholBlock * kCholBlock * 8);
-    gemm(c, F64, n, n, m, 1.0, A, gq(n, m), gq(m, 1), true, A, gq(m, 1), gq(n, m), false, 0.0, G, gq(n, 1), gq(n, n));
-    double ratio = 0.0;
-    const bool ok = cholesky_blocked(c, n, G, &ratio, Linv);
-    if (c->knobs.verbose) fprintf(stderr, "[t4b] qr %lld x %lld: Cholesky QR %s (diag ratio %.3e)\n", (long long)m, (long long)n, ok ? "taken" : "rejected", ratio);
+    char* G = (char*)alloc(c, (size_t)n * n * es);
+    char* Linv = (char*)alloc(c, (size_t)nblk * kCholBlock * kCholBlock * es);
+    gemm(c, dt, n, n, m, 1.0, In, gq(n, m), gq(m, 1), true, In, gq(m, 1), gq(n, m), false, 0.0, G, gq(n, 1), gq(n, n));
+    const bool ok = cholesky_blocked(c, dt, n, G, ratio_out, Linv, min_ratio);
     if (ok) {
         int64_t g1d = (n * n + 255) / 256;
         if (g1d > (int64_t)c->num_sms * 8) g1d = (int64_t)c->num_sms * 8;
-        lower_to_upper_kernel<<<(unsigned)g1d, 256, 0, c->stream>>>(G, n, n, R);
+        if (dt == C64) lower_to_upper_kernel<true><<<(unsigned)g1d, 256, 0, c->stream>>>((const double*)G, n, n, (double*)Rout);
+        else lower_to_upper_kernel<false><<<(unsigned)g1d, 256, 0, c->stream>>>((const double*)G, n, n, (double*)Rout);
         c->launched("qr_extract_r");
         for (int64_t b = 0; b < nblk; ++b) {
             const int64_t j0 = b * kCholBlock;
             const int64_t nb = std::min<int64_t>(kCholBlock, n - j0);
-            double* Ab = A + j0 * m;
+            char* Ab = In + (size_t)j0 * m * es;
             if (b > 0) {
-                // A_b -= Q[:, 0:j0] L[j0:j0+nb, 0:j0]^H
-                gemm(c, F64, m, nb, j0, -1.0, Q, gq(m, 1), gq(j0, m), false, G + j0, gq(j0, n), gq(nb, 1), true, 1.0, Ab,
+                // In_b -= Out[:, 0:j0] L[j0:j0+nb, 0:j0]^H
+                gemm(c, dt, m, nb, j0, -1.0, Out, gq(m, 1), gq(j0, m), false, G + (size_t)j0 * es, gq(j0, n), gq(nb, 1), true, 1.0, Ab,
                      gq(m, 1), gq(nb, m));
             }
-            // Q_b = A_b Linv_bb^H
-            const double* Lb = Linv + b * (size_t)kCholBlock * kCholBlock;
-            gemm(c, F64, m, nb, nb, 1.0, Ab, gq(m, 1), gq(nb, m), false, Lb, gq(nb, nb), gq(nb, 1), true, 0.0, Q + j0 * m,
+            // Out_b = In_b Linv_bb^H
+            const char* Lb = Linv + (size_t)b * kCholBlock * kCholBlock * es;
+            gemm(c, dt, m, nb, nb, 1.0, Ab, gq(m, 1), gq(nb, m), false, Lb, gq(nb, nb), gq(nb, 1), true, 0.0, Out + (size_t)j0 * m * es,
                  gq(m, 1), gq(nb, m));
         }
     }
     release(c, Linv);
     release(c, G);
+    return ok;
+}
+
+// out[0] = max |G - I| over an n x n matrix (non-negative doubles compare like their bit patterns)
+template <bool CPLX>
+__global__ void identity_defect_kernel(const double* __restrict__ Gd, int64_t n, unsigned long long* __restrict__ out) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const T* G = reinterpret_cast<const T*>(Gd);
+    double mx = 0.0;
+    const int64_t total = n * n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t j = e / n, i = e - j * n;
+        const T v = i == j ? S::sub(G[e], S::one()) : G[e];
+        const double a2 = S::abs2(v);
+        mx = a2 > mx ? a2 : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = other > mx ? other : mx;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(sqrt(mx)));
+}
+
+// A (m x n, destroyed) = Q R by ADAPTIVE Cholesky QR: pass 1 on A (pivot gate 1/32), then the orthogonality defect
+// max |Q1^H Q1 - I| is measured (one GEMM + one reduction); below 1e-13 the single pass stands (well-conditioned
+// isometry sweeps: defect ~ eps kappa^2), otherwise pass 2 on Q1 (CholeskyQR2) restores ||Q^H Q - I|| = O(eps) and
+// R = R2 R1.  false = rejected in pass 1 (A untouched) - the caller runs the Householder TSQR.
+static bool qr_thin_cholesky(Ctx* c, DType dt, int64_t m, int64_t n, void* Av, void* Qv, void* R) {
+    auto gq = [](int64_t dim, int64_t str) { Group g; g.nd = 1; g.dim[0] = dim; g.str[0] = str; return g; };
+    const size_t es = dtype_size(dt);
+    char* A = (char*)Av;
+    char* Q = (char*)Qv;
+    double ratio = 0.0;
+    bool ok = cholqr_pass(c, dt, m, n, A, Q, R, 1.0 / 32.0, &ratio);            // Q <- Q1, R <- R1, A destroyed
+    double defect = 0.0;
+    bool second = false;
+    if (ok) {
+        char* G2 = (char*)alloc(c, (size_t)n * n * es);
+        unsigned long long* dd = (unsigned long long*)alloc(c, 8);
+        zero(c, dd, 8);
+        gemm(c, dt, n, n, m, 1.0, Q, gq(n, m), gq(m, 1), true, Q, gq(m, 1), gq(n, m), false, 0.0, G2, gq(n, 1), gq(n, n));
+        int64_t g1d = (n * n + 255) / 256;
+        if (g1d > (int64_t)c->num_sms * 4) g1d = (int64_t)c->num_sms * 4;
+        if (dt == C64) identity_defect_kernel<true><<<(unsigned)g1d, 256, 0, c->stream>>>((const double*)G2, n, dd);
+        else identity_defect_kernel<false><<<(unsigned)g1d, 256, 0, c->stream>>>((const double*)G2, n, dd);
+        c->launched("qr_defect");
+        d2h(c, &defect, dd, 8);
+        sync(c);
+        release(c, dd);
+        release(c, G2);
+        if (!(defect <= 1e-13)) {
+            second = true;
+            char* R1 = (char*)alloc(c, (size_t)n * n * es);
+            char* R2 = (char*)alloc(c, (size_t)n * n * es);
+            d2d(c, R1, R, (size_t)n * n * es);
+            double ratio2 = 0.0;
+            if (cholqr_pass(c, dt, m, n, Q, A, R2, 0.5, &ratio2)) {              // A <- Q2 = Q1 R2^-1
+                d2d(c, Q, A, (size_t)m * n * es);
+                gemm(c, dt, n, n, n, 1.0, R2, gq(n, 1), gq(n, n), false, R1, gq(n, 1), gq(n, n), false, 0.0, R, gq(n, 1), gq(n, n));
+            }
+            release(c, R2);
+            release(c, R1);
+        }
+    }
+    if (c->knobs.verbose) fprintf(stderr, "[t4b] qr %lld x %lld: Cholesky QR %s (diag ratio %.3e, defect %.1e%s)\n", (long long)m, (long long)n, ok ? "taken" : "rejected", ratio, defect, second ? ", second pass" : "");
     return ok;
 }
 
@@ -1680,12 +1755,12 @@ void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rou
     if (k == 0) return;
     const size_t es = dtype_size(dt);
     const bool cplx = dt == C64;
-    if (!cplx && Q && Rout && !c->knobs.svd_nogram && n >= 2 * kCholBlock && m >= 2 * n) {
-        // Cholesky QR for tall f64 matrices whose Gram pivots certify a small condition number (the isometry sweeps of
-        // a canonical tensor train): A^H A = L L^H (one DMMA GEMM + the blocked Cholesky), R = L^H, Q = A R^-1 by block
-        // forward substitution with the inverted diagonal blocks - GEMMs only, no chain of dependent panel
-        // factorisations.  ||Q^H Q - I|| ~ eps kappa^2; rejected matrices take the Householder TSQR below.
-        if (qr_thin_cholesky(c, m, n, (double*)A, (double*)Q, (double*)Rout)) return;
+    if (Q && Rout && !c->knobs.svd_nogram && n >= 2 * kCholBlock && m >= 2 * n) {
+        // Cholesky QR2 for tall matrices whose Gram pivots pass the gate (the isometry sweeps of a canonical tensor
+        // train): A^H A = L L^H (one DMMA GEMM + the blocked Cholesky), R = L^H, Q = A R^-1 by block forward substitution
+        // with the inverted diagonal blocks - GEMMs only, no chain of dependent panel factorisations - and a second pass
+        // on Q that restores orthogonality to O(eps).  Rejected matrices take the Householder TSQR below.
+        if (qr_thin_cholesky(c, dt, m, n, A, Q, Rout)) return;
     }
     if (!c->knobs.qr_old) {
         if (cplx ? qr_thin_tsqr<true>(c, m, n, A, Q, Rout) : qr_thin_tsqr<false>(c, m, n, A, Q, Rout)) return;

@@ -320,8 +320,15 @@ int64_t rrlu(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t max_rank, 
     int per_sm = 0;
     T4B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LT, smem));
     if (per_sm < 1) throw Error(ST_CUDA_ERROR, "rrlu: kernel does not fit on an SM");
-    // one block per SM is enough (the pass is latency-bound); fewer blocks for tiny matrices
-    int grid = c->num_sms;
+    // One block per SM for small matrices (the pass is barrier / latency bound), up to four resident blocks per SM for
+    // large ones: the fused update + argmax pass streams the L2-resident trailing block, and with 8 warps per SM
+    // (ncu: warps_active 12.5%) there are too few loads in flight to use the L2 bandwidth (2400 x 2400: 1.2 TB/s).
+    int bps = (int)std::min<int64_t>((m * n) / ((int64_t)c->num_sms * LT * 32), 4);
+    if (bps < 2) bps = 2;     // measured (bench.py --workload c4): 600 x 600 7.0 ms with 1 block per SM, 4.3 ms with 2;
+                              // 2400 x 2400 25.2 / 15.2 / 11.6 ms with 1 / 2 / 4
+    if (bps > per_sm) bps = per_sm;
+    if (c->knobs.rrlu_bps > 0) bps = std::min(c->knobs.rrlu_bps, per_sm);
+    int grid = c->num_sms * bps;
     int64_t items = n * ((m + CHUNK - 1) / CHUNK);
     int64_t want = (items + (LT / 32) - 1) / (LT / 32);
     if (want < grid) grid = (int)std::max<int64_t>(want, 1);

@@ -1080,25 +1080,30 @@ constexpr int CHB = kCholBlock;     // Cholesky block (ctx.cuh)
 // publish the column through shared memory, ONE barrier, and every thread applies the rank-1 update to its 64 entries
 // (independent FMAs) - against a left-looking column loop whose j-th step is a serial chain of j FMAs.  The inverse is
 // the same scheme on the identity (forward substitution, right-looking): row j of L^-1 is final after j updates.
-__global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ G, int64_t ld, int nb,
-                                                           double* __restrict__ Linv, int* __restrict__ info,
+template <bool CPLX>
+__global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ Gd, int64_t ld, int nb,
+                                                           double* __restrict__ Linvd, int* __restrict__ info,
                                                            double* __restrict__ stat) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    T* G = reinterpret_cast<T*>(Gd);
+    T* Linv = reinterpret_cast<T*>(Linvd);
     constexpr int LP = CHB + 1;
     extern __shared__ __align__(16) unsigned char chol_smem[];
-    double* Ls = reinterpret_cast<double*>(chol_smem);          // [CHB][LP] column-major: L[i + j * LP]
-    double* vec = Ls + (size_t)CHB * LP;                        // [2][CHB] published column / row (double buffered)
-    double* dinv = vec + 2 * CHB;                               // [CHB] 1 / L[j][j]
+    T* Ls = reinterpret_cast<T*>(chol_smem);                    // [CHB][LP] column-major: L[i + j * LP]
+    T* vec = Ls + (size_t)CHB * LP;                             // [2][CHB] published column / row (double buffered)
+    double* dinv = reinterpret_cast<double*>(vec + 2 * CHB);    // [CHB] 1 / L[j][j] (real)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     __shared__ int bad;
     if (tid == 0) bad = info[0];
     constexpr int TB = CHB / 16;     // register tile edge
-    double a[TB][TB];
+    T a[TB][TB];
 #pragma unroll
     for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
         for (int ib = 0; ib < TB; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
-            a[ia][ib] = (i < nb && j < nb && i >= j) ? G[i + (int64_t)j * ld] : (i == j ? 1.0 : 0.0);   // identity padding
+            a[ia][ib] = (i < nb && j < nb && i >= j) ? G[i + (int64_t)j * ld] : (i == j ? S::one() : S::zero());   // identity padding
         }
     __syncthreads();
     if (bad) return;
@@ -1107,7 +1112,7 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
     // (rsqrt instead of sqrt + division: the pivot step is on the critical path of every column; slices of the register
     // block that lie entirely at or above the pivot are skipped - the bound 16 ia + 15 > j is uniform over the CTA)
     for (int j = 0; j < CHB; ++j) {
-        double* col = vec + (j & 1) * CHB;
+        T* col = vec + (j & 1) * CHB;
         if (tx == (j & 15)) {
             const int jb = j >> 4;      // (register arrays are only ever indexed by unrolled constants)
 #pragma unroll
@@ -1117,7 +1122,7 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
                     if (ib == jb) col[ty + 16 * ia] = a[ia][ib];
         }
         __syncthreads();
-        const double d = col[j];
+        const double d = S::real(col[j]);
         if (!(d > 0.0) || !isfinite(d)) {
             if (tid == 0) info[0] = 1;
             return;
@@ -1125,17 +1130,17 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
         const double inv = rsqrt(d), sd = d * inv;
         if (tid == 0) dinv[j] = inv;
         if (j < nb) { dmin = sd < dmin ? sd : dmin; dmax = sd > dmax ? sd : dmax; }
-        double li[TB], lc[TB];
+        T li[TB], lc[TB];
 #pragma unroll
-        for (int ia = 0; ia < TB; ++ia) { const int i = ty + 16 * ia; li[ia] = i > j ? col[i] * inv : 0.0; }
+        for (int ia = 0; ia < TB; ++ia) { const int i = ty + 16 * ia; li[ia] = i > j ? S::scale(col[i], inv) : S::zero(); }
 #pragma unroll
-        for (int ib = 0; ib < TB; ++ib) { const int c = tx + 16 * ib; lc[ib] = c > j ? col[c] * inv : 0.0; }
+        for (int ib = 0; ib < TB; ++ib) { const int c = tx + 16 * ib; lc[ib] = c > j ? S::conj(S::scale(col[c], inv)) : S::zero(); }   // conj: A22 -= l l^H
 #pragma unroll
         for (int ia = 0; ia < TB; ++ia) {
             if (16 * ia + 15 > j) {
 #pragma unroll
                 for (int ib = 0; ib < TB; ++ib)
-                    if (16 * ib + 15 > j) a[ia][ib] = fma(-li[ia], lc[ib], a[ia][ib]);
+                    if (16 * ib + 15 > j) a[ia][ib] = S::sub(a[ia][ib], S::mul(li[ia], lc[ib]));
             }
         }
         if (tx == (j & 15)) {
@@ -1144,7 +1149,7 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
 #pragma unroll
             for (int ia = 0; ia < TB; ++ia) {
                 const int i = ty + 16 * ia;
-                const double v = i > j ? li[ia] : (i == j ? sd : 0.0);
+                const T v = i > j ? li[ia] : (i == j ? S::from_real(sd) : S::zero());
 #pragma unroll
                 for (int ib = 0; ib < TB; ++ib)
                     if (ib == jb) a[ia][ib] = v;
@@ -1165,9 +1170,9 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
 #pragma unroll
     for (int ia = 0; ia < TB; ++ia)
 #pragma unroll
-        for (int ib = 0; ib < TB; ++ib) a[ia][ib] = (ty + 16 * ia) == (tx + 16 * ib) ? 1.0 : 0.0;
+        for (int ib = 0; ib < TB; ++ib) a[ia][ib] = (ty + 16 * ia) == (tx + 16 * ib) ? S::one() : S::zero();
     for (int j = 0; j < CHB; ++j) {
-        double* row = vec + (j & 1) * CHB;
+        T* row = vec + (j & 1) * CHB;
         const double inv = dinv[j];
         if (ty == (j & 15)) {
             const int ja = j >> 4;
@@ -1176,15 +1181,15 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
 #pragma unroll
                 for (int ib = 0; ib < TB; ++ib)
                     if (ia == ja) {
-                        const double y = a[ia][ib] * inv;        // row j of L^-1 is final
+                        const T y = S::scale(a[ia][ib], inv);    // row j of L^-1 is final
                         a[ia][ib] = y;
                         row[tx + 16 * ib] = y;
                     }
         }
         __syncthreads();
-        double lj[TB], yr[TB];
+        T lj[TB], yr[TB];
 #pragma unroll
-        for (int ia = 0; ia < TB; ++ia) { const int i = ty + 16 * ia; lj[ia] = i > j ? Ls[i + j * LP] : 0.0; }
+        for (int ia = 0; ia < TB; ++ia) { const int i = ty + 16 * ia; lj[ia] = i > j ? Ls[i + j * LP] : S::zero(); }
 #pragma unroll
         for (int ib = 0; ib < TB; ++ib) yr[ib] = row[tx + 16 * ib];
         // row j of the inverse is zero beyond column j, and only rows below j are updated
@@ -1193,7 +1198,7 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
             if (16 * ia + 15 > j) {
 #pragma unroll
                 for (int ib = 0; ib < TB; ++ib)
-                    if (16 * ib <= j) a[ia][ib] = fma(-lj[ia], yr[ib], a[ia][ib]);
+                    if (16 * ib <= j) a[ia][ib] = S::sub(a[ia][ib], S::mul(lj[ia], yr[ib]));
             }
         }
     }
@@ -1202,19 +1207,24 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
 #pragma unroll
         for (int ib = 0; ib < TB; ++ib) {
             const int i = ty + 16 * ia, j = tx + 16 * ib;
-            if (i < nb && j < nb) Linv[i + (size_t)j * nb] = i >= j ? a[ia][ib] : 0.0;
+            if (i < nb && j < nb) Linv[i + (size_t)j * nb] = i >= j ? a[ia][ib] : S::zero();
         }
     if (tid == 0) { stat[0] = dmin; stat[1] = dmax; }
 }
 
 // X (ldx x npad) = lower triangle of L (n x n, ld = ldl), zero elsewhere
-__global__ void init_x_lower_kernel(const double* __restrict__ L, int64_t ldl, int64_t n, int64_t ldx, int64_t npad,
-                                    double* __restrict__ X) {
+template <bool CPLX>
+__global__ void init_x_lower_kernel(const double* __restrict__ Ld, int64_t ldl, int64_t n, int64_t ldx, int64_t npad,
+                                    double* __restrict__ Xd) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const T* L = reinterpret_cast<const T*>(Ld);
+    T* X = reinterpret_cast<T*>(Xd);
     const int64_t total = ldx * npad;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int64_t j = e / ldx, i = e - j * ldx;
-        X[e] = (j < n && i < n && i >= j) ? L[i + j * ldl] : 0.0;
+        X[e] = (j < n && i < n && i >= j) ? L[i + j * ldl] : S::zero();
     }
 }
 
@@ -1223,38 +1233,43 @@ __global__ void init_x_lower_kernel(const double* __restrict__ L, int64_t ldl, i
 // G (n x n, ld = n, full Hermitian on entry) -> lower Cholesky factor in its lower triangle.  Returns false when a
 // pivot was not positive or the diagonal ratio certifies nothing (see above); G is garbage then.  linv_all (optional):
 // the inverses of the diagonal blocks, block b (nb x nb, ld = nb) at linv_all + b * CHB * CHB.
-bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out, double* linv_all) {
+bool cholesky_blocked(Ctx* c, DType dt, int64_t n, void* Gv, double* ratio_out, void* linv_all, double min_ratio) {
+    const size_t es = dtype_size(dt);
+    char* G = (char*)Gv;
     int* info = (int*)alloc(c, sizeof(int) + 2 * sizeof(double) + 8);
     double* stat = reinterpret_cast<double*>(reinterpret_cast<char*>(info) + 8);
     {
         struct { int info, pad; double dmin, dmax; } init = {0, 0, 1e308, 0.0};
         h2d(c, info, &init, sizeof(init));
     }
-    double* Linv1 = linv_all ? nullptr : (double*)alloc(c, (size_t)CHB * CHB * 8);
-    double* Pc = n > CHB ? (double*)alloc(c, (size_t)(n - CHB) * CHB * 8) : nullptr;
-    const size_t smem = (size_t)CHB * (CHB + 1) * 8 + (size_t)3 * CHB * 8;
-    if (c->first_use((const void*)potrf_inv_kernel))
-        T4B_CUDA_CHECK(cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    char* Linv1 = linv_all ? nullptr : (char*)alloc(c, (size_t)CHB * CHB * es);
+    char* Pc = n > CHB ? (char*)alloc(c, (size_t)(n - CHB) * CHB * es) : nullptr;
+    const size_t smem = (size_t)CHB * (CHB + 1) * es + (size_t)2 * CHB * es + (size_t)CHB * 8;
+    auto kr = potrf_inv_kernel<false>;
+    auto kc = potrf_inv_kernel<true>;
+    if (c->first_use(dt == C64 ? (const void*)kc : (const void*)kr))
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(dt == C64 ? (const void*)kc : (const void*)kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t k = 0; k < n; k += CHB) {
         const int nb = (int)std::min<int64_t>(CHB, n - k);
-        double* Gkk = G + k + k * n;
-        double* Linv = linv_all ? linv_all + (k / CHB) * (size_t)CHB * CHB : Linv1;
-        potrf_inv_kernel<<<1, 256, smem, c->stream>>>(Gkk, n, nb, Linv, info, stat);
+        char* Gkk = G + (size_t)(k + k * n) * es;
+        char* Linv = linv_all ? (char*)linv_all + (size_t)(k / CHB) * CHB * CHB * es : Linv1;
+        if (dt == C64) kc<<<1, 256, smem, c->stream>>>((double*)Gkk, n, nb, (double*)Linv, info, stat);
+        else kr<<<1, 256, smem, c->stream>>>((double*)Gkk, n, nb, (double*)Linv, info, stat);
         c->launched("chol_potrf");
         const int64_t r = n - k - nb;
         if (r <= 0) break;
-        double* P = G + (k + nb) + k * n;            // r x nb panel below the diagonal block
+        char* P = G + (size_t)((k + nb) + k * n) * es;            // r x nb panel below the diagonal block
         // panel <- panel Linv^H (out of place through a contiguous copy of the panel)
         {
             Group g;
             g.nd = 2; g.dim[0] = r; g.str[0] = 1; g.dim[1] = nb; g.str[1] = n;
-            permute(c, F64, Pc, P, g, false);
+            permute(c, dt, Pc, P, g, false);
         }
-        gemm(c, F64, r, nb, nb, 1.0, Pc, gg(r, 1), gg(nb, r), false, Linv, gg(nb, nb), gg(nb, 1), true, 0.0, P,
+        gemm(c, dt, r, nb, nb, 1.0, Pc, gg(r, 1), gg(nb, r), false, Linv, gg(nb, nb), gg(nb, 1), true, 0.0, P,
              gg(r, 1), gg(nb, n));
         // trailing block -= panel panel^H (full update: the upper triangle is never read)
-        double* G22 = G + (k + nb) + (k + nb) * n;
-        gemm(c, F64, r, r, nb, -1.0, P, gg(r, 1), gg(nb, n), false, P, gg(nb, n), gg(r, 1), true, 1.0, G22, gg(r, 1),
+        char* G22 = G + (size_t)((k + nb) + (k + nb) * n) * es;
+        gemm(c, dt, r, r, nb, -1.0, P, gg(r, 1), gg(nb, n), false, P, gg(nb, n), gg(r, 1), true, 1.0, G22, gg(r, 1),
              gg(r, n));
     }
     struct { int info, pad; double dmin, dmax; } res;
@@ -1265,7 +1280,7 @@ bool cholesky_blocked(Ctx* c, int64_t n, double* G, double* ratio_out, double* l
     release(c, info);
     const double ratio = (res.info == 0 && res.dmax > 0.0) ? res.dmin / res.dmax : 0.0;
     if (ratio_out) *ratio_out = ratio;
-    return res.info == 0 && ratio >= 1.0 / 32.0;
+    return res.info == 0 && ratio >= min_ratio;
 }
 
 namespace {
@@ -1274,7 +1289,8 @@ namespace {
 // path reads it directly and the m x n copy `A` is only materialised (by the caller-supplied buffer rule below) when
 // the Householder path has to run.  A may be null then.
 template <bool CPLX>
-void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh, const void* Ah = nullptr) {
+void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh, const void* Ah = nullptr,
+              bool allow_gram = true) {
     const DType dt = CPLX ? C64 : F64;
     const size_t es = CPLX ? 16 : 8;
     const int64_t npad = (n + PW - 1) / PW * PW;
@@ -1288,41 +1304,40 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     bool gram_done = false;
     bool gram_tried = false;
     bool gram_u = false;          // left vectors through U = A V Sigma^-1 (V = left vectors of the Cholesky factor)
-    if constexpr (!CPLX) {
-        if (want_u && !want_v && !Ah && !c->knobs.svd_nogram && n >= 2 * CHB && m >= 2 * n) {
-            // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
-            // L = U_X Sigma J^H, i.e. the RIGHT singular vectors of A are U_X and U = A U_X Sigma^-1 - no Q is ever
-            // formed.  Orthogonality of U is eps kappa^2, so the same pivot certificate gates the path.
-            double* G = (double*)alloc(c, (size_t)n * n * 8);
-            gemm(c, F64, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
-            double ratio = 0.0;
-            gram_tried = true;
-            gram_u = cholesky_blocked(c, n, G, &ratio, nullptr);
-            if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld (U): Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_u ? "taken" : "rejected", ratio);
-            if (gram_u) {
-                gram_done = true;
-                X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
-                init_x_lower_kernel<<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>(G, n, n, pl.ldx, npad, X);
-                c->launched("svd_init_x");
-            }
-            release(c, G);
+    if (want_u && !want_v && !Ah && allow_gram && !c->knobs.svd_nogram && n >= 2 * CHB && m >= 2 * n) {
+        // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
+        // L = U_X Sigma J^H, i.e. the RIGHT singular vectors of A are U_X and U = A U_X Sigma^-1 - no Q is ever formed.
+        // ||U^H U - I|| = O(eps kappa^2): accepted a posteriori only for kappa <= 32 (see below).
+        double* G = (double*)alloc(c, (size_t)n * n * es);
+        gemm(c, dt, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
+        double ratio = 0.0;
+        gram_tried = true;
+        gram_u = cholesky_blocked(c, dt, n, G, &ratio, nullptr, 0.125);
+        if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld (U): Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_u ? "taken" : "rejected", ratio);
+        if (gram_u) {
+            gram_done = true;
+            X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
+            init_x_lower_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>(G, n, n, pl.ldx, npad, X);
+            c->launched("svd_init_x");
         }
-        if (!want_u && want_v && !c->knobs.svd_nogram && n >= 2 * CHB) {
-            // Gram + Cholesky preconditioner: X = L with L L^H = A^H A (= R^H up to column signs)
-            double* G = (double*)alloc(c, (size_t)n * n * 8);
-            if (Ah) gemm(c, F64, n, n, m, 1.0, Ah, gg(n, 1), gg(m, n), false, Ah, gg(m, n), gg(n, 1), true, 0.0, G, gg(n, 1), gg(n, n));
-            else gemm(c, F64, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
-            double ratio = 0.0;
-            gram_tried = true;
-            gram_done = cholesky_blocked(c, n, G, &ratio, nullptr);
-            if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld: Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_done ? "taken" : "rejected", ratio);
-            if (gram_done) {
-                X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
-                init_x_lower_kernel<<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>(G, n, n, pl.ldx, npad, X);
-                c->launched("svd_init_x");
-            }
-            release(c, G);
+        release(c, G);
+    }
+    if (!want_u && want_v && allow_gram && !c->knobs.svd_nogram && n >= 2 * CHB) {
+        // Gram + Cholesky preconditioner (right vectors only): X = L with L L^H = A^H A (= R^H up to column signs).
+        // A priori gate: pivot ratio >= 1/8; a posteriori gate below: the computed spectrum must have kappa <= 64.
+        double* G = (double*)alloc(c, (size_t)n * n * es);
+        if (Ah) gemm(c, dt, n, n, m, 1.0, Ah, gg(n, 1), gg(m, n), false, Ah, gg(m, n), gg(n, 1), true, 0.0, G, gg(n, 1), gg(n, n));
+        else gemm(c, dt, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
+        double ratio = 0.0;
+        gram_tried = true;
+        gram_done = cholesky_blocked(c, dt, n, G, &ratio, nullptr, 0.125);
+        if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld: Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_done ? "taken" : "rejected", ratio);
+        if (gram_done) {
+            X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
+            init_x_lower_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>(G, n, n, pl.ldx, npad, X);
+            c->launched("svd_init_x");
         }
+        release(c, G);
     }
     if (!gram_done) {
         if (!A) {
@@ -1334,15 +1349,10 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
             permute(c, dt, Aown, Ah, g, true);
             A = Aown;
         }
-        // QR preconditioner
+        // QR preconditioner (qr_thin: Cholesky QR2 when certified - left vectors wanted -, Householder TSQR otherwise)
         Q = want_u ? alloc(c, (size_t)m * n * es) : nullptr;
         Rm = alloc(c, (size_t)n * n * es);
-        {
-            // a Gram matrix that was just rejected above would be rejected again by the Cholesky QR: go straight to
-            // the Householder factorisation (when no Gram was tried, e.g. both vector sets wanted, qr_thin decides)
-            struct NoGram { Ctx* c; bool saved; NoGram(Ctx* cc, bool on) : c(cc), saved(cc->knobs.svd_nogram) { if (on) cc->knobs.svd_nogram = true; } ~NoGram() { c->knobs.svd_nogram = saved; } } guard(c, gram_tried);
-            qr_thin(c, dt, m, n, A, Q, Rm);
-        }
+        qr_thin(c, dt, m, n, A, Q, Rm);
         // X = R (left vectors wanted) or R^H (only right vectors wanted)
         const bool adjoint = !want_u;
         X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
@@ -1363,13 +1373,31 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     c->launched("svd_colnorm");
     sort_rank_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, c->stream>>>(sig2, npad, rank, S, n);
     c->launched("svd_sort_rank");
+    if (gram_done) {
+        // A posteriori certificate of the Gram route: sigma_i of the Cholesky factor carries a relative error
+        // ~ eps kappa_i^2 / 2, its vectors are kappa_i / 2 times less accurate than Householder's.  The pivot ratio is
+        // only a heuristic; now the spectrum is known: beyond kappa = 64 the result is discarded and recomputed on the
+        // Householder factor (rare: the pivot gate has already removed graded and rank-deficient matrices).
+        double ends[2] = {0.0, 0.0};
+        d2h(c, &ends[0], S, sizeof(double));
+        d2h(c, &ends[1], S + (n - 1), sizeof(double));
+        sync(c);
+        // (U = A V Sigma^-1 loses orthogonality like kappa^2: the tighter bound applies there)
+        const bool ok = ends[1] > 0.0 && ends[0] <= (gram_u ? 32.0 : 64.0) * ends[1];
+        if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld: Gram route kappa %.3e %s\n", (long long)m, (long long)n, ends[1] > 0.0 ? ends[0] / ends[1] : 0.0, ok ? "accepted" : "REJECTED a posteriori");
+        if (!ok) {
+            release(c, sig2); release(c, rank); release(c, X);
+            svd_tall<CPLX>(c, m, n, A, U, S, Vh, Ah, false);
+            return;
+        }
+    }
     const double eps = 2.220446049250313e-16;
     const double floor_rel = (eps * (double)n) * (eps * (double)n);   // on sigma^2 / sigma_max^2
     if (want_u) {
         // U_X = sorted, normalised columns of X (n x n); U = Q U_X
         double* UX = (double*)alloc(c, (size_t)n * n * es);
         zero(c, UX, (size_t)n * n * es);
-        // Householder path: U = Q U_X.  Gram path: U = A U_X Sigma^-1 = A (x_j / sigma_j^2)
+        // Householder / Cholesky-QR path: U = Q U_X.  Gram path: U = A U_X Sigma^-1 = A (x_j / sigma_j^2)
         gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, gram_u ? 2 : 1, 0, UX, n, n, S);
         c->launched("svd_gather_u");
         gemm(c, dt, m, n, n, 1.0, gram_u ? A : Q, gg(m, 1), gg(n, m), false, UX, gg(n, 1), gg(n, n), false, 0.0, U,
@@ -1706,11 +1734,12 @@ void svd_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* U, double* 
         return;
     }
     // wide: factor B = A^H (n x m, tall): B = Ub S Vb^H  =>  A = Vb S Ub^H
-    if (dt == F64 && U && !Vh && !c->knobs.svd_nogram) {
+    if (U && !Vh && !c->knobs.svd_nogram) {
         // left vectors only (the zip-up / two-site case): B is never materialised unless the Gram preconditioner is
         // rejected - svd_tall reads A as the adjoint operand
         void* Vbh = alloc(c, (size_t)m * m * es);
-        svd_tall<false>(c, n, m, nullptr, nullptr, S, Vbh, A);
+        if (dt == C64) svd_tall<true>(c, n, m, nullptr, nullptr, S, Vbh, A);
+        else svd_tall<false>(c, n, m, nullptr, nullptr, S, Vbh, A);
         Group g;
         g.nd = 2; g.dim[0] = m; g.str[0] = m; g.dim[1] = m; g.str[1] = 1;
         permute(c, dt, U, Vbh, g, true);

@@ -85,3 +85,39 @@ def test_sharded_cabi_single_rank_matches_oracle(ctx):
     owner, cost = tpatch.lpt_assign_cabi(bd, 2, 3)
     want = tpatch.lpt_assign([tpatch.patch_cost(list(r), 2) for r in bd], 3)
     assert list(owner) == want
+
+
+def test_parallel_executor_is_bit_identical_to_the_serial_loop(monkeypatch):
+    """The owned patches are truncated by several host threads with child contexts (T4B_PATCH_WORKERS, default 4); every
+    patch's result must not depend on which context computed it: 1 worker and 6 workers give bit-identical site tensors,
+    and the handles stay usable (canonicalize / norm / release) after the call."""
+    rng = np.random.default_rng(24)
+    L, d, n = 8, 2, 23
+    raw = []
+    for k in range(n):
+        arrays, ids = random_mps(rng, L, d, int(rng.integers(6, 17)))
+        raw.append((arrays, ids))
+    volumes = [d ** L] * n
+    results = []
+    for workers in ("1", "6"):
+        monkeypatch.setenv("T4B_PATCH_WORKERS", workers)      # knobs are read at context creation
+        c = t4b.Context(0)
+        tns = {i: t4tt.chain_from_arrays(c, a, ids) for i, (a, ids) in enumerate(raw)}
+        res = tpatch.truncate_adaptive_sharded(c, None, 0, 1, [0] * n, tns, volumes, 0, 1e-5, 6, gather_root=-1, nbonds=L - 1)
+        sites = {i: [s[0].copy() for s in tns[i].sites()] for i in range(n)}
+        # the patches were produced by child contexts: they must remain ordinary handles of the parent
+        for i in (0, n - 1):
+            before = tns[i].norm_sqr()
+            tns[i].canonicalize(L - 1)
+            assert abs(tns[i].norm_sqr() - before) <= 1e-12 * before
+        results.append((res["keep"].copy(), res["bond_dims"].copy(), res["norm_after"].copy(), sites))
+        for t in tns.values():
+            t.release()
+        c.close()
+    k1, b1, n1, s1 = results[0]
+    k2, b2, n2, s2 = results[1]
+    assert np.array_equal(k1, k2) and np.array_equal(b1, b2) and np.array_equal(n1, n2)
+    for i in range(n):
+        for x, y in zip(s1[i], s2[i]):
+            assert np.array_equal(x, y)
+    assert b1.max() <= 6 and k1.sum() > 0

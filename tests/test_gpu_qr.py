@@ -71,20 +71,24 @@ def test_qr_c3_zipup_shape_r_only(ctx):
     assert np.linalg.norm(sg[:, None] * r - r_ref) <= 1e-12 * np.linalg.norm(r_ref)
 
 
+@pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("kind", ["well", "graded", "deficient"])
-def test_qr_cholesky_path_and_householder_fallback(ctx, kind):
+def test_qr_cholesky_path_and_householder_fallback(ctx, kind, cplx):
     """Tall f64 matrices take the Cholesky QR (Gram + blocked Cholesky + block forward substitution) when the pivots
     certify a small condition number; graded / rank-deficient ones must be rejected and factored by the Householder
     TSQR - either way Q is an isometry and Q R reproduces A to working accuracy."""
     rng = np.random.default_rng(91)
     m, n = 1536, 384
-    u0, _ = np.linalg.qr(rng.standard_normal((m, n)))
-    v0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    def rnd(shape):
+        x = rng.standard_normal(shape)
+        return x + 1j * rng.standard_normal(shape) if cplx else x
+    u0, _ = np.linalg.qr(rnd((m, n)))
+    v0, _ = np.linalg.qr(rnd((n, n)))
     sv = {"well": np.linspace(1.0, 0.3, n), "graded": np.logspace(0, -9, n),
           "deficient": np.concatenate([np.linspace(1, 0.5, n - 40), np.zeros(40)])}[kind]
-    a = np.asfortranarray((u0 * sv) @ v0.T)
+    a = np.asfortranarray((u0 * sv) @ v0.conj().T)
     q, r = ctx.qr_thin(ctx.upload(a))
     q, r = q.get(), r.get()
     assert np.linalg.norm(np.tril(r, -1)) == 0.0
-    assert np.linalg.norm(q.T @ q - np.eye(n)) <= 1e-12 * n
+    assert np.linalg.norm(q.conj().T @ q - np.eye(n)) <= 1e-12 * n
     assert np.linalg.norm(q @ r - a) <= 1e-13 * np.linalg.norm(a) * np.sqrt(n)

@@ -152,27 +152,28 @@ def test_svd_reports_non_convergence(monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("kind", ["flat", "graded", "rank_deficient", "tall_vh_only"])
-def test_svd_gram_cholesky_preconditioner_and_fallback(ctx, kind):
+def test_svd_gram_cholesky_preconditioner_and_fallback(ctx, kind, cplx):
     """The R-only preconditioner of wide f64 matrices (U only) is the Cholesky factor of the Gram matrix when the
     pivots certify a small condition number, and the Householder TSQR otherwise: a flat spectrum takes the fast path,
     a graded (kappa = 1e10) or rank-deficient matrix must be REJECTED and still come out to LAPACK accuracy."""
     rng = np.random.default_rng(77)
     m, n = 384, 900
     if kind == "tall_vh_only":
-        a = np.asfortranarray(rng.standard_normal((n, m)))
+        a = _rand(rng, (n, m), cplx)
         _, s, vh = ctx.svd_thin(ctx.upload(a), want_u=False)
         _check(a, None, s.get(), vh.get())
         return
-    u0, _ = np.linalg.qr(rng.standard_normal((m, m)))
-    v0, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    u0, _ = np.linalg.qr(_rand(rng, (m, m), cplx))
+    v0, _ = np.linalg.qr(_rand(rng, (n, m), cplx))
     if kind == "flat":
         sv = np.linspace(1.0, 0.2, m)
     elif kind == "graded":
         sv = np.logspace(0, -10, m)
     else:
         sv = np.concatenate([np.linspace(1.0, 0.5, m // 2), np.zeros(m - m // 2)])
-    a = np.asfortranarray((u0 * sv) @ v0.T)
+    a = np.asfortranarray((u0 * sv) @ v0.conj().T)
     u, s, _ = ctx.svd_thin(ctx.upload(a), want_vh=False)
     u, s = u.get(), s.get()
     s_ref = np.linalg.svd(a, compute_uv=False)
@@ -187,22 +188,23 @@ def test_svd_gram_cholesky_preconditioner_and_fallback(ctx, kind):
     assert np.linalg.norm(u[:, :r].conj().T @ u[:, :r] - np.eye(r)) <= 1e-11 * r
 
 
+@pytest.mark.parametrize("cplx", [False, True])
 @pytest.mark.parametrize("kind", ["flat", "graded"])
-def test_svd_tall_left_vectors_gram_path(ctx, kind):
+def test_svd_tall_left_vectors_gram_path(ctx, kind, cplx):
     """Tall f64, left vectors only (the two-site truncation step): U = A V Sigma^-1 from the Cholesky factor of the Gram
     matrix when certified, Householder otherwise; U must be an isometry spanning the column space."""
     rng = np.random.default_rng(78)
     m, n = 1280, 320
-    u0, _ = np.linalg.qr(rng.standard_normal((m, n)))
-    v0, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    u0, _ = np.linalg.qr(_rand(rng, (m, n), cplx))
+    v0, _ = np.linalg.qr(_rand(rng, (n, n), cplx))
     sv = np.linspace(1.0, 0.25, n) if kind == "flat" else np.logspace(0, -9, n)
-    a = np.asfortranarray((u0 * sv) @ v0.T)
+    a = np.asfortranarray((u0 * sv) @ v0.conj().T)
     u, s, _ = ctx.svd_thin(ctx.upload(a), want_vh=False)
     u, s = u.get(), s.get()
     s_ref = np.linalg.svd(a, compute_uv=False)
     assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
-    assert np.linalg.norm(u.T @ u - np.eye(n)) <= 1e-11 * n
-    assert np.linalg.norm(u @ (u.T @ a) - a) <= 1e-11 * np.linalg.norm(a)
+    assert np.linalg.norm(u.conj().T @ u - np.eye(n)) <= 1e-11 * n
+    assert np.linalg.norm(u @ (u.conj().T @ a) - a) <= 1e-11 * np.linalg.norm(a)
     # S Vh = U^H A reproduces the singular values as row norms
-    rn = np.linalg.norm(u.T @ a, axis=1)
+    rn = np.linalg.norm(u.conj().T @ a, axis=1)
     assert np.max(np.abs(rn - s_ref)) <= 1e-11 * s_ref[0]
