@@ -381,11 +381,37 @@ def ncu_capture(name):
 
 
 # ---- C5: patch-sharded adaptive truncation (strong scaling) ------------------------------------------
-def run_c5(env, n=256, L=24, d=2, reps=2, cutoff=1e-10, max_bond=64):
+def run_c5(env, n=256, L=24, d=2, reps=2, cutoff=1e-10, max_bond=64, both=True):
+    """C5 through t4b_patches_truncate_adaptive_sharded.  The headline figure is the default (batched) mode: every sweep
+    position of all patches a rank owns is one SVD launch + one GEMM launch.  With `both`, the per-patch mode
+    (T4B_PATCH_BATCHED=0: one launch chain per patch, worker threads) is timed as well and reported under
+    `per_patch_launch_chains` - it is the slower implementation whose strong scaling is nearly ideal, because its
+    time is all per-patch host and launch latency."""
+    rec = _run_c5_mode(env, env.ctx, n, L, d, reps, cutoff, max_bond)
+    if both:
+        import t4b
+        old = os.environ.get("T4B_PATCH_BATCHED")
+        os.environ["T4B_PATCH_BATCHED"] = "0"
+        ctx0 = t4b.Context(env.local_rank, env.stream.cuda_stream)     # knobs are read at context creation
+        if old is None:
+            del os.environ["T4B_PATCH_BATCHED"]
+        else:
+            os.environ["T4B_PATCH_BATCHED"] = old
+        try:
+            r0 = _run_c5_mode(env, ctx0, n, L, d, 1, cutoff, max_bond)
+        finally:
+            ctx0.close()
+        if rec is not None and r0 is not None:
+            rec["mode"] = "batched sweeps over the owned patches (default)"
+            rec["per_patch_launch_chains"] = {k: r0[k] for k in ("value", "unit", "ms", "phase_ms", "checksum_norm")}
+    return rec
+
+
+def _run_c5_mode(env, ctx, n, L, d, reps, cutoff, max_bond):
     import torch
     from t4b import patches as tp
     from t4b import tt as t4tt
-    ctx, rank, world, stream = env.ctx, env.rank, env.world, env.stream
+    rank, world, stream = env.rank, env.world, env.stream
     chis = c5_chis(n)
     bd = np.array([bond_dims(L, d, chis[k]) for k in range(n)], dtype=np.int64)
     owner, costs = tp.lpt_assign_cabi(bd, d, world)

@@ -1,4 +1,5 @@
 #include "patching.h"
+#include "chain_batched.h"
 #include "parallel.h"
 
 #include <algorithm>
@@ -35,27 +36,43 @@ AdaptivePlan adaptive_cutoffs(const std::vector<double>& norm_sqr, const std::ve
     return p;
 }
 
-void truncate_patch_with_cutoff(dla::Ctx* c, ChainTN& tn, int center, double local_cutoff_sqr,
-                                std::optional<int64_t> max_bond_dim) {
+SvdTruncationPolicy patch_policy(double local_cutoff_sqr) {
     T4B_REQUIRE(std::isfinite(local_cutoff_sqr) && local_cutoff_sqr >= 0.0, "non-finite adaptive cutoff");
     SvdTruncationPolicy policy;
     policy.threshold = local_cutoff_sqr;
     policy.scale = ThresholdScale::Absolute;
     policy.measure = SingularValueMeasure::SquaredValue;
     policy.rule = TruncationRule::DiscardedTailSum;
-    truncate(c, tn, center, policy, max_bond_dim);
+    return policy;
+}
+
+void truncate_patch_with_cutoff(dla::Ctx* c, ChainTN& tn, int center, double local_cutoff_sqr,
+                                std::optional<int64_t> max_bond_dim) {
+    truncate(c, tn, center, patch_policy(local_cutoff_sqr), max_bond_dim);
 }
 
 std::vector<char> truncate_adaptive(dla::Ctx* c, std::vector<ChainTN*>& patches,
                                     const std::vector<uint64_t>& volume, int center, double cutoff,
                                     std::optional<int64_t> max_bond_dim) {
     validate_svd_truncation_options(max_bond_dim, std::nullopt);
+    // Patches of one partition share the chain structure: every sweep position of ALL of them is then one SVD launch
+    // + one GEMM launch (chain_batched.h).  The canonical form at the centre gives the norms for free.
+    const bool batched = dla::ctx_patch_batched(c) && chains_batchable(patches, center);
     std::vector<double> norms(patches.size());
-    for (size_t i = 0; i < patches.size(); ++i) norms[i] = norm_sqr(c, *patches[i]);
+    if (batched) canonicalize_batched(c, patches, center, &norms);
+    else
+        for (size_t i = 0; i < patches.size(); ++i) norms[i] = norm_sqr(c, *patches[i]);
     AdaptivePlan plan = adaptive_cutoffs(norms, volume, cutoff);
     std::vector<size_t> kept;
     for (size_t i = 0; i < patches.size(); ++i)
         if (plan.keep[i]) kept.push_back(i);
+    if (batched) {
+        std::vector<ChainTN*> tk;
+        std::vector<SvdTruncationPolicy> pk;
+        for (size_t i : kept) { tk.push_back(patches[i]); pk.push_back(patch_policy(plan.local_cutoff_sqr[i])); }
+        if (!tk.empty()) truncate_sweep_batched(c, tk, center, pk, max_bond_dim, nullptr);
+        return plan.keep;
+    }
     parallel_for_independent(c, kept.size(), [&](dla::Ctx* wc, size_t k) {
         const size_t i = kept[k];
         truncate_patch_with_cutoff(wc, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);

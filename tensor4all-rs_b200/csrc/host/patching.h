@@ -22,6 +22,7 @@ struct AdaptivePlan {
 AdaptivePlan adaptive_cutoffs(const std::vector<double>& norm_sqr, const std::vector<uint64_t>& volume,
                               double cutoff);
 // Absolute x SquaredValue x DiscardedTailSum policy with threshold local_cutoff_sqr (:970-978)
+SvdTruncationPolicy patch_policy(double local_cutoff_sqr);
 void truncate_patch_with_cutoff(dla::Ctx*, ChainTN& tn, int center, double local_cutoff_sqr,
                                 std::optional<int64_t> max_bond_dim);
 // Single-device version: returns keep flags; kept patches are truncated in place.

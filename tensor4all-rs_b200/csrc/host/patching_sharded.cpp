@@ -5,6 +5,7 @@
 
 #include "nccl_shim.h"
 #include "patching.h"
+#include "chain_batched.h"
 #include "parallel.h"
 
 namespace t4b {
@@ -78,8 +79,21 @@ ShardedResult truncate_adaptive_sharded(dla::Ctx* c, void* comm_v, int rank, int
     // ---- 1. statistics -----------------------------------------------------------------------------------------
     double t0 = now_ms();
     std::vector<double> norms(n, 0.0);
+    // owned patches as one batch (chain_batched.h) when they share the chain structure: the canonical form at the
+    // centre gives the norms for free, and every sweep position of all owned patches is one SVD + one GEMM launch
+    std::vector<ChainTN*> owned;
+    std::vector<size_t> owned_ix;
     for (size_t i = 0; i < n; ++i)
-        if (owner[i] == rank) norms[i] = norm_sqr(c, *patches[i]);
+        if (owner[i] == rank) { owned.push_back(patches[i]); owned_ix.push_back(i); }
+    const bool batched = dla::ctx_patch_batched(c) && !owned.empty() && chains_batchable(owned, center);
+    if (batched) {
+        std::vector<double> nl;
+        canonicalize_batched(c, owned, center, &nl);
+        for (size_t k = 0; k < owned.size(); ++k) norms[owned_ix[k]] = nl[k];
+    } else {
+        for (size_t i = 0; i < n; ++i)
+            if (owner[i] == rank) norms[i] = norm_sqr(c, *patches[i]);
+    }
     // chain length and dtype must agree across ranks (a rank may own nothing): carried in two extra slots
     std::vector<double> hdr(n + 2, 0.0);
     for (size_t i = 0; i < n; ++i) hdr[i] = norms[i];
@@ -107,15 +121,25 @@ ShardedResult truncate_adaptive_sharded(dla::Ctx* c, void* comm_v, int rank, int
 
     // ---- 2. local truncation -------------------------------------------------------------------------------------
     t0 = now_ms();
+    std::vector<double> norms_after(n, -1.0);
     {
-        // the owned, kept patches are independent: several host threads / child contexts keep the GPU busy
         std::vector<size_t> mine;
         for (size_t i = 0; i < n; ++i)
             if (owner[i] == rank && plan.keep[i]) mine.push_back(i);
-        parallel_for_independent(c, mine.size(), [&](dla::Ctx* wc, size_t k) {
-            const size_t i = mine[k];
-            truncate_patch_with_cutoff(wc, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
-        });
+        if (batched) {
+            std::vector<ChainTN*> tk;
+            std::vector<SvdTruncationPolicy> pk;
+            for (size_t i : mine) { tk.push_back(patches[i]); pk.push_back(patch_policy(plan.local_cutoff_sqr[i])); }
+            std::vector<double> na;
+            if (!tk.empty()) truncate_sweep_batched(c, tk, center, pk, max_bond_dim, &na);
+            for (size_t k = 0; k < mine.size(); ++k) norms_after[mine[k]] = na[k];
+        } else {
+            // the owned, kept patches are independent: several host threads / child contexts keep the GPU busy
+            parallel_for_independent(c, mine.size(), [&](dla::Ctx* wc, size_t k) {
+                const size_t i = mine[k];
+                truncate_patch_with_cutoff(wc, *patches[i], center, plan.local_cutoff_sqr[i], max_bond_dim);
+            });
+        }
     }
     dla::sync(c);
     res.ms_truncate = now_ms() - t0;
@@ -130,7 +154,7 @@ ShardedResult truncate_adaptive_sharded(dla::Ctx* c, void* comm_v, int rank, int
         const ChainTN& tn = *patches[i];
         T4B_REQUIRE((int)tn.length() == L, "truncate_adaptive_sharded: patches must have the same length");
         double* row = table.data() + i * rec;
-        row[0] = norm_sqr(c, tn);
+        row[0] = norms_after[i] >= 0.0 ? norms_after[i] : norm_sqr(c, tn);
         for (int s = 0; s < L; ++s) {
             const Tensor& t = tn.sites[s];
             T4B_REQUIRE((int)t.rank() <= kMaxRank, "truncate_adaptive_sharded: site rank exceeds 6");

@@ -87,10 +87,12 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.gemm_nows = getb("T4B_GEMM_NOWS"); k.gemm_noskinny = getb("T4B_GEMM_NOSKINNY");
         k.gemm_trace = getb("T4B_GEMM_TRACE"); k.gemm_nopersist = getb("T4B_GEMM_NOPERSIST");
         k.svd_nobatch = getb("T4B_SVD_NOBATCH"); k.svd_nogram = getb("T4B_SVD_NOGRAM");
+        k.gram_off = geti("T4B_GRAM_OFF", 0);
         k.svd_small_single_max = geti("T4B_SVD_SMALL_MAX", 32);
         k.patch_workers = geti("T4B_PATCH_WORKERS", 4);
         if (k.patch_workers < 1) k.patch_workers = 1;
         if (k.patch_workers > 16) k.patch_workers = 16;
+        k.patch_batched = geti("T4B_PATCH_BATCHED", 1) != 0;
         k.rrlu_bps = geti("T4B_RRLU_BPS", 0);
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;
@@ -117,6 +119,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
 }
 
 int ctx_patch_workers(Ctx* c) { return c->knobs.patch_workers; }
+bool ctx_patch_batched(Ctx* c) { return c->knobs.patch_batched; }
 
 std::vector<Ctx*> ctx_workers(Ctx* c, int k) {
     while ((int)c->workers.size() < k) {

@@ -1755,7 +1755,7 @@ void qr_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* Q, void* Rou
     if (k == 0) return;
     const size_t es = dtype_size(dt);
     const bool cplx = dt == C64;
-    if (Q && Rout && !c->knobs.svd_nogram && n >= 2 * kCholBlock && m >= 2 * n) {
+    if (Q && Rout && !c->knobs.svd_nogram && !(c->knobs.gram_off & 4) && n >= 2 * kCholBlock && m >= 2 * n) {
         // Cholesky QR2 for tall matrices whose Gram pivots pass the gate (the isometry sweeps of a canonical tensor
         // train): A^H A = L L^H (one DMMA GEMM + the blocked Cholesky), R = L^H, Q = A R^-1 by block forward substitution
         // with the inverted diagonal blocks - GEMMs only, no chain of dependent panel factorisations - and a second pass

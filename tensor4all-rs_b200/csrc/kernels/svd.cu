@@ -1304,7 +1304,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     bool gram_done = false;
     bool gram_tried = false;
     bool gram_u = false;          // left vectors through U = A V Sigma^-1 (V = left vectors of the Cholesky factor)
-    if (want_u && !want_v && !Ah && allow_gram && !c->knobs.svd_nogram && n >= 2 * CHB && m >= 2 * n) {
+    if (want_u && !want_v && !Ah && allow_gram && !c->knobs.svd_nogram && !(c->knobs.gram_off & 2) && n >= 2 * CHB && m >= 2 * n) {
         // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
         // L = U_X Sigma J^H, i.e. the RIGHT singular vectors of A are U_X and U = A U_X Sigma^-1 - no Q is ever formed.
         // ||U^H U - I|| = O(eps kappa^2): accepted a posteriori only for kappa <= 32 (see below).
@@ -1322,7 +1322,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         }
         release(c, G);
     }
-    if (!want_u && want_v && allow_gram && !c->knobs.svd_nogram && n >= 2 * CHB) {
+    if (!want_u && want_v && allow_gram && !c->knobs.svd_nogram && !(c->knobs.gram_off & 1) && n >= 2 * CHB) {
         // Gram + Cholesky preconditioner (right vectors only): X = L with L L^H = A^H A (= R^H up to column signs).
         // A priori gate: pivot ratio >= 1/8; a posteriori gate below: the computed spectrum must have kappa <= 64.
         double* G = (double*)alloc(c, (size_t)n * n * es);

@@ -121,3 +121,66 @@ def test_parallel_executor_is_bit_identical_to_the_serial_loop(monkeypatch):
         for x, y in zip(s1[i], s2[i]):
             assert np.array_equal(x, y)
     assert b1.max() <= 6 and k1.sum() > 0
+
+
+def _truncate_adaptive_cabi(ctx, tns, volumes, center, cutoff, max_bond):
+    import ctypes as C
+    n = len(tns)
+    handles = (C.c_void_p * n)(*[t.h for t in tns])
+    vol = np.array(volumes, dtype=np.uint64)
+    keep = np.zeros(n, np.int32)
+    t4b._check(t4b.lib().t4b_patches_truncate_adaptive(ctx.h, C.c_int64(n), handles, vol.ctypes.data_as(C.c_void_p),
+                                                       center, C.c_double(cutoff), C.c_int64(max_bond),
+                                                       keep.ctypes.data_as(C.c_void_p)))
+    return list(keep.astype(bool))
+
+
+@pytest.mark.parametrize("cplx,center,pre", [(False, 0, False), (False, 3, True), (True, 5, False), (False, 7, True)])
+def test_batched_sweeps_equal_per_patch_path(ctx, monkeypatch, cplx, center, pre):
+    """The batched sweeps (one SVD launch + one GEMM launch per sweep position for ALL patches, host/chain_batched.cpp)
+    against the per-patch launch chains (T4B_PATCH_BATCHED=0) and the oracle: same keep flags and bond dimensions, same
+    tensors to 1e-10.  `pre` first truncates the inputs through the per-patch API, which leaves site tensors in
+    [site, right, left] storage order and mixed orthogonality flags (the batched path has to re-order and cannot skip)."""
+    rng = np.random.default_rng(77 + center)
+    L, d, n = 8, 2, 24
+    raw = []
+    for k in range(n):
+        arrays, ids = random_mps(rng, L, d, int(rng.integers(2, 17)), cplx)
+        arrays[0] = arrays[0] * 10.0 ** rng.uniform(-6, 0)
+        raw.append((arrays, ids))
+    volumes = [int(d ** (L - int(rng.integers(0, 3)))) for _ in range(n)]
+    cutoff, cap = 1e-7, 9
+    monkeypatch.setenv("T4B_PATCH_BATCHED", "0")
+    ctx0 = t4b.Context(0)                     # knobs are read when a context is created
+    monkeypatch.delenv("T4B_PATCH_BATCHED")
+    try:
+        a = [t4tt.chain_from_arrays(ctx0, x, i) for x, i in raw]
+        b = [t4tt.chain_from_arrays(ctx, x, i) for x, i in raw]
+        ochains = [to_oracle_chain(x, i) for x, i in raw]
+        if pre:
+            for k in range(n):
+                c0 = (k * 3) % L
+                a[k].truncate(c0, t4tt.SvdPolicy(1e-13), 12)
+                b[k].truncate(c0, t4tt.SvdPolicy(1e-13), 12)
+        keep_a = _truncate_adaptive_cabi(ctx0, a, volumes, center, cutoff, cap)
+        launches0 = ctx.launch_count()
+        keep_b = _truncate_adaptive_cabi(ctx, b, volumes, center, cutoff, cap)
+        launches = ctx.launch_count() - launches0
+        assert keep_a == keep_b
+        if not pre:
+            ref, keep_ref = opatch.truncate_adaptive(ochains, volumes, center, cutoff, cap)
+            assert keep_b == keep_ref
+        assert 0 < sum(keep_b) <= n
+        for k in range(n):
+            if not keep_b[k]:
+                continue
+            assert a[k].bond_dims() == b[k].bond_dims(), k
+            assert max(b[k].bond_dims()) <= cap
+            assert relerr(gpu_chain_dense(b[k]), gpu_chain_dense(a[k])) <= 1e-10, k
+            if not pre:
+                assert b[k].bond_dims() == ref[k].bond_dims()
+                assert relerr(gpu_chain_dense(b[k]), oracle_chain_dense(ref[k])) <= 1e-10, k
+        # the batched path costs a handful of launches per sweep position, not per patch and position
+        assert launches < 40 * 3 * L + 16 * n, launches
+    finally:
+        ctx0.close()
