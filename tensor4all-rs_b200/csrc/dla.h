@@ -47,10 +47,13 @@ void release(Ctx*, void* p);
 // Child contexts on the same device (own stream, own allocator), created on first use and owned by `parent`: the
 // executors of parallel_for_independent() (host/parallel.h).  set_foreign_owner / flush_deferred: see ctx.cu.
 std::vector<Ctx*> ctx_workers(Ctx* parent, int k);
-int ctx_patch_workers(Ctx*);   // T4B_PATCH_WORKERS (default 4)
+int ctx_patch_workers(Ctx*);   // T4B_PATCH_WORKERS (default: host threads per visible GPU, clamped to 2..8)
 bool ctx_patch_batched(Ctx*);  // T4B_PATCH_BATCHED (default 1): batched sweeps over the patches of a partitioned TreeTN
 void set_foreign_owner(Ctx* parent);
 void flush_deferred(Ctx* parent);
+// pool the idle cached blocks of the parent and its first k workers for the duration of a parallel phase (ctx.cuh)
+void parallel_phase_begin(Ctx* parent, int k);
+void parallel_phase_end(Ctx* parent);
 void h2d(Ctx*, void* dst, const void* src, size_t bytes);
 void d2h(Ctx*, void* dst, const void* src, size_t bytes);  // asynchronous; call sync() before reading dst
 void d2d(Ctx*, void* dst, const void* src, size_t bytes);

@@ -17,6 +17,10 @@ void parallel_for_independent(dla::Ctx* c, size_t n, const std::function<void(dl
     // inputs were produced on the parent's stream
     dla::sync(c);
     std::vector<dla::Ctx*> workers = dla::ctx_workers(c, nthreads - 1);
+    // idle cached blocks of all executors are pooled for the phase: dynamic work assignment would otherwise leave every
+    // executor with a cache that fits the patches it saw LAST time, and the misses go to cudaMalloc
+    dla::parallel_phase_begin(c, nthreads - 1);
+    struct PhaseGuard { dla::Ctx* c; ~PhaseGuard() { try { dla::parallel_phase_end(c); } catch (...) {} } } phase_guard{c};
     std::atomic<size_t> next{0};
     std::vector<std::exception_ptr> errs((size_t)nthreads);
     auto body = [&](dla::Ctx* wc, int slot, bool foreign) {

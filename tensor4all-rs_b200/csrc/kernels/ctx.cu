@@ -6,6 +6,7 @@
 #include <cstdlib>
 
 #include <mutex>
+#include <thread>
 #include <unordered_set>
 
 namespace t4b {
@@ -89,7 +90,14 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.svd_nobatch = getb("T4B_SVD_NOBATCH"); k.svd_nogram = getb("T4B_SVD_NOGRAM");
         k.gram_off = geti("T4B_GRAM_OFF", 0);
         k.svd_small_single_max = geti("T4B_SVD_SMALL_MAX", 32);
-        k.patch_workers = geti("T4B_PATCH_WORKERS", 4);
+        {
+            // default: the host threads this GPU's share of the box can keep busy, between 2 and 8 (measured on C5:
+            // 1 / 4 / 8 executors = 6.4 / 2.0 / 1.5 s for 256 patches; beyond 8 the launch path saturates)
+            int hw = (int)std::thread::hardware_concurrency();
+            int dflt = hw > 0 ? hw / (ndev > 0 ? ndev : 1) : 4;
+            dflt = dflt < 2 ? 2 : (dflt > 8 ? 8 : dflt);
+            k.patch_workers = geti("T4B_PATCH_WORKERS", dflt);
+        }
         if (k.patch_workers < 1) k.patch_workers = 1;
         if (k.patch_workers > 16) k.patch_workers = 16;
         k.patch_batched = geti("T4B_PATCH_BATCHED", 1) != 0;
@@ -106,6 +114,8 @@ Ctx* ctx_create(int device, void* cuda_stream) {
     }
     T4B_CUDA_CHECK(cudaMalloc((void**)&c->fail_dev, sizeof(unsigned)));
     T4B_CUDA_CHECK(cudaMemset(c->fail_dev, 0, sizeof(unsigned)));
+    T4B_CUDA_CHECK(cudaMallocHost((void**)&c->fail_host, sizeof(unsigned)));
+    *c->fail_host = 0;
     // keep freed blocks cached in the default pool: sweeps re-allocate the same shapes
     cudaMemPool_t pool;
     T4B_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -144,6 +154,7 @@ void ctx_destroy(Ctx* c) {
     if (c->sk_ws) cudaFree(c->sk_ws);
     if (c->sk_flags) cudaFree(c->sk_flags);
     if (c->fail_dev) cudaFree(c->fail_dev);
+    if (c->fail_host) cudaFreeHost(c->fail_host);
     if (c->scratch) cudaFreeAsync(c->scratch, c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto& kv : c->free_lists)
@@ -186,8 +197,14 @@ struct HostTimer {
 // the same handful of shapes at every site, so after the first site the hit rate is ~100% and no
 // driver allocation (which costs milliseconds for the 64 MB work buffers) is on the hot path.
 static size_t round_size(size_t bytes) {
+    // size classes: multiples of 256 bytes up to 4 KB, then eight classes per octave (<= 12.5% slack).  Sweeps over
+    // RAGGED shapes (patches with different bond dimensions, truncated ranks) then hit the cache as well; with exact
+    // sizes every new rank meant a cudaMalloc on the hot path.
     if (bytes < 256) return 256;
-    return (bytes + 255) / 256 * 256;
+    if (bytes <= 4096) return (bytes + 255) / 256 * 256;
+    int hi = 63 - __builtin_clzll((unsigned long long)(bytes - 1));     // bytes in (2^hi, 2^(hi+1)]
+    const size_t step = (size_t)1 << (hi - 3 > 8 ? hi - 3 : 8);
+    return (bytes + step - 1) / step * step;
 }
 // While a worker thread of parallel_for_independent() runs, blocks of the PARENT context that it releases (the old site
 // tensors of the patch it is rewriting) may still be read by kernels queued on the worker's stream; the parent's
@@ -204,6 +221,46 @@ void flush_deferred(Ctx* c) {
     for (void* p : d) release(c, p);
 }
 
+void parallel_phase_begin(Ctx* parent, int k) {
+    // every stream involved is idle (the caller synchronised the parent; workers were synchronised when their last
+    // phase ended and nothing has been queued on them since)
+    auto drain = [&](Ctx* x) {
+        std::lock_guard<std::mutex> mem_lock(x->mem_mu);          // lock order everywhere: mem_mu, then idle_mu
+        std::lock_guard<std::mutex> idle_lock(parent->idle_mu);
+        for (auto& kv : x->free_lists) {
+            auto& dst = parent->idle_lists[kv.first];
+            dst.insert(dst.end(), kv.second.begin(), kv.second.end());
+        }
+        x->free_lists.clear();
+        x->cached_bytes = 0;
+        x->pool_parent = parent;
+    };
+    drain(parent);
+    for (int i = 0; i < k && i < (int)parent->workers.size(); ++i) drain(parent->workers[(size_t)i]);
+}
+void parallel_phase_end(Ctx* parent) {
+    // all streams synchronised by the caller: every cached block is idle again and goes back to the parent
+    auto give = [&](size_t sz, std::vector<void*>& blocks) {
+        auto& dst = parent->free_lists[sz];
+        dst.insert(dst.end(), blocks.begin(), blocks.end());
+        parent->cached_bytes += sz * blocks.size();
+    };
+    for (Ctx* w : parent->workers) {
+        std::lock_guard<std::mutex> wl(w->mem_mu);
+        w->pool_parent = nullptr;
+        if (w->free_lists.empty()) continue;
+        std::lock_guard<std::mutex> pl(parent->mem_mu);
+        for (auto& kv : w->free_lists) give(kv.first, kv.second);
+        w->free_lists.clear();
+        w->cached_bytes = 0;
+    }
+    std::lock_guard<std::mutex> pl(parent->mem_mu);
+    std::lock_guard<std::mutex> idle_lock(parent->idle_mu);
+    parent->pool_parent = nullptr;
+    for (auto& kv : parent->idle_lists) give(kv.first, kv.second);
+    parent->idle_lists.clear();
+}
+
 void* alloc(Ctx* c, size_t bytes) {
     std::lock_guard<std::mutex> mem_lock(c->mem_mu);
     HostTimer t(c->host_alloc_s);
@@ -216,6 +273,17 @@ void* alloc(Ctx* c, size_t bytes) {
         c->cached_bytes -= sz;
         c->live[p] = sz;
         return p;
+    }
+    if (Ctx* pp = c->pool_parent) {
+        // parallel phase: idle blocks pooled by parallel_phase_begin()
+        std::lock_guard<std::mutex> idle_lock(pp->idle_mu);
+        auto jt = pp->idle_lists.find(sz);
+        if (jt != pp->idle_lists.end() && !jt->second.empty()) {
+            void* p = jt->second.back();
+            jt->second.pop_back();
+            c->live[p] = sz;
+            return p;
+        }
     }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, sz);
@@ -268,22 +336,32 @@ void zero(Ctx* c, void* dst, size_t bytes) {
 void sync(Ctx* c) {
     HostTimer t(c->host_sync_s);
     ++c->host_sync_n;
+    // the sticky failure counter rides on the same stream synchronisation (pinned target, no second round trip and
+    // no blocking copy on the NULL stream)
+    if (c->fail_dev) T4B_CUDA_CHECK(cudaMemcpyAsync(c->fail_host, c->fail_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->fail_dev) {
-        unsigned h = 0;
-        T4B_CUDA_CHECK(cudaMemcpy(&h, c->fail_dev, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        const unsigned h = *c->fail_host;
         if (h) {
-            cudaMemset(c->fail_dev, 0, sizeof(unsigned));
+            T4B_CUDA_CHECK(cudaMemsetAsync(c->fail_dev, 0, sizeof(unsigned), c->stream));
+            T4B_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            *c->fail_host = 0;
             throw Error(ST_NOT_CONVERGED, "svd: the Jacobi iteration did not converge within its sweep limit (" +
                                               std::to_string(h) + " factorisation(s))");
         }
     }
 }
 std::string host_stats(Ctx* c) {
+    // the context and its worker contexts (parallel_for_independent) together
+    long long alloc_n = c->host_alloc_n, sync_n = c->host_sync_n, launches = c->launches;
+    double alloc_s = c->host_alloc_s, free_s = c->host_free_s, sync_s = c->host_sync_s;
+    for (Ctx* w : c->workers) {
+        alloc_n += w->host_alloc_n; sync_n += w->host_sync_n; launches += w->launches;
+        alloc_s += w->host_alloc_s; free_s += w->host_free_s; sync_s += w->host_sync_s;
+    }
     char buf[256];
-    snprintf(buf, sizeof(buf), "alloc_n %lld alloc_s %.4f free_s %.4f sync_n %lld sync_s %.4f launches %lld",
-             (long long)c->host_alloc_n, c->host_alloc_s, c->host_free_s, (long long)c->host_sync_n, c->host_sync_s,
-             (long long)c->launches);
+    snprintf(buf, sizeof(buf), "alloc_n %lld alloc_s %.4f free_s %.4f sync_n %lld sync_s %.4f launches %lld workers %d",
+             alloc_n, alloc_s, free_s, sync_n, sync_s, launches, (int)c->workers.size());
     return buf;
 }
 

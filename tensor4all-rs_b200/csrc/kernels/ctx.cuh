@@ -38,7 +38,7 @@ struct Knobs {
     bool svd_nogram = false;      // T4B_SVD_NOGRAM: never take the Gram + Cholesky preconditioner
     int gram_off = 0;             // T4B_GRAM_OFF bit mask: 1 = R-only (wide / right-vector) SVD route off, 2 = tall U = A V S^-1 route off, 4 = Cholesky QR off
     int svd_small_single_max = 32;   // T4B_SVD_SMALL_MAX: largest min(m, n) a SINGLE svd_thin sends to the one-CTA kernel
-    int patch_workers = 4;        // T4B_PATCH_WORKERS: host threads (child contexts) for independent patches / groups
+    int patch_workers = 4;        // T4B_PATCH_WORKERS: host threads (child contexts) for independent patches / groups (default: host threads per GPU, 2..8)
     bool patch_batched = true;    // T4B_PATCH_BATCHED=0: one launch chain per patch (worker threads) instead of the batched sweeps
     int rrlu_bps = 0;             // T4B_RRLU_BPS: resident prrLU blocks per SM (0 = planned from the matrix size)
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
@@ -92,7 +92,7 @@ struct Ctx {
     // host-side overhead counters (seconds / counts), see host_stats()
     double host_alloc_s = 0.0, host_free_s = 0.0, host_sync_s = 0.0;
     int64_t host_alloc_n = 0, host_sync_n = 0;
-    // exact-size caching allocator (see alloc()/release() in ctx.cu); mem_mu guards it because a worker thread of
+    // size-class caching allocator (see alloc()/release() in ctx.cu); mem_mu guards it because a worker thread of
     // parallel_for_independent() may drop the last reference to a block of ANOTHER context (deferred, see release())
     std::mutex mem_mu;
     std::vector<void*> deferred;            // blocks released by a foreign thread: returned to the cache by flush_deferred()
@@ -100,6 +100,14 @@ struct Ctx {
     std::unordered_map<size_t, std::vector<void*>> free_lists;
     std::unordered_map<void*, size_t> live;
     size_t cached_bytes = 0;
+    // Parallel phase (parallel_for_independent): the cached blocks of the parent and of every worker, all idle because
+    // every stream has been synchronised, are pooled in the PARENT's idle_lists; a context that misses its own cache
+    // takes from that pool before it asks the driver (idle_mu), whatever patch it happens to be handed.  Blocks
+    // released during the phase stay in the releasing context's stream-ordered cache; parallel_phase_end() returns
+    // everything to the parent.  pool_parent != null only while a phase is active.
+    Ctx* pool_parent = nullptr;
+    std::mutex idle_mu;
+    std::unordered_map<size_t, std::vector<void*>> idle_lists;
     bool profiling = false;
     // "gemm" = tensor contraction called by the sweep drivers; "gemm_factor" = GEMMs issued from
     // inside the QR / SVD factorisation kernels (panel updates, Q formation)
@@ -111,6 +119,7 @@ struct Ctx {
     double* dev_stats = nullptr;
     // sticky device-side failure counter (e.g. a Jacobi iteration that hit its sweep limit); checked by sync()
     unsigned* fail_dev = nullptr;
+    unsigned* fail_host = nullptr;   // pinned mirror of fail_dev, refreshed by every sync()
     // high-priority side stream + events for look-ahead inside a factorisation (qr.cu); always joined
     // back into `stream` before the factorisation returns
     cudaStream_t side = nullptr;

@@ -88,7 +88,7 @@ def test_sharded_cabi_single_rank_matches_oracle(ctx):
 
 
 def test_parallel_executor_is_bit_identical_to_the_serial_loop(monkeypatch):
-    """The owned patches are truncated by several host threads with child contexts (T4B_PATCH_WORKERS, default 4); every
+    """The owned patches are truncated by several host threads with child contexts (T4B_PATCH_WORKERS, default: host threads per GPU, 2..8); every
     patch's result must not depend on which context computed it: 1 worker and 6 workers give bit-identical site tensors,
     and the handles stay usable (canonicalize / norm / release) after the call."""
     rng = np.random.default_rng(24)

@@ -37,7 +37,15 @@ def run():
     return dt, int(keep.sum()), mb
 
 
-for rep in range(3):
-    print("wall ms", round(run()[0] * 1e3, 1))
+def host_stats():
+    buf = C.create_string_buffer(512)
+    t4b._check(t4b.lib().t4b_ctx_host_stats(ctx.h, buf, C.c_size_t(512)))
+    return buf.value.decode()
+
+
+for rep in range(int(os.environ.get("C5_REPS", "4"))):
+    print("wall ms", round(run()[0] * 1e3, 1), "|", host_stats())
+if os.environ.get("C5_NOPROF"):
+    sys.exit(0)
 prof = profile(ctx, run)
 print(json.dumps({k: (v["launches"], round(v["ms"], 2)) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}))
