@@ -381,15 +381,20 @@ def ncu_capture(name):
 
 
 # ---- C5: patch-sharded adaptive truncation (strong scaling) ------------------------------------------
-def run_c5(env, n=256, L=24, d=2, reps=2, cutoff=1e-10, max_bond=64, both=True):
-    """C5 through t4b_patches_truncate_adaptive_sharded.  The headline figure is the default (batched) mode: every sweep
-    position of all patches a rank owns is one SVD launch + one GEMM launch.  With `both`, the per-patch mode
-    (T4B_PATCH_BATCHED=0: one launch chain per patch, worker threads) is timed as well and reported under
-    `per_patch_launch_chains` - it is the slower implementation whose strong scaling is nearly ideal, because its
-    time is all per-patch host and launch latency."""
+def run_c5(env, n=256, L=24, d=2, reps=2, cutoff=1e-10, max_bond=64, small=True):
+    """C5 through t4b_patches_truncate_adaptive_sharded.  The C5 patches arrive with bonds up to 256, beyond the one-CTA
+    SVD kernel, so every patch is one launch chain and the owned patches are spread over host threads with child
+    contexts (the record's `mode`).  With `small`, the same partition with bonds <= 48 is timed as well: there every
+    sweep position of ALL owned patches is one SVD launch + one GEMM launch (host/chain_batched.cpp), next to the same
+    patches through the per-patch chains (T4B_PATCH_BATCHED=0) - the small-chi regime of the north star."""
     rec = _run_c5_mode(env, env.ctx, n, L, d, reps, cutoff, max_bond)
-    if both:
+    if rec is not None:
+        rec["mode"] = ("one launch chain per patch (bonds up to 256 exceed the one-CTA SVD kernel), owned patches spread "
+                       "over host threads with child contexts and a shared idle-block pool")
+    if small:
         import t4b
+        chis = [int(c) // 8 + 16 for c in c5_chis(n)]          # 24 ... 48
+        rb = _run_c5_mode(env, env.ctx, n, L, d, reps, cutoff, 32, chis=chis)
         old = os.environ.get("T4B_PATCH_BATCHED")
         os.environ["T4B_PATCH_BATCHED"] = "0"
         ctx0 = t4b.Context(env.local_rank, env.stream.cuda_stream)     # knobs are read at context creation
@@ -398,21 +403,24 @@ def run_c5(env, n=256, L=24, d=2, reps=2, cutoff=1e-10, max_bond=64, both=True):
         else:
             os.environ["T4B_PATCH_BATCHED"] = old
         try:
-            r0 = _run_c5_mode(env, ctx0, n, L, d, 1, cutoff, max_bond)
+            r0 = _run_c5_mode(env, ctx0, n, L, d, 1, cutoff, 32, chis=chis)
         finally:
             ctx0.close()
-        if rec is not None and r0 is not None:
-            rec["mode"] = "batched sweeps over the owned patches (default)"
-            rec["per_patch_launch_chains"] = {k: r0[k] for k in ("value", "unit", "ms", "phase_ms", "checksum_norm")}
+        if rec is not None and rb is not None and r0 is not None:
+            keys = ("value", "unit", "ms", "phase_ms", "checksum_norm", "max_bond_after")
+            rec["small_chi_variant"] = {
+                "config": "same partition, incoming bonds 24...48, max_bond_dim 32: every bond matrix fits the one-CTA SVD kernel",
+                "batched_sweeps": {k: rb[k] for k in keys},
+                "per_patch_launch_chains": {k: r0[k] for k in keys}}
     return rec
 
 
-def _run_c5_mode(env, ctx, n, L, d, reps, cutoff, max_bond):
+def _run_c5_mode(env, ctx, n, L, d, reps, cutoff, max_bond, chis=None):
     import torch
     from t4b import patches as tp
     from t4b import tt as t4tt
     rank, world, stream = env.rank, env.world, env.stream
-    chis = c5_chis(n)
+    chis = chis or c5_chis(n)
     bd = np.array([bond_dims(L, d, chis[k]) for k in range(n)], dtype=np.int64)
     owner, costs = tp.lpt_assign_cabi(bd, d, world)
     volumes = [d ** L] * n

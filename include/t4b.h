@@ -92,7 +92,11 @@ int t4b_qr_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void
  * vh (k x n) = V^H, k = min(m,n).  u_dev or vh_dev may be NULL when the caller rebuilds that
  * side by a contraction (saves the vector accumulation).  QR-preconditioned one-sided block
  * Jacobi.  Replaces svd_backend (tensorbackend/src/backend.rs:715-734) and EagerTensor::svd
- * (core/src/defaults/svd.rs:265-267). */
+ * (core/src/defaults/svd.rs:265-267).
+ * Rank-deficient input: singular directions with sigma_i <= eps * k * sigma_max are returned as ZERO columns of u /
+ * rows of vh (LAPACK completes them to an orthonormal basis).  u diag(s) vh and every truncated factorisation built
+ * on it are unaffected (those directions carry no weight); a caller that needs U^H U = I on the null space as well
+ * must complete the basis itself. */
 int t4b_svd_thin(t4b_ctx* ctx, int dtype, int64_t m, int64_t n, void* a_dev, void* u_dev,
                  double* s_dev, void* vh_dev);
 

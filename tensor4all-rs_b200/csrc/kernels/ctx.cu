@@ -75,7 +75,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         auto geti = [](const char* n, int dflt) { const char* v = getenv(n); return v ? atoi(v) : dflt; };
         auto getb = [](const char* n) { return getenv(n) != nullptr; };
         Knobs& k = c->knobs;
-        k.verbose = getenv("T4B_VERBOSE") ? (atoi(getenv("T4B_VERBOSE")) > 0 ? atoi(getenv("T4B_VERBOSE")) : 1) : 0;
+        k.verbose = getenv("T4B_VERBOSE") ? (atoi(getenv("T4B_VERBOSE")) > 0 ? atoi(getenv("T4B_VERBOSE")) : (getenv("T4B_VERBOSE")[0] == '0' ? 0 : 1)) : 0;
         k.jac_smemcap_kb = (size_t)geti("T4B_JAC_SMEMCAP", 0);
         k.jac_cs = geti("T4B_JAC_CS", 0);
         k.jac_max_sweeps = geti("T4B_JAC_MAXSWEEPS", 40);

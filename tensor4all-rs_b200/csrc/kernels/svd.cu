@@ -40,7 +40,7 @@ constexpr int JB = 16;     // column block width
 constexpr int PW = 32;     // pair panel width
 constexpr int JT = 256;    // threads per CTA
 constexpr int JW = JT / 32;
-constexpr int WP = 36;     // pitch of the W matrix in shared memory
+constexpr int WP = 37;     // pitch of the W matrix in shared memory: odd, so that the column-pair updates of the inner eigen-solve (16 lanes = 16 columns, same row) are free of bank conflicts (36 made them 2x conflicted; the 32 one-off fragment loads of the update pass pay 1.5x instead)
 constexpr int GP = 33;     // pitch of the G matrix in shared memory
 constexpr int MAXCS = 16;
 
