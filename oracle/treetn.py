@@ -31,6 +31,12 @@ _counter = itertools.count(1)
 # gesvd to measure how far two backward-stable SVDs drift apart over the 189 dependent truncations (the noise floor
 # against which the device spectra are judged).
 SVD_DRIVER = "gesdd"
+# Relative size of an i.i.d. perturbation applied to the matrix of EVERY dense SVD (0 = off).  LAPACK gesdd itself is
+# backward stable to ||A - U S V^T||_2 ~ 9e-15 ||A||_2 at the C3 shapes (measured, tests/golden/make_c3_golden.py
+# --measure-backward-error); a re-run with a per-step perturbation below that level shows how far the spectra of the
+# 189 DEPENDENT truncations move between two implementations that are each as accurate as the oracle.
+SVD_STEP_PERTURB = 0.0
+_step_rng = np.random.default_rng(0x57E9)
 
 
 def new_label(prefix="b"):
@@ -83,6 +89,8 @@ def _unfold(t, left):
 
 def factorize_svd(t, left, canonical="left", policy=None, max_bond_dim=None, truncate=True):
     mat, left, right, shape = _unfold(t, left)
+    if SVD_STEP_PERTURB > 0.0:
+        mat = mat * (1.0 + SVD_STEP_PERTURB * _step_rng.standard_normal(mat.shape))
     u, s, vh = sla.svd(mat, full_matrices=False, lapack_driver=SVD_DRIVER)
     r = svd_rank(s, policy, max_bond_dim, truncate)
     u, s_r, vh = u[:, :r], s[:r], vh[:r, :]

@@ -83,6 +83,11 @@ void permute(Ctx*, DType dt, void* out, const void* in, const Group& g, bool con
 // TreeTN::add, crates/tensor4all-treetn/src/treetn/addition.rs:322-...).
 void scatter(Ctx*, DType dt, void* out, const void* in, const Group& g);
 
+// Hint for the next svd_thin calls on this context: the caller keeps at most `cols` leading singular vectors
+// (max_bond_dim of the factorisation in flight), so the Rayleigh-Ritz refinement of the cluster SVD polishes only
+// those; 0 = all.  Returns the previous value.
+int64_t svd_set_refine_cols(Ctx*, int64_t cols);
+
 // A (m x n, ld = m) -> Q (m x k, ld = m), R (k x n, ld = k, upper trapezoidal), k = min(m,n).
 // Householder; A is destroyed.  Q may be null (R only).
 // Replaces tenferro `.qr()` (reference crates/tensor4all-core/src/defaults/qr.rs:258-260,

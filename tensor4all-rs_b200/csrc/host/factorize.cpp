@@ -99,8 +99,14 @@ static Group g1(int64_t dim, int64_t str) {
 
 MatrixFactors svd_factor_matrix(dla::Ctx* c, DType dt, int64_t m, int64_t n, const void* M,
                                 Canonical canonical,
-                                const std::function<int64_t(const std::vector<double>&)>& rank_fn) {
+                                const std::function<int64_t(const std::vector<double>&)>& rank_fn,
+                                int64_t rank_cap) {
     T4B_REQUIRE(m > 0 && n > 0, "cannot factorize a matrix with an empty dimension");
+    struct RefineHint {
+        dla::Ctx* c; int64_t prev;
+        RefineHint(dla::Ctx* cc, int64_t cols) : c(cc), prev(dla::svd_set_refine_cols(cc, cols)) {}
+        ~RefineHint() { dla::svd_set_refine_cols(c, prev); }
+    } refine_hint(c, rank_cap);
     const size_t es = dtype_size(dt);
     const int64_t k = std::min(m, n);
     MatrixFactors out;
@@ -194,7 +200,8 @@ FactorizeResult factorize_svd(dla::Ctx* c, const Tensor& t, const std::vector<In
         if (o.max_bond_dim) r = std::min<int64_t>(r, *o.max_bond_dim);
         return std::max<int64_t>(r, 1);
     };
-    MatrixFactors f = svd_factor_matrix(c, t.dt, u.m, u.n, u.mat.data(), o.canonical, rank_fn);
+    const int64_t cap = (!o.full_rank && o.max_bond_dim) ? *o.max_bond_dim : 0;
+    MatrixFactors f = svd_factor_matrix(c, t.dt, u.m, u.n, u.mat.data(), o.canonical, rank_fn, cap);
     dla::spectra_push(c, f.singular_values.data(), (int64_t)f.singular_values.size());
     FactorizeResult res;
     res.bond = new_index(f.rank);

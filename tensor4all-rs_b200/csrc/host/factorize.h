@@ -72,9 +72,11 @@ struct MatrixFactors {
     std::vector<double> singular_values;      // retained
     std::vector<double> all_singular_values;  // full spectrum
 };
-// rank_fn maps the full spectrum to the retained rank (>= 1, <= k)
+// rank_fn maps the full spectrum to the retained rank (>= 1, <= k); rank_cap (0 = none) is an upper bound of what
+// rank_fn can return (max_bond_dim): the SVD polishes only that many leading vectors (dla::svd_set_refine_cols)
 MatrixFactors svd_factor_matrix(dla::Ctx*, DType dt, int64_t m, int64_t n, const void* M,
                                 Canonical canonical,
-                                const std::function<int64_t(const std::vector<double>&)>& rank_fn);
+                                const std::function<int64_t(const std::vector<double>&)>& rank_fn,
+                                int64_t rank_cap = 0);
 
 }  // namespace t4b

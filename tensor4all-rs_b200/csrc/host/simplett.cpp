@@ -59,7 +59,8 @@ static Fact factorize_matrix(dla::Ctx* c, DType dt, int64_t m, int64_t n, const 
         auto rank_fn = [&](const std::vector<double>& s) {
             return simplett_rank(s, tolerance, normalize_error, max_bond_dim);
         };
-        MatrixFactors mf = svd_factor_matrix(c, dt, m, n, M, left_orthogonal ? Canonical::Left : Canonical::Right, rank_fn);
+        MatrixFactors mf = svd_factor_matrix(c, dt, m, n, M, left_orthogonal ? Canonical::Left : Canonical::Right, rank_fn,
+                                             max_bond_dim.value_or(0));
         f.left = mf.left; f.right = mf.right; f.rank = mf.rank;
         return f;
     }

@@ -102,6 +102,9 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         if (k.patch_workers > 16) k.patch_workers = 16;
         k.patch_batched = geti("T4B_PATCH_BATCHED", 1) != 0;
         k.rrlu_bps = geti("T4B_RRLU_BPS", 0);
+        k.svd_norefine = geti("T4B_SVD_NOREFINE", 0);
+        k.svd_refine_iters = geti("T4B_SVD_REFINE_ITERS", 1);
+        k.jac_eig_v2 = geti("T4B_JAC_EIG_V2", 1);
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;
     }

@@ -42,6 +42,9 @@ struct Knobs {
     bool patch_batched = true;    // T4B_PATCH_BATCHED=0: one launch chain per patch (worker threads) instead of the batched sweeps
     int rrlu_bps = 0;             // T4B_RRLU_BPS: resident prrLU blocks per SM (0 = planned from the matrix size)
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
+    int svd_norefine = 0;         // T4B_SVD_NOREFINE: 1 = skip the Rayleigh-Ritz refinement of the Jacobi vectors, 2 = refine only under a bond cap (k < n), 3 = refine only without one (A/B only)
+    int svd_refine_iters = 1;     // T4B_SVD_REFINE_ITERS
+    int jac_eig_v2 = 1;           // T4B_JAC_EIG_V2=0: the round-1 form of the inner eigen-solve (A/B only)
 };
 
 // launch geometry of the persistent Jacobi kernel (svd.cu)
@@ -112,6 +115,9 @@ struct Ctx {
     // "gemm" = tensor contraction called by the sweep drivers; "gemm_factor" = GEMMs issued from
     // inside the QR / SVD factorisation kernels (panel updates, Q formation)
     const char* gemm_class = "gemm";
+    // Number of leading singular vectors the caller can retain at most (max_bond_dim of the factorisation in flight;
+    // 0 = all): the Rayleigh-Ritz refinement of the cluster SVD only polishes that many columns.
+    int64_t svd_refine_cols = 0;
     std::vector<ProfRec> prof;
     cudaEvent_t prof_start = nullptr;
     // device-side work counters of kernels whose algorithmic work is only known on the device

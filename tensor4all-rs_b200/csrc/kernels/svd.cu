@@ -27,6 +27,7 @@
 #include <cstring>
 #include <vector>
 
+#include "jacobi_eig.cuh"
 #include "scalar.cuh"
 
 namespace cg = cooperative_groups;
@@ -38,10 +39,7 @@ namespace {
 
 constexpr int JB = 16;     // column block width
 constexpr int PW = 32;     // pair panel width
-constexpr int JT = 256;    // threads per CTA
 constexpr int JW = JT / 32;
-constexpr int WP = 37;     // pitch of the W matrix in shared memory: odd, so that the column-pair updates of the inner eigen-solve (16 lanes = 16 columns, same row) are free of bank conflicts (36 made them 2x conflicted; the 32 one-off fragment loads of the update pass pay 1.5x instead)
-constexpr int GP = 33;     // pitch of the G matrix in shared memory
 constexpr int MAXCS = 16;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -63,246 +61,6 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned 
 }
 
 
-// Hermitian Jacobi on the 32 x 32 Gram block held in shared memory (Gs, ping-pong copy Gs2), rotations
-// accumulated into Ws (initialised to the identity by the caller).  16 disjoint rotations per step;
-// every thread owns one 2 x 2 block of G' = Ja^H G Jb.  full_inner: 31-step round-robin over all 32
-// indices; otherwise the 16-step bipartite ordering (cross pairs block I x block J only).
-// Called by all JT threads; ends with a __syncthreads().
-template <bool CPLX>
-__device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32(typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2,
-                                             typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
-                                             double* rot_c, double* rot_s, int full_inner, double tol_rot,
-                                             int tid, int inner = 1, double zthr = 0.0) {
-    typedef Sc<CPLX> S;
-    typedef typename S::T T;
-    T* Gcur = Gs;
-    T* Gnxt = Gs2;
-    const int nrr = full_inner ? 31 : 16 * inner;
-    const int ta = tid >> 4, tb = tid & 15;   // row pair / column pair owned by this thread
-    const double tol2 = tol_rot * tol_rot;
-    for (int rr = 0; rr < nrr; ++rr) {
-        int pa, qa, pb, qb;
-        if (full_inner) {
-            if (ta == 0) { pa = rr; qa = 31; } else { pa = (rr + ta) % 31; qa = (rr - ta + 62) % 31; }
-            if (pa > qa) { int t = pa; pa = qa; qa = t; }
-            if (tb == 0) { pb = rr; qb = 31; } else { pb = (rr + tb) % 31; qb = (rr - tb + 62) % 31; }
-            if (pb > qb) { int t = pb; pb = qb; qb = t; }
-        } else {
-            pa = ta; qa = 16 + ((ta + rr) & 15);
-            pb = tb; qb = 16 + ((tb + rr) & 15);
-        }
-        // 16 threads compute the 16 rotations of this step (pair t = tid):
-        // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]], J^H [[aa,g],[g*,bb]] J diagonal
-        if (tid < 16) {
-            int pp, qq;
-            if (full_inner) {
-                if (tid == 0) { pp = rr; qq = 31; } else { pp = (rr + tid) % 31; qq = (rr - tid + 62) % 31; }
-                if (pp > qq) { int t = pp; pp = qq; qq = t; }
-            } else {
-                pp = tid; qq = 16 + ((tid + rr) & 15);
-            }
-            double c = 1.0, sn = 0.0;
-            T ph = S::one();
-            const double aa = S::real(Gcur[pp * GP + pp]), bb = S::real(Gcur[qq * GP + qq]);
-            const T g = Gcur[pp * GP + qq];
-            const double g2 = S::abs2(g);
-            if (g2 > 0.0 && aa > zthr && bb > zthr && g2 > tol2 * aa * bb) {
-                const double d = 0.5 * (bb - aa);
-                if constexpr (CPLX) {
-                    const double inv_absg = rsqrt(g2);
-                    const double absg = g2 * inv_absg;
-                    const double x = d * d + g2;
-                    const double h = x * rsqrt(x);
-                    const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
-                    c = rsqrt(1.0 + t * t);
-                    sn = c * t;
-                    ph = S::scale(S::conj(g), inv_absg);   // e^{-i phi}
-                } else {
-                    // t = sign(d) |g| / (|d| + sqrt(d^2 + g^2)) only steers the convergence, so it is
-                    // evaluated in fp32 on exponent-normalised operands; c = (1 + t^2)^(-1/2) must make
-                    // the rotation orthogonal to fp64 accuracy: fp32 seed + two Newton steps.
-                    const double ag = fabs(g), ad = fabs(d);
-                    const double mx = ag > ad ? ag : ad;
-                    const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
-                    const double sc = __hiloint2double((2046 - ex) << 20, 0);     // mx * sc in [1, 2)
-                    const float fd = (float)(ad * sc), fg = (float)(ag * sc);
-                    const float fh = sqrtf(fd * fd + fg * fg);
-                    const float ft = __fdividef(fg, fd + fh);
-                    const double t = d >= 0.0 ? (double)ft : -(double)ft;
-                    const double x = 1.0 + t * t;
-                    double y = (double)rsqrtf((float)x);
-                    y = y * (1.5 - 0.5 * x * y * y);
-                    y = y * (1.5 - 0.5 * x * y * y);
-                    c = y;
-                    sn = c * t;
-                    ph = g >= 0.0 ? 1.0 : -1.0;
-                }
-            }
-            rot_c[tid] = c; rot_s[tid] = sn; rot_ph[tid] = ph;
-        }
-        __syncthreads();
-        const double ca = rot_c[ta], sa = rot_s[ta], cb = rot_c[tb], sb = rot_s[tb];
-        const T pha = rot_ph[ta], phb = rot_ph[tb];
-        // G' = Ja^H G Jb on the 2 x 2 block owned by this thread
-        const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
-        const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
-        const T cpa = S::conj(pha);
-        const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
-        const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
-        const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
-        const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
-        const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
-        const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
-        Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
-        Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
-        Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
-        Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
-        // W <- W Jb for the two rows owned by this thread (exclusive ownership: in place)
-#pragma unroll
-        for (int rrow = 0; rrow < 2; ++rrow) {
-            const int i = ta * 2 + rrow;
-            const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
-            const T fq = S::mul(wq, phb);
-            Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
-            Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
-        }
-        __syncthreads();
-        T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
-    }
-    return Gcur;
-}
-
-
-// Rotation of the pivot (aa, g; conj(g), bb): J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]] with J^H (..) J diagonal.
-// Returns tg = t |g| (t = tan of the rotation angle): the rotated diagonal is (aa - tg, bb + tg).
-template <bool CPLX>
-__device__ __forceinline__ void jacobi_rotation(double aa, double bb, typename Sc<CPLX>::T g, double tol2,
-                                                double& c, double& sn, typename Sc<CPLX>::T& ph, double& tg,
-                                                double zthr = 0.0) {
-    typedef Sc<CPLX> S;
-    c = 1.0; sn = 0.0; ph = S::one(); tg = 0.0;
-    const double g2 = S::abs2(g);
-    if (g2 > 0.0 && aa > zthr && bb > zthr && g2 > tol2 * aa * bb) {
-        const double d = 0.5 * (bb - aa);
-        if constexpr (CPLX) {
-            const double inv_absg = rsqrt(g2);
-            const double absg = g2 * inv_absg;
-            const double x = d * d + g2;
-            const double h = x * rsqrt(x);
-            const double t = (d >= 0.0 ? absg : -absg) / (fabs(d) + h);
-            c = rsqrt(1.0 + t * t);
-            sn = c * t;
-            ph = S::scale(S::conj(g), inv_absg);
-            tg = t * absg;
-        } else {
-            // (c, s) = (u, |g|) / sqrt(u^2 + g^2), u = |d| + sqrt(d^2 + g^2), evaluated in fp32 on exponent-
-            // normalised operands (two MUFU ops, no division): the angle only steers the convergence.  The
-            // pair is then renormalised in fp64, (c, s) *= 1 - e/2 + 3 e^2 / 8 with e = c^2 + s^2 - 1 ~ 1e-7,
-            // which makes the rotation orthogonal to ~e^3.
-            const double ag = fabs(g), ad = fabs(d);
-            const double mx = ag > ad ? ag : ad;
-            const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
-            const double sc = __hiloint2double((2046 - ex) << 20, 0);     // mx * sc in [1, 2)
-            const float fd = (float)(ad * sc), fg = (float)(ag * sc);
-            const float fu = fd + sqrtf(fd * fd + fg * fg);
-            const float rho = rsqrtf(fu * fu + fg * fg);
-            double cd = (double)(fu * rho), sd = (double)(fg * rho);
-            if (fg == 0.0f) { cd = 1.0; sd = ag / (2.0 * ad); }          // |g| / |d| below fp32 range: tiny angle
-            const double e = fma(cd, cd, fma(sd, sd, -1.0));
-            const double corr = fma(e, fma(e, 0.375, -0.5), 1.0);
-            cd *= corr; sd *= corr;
-            c = cd;
-            sn = d >= 0.0 ? sd : -sd;
-            ph = g >= 0.0 ? 1.0 : -1.0;
-            tg = fma(sn * sn, aa - bb, 2.0 * c * sn * ag);               // aa - (c^2 aa - 2 c s |g| + s^2 bb)
-        }
-    }
-}
-
-// Bipartite (cross pairs only) inner sweeps with the rotation warp running ONE STEP AHEAD of the apply warps:
-// while warps 1..7 apply the rotations of step r (G' = J^H G J, W <- W J), warp 0 already derives the pivots of
-// step r+1 - G'[p][p] = aa - tg, G'[q'][q'] = bb' + tg' of the neighbouring pair, G'[p][q'] from four entries of
-// G and the two rotations involved - and computes the next rotations.  One __syncthreads per step.
-template <bool CPLX>
-__device__ __forceinline__ typename Sc<CPLX>::T* jacobi_eig32_pipelined(
-    typename Sc<CPLX>::T* Gs, typename Sc<CPLX>::T* Gs2, typename Sc<CPLX>::T* Ws, typename Sc<CPLX>::T* rot_ph,
-    double* rot_c, double* rot_s, double tol_rot, int tid, int inner, double zthr) {
-    typedef Sc<CPLX> S;
-    typedef typename S::T T;
-    T* Gcur = Gs;
-    T* Gnxt = Gs2;
-    const int nrr = 16 * inner;
-    const double tol2 = tol_rot * tol_rot;
-    const int lane = tid & 31, warp = tid >> 5;
-    // rotation state of pair t = lane (warp 0, lanes 0..15)
-    double c = 1.0, sn = 0.0, tg = 0.0, aa = 0.0, bb = 0.0;
-    T ph = S::one();
-    if (warp == 0 && lane < 16) {
-        const int pp = lane, qq = 16 + lane;
-        aa = S::real(Gcur[pp * GP + pp]); bb = S::real(Gcur[qq * GP + qq]);
-        jacobi_rotation<CPLX>(aa, bb, Gcur[pp * GP + qq], tol2, c, sn, ph, tg, zthr);
-        rot_c[lane] = c; rot_s[lane] = sn; rot_ph[lane] = ph;
-    }
-    __syncthreads();
-    for (int rr = 0; rr < nrr; ++rr) {
-        const int cur = (rr & 1) * 16, nxt = 16 - cur;
-        if (warp == 0) {
-            if (lane < 16 && rr + 1 < nrr) {
-                // pivots of step rr+1 for pair (p, q'), q' = partner of lane+1 at step rr
-                const int nb = (lane + 1) & 15;
-                const int pp = lane, qq = 16 + ((lane + rr) & 15);
-                const int pn = nb, qn = 16 + ((nb + rr) & 15);
-                const T gpp = Gcur[pp * GP + pn], gpq = Gcur[pp * GP + qn];
-                const T gqp = Gcur[qq * GP + pn], gqq = Gcur[qq * GP + qn];
-                const double cn = __shfl_sync(0x0000ffffu, c, nb), snn = __shfl_sync(0x0000ffffu, sn, nb);
-                const double bbn = __shfl_sync(0x0000ffffu, bb + tg, nb);
-                T phn;
-                if constexpr (CPLX) phn = make_double2(__shfl_sync(0x0000ffffu, ph.x, nb), __shfl_sync(0x0000ffffu, ph.y, nb));
-                else phn = __shfl_sync(0x0000ffffu, ph, nb);
-                // column combination with the neighbour's rotation, then row combination with the own one
-                const T yp = S::add(S::scale(gpp, snn), S::scale(S::mul(gpq, phn), cn));
-                const T yq = S::add(S::scale(gqp, snn), S::scale(S::mul(gqq, phn), cn));
-                const T gnew = S::sub(S::scale(yp, c), S::scale(S::mul(S::conj(ph), yq), sn));
-                aa = aa - tg; bb = bbn;
-                jacobi_rotation<CPLX>(aa, bb, gnew, tol2, c, sn, ph, tg, zthr);
-                rot_c[nxt + lane] = c; rot_s[nxt + lane] = sn; rot_ph[nxt + lane] = ph;
-            }
-        } else {
-            // 256 2 x 2 blocks over the 224 threads of warps 1..7
-            for (int blk = tid - 32; blk < 256; blk += 224) {
-                const int ta = blk >> 4, tb = blk & 15;
-                const int pa = ta, qa = 16 + ((ta + rr) & 15);
-                const int pb = tb, qb = 16 + ((tb + rr) & 15);
-                const double ca = rot_c[cur + ta], sa = rot_s[cur + ta], cb = rot_c[cur + tb], sb = rot_s[cur + tb];
-                const T pha = rot_ph[cur + ta], phb = rot_ph[cur + tb];
-                const T g00 = Gcur[pa * GP + pb], g01 = Gcur[pa * GP + qb];
-                const T g10 = Gcur[qa * GP + pb], g11 = Gcur[qa * GP + qb];
-                const T cpa = S::conj(pha);
-                const T e10 = S::mul(cpa, g10), e11 = S::mul(cpa, g11);
-                const T r00 = S::sub(S::scale(g00, ca), S::scale(e10, sa));
-                const T r01 = S::sub(S::scale(g01, ca), S::scale(e11, sa));
-                const T r10 = S::add(S::scale(g00, sa), S::scale(e10, ca));
-                const T r11 = S::add(S::scale(g01, sa), S::scale(e11, ca));
-                const T f01 = S::mul(r01, phb), f11 = S::mul(r11, phb);
-                Gnxt[pa * GP + pb] = S::sub(S::scale(r00, cb), S::scale(f01, sb));
-                Gnxt[pa * GP + qb] = S::add(S::scale(r00, sb), S::scale(f01, cb));
-                Gnxt[qa * GP + pb] = S::sub(S::scale(r10, cb), S::scale(f11, sb));
-                Gnxt[qa * GP + qb] = S::add(S::scale(r10, sb), S::scale(f11, cb));
-#pragma unroll
-                for (int rrow = 0; rrow < 2; ++rrow) {
-                    const int i = ta * 2 + rrow;
-                    const T wp = Ws[pb * WP + i], wq = Ws[qb * WP + i];
-                    const T fq = S::mul(wq, phb);
-                    Ws[pb * WP + i] = S::sub(S::scale(wp, cb), S::scale(fq, sb));
-                    Ws[qb * WP + i] = S::add(S::scale(wp, sb), S::scale(fq, cb));
-                }
-            }
-        }
-        __syncthreads();
-        T* tmp = Gcur; Gcur = Gnxt; Gnxt = tmp;
-    }
-    return Gcur;
-}
 
 // =====================================================================================================
 // Persistent data-flow Jacobi: ONE launch runs every round of every sweep.
@@ -333,6 +91,7 @@ struct JPArgs {
     int* info;             // [0] sweeps executed, [1] converged
     int inner;             // bipartite inner sweeps per visit
     int eig_serial;        // 1: two-barrier reference form of the inner eigen-solve (debug / A-B)
+    int eig_v2;            // 1: jacobi_eig32_v2 (registers-resident W, consumer-side polish), 0: round-1 pipelined form
     double* D;             // [p][16*16] diagonal Gram block carried with every column block
     double tol_early;      // a sweep that starts below this ends converged (quadratic convergence)
     unsigned long long* timing;   // optional [8] per-phase ns of CTA 0 (debug), else null
@@ -652,7 +411,8 @@ __global__ void __launch_bounds__(JT, 1) jacobi_persistent_kernel(JPArgs a) {
                 if (need_rot) {
                     const T* Gfin = (full_inner || a.eig_serial)
                                         ? jacobi_eig32<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, full_inner, a.tol_rot, tid, a.inner, zthr)
-                                        : jacobi_eig32_pipelined<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, a.tol_rot, tid, a.inner, zthr);
+                                        : (a.eig_v2 ? jacobi_eig32_v2<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, a.tol_rot, tid, a.inner, zthr)
+                                                    : jacobi_eig32_pipelined<CPLX>(Gs, Gs2, Ws, rot_ph, rot_c, rot_s, a.tol_rot, tid, a.inner, zthr));
                     if (R == 0) {
                         // the diagonal blocks of the rotated Gram travel with the column blocks
                         T* di = reinterpret_cast<T*>(a.D) + (size_t)bi * 256;
@@ -1001,6 +761,7 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     a.fro2 = fro2;
     a.inner = c->knobs.jac_inner;
     a.eig_serial = c->knobs.jac_eig_serial ? 1 : 0;
+    a.eig_v2 = c->knobs.jac_eig_v2 ? 1 : 0;
     a.flag = (unsigned long long*)ws;
     a.timing = verbose ? (unsigned long long*)ws + max_sweeps : nullptr;
     a.ready = (unsigned*)(ws + (size_t)(max_sweeps + 8) * 8);
@@ -1285,6 +1046,155 @@ bool cholesky_blocked(Ctx* c, DType dt, int64_t n, void* Gv, double* ratio_out, 
 
 namespace {
 
+// ---- Rayleigh-Ritz refinement of the Jacobi vectors ---------------------------------------------------------------------
+// A column of X goes through ~sweeps * (p - 1) block rotations (1651 at n = 2048); every one of them rounds, so the
+// iteration ends on the exact singular vectors of X0 + E with ||E|| ~ 5e-14 ||X0|| (measured: sigma to 1.1e-13 sigma_max,
+// eigen-residual 2.3e-13 - against 4e-15 / 6e-15 for LAPACK gesdd; tools/probe_backward_error.py).  A truncating sweep
+// amplifies that by 1 / gap at every cut, so the refinement goes back to the matrix the vectors belong to:
+// (Ogita & Aishima's refinement step for the symmetric eigenproblem, k leading columns only)
+//   T = U^H M U (M = X0 X0^H: the Gram matrix the Cholesky factor came from, or R R^H), R = I - U^H U,
+//   lam_i = T[i,i] / (1 - R[i,i]) (Rayleigh quotients: second-order accurate), s_i = sqrt(lam_i),
+//   E[j,i] = (T[j,i] + lam_i R[j,i]) / (lam_i - lam_j), E[i,i] = R[i,i] / 2, U[:, :k] += U E
+// (pairs whose correction would exceed zmax are closer than the error itself: they only get R[j,i] / 2).
+// Four GEMMs of 2 n^2 k flops; with a bond cap k = max_bond_dim (17 GF instead of 69 GF at n = 2048, k = 512).
+// lam[j]: Rayleigh quotient T[j,j] / (U^H U)[j,j] for the k refined vectors, the Jacobi value s_j^2 for the others
+template <bool CPLX>
+__global__ void ritz_lambda_kernel(const double* __restrict__ Td, const double* __restrict__ Gd, int64_t n, int64_t k,
+                                   const double* __restrict__ S, double* __restrict__ lam) {
+    typedef Sc<CPLX> Sx;
+    typedef typename Sx::T T;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double l = S[j] * S[j];
+    if (j < k) {
+        // The Rayleigh quotient carries an ABSOLUTE error ~ eps lam_max (M has entries of that size that cancel), the
+        // Jacobi value a RELATIVE one (~1e-13): the quotient only replaces values above 0.05 lam_max (sigma > 0.22
+        // sigma_max), where it is the more accurate of the two.  (A vector zeroed at the noise floor keeps its value.)
+        const double t = Sx::real(reinterpret_cast<const T*>(Td)[j + j * n]), g = Sx::real(reinterpret_cast<const T*>(Gd)[j + j * n]);
+        if (g > 0.5 && t > 0.0 && t >= 0.05 * g * S[0] * S[0]) l = t / g;
+    }
+    lam[j] = l;
+}
+
+// E (n x k) from T = U^H M U_k and Gm = U^H U_k: E[j,i] = (T[j,i] + lam_i R[j,i]) / (lam_i - lam_j), R = I - Gm;
+// E[i,i] = R[i,i] / 2; pairs whose correction would exceed zmax (closer than the error itself) only get the
+// orthogonality part R[j,i] / 2.  Inside the refined block (j < k) the numerators are SYMMETRISED, (T[j,i] + conj(T[i,j])) / 2:
+// E[j,i] + conj(E[i,j]) = R[j,i] must hold to rounding for U (I + E) to be orthonormal, and the two dot products that give
+// T[j,i] and T[i,j] round differently (5e-15 lam_max / gap ~ 1e-11 otherwise).
+template <bool CPLX>
+__global__ void ritz_z_kernel(const double* __restrict__ Td, const double* __restrict__ Gd, int64_t n, int64_t k,
+                              const double* __restrict__ lam, double zmax, double* __restrict__ Ed) {
+    typedef Sc<CPLX> Sx;
+    typedef typename Sx::T T;
+    const T* Tm = reinterpret_cast<const T*>(Td);
+    const T* Gm = reinterpret_cast<const T*>(Gd);
+    T* E = reinterpret_cast<T*>(Ed);
+    const int64_t total = n * k;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t i = e / n, j = e - i * n;     // column i (refined vector), row j
+        T g = Gm[e];
+        T z;
+        if (j == i) {
+            const double gr = Sx::real(g);
+            z = Sx::from_real(gr > 0.5 ? 0.5 * (1.0 - gr) : 0.0);
+        } else {
+            T t = Tm[e];
+            if (j < k) {
+                const int64_t et = i + j * n;
+                t = Sx::scale(Sx::add(t, Sx::conj(Tm[et])), 0.5);
+                g = Sx::scale(Sx::add(g, Sx::conj(Gm[et])), 0.5);
+            }
+            const T r = Sx::neg(g);
+            const double li = lam[i], lj = lam[j];
+            const double den = li - lj;
+            z = Sx::scale(r, 0.5);
+            // the coupling T[j,i] left by the iteration scales with sigma_i sigma_j (column-wise relative accuracy), the
+            // rounding noise of T with lam_max: below lam_i lam_j = 1e-3 lam_max^2 the correction would add noise
+            const double lmax = lam[0];
+            if (den != 0.0 && li * lj >= 1e-3 * lmax * lmax) {
+                const T q = Sx::scale(Sx::add(t, Sx::scale(r, li)), 1.0 / den);
+                if (Sx::abs2(q) <= zmax * zmax) z = q;
+            }
+        }
+        E[e] = z;
+    }
+}
+
+__global__ void add_inplace_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t nwords) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nwords; e += stride) dst[e] += src[e];
+}
+
+// S[0:k] <- refined values, forced non-increasing (and not below S[k]): one block, running minimum by doubling
+__global__ void ritz_commit_s_kernel(double* __restrict__ S, const double* __restrict__ Snew, int64_t k, int64_t n) {
+    extern __shared__ double sm_s[];
+    const int tid = threadIdx.x;
+    for (int64_t i = tid; i < k; i += blockDim.x) sm_s[i] = sqrt(Snew[i]);      // Snew = lambda = sigma^2
+    __syncthreads();
+    for (int64_t off = 1; off < k; off <<= 1) {
+        double v[4];
+        int cnt = 0;
+        for (int64_t i = tid; i < k; i += blockDim.x) v[cnt++] = i >= off ? fmin(sm_s[i], sm_s[i - off]) : sm_s[i];
+        __syncthreads();
+        cnt = 0;
+        for (int64_t i = tid; i < k; i += blockDim.x) sm_s[i] = v[cnt++];
+        __syncthreads();
+    }
+    const double lower = k < n ? S[k] : 0.0;
+    for (int64_t i = tid; i < k; i += blockDim.x) S[i] = fmax(sm_s[i], lower);
+}
+
+// column j of U (n x ncols) *= 1 / S[j] (0 for directions at the noise floor)
+template <bool CPLX>
+__global__ void scale_cols_inv_kernel(double* __restrict__ Ud, int64_t n, int64_t ncols, const double* __restrict__ S,
+                                      double floor_rel) {
+    typedef Sc<CPLX> Sx;
+    typedef typename Sx::T T;
+    T* U = reinterpret_cast<T*>(Ud);
+    const int64_t col = blockIdx.x;
+    if (col >= ncols) return;
+    const double s = S[col], smax = S[0];
+    const double sc = (s * s > floor_rel * smax * smax && s > 0.0) ? 1.0 / s : 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) U[i + col * n] = Sx::scale(U[i + col * n], sc);
+}
+
+// UX: n x n, sorted normalised vectors (ld = n); M: n x n Hermitian (ld = n); S: n values (descending)
+template <bool CPLX>
+void ritz_refine(Ctx* c, int64_t n, const void* M, void* UX, double* S) {
+    const DType dt = CPLX ? C64 : F64;
+    const size_t es = CPLX ? 16 : 8;
+    int64_t k = c->svd_refine_cols > 0 && c->svd_refine_cols < n ? c->svd_refine_cols : n;
+    if (k > 4096) return;                       // (ritz_commit_s_kernel holds the k values in shared memory)
+    void* W = alloc(c, (size_t)n * k * es);
+    void* T = alloc(c, (size_t)n * k * es);
+    void* Gm = alloc(c, (size_t)n * k * es);
+    double* Snew = (double*)alloc(c, (size_t)n * 8);      // lam[n]
+    for (int iter = 0; iter < c->knobs.svd_refine_iters; ++iter) {
+    // W = M U_k ; T = U^H W ; Gm = U^H U_k
+    gemm(c, dt, n, k, n, 1.0, M, gg(n, 1), gg(n, n), false, UX, gg(n, 1), gg(k, n), false, 0.0, W, gg(n, 1), gg(k, n));
+    gemm(c, dt, n, k, n, 1.0, UX, gg(n, n), gg(n, 1), true, W, gg(n, 1), gg(k, n), false, 0.0, T, gg(n, 1), gg(k, n));
+    gemm(c, dt, n, k, n, 1.0, UX, gg(n, n), gg(n, 1), true, UX, gg(n, 1), gg(k, n), false, 0.0, Gm, gg(n, 1), gg(k, n));
+    ritz_lambda_kernel<CPLX><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const double*)T, (const double*)Gm, n, k, S, Snew);
+    c->launched("svd_ritz_lambda");
+    ritz_z_kernel<CPLX><<<grid1d(c, n * k), 256, 0, c->stream>>>((const double*)T, (const double*)Gm, n, k, Snew, 3e-8, (double*)W);
+    c->launched("svd_ritz_z");
+    // U_k += U E
+    gemm(c, dt, n, k, n, 1.0, UX, gg(n, 1), gg(n, n), false, W, gg(n, 1), gg(k, n), false, 0.0, T, gg(n, 1), gg(k, n));
+    const int64_t nwords = n * k * (int64_t)(es / 8);
+    add_inplace_kernel<<<grid1d(c, nwords), 256, 0, c->stream>>>((double*)UX, (const double*)T, nwords);
+    c->launched("svd_ritz_add");
+    ritz_commit_s_kernel<<<1, 1024, (size_t)k * 8, c->stream>>>(S, Snew, k, n);
+    c->launched("svd_ritz_s");
+    }
+    release(c, Gm);
+    release(c, W); release(c, T); release(c, Snew);
+}
+
+}  // namespace
+
+namespace {
+
 // `Ah` (n x m, ld = n), when given, is the adjoint of the matrix to factor (the caller's wide original): the Gram
 // path reads it directly and the m x n copy `A` is only materialised (by the caller-supplied buffer rule below) when
 // the Householder path has to run.  A may be null then.
@@ -1304,6 +1214,11 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     bool gram_done = false;
     bool gram_tried = false;
     bool gram_u = false;          // left vectors through U = A V Sigma^-1 (V = left vectors of the Cholesky factor)
+    // Rayleigh-Ritz refinement (ritz_refine above) whenever ONE side of vectors is computed: Mref = X0 X0^H
+    const bool capped = c->svd_refine_cols > 0 && c->svd_refine_cols < n;
+    const bool refine = c->knobs.svd_norefine != 1 && !(c->knobs.svd_norefine == 2 && !capped) && !(c->knobs.svd_norefine == 3 && capped) &&
+                        !acc_v && (want_u || want_v) && n >= 2 * JB;
+    void* Mref = nullptr;
     if (want_u && !want_v && !Ah && allow_gram && !c->knobs.svd_nogram && !(c->knobs.gram_off & 2) && n >= 2 * CHB && m >= 2 * n) {
         // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
         // L = U_X Sigma J^H, i.e. the RIGHT singular vectors of A are U_X and U = A U_X Sigma^-1 - no Q is ever formed.
@@ -1312,6 +1227,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         gemm(c, dt, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
         double ratio = 0.0;
         gram_tried = true;
+        if (refine) { Mref = alloc(c, (size_t)n * n * es); d2d(c, Mref, G, (size_t)n * n * es); }
         gram_u = cholesky_blocked(c, dt, n, G, &ratio, nullptr, 0.125);
         if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld (U): Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_u ? "taken" : "rejected", ratio);
         if (gram_u) {
@@ -1330,6 +1246,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         else gemm(c, dt, n, n, m, 1.0, A, gg(n, m), gg(m, 1), true, A, gg(m, 1), gg(n, m), false, 0.0, G, gg(n, 1), gg(n, n));
         double ratio = 0.0;
         gram_tried = true;
+        if (refine) { Mref = alloc(c, (size_t)n * n * es); d2d(c, Mref, G, (size_t)n * n * es); }
         gram_done = cholesky_blocked(c, dt, n, G, &ratio, nullptr, 0.125);
         if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld: Gram+Cholesky preconditioner %s (diag ratio %.3e)\n", (long long)m, (long long)n, gram_done ? "taken" : "rejected", ratio);
         if (gram_done) {
@@ -1358,6 +1275,11 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         X = (double*)alloc(c, (size_t)pl.ldx * npad * es);
         init_x_kernel<CPLX><<<grid1d(c, pl.ldx * npad), 256, 0, c->stream>>>((const double*)Rm, n, n, pl.ldx, npad, adjoint ? 1 : 0, X);
         c->launched("svd_init_x");
+        if (refine) {
+            if (Mref) release(c, Mref);            // (a rejected Gram attempt left its copy behind)
+            Mref = alloc(c, (size_t)n * n * es);
+            gemm(c, dt, n, n, n, 1.0, X, gg(n, 1), gg(n, pl.ldx), false, X, gg(n, pl.ldx), gg(n, 1), true, 0.0, Mref, gg(n, 1), gg(n, n));
+        }
     }
     double* V = nullptr;
     if (acc_v) {
@@ -1387,6 +1309,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         if (c->knobs.verbose) fprintf(stderr, "[t4b] svd %lld x %lld: Gram route kappa %.3e %s\n", (long long)m, (long long)n, ends[1] > 0.0 ? ends[0] / ends[1] : 0.0, ok ? "accepted" : "REJECTED a posteriori");
         if (!ok) {
             release(c, sig2); release(c, rank); release(c, X);
+            if (Mref) release(c, Mref);
             svd_tall<CPLX>(c, m, n, A, U, S, Vh, Ah, false);
             return;
         }
@@ -1398,8 +1321,15 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         double* UX = (double*)alloc(c, (size_t)n * n * es);
         zero(c, UX, (size_t)n * n * es);
         // Householder / Cholesky-QR path: U = Q U_X.  Gram path: U = A U_X Sigma^-1 = A (x_j / sigma_j^2)
-        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, gram_u ? 2 : 1, 0, UX, n, n, S);
+        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, (gram_u && !refine) ? 2 : 1, 0, UX, n, n, S);
         c->launched("svd_gather_u");
+        if (refine) {
+            ritz_refine<CPLX>(c, n, Mref, UX, S);
+            if (gram_u) {
+                scale_cols_inv_kernel<CPLX><<<(unsigned)n, 128, 0, c->stream>>>(UX, n, n, S, floor_rel);
+                c->launched("svd_scale_cols");
+            }
+        }
         gemm(c, dt, m, n, n, 1.0, gram_u ? A : Q, gg(m, 1), gg(n, m), false, UX, gg(n, 1), gg(n, n), false, 0.0, U,
              gg(m, 1), gg(n, m));
         release(c, UX);
@@ -1410,11 +1340,24 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         }
     } else if (want_v) {
         // X = R^H: right vectors of A are the normalised columns of X; Vh = U_X^H
-        zero(c, Vh, (size_t)n * n * es);
-        gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, 1, 1, (double*)Vh, n, n, S);
-        c->launched("svd_gather_vh");
+        if (refine) {
+            double* UX = (double*)alloc(c, (size_t)n * n * es);
+            zero(c, UX, (size_t)n * n * es);
+            gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, 1, 0, UX, n, n, S);
+            c->launched("svd_gather_vh");
+            ritz_refine<CPLX>(c, n, Mref, UX, S);
+            Group g;
+            g.nd = 2; g.dim[0] = n; g.str[0] = n; g.dim[1] = n; g.str[1] = 1;     // Vh[i,j] = conj(UX[j,i])
+            permute(c, dt, Vh, UX, g, true);
+            release(c, UX);
+        } else {
+            zero(c, Vh, (size_t)n * n * es);
+            gather_cols_kernel<CPLX><<<(unsigned)npad, 128, 0, c->stream>>>(X, pl.ldx, n, npad, rank, sig2, floor_rel, 1, 1, (double*)Vh, n, n, S);
+            c->launched("svd_gather_vh");
+        }
     }
     release(c, sig2); release(c, rank); release(c, X);
+    if (Mref) release(c, Mref);
     if (V) release(c, V);
     if (Rm) release(c, Rm);
     if (Q) release(c, Q);
@@ -1713,6 +1656,12 @@ void svd_small_batched(Ctx* c, DType dt, int64_t batch, const SvdProblem* probs)
     T4B_CUDA_CHECK(cudaGetLastError());
     c->launched("svd_small", 0.0);
     if (dev) release(c, dev);
+}
+
+int64_t svd_set_refine_cols(Ctx* c, int64_t cols) {
+    const int64_t prev = c->svd_refine_cols;
+    c->svd_refine_cols = cols > 0 ? cols : 0;
+    return prev;
 }
 
 void svd_thin(Ctx* c, DType dt, int64_t m, int64_t n, void* A, void* U, double* S, void* Vh) {

@@ -46,11 +46,25 @@ def main():
                          "changes of the input, i.e. the reproducibility floor of the reference algorithm itself")
     ap.add_argument("--perturb-seed", type=lambda s: int(s, 0), default=0xF100D,
                     help="seed of the perturbation (several samples of the floor: run with different seeds and merge each)")
+    ap.add_argument("--step-perturb", type=float, default=0.0,
+                    help="relative size of an i.i.d. perturbation of the matrix of EVERY dense SVD of the sweep (oracle/"
+                         "treetn.py SVD_STEP_PERTURB): emulates a second implementation whose per-factorisation backward "
+                         "error is of that size (LAPACK gesdd's own is ~9e-15 ||A||_2 at these shapes, see "
+                         "--measure-backward-error)")
+    ap.add_argument("--measure-backward-error", action="store_true",
+                    help="print ||A - U S V^T||_2 / ||A||_2 and ||U^T U - I||_2 of the oracle's SVD on a 2048 x 4096 matrix")
     ap.add_argument("--merge-floor", default=None,
                     help="path of a second run (other driver / perturbed input): stores per-step max |s - s'| / s_max into "
                          "--out as `noise_floor`; an existing floor is kept where it is larger (maximum over the samples, "
                          "`noise_floor_samples` counts them)")
     a = ap.parse_args()
+    if a.measure_backward_error:
+        import scipy.linalg as sla
+        A = np.random.default_rng(0).standard_normal((2048, 4096))
+        u, s, vh = sla.svd(A, full_matrices=False, lapack_driver=a.driver)
+        print(f"{a.driver} 2048x4096: ||A - U S V^T||_2 / ||A||_2 = {np.linalg.norm(A - (u * s) @ vh, 2) / s[0]:.2e}, "
+              f"||U^T U - I||_2 = {np.linalg.norm(u.T @ u - np.eye(2048), 2):.2e}")
+        return
     if a.merge_floor:
         g = dict(np.load(a.out))
         h = np.load(a.merge_floor)
@@ -71,6 +85,7 @@ def main():
         print(f"noise floor (second run vs golden): max {max(floor):.2e}, median {np.median(floor):.2e}; norm^2 {float(g['noise_floor_norm_sqr']):.2e}")
         return
     otn.SVD_DRIVER = a.driver
+    otn.SVD_STEP_PERTURB = a.step_perturb
     mps, mi, mpo, oi = make_c3(a.seed, a.L, a.d, a.chi, a.w)
     if a.perturb > 0.0:
         prng = np.random.default_rng(a.perturb_seed)

@@ -54,14 +54,16 @@ def test_c3_full_sweep_matches_oracle_golden(ctx):
     assert out.bond_dims() == [int(x) for x in g["bond_dims"]]
     assert len(got) == len(want) == 189
     # Gate: 1e-12 * sigma_max per step (north_star).  The 189 factorisations are DEPENDENT (every truncation feeds the
-    # next one through a 512-of-2048 cut with relative gaps ~1e-3), so rounding-level differences are amplified along
-    # the sweep in ANY implementation: the golden file holds `noise_floor`, the per-step movement of the ORACLE's own
-    # spectra when every input entry is perturbed by one ulp (make_c3_golden.py --perturb 2.2e-16 --merge-floor:
-    # median 6e-14, 8 steps above 1e-12, max 1.8e-12 at the step where the device deviates most).  One perturbation is
-    # one sample of that sensitivity, and the device rounds differently in every operation, not only in the input:
-    # every step is held to max(2e-12, 4 x the largest sampled floor within +-8 steps); the printed line reports how
-    # many steps exceed the plain 1e-12 (about 35 of 189, all inside the band where the oracle itself moves) and the
-    # worst device / floor ratio (observed 2.4 - 3.4 across builds).
+    # next one through a 512-of-2048 cut with relative gaps ~1e-3), so rounding-level differences are amplified along the
+    # sweep in ANY implementation: the golden file holds `noise_floor`, the per-step movement of the ORACLE's own spectra
+    # under rounding-level changes (make_c3_golden.py: re-runs with every input entry moved by one ulp, four seeds, and one
+    # with a 2e-15 relative perturbation of every SVD input - LAPACK gesdd's own backward error at these shapes is 9e-15;
+    # maximum over the samples: median 9e-14, 12 steps above 1e-12, 2.0e-12 at the most sensitive steps 68 / 183).
+    # Every step is held to 1e-12, or to twice the oracle's own floor (maximum over +-8 neighbouring steps) where that is
+    # larger.  Measured with the Rayleigh-Ritz refinement of the Jacobi vectors (svd.cu ritz_refine): worst step
+    # 9.2e-13 - no step above the plain 1e-12 -, median 2e-14, at most 0.5 x the floor (before the refinement the device
+    # SVD carried a backward error of 1e-13 per factorisation against LAPACK's 9e-15 and the sweep deviated by up to
+    # 1.2e-11, six times the floor; tools/probe_backward_error.py, tools/probe_gram_parity.py).
     floor = g["noise_floor"]
     errs = np.array([float(np.max(np.abs(sg - sw)) / sw[0]) if len(sg) == len(sw) else np.inf
                      for sg, sw in zip(got, want)])
@@ -75,7 +77,7 @@ def test_c3_full_sweep_matches_oracle_golden(ctx):
     worst = float(errs.max())
     worst_ratio = float(np.max(errs / np.maximum(fk, 5e-13)))
     over = int(np.sum(errs > 1e-12))
-    bad = [(k, errs[k], fk[k]) for k in range(len(errs)) if errs[k] > max(2e-12, 4.0 * fk[k])]
+    bad = [(k, errs[k], fk[k]) for k in range(len(errs)) if errs[k] > max(1e-12, 2.0 * fk[k])]
     assert not bad, bad
     n2 = out.norm_sqr()
     assert abs(n2 - float(g["norm_sqr"])) <= 1e-10 * float(g["norm_sqr"])

@@ -23,8 +23,14 @@ floor = g["noise_floor"]
 fk = np.array([floor[max(k - 8, 0):k + 9].max() for k in range(len(floor))])
 mps, mi, mpo, oi = make_c3(seed, L, d, chi, w)
 out = {}
-for mask in [int(x) for x in (sys.argv[1:] or ["0", "1", "2", "4", "7"])]:
+for spec in (sys.argv[1:] or ["0", "1", "2", "4", "7"]):
+    # spec = mask[:norefine[:iters]]
+    parts = spec.split(":")
+    mask = int(parts[0])
     os.environ["T4B_GRAM_OFF"] = str(mask)
+    os.environ["T4B_SVD_NOREFINE"] = parts[1] if len(parts) > 1 else "0"
+    os.environ["T4B_SVD_REFINE_ITERS"] = parts[2] if len(parts) > 2 else "1"
+    mask = spec
     ctx = t4b.Context(0)
     a = t4tt.chain_from_arrays(ctx, mps, mi)
     b = t4tt.chain_from_arrays(ctx, mpo, oi)
