@@ -104,6 +104,10 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.rrlu_bps = geti("T4B_RRLU_BPS", 0);
         k.svd_norefine = geti("T4B_SVD_NOREFINE", 0);
         k.svd_refine_iters = geti("T4B_SVD_REFINE_ITERS", 1);
+        k.jac_tolx = geti("T4B_JAC_TOLX", 2);
+        if (k.jac_tolx < 1) k.jac_tolx = 1;
+        k.jac_rotx = geti("T4B_JAC_ROTX", 8);
+        if (k.jac_rotx < 1) k.jac_rotx = 1;
         k.jac_eig_v2 = geti("T4B_JAC_EIG_V2", 1);
         k.svd_lpp = geti("T4B_SVD_LPP", 0);
         if (k.svd_lpp != 0 && k.svd_lpp != 4 && k.svd_lpp != 8 && k.svd_lpp != 16 && k.svd_lpp != 32) k.svd_lpp = 0;

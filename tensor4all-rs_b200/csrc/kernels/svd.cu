@@ -725,7 +725,7 @@ JPPlan plan_jp(Ctx* c, int64_t nx, int64_t npad, bool with_v) {
 // One-sided block Jacobi on X (ldx x npad, nx live rows); V (ldv x npad) optional.  Asynchronous: the
 // whole iteration (all sweeps, convergence decision included) is one kernel launch.
 template <bool CPLX>
-void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t npad, double* V) {
+void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t npad, double* V, double tol_mult = 1.0, double rot_mult = 1.0) {
     const size_t es = CPLX ? 16 : 8;
     const int p = (int)(npad / JB);
     const int max_sweeps = c->knobs.jac_max_sweeps;
@@ -739,14 +739,17 @@ void jacobi_persistent(Ctx* c, const JPPlan& pl, double* X, int64_t nx, int64_t 
     // |x_i^H x_j| <= tol ||x_i|| ||x_j||.  The cosines come from DMMA Gram blocks (and diagonal blocks carried
     // across rounds), whose rounding noise sits at a few eps sqrt(nx): the factor 4 keeps the target above that
     // floor (measured plateaus: 2.6e-15 at n = 2048, 8.3e-15 at n = 512).
-    const double tol = 4.0 * eps * sqrt((double)(nx > 4 ? nx : 4));
+    // tol_mult > 1: the caller polishes the vectors afterwards (ritz_refine removes couplings of that size exactly),
+    // so cosines between the noise floor and tol_mult x the floor are not chased - the last sweep of a converged
+    // iteration then skips every update instead of rotating on Gram rounding noise.
+    const double tol = tol_mult * 4.0 * eps * sqrt((double)(nx > 4 ? nx : 4));
     JPArgs a{};
     a.X = X; a.ldx = pl.ldx;
     a.V = V; a.ldv = pl.ldv;
     a.p = p; a.cs = pl.cs; a.nclusters = pl.nclusters; a.pairs = pl.pairs;
     a.rpcx = pl.rpcx; a.rpcv = V ? pl.rpcv : 0; a.ch = pl.ch; a.ldp = pl.ldp;
     a.max_sweeps = max_sweeps;
-    a.tol = tol; a.tol_rot = tol * 0.0625;
+    a.tol = tol; a.tol_rot = tol * 0.0625 * rot_mult;
     // off_after <~ n * off_before^2 once the iteration converges quadratically: a sweep that starts
     // below sqrt(0.1 tol / n) leaves the columns orthogonal to working accuracy (n off^2 <= 0.1 tol)
     a.tol_early = sqrt(0.1 * tol / (double)npad);
@@ -1287,7 +1290,7 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
         set_eye_kernel<CPLX><<<grid1d(c, pl.ldv * npad), 256, 0, c->stream>>>(V, pl.ldv, npad);
         c->launched("svd_set_eye");
     }
-    jacobi_persistent<CPLX>(c, pl, X, n, npad, V);
+    jacobi_persistent<CPLX>(c, pl, X, n, npad, V, refine ? (double)c->knobs.jac_tolx : 1.0, refine ? (double)c->knobs.jac_rotx : 1.0);
 
     double* sig2 = (double*)alloc(c, (size_t)npad * 8);
     int64_t* rank = (int64_t*)alloc(c, (size_t)npad * 8);

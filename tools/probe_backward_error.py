@@ -33,7 +33,7 @@ for name, (m, n) in {"zipup_2048x4096": (2048, 4096), "twosite_2048x512": (2048,
     a = np.asfortranarray(rng.standard_normal((m, n)))
     ul, sl, _ = sla.svd(a, full_matrices=False, lapack_driver="gesdd")
     rec = {"lapack_gesdd": quality(a, ul, sl)}
-    for mask, norefine, iters in ((0, False, 1), (0, False, 2), (0, True, 1)):
+    for mask, norefine, iters in ((0, False, 1), (0, True, 1)):
         os.environ["T4B_GRAM_OFF"] = str(mask)
         os.environ.pop("T4B_SVD_NOREFINE", None)
         if norefine:

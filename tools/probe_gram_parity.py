@@ -30,6 +30,10 @@ for spec in (sys.argv[1:] or ["0", "1", "2", "4", "7"]):
     os.environ["T4B_GRAM_OFF"] = str(mask)
     os.environ["T4B_SVD_NOREFINE"] = parts[1] if len(parts) > 1 else "0"
     os.environ["T4B_SVD_REFINE_ITERS"] = parts[2] if len(parts) > 2 else "1"
+    if len(parts) > 3:
+        os.environ["T4B_JAC_TOLX"] = parts[3]
+    if len(parts) > 4:
+        os.environ["T4B_JAC_ROTX"] = parts[4]
     mask = spec
     ctx = t4b.Context(0)
     a = t4tt.chain_from_arrays(ctx, mps, mi)
