@@ -106,6 +106,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.svd_refine_iters = geti("T4B_SVD_REFINE_ITERS", 1);
         k.jac_tolx = geti("T4B_JAC_TOLX", 2);
         if (k.jac_tolx < 1) k.jac_tolx = 1;
+        k.chol_old = getb("T4B_CHOL_OLD");
         k.jac_rotx = geti("T4B_JAC_ROTX", 8);
         if (k.jac_rotx < 1) k.jac_rotx = 1;
         k.jac_eig_v2 = geti("T4B_JAC_EIG_V2", 1);

@@ -976,6 +976,168 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
     if (tid == 0) { stat[0] = dmin; stat[1] = dmax; }
 }
 
+// ---- potrf_inv_fast_kernel: the same contract as potrf_inv_kernel, blocked 16 inside the 64 x 64 block -------------------
+// The right-looking column loop above pays one CTA barrier per column and per phase (128 x ~470 ns = 60 us per block,
+// 32 blocks in a row for n = 2048: the Cholesky chain of the C3 sweep was 195 ms).  Here the only serial scalar work is
+// the factorisation of the four 16 x 16 diagonal blocks by ONE warp (a row per lane, columns broadcast by shuffles, no
+// barrier) together with their inverses; the panel solves, trailing updates and the assembly of the 64 x 64 inverse
+// (recursive 2 x 2 blocking: -B^-1 C A^-1) are small DMMA products on shared-memory operands.
+// C (M8*8 x N8*8) = sum_k a_at(i, k) b_at(k, j), k < K4*4; 8 x 8 tiles over the 8 warps; c_out(i, j, value) per element.
+template <bool CPLX, class FA, class FB, class FC>
+__device__ __forceinline__ void smem_mma(int M8, int N8, int K4, FA a_at, FB b_at, FC c_out, int warp, int lane,
+                                         bool lower_only = false) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    const int grp = lane >> 2, tig = lane & 3;
+    for (int tile = warp; tile < M8 * N8; tile += 8) {
+        const int ti = tile % M8, tj = tile / M8;
+        if (lower_only && ti < tj) continue;
+        T acc[2];
+        acc[0] = acc[1] = S::zero();
+        for (int ks = 0; ks < K4; ++ks) mma_frag<CPLX, false>(acc, a_at(ti * 8 + grp, ks * 4 + tig), b_at(ks * 4 + tig, tj * 8 + grp));
+        c_out(ti * 8 + grp, tj * 8 + 2 * tig, acc[0]);
+        c_out(ti * 8 + grp, tj * 8 + 2 * tig + 1, acc[1]);
+    }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256, 1) potrf_inv_fast_kernel(double* __restrict__ Gd, int64_t ld, int nb,
+                                                                double* __restrict__ Linvd, int* __restrict__ info,
+                                                                double* __restrict__ stat) {
+    typedef Sc<CPLX> S;
+    typedef typename S::T T;
+    T* G = reinterpret_cast<T*>(Gd);
+    T* Linv = reinterpret_cast<T*>(Linvd);
+    constexpr int LP = CHB + 1, TP = 49;
+    extern __shared__ __align__(16) unsigned char chol_smem[];
+    T* As = reinterpret_cast<T*>(chol_smem);            // [CHB][LP] column-major: A / L [i + j * LP]
+    T* Ys = As + (size_t)CHB * LP;                       // [CHB][LP] the inverse under construction
+    T* Tm = Ys + (size_t)CHB * LP;                       // [32 columns][TP] scratch of the small products (<= 48 rows)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int bad;
+    __shared__ double dstat[2];
+    if (tid == 0) { bad = info[0]; dstat[0] = stat[0]; dstat[1] = stat[1]; }
+    for (int e = tid; e < CHB * CHB; e += 256) {
+        const int i = e & (CHB - 1), j = e >> 6;
+        As[i + j * LP] = (i < nb && j < nb && i >= j) ? G[i + (int64_t)j * ld] : (i == j ? S::one() : S::zero());   // identity padding
+        Ys[i + j * LP] = S::zero();
+    }
+    __syncthreads();
+    if (bad) return;
+    for (int kb = 0; kb < CHB; kb += 16) {
+        if (warp == 0) {
+            // ---- 16 x 16 diagonal block: lane r (r < 16; the upper half mirrors it and stays silent) owns row r ----
+            const int r = lane & 15;
+            T a[16];
+            double dinv[16];
+#pragma unroll
+            for (int cc = 0; cc < 16; ++cc) a[cc] = As[(kb + r) + (kb + cc) * LP];
+            bool ok = true;
+            double dmin = dstat[0], dmax = dstat[1];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double d = __shfl_sync(0xffffffffu, S::real(a[j]), j);
+                if (!(d > 0.0) || !isfinite(d)) ok = false;
+                const double inv = rsqrt(d), sd = d * inv;
+                dinv[j] = inv;
+                if (kb + j < nb) { dmin = sd < dmin ? sd : dmin; dmax = sd > dmax ? sd : dmax; }
+                const T l = r > j ? S::scale(a[j], inv) : (r == j ? S::from_real(sd) : S::zero());
+                a[j] = l;
+#pragma unroll
+                for (int cc = j + 1; cc < 16; ++cc) {
+                    const T lc = shfl_t<CPLX>(l, cc);                 // L[cc][j]
+                    a[cc] = S::sub(a[cc], S::mul(l, S::conj(lc)));
+                }
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc) As[(kb + r) + (kb + cc) * LP] = cc <= r ? a[cc] : S::zero();
+            }
+            if (lane == 0) { dstat[0] = dmin; dstat[1] = dmax; if (!ok) bad = 1; }
+            __syncwarp();
+            // inverse of the block, right-looking forward substitution: lane c owns column c of Y = L_d^-1
+            T y[16];
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) y[rr] = rr == r ? S::one() : S::zero();      // residual, starts as e_c
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                y[t] = S::scale(y[t], dinv[t]);
+#pragma unroll
+                for (int rr = t + 1; rr < 16; ++rr) y[rr] = S::sub(y[rr], S::mul(As[(kb + rr) + (kb + t) * LP], y[t]));
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) Ys[(kb + rr) + (kb + r) * LP] = rr >= r ? y[rr] : S::zero();
+            }
+        }
+        __syncthreads();
+        if (bad) {
+            if (tid == 0) info[0] = 1;
+            return;
+        }
+        const int rem = CHB - kb - 16;       // rows below the diagonal block
+        if (rem > 0) {
+            const int r0 = kb + 16;
+            // panel: L_panel = A_panel Y^H  (rem x 16 x 16)
+            smem_mma<CPLX>(rem / 8, 2, 4,
+                           [&](int i, int k) { return As[(r0 + i) + (kb + k) * LP]; },
+                           [&](int k, int j) { return S::conj(Ys[(kb + j) + (kb + k) * LP]); },
+                           [&](int i, int j, T v) { Tm[i + j * TP] = v; }, warp, lane);
+            __syncthreads();
+            for (int e = tid; e < rem * 16; e += 256) {
+                const int i = e % rem, j = e / rem;
+                As[(r0 + i) + (kb + j) * LP] = Tm[i + j * TP];
+            }
+            __syncthreads();
+            // trailing block -= panel panel^H (lower tiles)
+            smem_mma<CPLX>(rem / 8, rem / 8, 4,
+                           [&](int i, int k) { return As[(r0 + i) + (kb + k) * LP]; },
+                           [&](int k, int j) { return S::conj(As[(r0 + j) + (kb + k) * LP]); },
+                           [&](int i, int j, T v) { As[(r0 + i) + (r0 + j) * LP] = S::sub(As[(r0 + i) + (r0 + j) * LP], v); },
+                           warp, lane, true);
+            __syncthreads();
+        }
+    }
+    // L back to global memory (lower triangle only)
+    for (int e = tid; e < CHB * CHB; e += 256) {
+        const int i = e & (CHB - 1), j = e >> 6;
+        if (i < nb && j < nb && i >= j) G[i + (int64_t)j * ld] = As[e - j * CHB + j * LP];
+    }
+    // ---- inverse: Ys holds the four diagonal inverses.  Level 1: X10 = -Y1 (L10 Y0), X32 = -Y3 (L32 Y2) -------------------
+    for (int h = 0; h < 2; ++h) {
+        const int o = 32 * h;            // block rows o+16.., block column o..
+        smem_mma<CPLX>(2, 2, 4,
+                       [&](int i, int k) { return As[(o + 16 + i) + (o + k) * LP]; },
+                       [&](int k, int j) { return Ys[(o + k) + (o + j) * LP]; },
+                       [&](int i, int j, T v) { Tm[(16 * h + i) + j * TP] = v; }, warp, lane);
+    }
+    __syncthreads();
+    for (int h = 0; h < 2; ++h) {
+        const int o = 32 * h;
+        smem_mma<CPLX>(2, 2, 4,
+                       [&](int i, int k) { return Ys[(o + 16 + i) + (o + 16 + k) * LP]; },
+                       [&](int k, int j) { return Tm[(16 * h + k) + j * TP]; },
+                       [&](int i, int j, T v) { Ys[(o + 16 + i) + (o + j) * LP] = S::neg(v); }, warp, lane);
+    }
+    __syncthreads();
+    // Level 2: bottom-left 32 x 32 = -B^-1 (C A^-1), A^-1 = Ys[0:32, 0:32], B^-1 = Ys[32:64, 32:64], C = L[32:64, 0:32]
+    smem_mma<CPLX>(4, 4, 8,
+                   [&](int i, int k) { return As[(32 + i) + k * LP]; },
+                   [&](int k, int j) { return Ys[k + j * LP]; },
+                   [&](int i, int j, T v) { Tm[i + j * TP] = v; }, warp, lane);
+    __syncthreads();
+    smem_mma<CPLX>(4, 4, 8,
+                   [&](int i, int k) { return Ys[(32 + i) + (32 + k) * LP]; },
+                   [&](int k, int j) { return Tm[k + j * TP]; },
+                   [&](int i, int j, T v) { Ys[(32 + i) + j * LP] = S::neg(v); }, warp, lane);
+    __syncthreads();
+    for (int e = tid; e < CHB * CHB; e += 256) {
+        const int i = e & (CHB - 1), j = e >> 6;
+        if (i < nb && j < nb) Linv[i + (size_t)j * nb] = i >= j ? Ys[i + j * LP] : S::zero();
+    }
+    if (tid == 0) { stat[0] = dstat[0]; stat[1] = dstat[1]; }
+}
+
 // X (ldx x npad) = lower triangle of L (n x n, ld = ldl), zero elsewhere
 template <bool CPLX>
 __global__ void init_x_lower_kernel(const double* __restrict__ Ld, int64_t ldl, int64_t n, int64_t ldx, int64_t npad,
@@ -1008,9 +1170,11 @@ bool cholesky_blocked(Ctx* c, DType dt, int64_t n, void* Gv, double* ratio_out, 
     }
     char* Linv1 = linv_all ? nullptr : (char*)alloc(c, (size_t)CHB * CHB * es);
     char* Pc = n > CHB ? (char*)alloc(c, (size_t)(n - CHB) * CHB * es) : nullptr;
-    const size_t smem = (size_t)CHB * (CHB + 1) * es + (size_t)2 * CHB * es + (size_t)CHB * 8;
-    auto kr = potrf_inv_kernel<false>;
-    auto kc = potrf_inv_kernel<true>;
+    const bool fast = !c->knobs.chol_old;
+    const size_t smem = fast ? ((size_t)2 * CHB * (CHB + 1) + (size_t)49 * 32) * es
+                             : (size_t)CHB * (CHB + 1) * es + (size_t)2 * CHB * es + (size_t)CHB * 8;
+    auto kr = fast ? potrf_inv_fast_kernel<false> : potrf_inv_kernel<false>;
+    auto kc = fast ? potrf_inv_fast_kernel<true> : potrf_inv_kernel<true>;
     if (c->first_use(dt == C64 ? (const void*)kc : (const void*)kr))
         T4B_CUDA_CHECK(cudaFuncSetAttribute(dt == C64 ? (const void*)kc : (const void*)kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t k = 0; k < n; k += CHB) {
