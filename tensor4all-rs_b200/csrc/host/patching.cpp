@@ -61,7 +61,7 @@ std::vector<char> truncate_adaptive(dla::Ctx* c, std::vector<ChainTN*>& patches,
     std::vector<double> norms(patches.size());
     if (batched) canonicalize_batched(c, patches, center, &norms);
     else
-        for (size_t i = 0; i < patches.size(); ++i) norms[i] = norm_sqr(c, *patches[i]);
+        parallel_for_independent(c, patches.size(), [&](dla::Ctx* wc, size_t i) { norms[i] = norm_sqr(wc, *patches[i]); });
     AdaptivePlan plan = adaptive_cutoffs(norms, volume, cutoff);
     std::vector<size_t> kept;
     for (size_t i = 0; i < patches.size(); ++i)

@@ -91,8 +91,12 @@ ShardedResult truncate_adaptive_sharded(dla::Ctx* c, void* comm_v, int rank, int
         canonicalize_batched(c, owned, center, &nl);
         for (size_t k = 0; k < owned.size(); ++k) norms[owned_ix[k]] = nl[k];
     } else {
-        for (size_t i = 0; i < n; ++i)
-            if (owner[i] == rank) norms[i] = norm_sqr(c, *patches[i]);
+        // independent per patch (the reference's patch_stats_and_totals loop, patching.rs:883-897): spread over the
+        // worker contexts like the truncation below; every norm is computed by the same kernels whichever context runs
+        // it, so the vector - and with it the cutoffs - is bit-identical to the serial loop
+        parallel_for_independent(c, owned.size(), [&](dla::Ctx* wc, size_t k) {
+            norms[owned_ix[k]] = norm_sqr(wc, *owned[k]);
+        });
     }
     // chain length and dtype must agree across ranks (a rank may own nothing): carried in two extra slots
     std::vector<double> hdr(n + 2, 0.0);

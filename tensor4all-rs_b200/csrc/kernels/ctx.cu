@@ -104,6 +104,8 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.rrlu_bps = geti("T4B_RRLU_BPS", 0);
         k.svd_norefine = geti("T4B_SVD_NOREFINE", 0);
         k.svd_refine_iters = geti("T4B_SVD_REFINE_ITERS", 1);
+        k.svd_refine_min = geti("T4B_SVD_REFINE_MIN", 320);
+        if (k.svd_refine_min < 32) k.svd_refine_min = 32;
         k.jac_tolx = geti("T4B_JAC_TOLX", 2);
         if (k.jac_tolx < 1) k.jac_tolx = 1;
         k.chol_old = getb("T4B_CHOL_OLD");

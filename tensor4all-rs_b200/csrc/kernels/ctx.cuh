@@ -44,6 +44,7 @@ struct Knobs {
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
     int svd_norefine = 0;         // T4B_SVD_NOREFINE: 1 = skip the Rayleigh-Ritz refinement of the Jacobi vectors, 2 = refine only under a bond cap (k < n), 3 = refine only without one (A/B only)
     int svd_refine_iters = 1;     // T4B_SVD_REFINE_ITERS
+    int svd_refine_min = 320;     // T4B_SVD_REFINE_MIN: smallest n the refinement is applied to
     int jac_tolx = 2;             // T4B_JAC_TOLX: multiplier of the Jacobi tolerance when the vectors are refined afterwards
     bool chol_old = false;        // T4B_CHOL_OLD: the column-by-column diagonal-block kernel of the blocked Cholesky (A/B only)
     int jac_rotx = 8;             // T4B_JAC_ROTX: multiplier of the rotation threshold (tol / 16) in that case

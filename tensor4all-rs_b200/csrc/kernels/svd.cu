@@ -1381,10 +1381,12 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     bool gram_done = false;
     bool gram_tried = false;
     bool gram_u = false;          // left vectors through U = A V Sigma^-1 (V = left vectors of the Cholesky factor)
-    // Rayleigh-Ritz refinement (ritz_refine above) whenever ONE side of vectors is computed: Mref = X0 X0^H
+    // Rayleigh-Ritz refinement (ritz_refine above) whenever ONE side of vectors is computed: Mref = X0 X0^H.  Only from
+    // n = 320 on (T4B_SVD_REFINE_MIN): the accumulated rounding it removes grows with the number of rotations per column
+    // (sqrt(sweeps * n / 16)), and below that its seven launches cost more than they buy (C5, chi <= 256: -6 %)
     const bool capped = c->svd_refine_cols > 0 && c->svd_refine_cols < n;
     const bool refine = c->knobs.svd_norefine != 1 && !(c->knobs.svd_norefine == 2 && !capped) && !(c->knobs.svd_norefine == 3 && capped) &&
-                        !acc_v && (want_u || want_v) && n >= 2 * JB;
+                        !acc_v && (want_u || want_v) && n >= c->knobs.svd_refine_min;
     void* Mref = nullptr;
     if (want_u && !want_v && !Ah && allow_gram && !c->knobs.svd_nogram && !(c->knobs.gram_off & 2) && n >= 2 * CHB && m >= 2 * n) {
         // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
