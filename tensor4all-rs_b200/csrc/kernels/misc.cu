@@ -78,15 +78,66 @@ int grid_of(Ctx* c, int64_t total) {
 
 }  // namespace
 
+namespace {
+constexpr int64_t kTrsmLeaf = 128;      // largest triangle the one-thread-per-vector kernel solves directly
+
+Group tg1(int64_t dim, int64_t str) {
+    Group g;
+    g.nd = 1; g.dim[0] = dim; g.str[0] = str;
+    return g;
+}
+
+// Blocked solve (round 2): M = [[M11, 0], [M21, M22]] (effective lower) => x1 = M11^-1 b1, b2 -= M21 x1, x2 = M22^-1 b2
+// (mirrored for the effective upper case); the off-diagonal update is ONE DMMA GEMM over all right-hand sides, only
+// triangles of at most kTrsmLeaf rows reach the serial kernel.  M(i,j) = tr ? T[j,i] : T[i,j]; the vectors are the
+// columns of X (left side) or its rows (right side).
+void trsm_rec(Ctx* c, DType dt, bool left_side, bool lower, bool transpose, bool unit_diag, int64_t n, int64_t nrhs,
+              const char* T, int64_t ldt, char* X, int64_t ldx) {
+    const size_t es = dt == C64 ? 16 : 8;
+    if (n <= kTrsmLeaf) {
+        int grid = (int)((nrhs + 63) / 64);
+        if (dt == C64)
+            trsm_kernel<true><<<grid, 64, 0, c->stream>>>(left_side, lower, transpose, unit_diag, n, nrhs, (const double*)T, ldt, (double*)X, ldx);
+        else
+            trsm_kernel<false><<<grid, 64, 0, c->stream>>>(left_side, lower, transpose, unit_diag, n, nrhs, (const double*)T, ldt, (double*)X, ldx);
+        c->launched("trsm");
+        return;
+    }
+    const bool tr = left_side ? transpose : !transpose;
+    const bool eff_lower = lower != tr;
+    const int64_t n1 = ((n / 2 + 63) / 64) * 64, n2 = n - n1;
+    const char* T22 = T + (size_t)(n1 + n1 * ldt) * es;
+    char* X2 = X + (size_t)n1 * (left_side ? 1 : ldx) * es;
+    const int64_t si = tr ? ldt : 1, sj = tr ? 1 : ldt;      // strides of M along its row / column index
+    auto update = [&](bool second_from_first) {
+        // second_from_first: b2 -= M21 x1 (M21 = M[n1:, :n1]); otherwise b1 -= M12 x2 (M12 = M[:n1, n1:])
+        const int64_t rows = second_from_first ? n2 : n1, cols = second_from_first ? n1 : n2;
+        const char* Mo = second_from_first ? T + (size_t)(n1 * si) * es : T + (size_t)(n1 * sj) * es;
+        char* dst = second_from_first ? X2 : X;
+        const char* src = second_from_first ? X : X2;
+        if (left_side)
+            gemm(c, dt, rows, nrhs, cols, -1.0, Mo, tg1(rows, si), tg1(cols, sj), false, src, tg1(cols, 1), tg1(nrhs, ldx), false,
+                 1.0, dst, tg1(rows, 1), tg1(nrhs, ldx));
+        else
+            gemm(c, dt, nrhs, rows, cols, -1.0, src, tg1(nrhs, 1), tg1(cols, ldx), false, Mo, tg1(cols, sj), tg1(rows, si), false,
+                 1.0, dst, tg1(nrhs, 1), tg1(rows, ldx));
+    };
+    if (eff_lower) {
+        trsm_rec(c, dt, left_side, lower, transpose, unit_diag, n1, nrhs, T, ldt, X, ldx);
+        update(true);
+        trsm_rec(c, dt, left_side, lower, transpose, unit_diag, n2, nrhs, T22, ldt, X2, ldx);
+    } else {
+        trsm_rec(c, dt, left_side, lower, transpose, unit_diag, n2, nrhs, T22, ldt, X2, ldx);
+        update(false);
+        trsm_rec(c, dt, left_side, lower, transpose, unit_diag, n1, nrhs, T, ldt, X, ldx);
+    }
+}
+}  // namespace
+
 void trsm(Ctx* c, DType dt, bool left_side, bool lower, bool transpose, bool unit_diag, int64_t n,
           int64_t nrhs, const void* T, int64_t ldt, void* X, int64_t ldx) {
     if (n == 0 || nrhs == 0) return;
-    int grid = (int)((nrhs + 63) / 64);
-    if (dt == C64)
-        trsm_kernel<true><<<grid, 64, 0, c->stream>>>(left_side, lower, transpose, unit_diag, n, nrhs, (const double*)T, ldt, (double*)X, ldx);
-    else
-        trsm_kernel<false><<<grid, 64, 0, c->stream>>>(left_side, lower, transpose, unit_diag, n, nrhs, (const double*)T, ldt, (double*)X, ldx);
-    c->launched("trsm");
+    trsm_rec(c, dt, left_side, lower, transpose, unit_diag, n, nrhs, (const char*)T, ldt, (char*)X, ldx);
 }
 
 void permute_rows(Ctx* c, DType dt, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,

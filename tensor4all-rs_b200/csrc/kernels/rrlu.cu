@@ -50,6 +50,8 @@ struct RrluArgs {
     Cand* cand;                 // 2 x gridDim
     int* out_npivot;
     double* out_error;
+    unsigned char* gws;         // per-block replicas in GLOBAL memory when they exceed shared memory (else null)
+    size_t gws_stride;          // bytes per block
 };
 
 __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
@@ -92,8 +94,10 @@ __global__ void __launch_bounds__(LT) rrlu_kernel(RrluArgs a) {
     constexpr int NW = LT / 32;
     const int m = a.m, n = a.n;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // per-block replicas of the permutations + the pivot column of the previous step
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // per-block replicas of the permutations + the pivot column of the previous step: shared memory up to m + n ~ 16 k,
+    // a private slice of a global workspace beyond (the pass then reads them through L1/L2; the matrix traffic dominates)
+    unsigned char* smem_raw = a.gws ? a.gws + (size_t)blockIdx.x * a.gws_stride : smem_dyn;
     int* rp = reinterpret_cast<int*>(smem_raw);       // logical -> physical rows  [m]
     int* rinv = rp + m;                               // physical -> logical       [m]
     int* cp = rinv + m;                               // [n]
@@ -309,14 +313,15 @@ int64_t rrlu(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t max_rank, 
     const bool cplx = dt == C64;
     const size_t es = dtype_size(dt);
     const int64_t kcap = std::min<int64_t>(max_rank, std::min(m, n));
-    size_t smem = (((size_t)(2 * m + 2 * n) * sizeof(int) + 15) / 16) * 16 + (size_t)m * es;
-    if (smem > 200 * 1024)
-        throw Error(ST_UNSUPPORTED, "rrlu: matrix too large for the shared-memory permutation replicas");
+    const size_t replica = (((size_t)(2 * m + 2 * n) * sizeof(int) + 15) / 16) * 16 + (size_t)m * es;
+    const bool replicas_global = replica > 200 * 1024;
+    size_t smem = replicas_global ? 0 : replica;
 
     auto kern_r = rrlu_kernel<false>;
     auto kern_c = rrlu_kernel<true>;
     const void* kern = cplx ? (const void*)kern_c : (const void*)kern_r;
-    T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->first_use(kern))      // once per context (the attribute is per device): room for the largest shared-memory replica
+        T4B_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0;
     T4B_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LT, smem));
     if (per_sm < 1) throw Error(ST_CUDA_ERROR, "rrlu: kernel does not fit on an SM");
@@ -348,9 +353,16 @@ int64_t rrlu(Ctx* c, DType dt, int64_t m, int64_t n, void* A, int64_t max_rank, 
     a.A = (double*)A; a.m = (int)m; a.n = (int)n; a.max_rank = (int)kcap;
     a.rel_tol = rel_tol; a.abs_tol = abs_tol; a.left_orth = left_orthogonal ? 1 : 0;
     a.rp = rp; a.cp = cp; a.pv = pv; a.cand = cand; a.out_npivot = d_np; a.out_error = d_err;
+    unsigned char* gws = nullptr;
+    if (replicas_global) {
+        a.gws_stride = (replica + 255) / 256 * 256;
+        gws = (unsigned char*)alloc(c, a.gws_stride * (size_t)grid);
+        a.gws = gws;
+    }
     void* params[] = {&a};
     T4B_CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(LT), params, smem, c->stream));
     c->launched("rrlu");
+    if (gws) release(c, gws);     // stream-ordered allocator: the block is not handed out before the kernel has run
 
     struct { int np; int pad; double err; } host;
     d2h(c, &host, d_np, 16);

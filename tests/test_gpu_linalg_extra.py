@@ -89,6 +89,29 @@ def test_trsm_left(ctx, lower, transpose):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("left_side", [False, True])
+@pytest.mark.parametrize("lower", [False, True])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_trsm_blocked(ctx, lower, transpose, left_side, cplx):
+    """Triangles beyond the leaf size take the blocked path (diagonal solves + one GEMM per off-diagonal block):
+    all side / uplo / transpose combinations, unit and non-unit diagonal, against LAPACK trtrs."""
+    rng = np.random.default_rng(11)
+    n, nrhs = 333, 77
+    t = _rand(rng, (n, n), cplx) / np.sqrt(n)
+    t = np.tril(t) if lower else np.triu(t)
+    t = np.asfortranarray(t + 2.0 * np.eye(n))
+    b = _rand(rng, (n, nrhs) if left_side else (nrhs, n), cplx)
+    for unit in (False, True):
+        x = ctx.trsm(ctx.upload(t), ctx.upload(b), left_side=left_side, lower=lower, transpose=transpose,
+                     unit_diagonal=unit).get()
+        if left_side:      # op(T) X = B
+            ref = sla.solve_triangular(t, b, lower=lower, trans=1 if transpose else 0, unit_diagonal=unit)
+        else:              # X op(T) = B  <=>  op(T)^T X^T = B^T
+            ref = sla.solve_triangular(t, b.T, lower=lower, trans=0 if transpose else 1, unit_diagonal=unit).T
+        assert np.linalg.norm(x - ref) <= 1e-11 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_einsum_zipup_step(ctx, cplx):
     """nab,askc,bktd->nstcd: the zip-up site contraction (simplett/src/mpo/contract_zipup.rs:118-141)."""
     rng = np.random.default_rng(8)

@@ -74,6 +74,18 @@ def test_random_low_rank(ctx, shape, cplx, lo):
     _check(ctx, a, max_bond_dim=max(1, r // 2), left_orthogonal=lo)
 
 
+@pytest.mark.parametrize("shape", [(20000, 40), (48, 30000)])
+def test_beyond_the_shared_memory_replicas(ctx, shape):
+    """m + n beyond ~16 k: the per-block permutation replicas and the pivot column move from shared memory to a global
+    workspace (rrlu.cu); pivots, permutations and factors stay bit-identical to the oracle."""
+    rng = np.random.default_rng(shape[0] + shape[1])
+    m, n = shape
+    r = 12
+    a = rng.standard_normal((m, r)) @ rng.standard_normal((r, n))
+    _check(ctx, a, rel_tol=1e-10)
+    _check(ctx, a, max_bond_dim=7, left_orthogonal=False)
+
+
 def test_ties_follow_column_major_first_max(ctx):
     """Exactly tied candidates: the reference keeps the first maximum in column-major order."""
     a = np.ones((6, 6))
