@@ -1386,7 +1386,8 @@ void svd_tall(Ctx* c, int64_t m, int64_t n, void* A, void* U, double* S, void* V
     // (sqrt(sweeps * n / 16)), and below that its seven launches cost more than they buy (C5, chi <= 256: -6 %)
     const bool capped = c->svd_refine_cols > 0 && c->svd_refine_cols < n;
     const bool refine = c->knobs.svd_norefine != 1 && !(c->knobs.svd_norefine == 2 && !capped) && !(c->knobs.svd_norefine == 3 && capped) &&
-                        !acc_v && (want_u || want_v) && n >= c->knobs.svd_refine_min;
+                        !acc_v && (want_u || want_v) && n >= c->knobs.svd_refine_min &&
+                        (capped ? c->svd_refine_cols : n) <= 4096;     // (ritz_commit_s_kernel keeps the values in shared memory)
     void* Mref = nullptr;
     if (want_u && !want_v && !Ah && allow_gram && !c->knobs.svd_nogram && !(c->knobs.gram_off & 2) && n >= 2 * CHB && m >= 2 * n) {
         // Tall, left vectors only (two-site truncation steps): A^H A = L L^H, Jacobi on the columns of L gives
