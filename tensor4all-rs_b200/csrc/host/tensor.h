@@ -26,6 +26,9 @@ struct Buffer {
     bool owned;
     Buffer(dla::Ctx* c, size_t b) : ctx(c), p(dla::alloc(c, b)), bytes(b), owned(true) {}
     Buffer(dla::Ctx* c, void* ext, size_t b) : ctx(c), p(ext), bytes(b), owned(false) {}
+    // a view into `parent` (kept alive as long as the view lives): site tensors carved out of one receive buffer
+    Buffer(std::shared_ptr<Buffer> parent_, void* at, size_t b) : ctx(parent_->ctx), p(at), bytes(b), owned(false), parent(std::move(parent_)) {}
+    std::shared_ptr<Buffer> parent;
     ~Buffer() {
         if (owned) {
             try { dla::release(ctx, p); } catch (...) {}
