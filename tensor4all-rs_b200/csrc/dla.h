@@ -47,7 +47,7 @@ void release(Ctx*, void* p);
 // Child contexts on the same device (own stream, own allocator), created on first use and owned by `parent`: the
 // executors of parallel_for_independent() (host/parallel.h).  set_foreign_owner / flush_deferred: see ctx.cu.
 std::vector<Ctx*> ctx_workers(Ctx* parent, int k);
-int ctx_patch_workers(Ctx*);   // T4B_PATCH_WORKERS (default: host threads per visible GPU, clamped to 2..8)
+int ctx_patch_workers(Ctx*);   // T4B_PATCH_WORKERS (default: host threads per visible GPU, clamped to 2..12)
 bool ctx_patch_batched(Ctx*);  // T4B_PATCH_BATCHED (default 1): batched sweeps over the patches of a partitioned TreeTN
 void set_foreign_owner(Ctx* parent);
 void flush_deferred(Ctx* parent);

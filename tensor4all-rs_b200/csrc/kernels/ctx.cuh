@@ -38,7 +38,7 @@ struct Knobs {
     bool svd_nogram = false;      // T4B_SVD_NOGRAM: never take the Gram + Cholesky preconditioner
     int gram_off = 0;             // T4B_GRAM_OFF bit mask: 1 = R-only (wide / right-vector) SVD route off, 2 = tall U = A V S^-1 route off, 4 = Cholesky QR off
     int svd_small_single_max = 32;   // T4B_SVD_SMALL_MAX: largest min(m, n) a SINGLE svd_thin sends to the one-CTA kernel
-    int patch_workers = 4;        // T4B_PATCH_WORKERS: host threads (child contexts) for independent patches / groups (default: host threads per GPU, 2..8)
+    int patch_workers = 4;        // T4B_PATCH_WORKERS: host threads (child contexts) for independent patches / groups (default: host threads per GPU, 2..12)
     bool patch_batched = true;    // T4B_PATCH_BATCHED=0: one launch chain per patch (worker threads) instead of the batched sweeps
     int rrlu_bps = 0;             // T4B_RRLU_BPS: resident prrLU blocks per SM (0 = planned from the matrix size)
     int svd_lpp = 0;              // T4B_SVD_LPP (lanes per column pair of the single-CTA SVD; 0 = planned)
