@@ -78,7 +78,7 @@ Ctx* ctx_create(int device, void* cuda_stream) {
         k.verbose = getenv("T4B_VERBOSE") ? (atoi(getenv("T4B_VERBOSE")) > 0 ? atoi(getenv("T4B_VERBOSE")) : (getenv("T4B_VERBOSE")[0] == '0' ? 0 : 1)) : 0;
         k.jac_smemcap_kb = (size_t)geti("T4B_JAC_SMEMCAP", 0);
         k.jac_cs = geti("T4B_JAC_CS", 0);
-        k.jac_max_sweeps = geti("T4B_JAC_MAXSWEEPS", 40);
+        k.jac_max_sweeps = geti("T4B_JAC_MAXSWEEPS", 100);
         k.jac_inner = geti("T4B_JAC_INNER", 1);
         k.jac_eig_serial = getb("T4B_JAC_EIG_SERIAL");
         k.jac_coop = geti("T4B_JAC_COOP", 1);

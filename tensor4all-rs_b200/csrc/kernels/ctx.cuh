@@ -27,7 +27,7 @@ struct Knobs {
     int verbose = 0;              // T4B_VERBOSE
     size_t jac_smemcap_kb = 0;    // T4B_JAC_SMEMCAP (0 = full 227 KB)
     int jac_cs = 0;               // T4B_JAC_CS (0 = planned)
-    int jac_max_sweeps = 40;      // T4B_JAC_MAXSWEEPS
+    int jac_max_sweeps = 100;     // T4B_JAC_MAXSWEEPS (graded spectra on the un-pivoted R factor contract slowly: 1e-10 grading at n = 352 needs 41 sweeps)
     int jac_inner = 1;            // T4B_JAC_INNER
     bool jac_eig_serial = false;  // T4B_JAC_EIG_SERIAL
     int jac_coop = 1;             // T4B_JAC_COOP (default 1: cooperative, gang-scheduled launch; 0 for Nsight Compute replay)

@@ -113,6 +113,58 @@ def test_svd_c3_zipup_shape_full_size(ctx):
     assert np.max(np.abs(np.linalg.norm(b, axis=1) - s_ref[:r])) <= 1e-11 * s_ref[0]
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("side", ["u", "vh"])
+@pytest.mark.parametrize("kind", ["odd", "rank_deficient", "clusters", "graded"])
+def test_svd_refined_edge_cases(ctx, kind, side, cplx):
+    """One side of vectors and min(m, n) >= 320: the Jacobi vectors are polished by the Rayleigh-Ritz refinement
+    (svd.cu ritz_refine).  Its guards - pairs closer than the error itself, vectors zeroed at the noise floor, graded
+    spectra (Rayleigh quotients only where their absolute noise is below the iteration's relative error), odd sizes -
+    are exercised here: values against LAPACK, orthonormality and the projection identity on the significant part."""
+    rng = np.random.default_rng(77)
+
+    def rnd(*shape):
+        return rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if cplx else 0.0)
+
+    sv = None
+    if kind == "odd":
+        a = rnd(700, 333)
+    elif kind == "rank_deficient":
+        a = rnd(600, 100) @ rnd(100, 400)
+    else:
+        m, n = (640, 384) if kind == "clusters" else (500, 352)
+        qa, _ = np.linalg.qr(rnd(m, n))
+        qb, _ = np.linalg.qr(rnd(n, n))
+        sv = np.repeat([3.0, 2.0, 1.0, 0.5], n // 4) if kind == "clusters" else np.logspace(0, -10, n)
+        a = (qa * sv) @ qb.conj().T
+        if kind == "clusters":
+            a = a + 1e-9 * rnd(m, n)          # nearly (not exactly) degenerate
+    a = np.asfortranarray(a)
+    u, s, vh = ctx.svd_thin(ctx.upload(a), want_u=side == "u", want_vh=side == "vh")
+    s = s.get()
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert np.all(np.diff(s) <= 0)
+    assert np.max(np.abs(s - s_ref)) <= 1e-12 * s_ref[0]
+    if kind == "graded":
+        assert np.max(np.abs(s - sv) / sv) <= 1e-3     # high relative accuracy survives the refinement
+    sig = s_ref > 1e-8 * s_ref[0]
+    k = int(sig.sum())
+    if side == "u":
+        q = u.get()[:, :k]
+        proj = q.conj().T @ a                    # rows sigma_i v_i^H
+        norms = np.linalg.norm(proj, axis=1)
+    else:
+        q = vh.get()[:k, :].conj().T
+        proj = a @ q                             # columns sigma_i u_i
+        norms = np.linalg.norm(proj, axis=0)
+    assert np.all(np.isfinite(q))
+    assert np.linalg.norm(q.conj().T @ q - np.eye(k), 2) <= 1e-11
+    assert np.max(np.abs(norms - s_ref[:k])) <= 1e-11 * s_ref[0]
+    # the significant part of A lives in the span: ||A - P A|| is the tail of the spectrum
+    resid = a - (q @ proj if side == "u" else proj @ q.conj().T)
+    assert np.linalg.norm(resid, 2) <= s_ref[k] + 1e-11 * s_ref[0] if k < len(s_ref) else np.linalg.norm(resid, 2) <= 1e-11 * s_ref[0]
+
+
 def test_svd_degenerate_clusters(ctx):
     """Repeated singular values (only linear contraction inside the cluster): the early-exit heuristic of the
     Jacobi iteration must not fire; U and V stay orthonormal to working accuracy."""
