@@ -1338,21 +1338,21 @@ void ritz_refine(Ctx* c, int64_t n, const void* M, void* UX, double* S) {
     void* Gm = alloc(c, (size_t)n * k * es);
     double* Snew = (double*)alloc(c, (size_t)n * 8);      // lam[n]
     for (int iter = 0; iter < c->knobs.svd_refine_iters; ++iter) {
-    // W = M U_k ; T = U^H W ; Gm = U^H U_k
-    gemm(c, dt, n, k, n, 1.0, M, gg(n, 1), gg(n, n), false, UX, gg(n, 1), gg(k, n), false, 0.0, W, gg(n, 1), gg(k, n));
-    gemm(c, dt, n, k, n, 1.0, UX, gg(n, n), gg(n, 1), true, W, gg(n, 1), gg(k, n), false, 0.0, T, gg(n, 1), gg(k, n));
-    gemm(c, dt, n, k, n, 1.0, UX, gg(n, n), gg(n, 1), true, UX, gg(n, 1), gg(k, n), false, 0.0, Gm, gg(n, 1), gg(k, n));
-    ritz_lambda_kernel<CPLX><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const double*)T, (const double*)Gm, n, k, S, Snew);
-    c->launched("svd_ritz_lambda");
-    ritz_z_kernel<CPLX><<<grid1d(c, n * k), 256, 0, c->stream>>>((const double*)T, (const double*)Gm, n, k, Snew, 3e-8, (double*)W);
-    c->launched("svd_ritz_z");
-    // U_k += U E
-    gemm(c, dt, n, k, n, 1.0, UX, gg(n, 1), gg(n, n), false, W, gg(n, 1), gg(k, n), false, 0.0, T, gg(n, 1), gg(k, n));
-    const int64_t nwords = n * k * (int64_t)(es / 8);
-    add_inplace_kernel<<<grid1d(c, nwords), 256, 0, c->stream>>>((double*)UX, (const double*)T, nwords);
-    c->launched("svd_ritz_add");
-    ritz_commit_s_kernel<<<1, 1024, (size_t)k * 8, c->stream>>>(S, Snew, k, n);
-    c->launched("svd_ritz_s");
+        // W = M U_k ; T = U^H W ; Gm = U^H U_k
+        gemm(c, dt, n, k, n, 1.0, M, gg(n, 1), gg(n, n), false, UX, gg(n, 1), gg(k, n), false, 0.0, W, gg(n, 1), gg(k, n));
+        gemm(c, dt, n, k, n, 1.0, UX, gg(n, n), gg(n, 1), true, W, gg(n, 1), gg(k, n), false, 0.0, T, gg(n, 1), gg(k, n));
+        gemm(c, dt, n, k, n, 1.0, UX, gg(n, n), gg(n, 1), true, UX, gg(n, 1), gg(k, n), false, 0.0, Gm, gg(n, 1), gg(k, n));
+        ritz_lambda_kernel<CPLX><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const double*)T, (const double*)Gm, n, k, S, Snew);
+        c->launched("svd_ritz_lambda");
+        ritz_z_kernel<CPLX><<<grid1d(c, n * k), 256, 0, c->stream>>>((const double*)T, (const double*)Gm, n, k, Snew, 3e-8, (double*)W);
+        c->launched("svd_ritz_z");
+        // U_k += U E
+        gemm(c, dt, n, k, n, 1.0, UX, gg(n, 1), gg(n, n), false, W, gg(n, 1), gg(k, n), false, 0.0, T, gg(n, 1), gg(k, n));
+        const int64_t nwords = n * k * (int64_t)(es / 8);
+        add_inplace_kernel<<<grid1d(c, nwords), 256, 0, c->stream>>>((double*)UX, (const double*)T, nwords);
+        c->launched("svd_ritz_add");
+        ritz_commit_s_kernel<<<1, 1024, (size_t)k * 8, c->stream>>>(S, Snew, k, n);
+        c->launched("svd_ritz_s");
     }
     release(c, Gm);
     release(c, W); release(c, T); release(c, Snew);
