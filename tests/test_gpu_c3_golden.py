@@ -56,14 +56,15 @@ def test_c3_full_sweep_matches_oracle_golden(ctx):
     # Gate: 1e-12 * sigma_max per step (north_star).  The 189 factorisations are DEPENDENT (every truncation feeds the
     # next one through a 512-of-2048 cut with relative gaps ~1e-3), so rounding-level differences are amplified along the
     # sweep in ANY implementation: the golden file holds `noise_floor`, the per-step movement of the ORACLE's own spectra
-    # under rounding-level changes (make_c3_golden.py: re-runs with every input entry moved by one ulp, four seeds, and one
-    # with a 2e-15 relative perturbation of every SVD input - LAPACK gesdd's own backward error at these shapes is 9e-15;
-    # maximum over the samples: median 9e-14, 12 steps above 1e-12, 2.0e-12 at the most sensitive steps 68 / 183).
+    # between backward-stable variants of itself (make_c3_golden.py; maximum over six samples: every input entry moved
+    # by one ulp, four seeds; a 2e-15 relative perturbation of every SVD input - LAPACK gesdd's own backward error at
+    # these shapes is 9e-15; and the same sweep with the gesvd driver: median 3e-13, 35 steps above 1e-12, 4.2e-12 at
+    # the most sensitive steps 68 / 183).
     # Every step is held to 1e-12, or to twice the oracle's own floor (maximum over +-8 neighbouring steps) where that is
-    # larger.  Measured with the Rayleigh-Ritz refinement of the Jacobi vectors (svd.cu ritz_refine): worst step
-    # 9.2e-13 - no step above the plain 1e-12 -, median 2e-14, at most 0.5 x the floor (before the refinement the device
-    # SVD carried a backward error of 1e-13 per factorisation against LAPACK's 9e-15 and the sweep deviated by up to
-    # 1.2e-11, six times the floor; tools/probe_backward_error.py, tools/probe_gram_parity.py).
+    # larger.  Measured with the Rayleigh-Ritz refinement of the Jacobi vectors (svd.cu ritz_refine): median 6e-14, 183
+    # steps within the plain 1e-12, worst 0.8 - 1.4e-12 across builds, at most 0.85 x the floor (before the refinement the
+    # device SVD carried a backward error of 1e-13 per factorisation against LAPACK's 9e-15 and the sweep deviated by up
+    # to 1.2e-11; tools/probe_backward_error.py, tools/probe_gram_parity.py).
     floor = g["noise_floor"]
     errs = np.array([float(np.max(np.abs(sg - sw)) / sw[0]) if len(sg) == len(sw) else np.inf
                      for sg, sw in zip(got, want)])
